@@ -1,0 +1,96 @@
+/*
+ * professad_b200.h -- C ABI of the B200-native OFDFT hot path (drop-in for PROFESS-AD's
+ * energy-functional evaluation and density-optimisation loop).
+ *
+ * The reference (PROFESS-AD v1.0.1) is pure Python/PyTorch: it has no FFI of its own.  Its
+ * "operator interface" for this path is the Python callable contract
+ *     f(box_vecs, den) -> scalar energy,   differentiated by torch.autograd        (docs/source/functionals.rst:13-15)
+ * plus the optimisation loop in System.optimize_density (src/professad/system.py:774-908).
+ * Every entry point below replaces one such callable (energy AND analytic dE/dn in one call) or
+ * one stage of that loop; the citation on each says which.  The Python binding a reference
+ * maintainer would add (ctypes) is shown in INTEGRATION.md and shipped in
+ * profess_ad_b200/_native.py.
+ *
+ * Conventions
+ *   - all arrays are DEVICE pointers to fp64, C-contiguous (n0, n1, n2) grids, N = n0*n1*n2;
+ *     `box` is a HOST pointer to the 3x3 row-major lattice (rows = lattice vectors, bohr);
+ *   - energies are written to a DEVICE double (Hartree) -- no call synchronises the host;
+ *   - `v_out` may be NULL (energy only).  With `accumulate != 0` the call does E += ..., v += ...;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns immediately;
+ *   - return value 0 = ok, otherwise an error code; pad_last_error() gives the message
+ *     (thread-local).  Nothing here falls back to the CPU.
+ */
+#ifndef PROFESSAD_B200_H
+#define PROFESSAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pad_plan pad_plan;
+
+#define PAD_OK 0
+#define PAD_ERR_CUDA 1
+#define PAD_ERR_CUFFT 2
+#define PAD_ERR_ARG 3
+#define PAD_ERR_NCCL 4
+
+/* parts of a Wang-Teter style kinetic functional to include (functionals.py:669-670) */
+#define PAD_PART_TF 1
+#define PAD_PART_VW 2
+#define PAD_PART_NL 4
+#define PAD_PART_ALL 7
+
+/* local terms for pad_eval_local */
+#define PAD_LOCAL_TF 1          /* ThomasFermi               functionals.py:207-224  */
+#define PAD_LOCAL_LDAX 2        /* lda_exchange              functionals.py:1510-1512 */
+#define PAD_LOCAL_PZC 4         /* perdew_zunger_correlation functionals.py:1515-1521 */
+#define PAD_LOCAL_IONEL 8       /* IonElectron               functionals.py:31-46     */
+
+const char* pad_version(void);
+const char* pad_last_error(void);
+
+/* ---- plan: replaces wavevecs(box_vecs, shape) (functional_tools.py:135-162) and owns the cuFFT
+ *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */
+int pad_plan_create(pad_plan** plan, const double* box_host, const int* shape_host, int device);
+int pad_plan_destroy(pad_plan* plan);
+int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
+size_t pad_plan_workspace_bytes(const pad_plan* plan);
+
+/* ---- single functionals: E (+)= F[n],  v (+)= dF/dn --------------------------------------- */
+/* IonElectron / ThomasFermi / lda_exchange / perdew_zunger_correlation in one pass over n.
+ * `terms` is a mask of PAD_LOCAL_*; v_ext may be NULL unless PAD_LOCAL_IONEL is set.
+ * PerdewZunger (functionals.py:1540-1554) = PAD_LOCAL_LDAX | PAD_LOCAL_PZC. */
+int pad_eval_local(pad_plan* plan, const double* den, const double* v_ext, int terms,
+                   double* E_out, double* v_out, int accumulate, void* stream);
+/* Hartree (functionals.py:49-72) */
+int pad_eval_hartree(pad_plan* plan, const double* den, double* E_out, double* v_out, int accumulate, void* stream);
+/* Weizsaecker (functionals.py:227-246) */
+int pad_eval_weizsaecker(pad_plan* plan, const double* den, double* E_out, double* v_out, int accumulate, void* stream);
+/* WangTeter / Perrot / SmargiassiMadden / WangGovindCarter98 and non_local_KEF
+ * (functionals.py:644-725): `parts` selects TF, vW and the non-local term. */
+int pad_eval_wt(pad_plan* plan, const double* den, double alpha, double beta, int parts,
+                double* E_out, double* v_out, int accumulate, void* stream);
+/* WangTeterStyleFunctional building blocks (functionals.py:771-782): writes TF, vW, T_NL to
+ * E3_out[0..2] and the three potentials to v3_out (3*N doubles, may be NULL). */
+int pad_eval_wt_components(pad_plan* plan, const double* den, double alpha, double beta,
+                           double* E3_out, double* v3_out, void* stream);
+/* WangGovindCarter99.forward (functionals.py:941-985), 14-FFT analytic form; the kernel
+ * (generate_kernel, functionals.py:845-939) is built on the device and cached in the plan. */
+int pad_eval_wgc99(pad_plan* plan, const double* den, double alpha, double beta, double gamma, double kappa,
+                   double* E_out, double* v_out, int accumulate, void* stream);
+/* PerdewBurkeErnzerhof (functionals.py:1597-1635); `which`: 1 = exchange, 2 = correlation, 3 = both */
+int pad_eval_pbe(pad_plan* plan, const double* den, int which, double* E_out, double* v_out, int accumulate, void* stream);
+
+/* ---- spectral tools (functional_tools.py:166-227) ------------------------------------------ */
+int pad_gradient(pad_plan* plan, const double* f, double* gx, double* gy, double* gz, void* stream);
+int pad_laplacian(pad_plan* plan, const double* f, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

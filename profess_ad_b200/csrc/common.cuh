@@ -1,0 +1,217 @@
+// Shared device/host helpers for the B200 OFDFT hot path.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/professad_b200.h"
+
+#define PAD_MAX_RED 8            // reductions per kernel
+#define PAD_MAX_BLOCKS 1184      // 148 SMs x 8 resident 256-thread CTAs
+#define PAD_THREADS 256
+#define PAD_N_RBUF 8             // real scratch fields
+#define PAD_N_CBUF 4             // half-spectrum scratch fields
+#define PAD_N_SCAL 64            // device scalars
+
+constexpr double kPi = 3.14159265358979323846;
+// 0.3 (3 pi^2)^(2/3)
+constexpr double kCTF = 2.871234000188191;
+
+void pad_set_error(const char* fmt, ...);
+
+#define PAD_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            pad_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+            return PAD_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define PAD_CUFFT(call)                                                                         \
+    do {                                                                                        \
+        cufftResult r_ = (call);                                                                \
+        if (r_ != CUFFT_SUCCESS) {                                                              \
+            pad_set_error("cuFFT error %d at %s:%d (%s)", (int)r_, __FILE__, __LINE__, #call);  \
+            return PAD_ERR_CUFFT;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define PAD_TRY(call)                \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != PAD_OK) return rc_; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+//  reciprocal-space geometry: restates wavevecs() (functional_tools.py:135-162) per k-point
+// ---------------------------------------------------------------------------------------------
+struct KGeom {
+    int n0, n1, n2, nzh;     // grid and half-spectrum length along axis 2
+    int e0, e1, e2;          // axis length even?
+    double b[9];             // reciprocal lattice, rows = b_i = 2 pi inv(box^T)[i]
+    double inv_n;            // 1 / (n0 n1 n2): cuFFT transforms are unnormalised
+};
+
+struct KPoint {
+    double kx, ky, kz;       // k(p) with the reference's "Nyquist made positive" convention
+    double px, py, pz;       // k(pbar), the Hermitian partner on a self-conjugate plane
+    bool special;            // p lies on a self-conjugate plane AND carries a Nyquist index
+    int j0, j1, j2;
+};
+
+__device__ __forceinline__ KPoint make_kpoint(const KGeom& g, uint32_t idx) {
+    KPoint p;
+    uint32_t row = idx / (uint32_t)g.nzh;
+    p.j2 = (int)(idx - row * (uint32_t)g.nzh);
+    p.j0 = (int)(row / (uint32_t)g.n1);
+    p.j1 = (int)(row - (uint32_t)p.j0 * (uint32_t)g.n1);
+    const double f0 = (double)(p.j0 <= g.n0 / 2 ? p.j0 : p.j0 - g.n0);
+    const double f1 = (double)(p.j1 <= g.n1 / 2 ? p.j1 : p.j1 - g.n1);
+    const double f2 = (double)p.j2;
+    p.kx = f0 * g.b[0] + f1 * g.b[3] + f2 * g.b[6];
+    p.ky = f0 * g.b[1] + f1 * g.b[4] + f2 * g.b[7];
+    p.kz = f0 * g.b[2] + f1 * g.b[5] + f2 * g.b[8];
+    const bool nyq0 = g.e0 && (p.j0 == g.n0 / 2);
+    const bool nyq1 = g.e1 && (p.j1 == g.n1 / 2);
+    const bool nyq2 = g.e2 && (p.j2 == g.n2 / 2);
+    const bool selfconj = (p.j2 == 0) || nyq2;
+    p.special = selfconj && (nyq0 || nyq1 || nyq2);
+    p.px = p.kx; p.py = p.ky; p.pz = p.kz;
+    if (p.special) {
+        const double q0 = nyq0 ? f0 : -f0;
+        const double q1 = nyq1 ? f1 : -f1;
+        p.px = q0 * g.b[0] + q1 * g.b[3] + f2 * g.b[6];
+        p.py = q0 * g.b[1] + q1 * g.b[4] + f2 * g.b[7];
+        p.pz = q0 * g.b[2] + q1 * g.b[5] + f2 * g.b[8];
+    }
+    return p;
+}
+
+// Effective real multiplier M(|k|^2-like even function) on the half spectrum: on special points the
+// reference's irfftn sees the Hermitian part (M(p) + M(pbar)) / 2  (DESIGN.md "Nyquist semantics").
+template <class M>
+__device__ __forceinline__ double sym_even(const KPoint& p, M mult) {
+    double m = mult(p.kx, p.ky, p.kz);
+    if (p.special) m = 0.5 * (m + mult(p.px, p.py, p.pz));
+    return m;
+}
+
+// Effective wave-vector for the gradient multiplier i*k_c:  (k(p) - k(pbar)) / 2 on special points.
+__device__ __forceinline__ void sym_kvec(const KPoint& p, double& kx, double& ky, double& kz) {
+    kx = p.kx; ky = p.ky; kz = p.kz;
+    if (p.special) {
+        kx = 0.5 * (p.kx - p.px);
+        ky = 0.5 * (p.ky - p.py);
+        kz = 0.5 * (p.kz - p.pz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+//  block reduction: warp shuffles, then one shared-memory hop.  Deterministic for a fixed grid.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NRED>
+__device__ __forceinline__ void block_reduce_store(const double (&acc)[NRED], double* __restrict__ partials) {
+    __shared__ double sm[NRED][PAD_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < NRED; ++t) {
+        double v = warp_sum(acc[t]);
+        if (lane == 0) sm[t][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int t = 0; t < NRED; ++t) {
+            double v = lane < PAD_THREADS / 32 ? sm[t][lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) partials[(size_t)t * PAD_MAX_BLOCKS + blockIdx.x] = v;
+        }
+    }
+}
+
+// real-space elementwise kernel: f(i, acc) for every grid point, NRED block-reduced sums
+template <int NRED, class F>
+__global__ void __launch_bounds__(PAD_THREADS) ew_kernel(size_t n, F f, double* __restrict__ partials) {
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int t = 0; t < (NRED > 0 ? NRED : 1); ++t) acc[t] = 0.0;
+    const size_t stride = (size_t)gridDim.x * PAD_THREADS;
+    for (size_t i = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; i < n; i += stride) f(i, acc);
+    if (NRED > 0) block_reduce_store<(NRED > 0 ? NRED : 1)>(acc, partials);
+}
+
+// reciprocal-space kernel: f(idx, kpoint) for every half-spectrum point
+template <class F>
+__global__ void __launch_bounds__(PAD_THREADS) ks_kernel(KGeom g, uint32_t nk, F f) {
+    const uint32_t stride = gridDim.x * PAD_THREADS;
+    for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
+        KPoint p = make_kpoint(g, idx);
+        f(idx, p);
+    }
+}
+
+inline int pad_grid_for(size_t n) {
+    size_t b = (n + PAD_THREADS - 1) / PAD_THREADS;
+    if (b > PAD_MAX_BLOCKS) b = PAD_MAX_BLOCKS;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+//  the plan
+// ---------------------------------------------------------------------------------------------
+struct pad_plan {
+    int n0, n1, n2, nzh;
+    size_t N, Nk;
+    double box[9], recip[9], vol, dV;
+    int device;
+    KGeom geom;
+    cufftHandle d2z, z2d;
+    bool fft_ready;
+    void* fft_work;
+    size_t fft_work_bytes;
+    cudaStream_t fft_stream;
+    double* rbuf[PAD_N_RBUF];
+    cufftDoubleComplex* cbuf[PAD_N_CBUF];
+    double* partials;            // PAD_MAX_RED * PAD_MAX_BLOCKS
+    double* scal;                // PAD_N_SCAL device scalars
+    // WGC99 kernel cache: 4 half-spectrum real arrays W0, K1, K2, K3 and the key they were built for
+    double* wgc_kern;
+    double wgc_key[6];           // alpha, beta, gamma, kappa, + box generation, valid flag
+    uint64_t box_generation;
+    size_t bytes_allocated;
+};
+
+// scalar slots (device doubles in plan->scal)
+enum {
+    S_SUM_RHO = 0,      // sum of n over the grid
+    S_N0 = 1,           // mean density
+    S_NREF = 2,         // WGC99 reference density kappa * round(N_elec) / vol
+    S_NREF_KEY = 3,     // n_ref the cached WGC99 kernel was built for
+    S_TMP0 = 8,         // 8 slots of per-call temporaries
+    S_E_PARTS = 16      // component energies
+};
+
+int pad_get_rbuf(pad_plan* p, int i, double** out);
+int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
+int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
+int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
+
+// finalize: E_out (+)= sum_t coef[t] * (sum over blocks of partials[t]); optionally store raw sums
+struct FinalizeArgs {
+    int nblocks, nterms, accumulate;
+    double coef[PAD_MAX_RED];
+    double* sums_out;     // nterms raw sums (may be null)
+    double* E_out;        // may be null
+};
+void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s);

@@ -1,0 +1,723 @@
+// Energy functionals + analytic potentials: fused real-space kernels, fused reciprocal-space
+// kernel multiplies, cuFFT D2Z/Z2D in between.  Each entry point cites the reference callable it
+// replaces; formulas are the ones validated on CPU in tests/analytic_model.py.
+#include "common.cuh"
+
+namespace {
+
+constexpr double kCX = -0.7385587663820223;        // -(3/4)(3/pi)^(1/3)
+constexpr double kRS13 = 0.6203504908994001;       // (3/(4 pi))^(1/3)
+constexpr double k3Pi2 = 29.608813203268074;       // 3 pi^2
+
+inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+__device__ __forceinline__ double pow_pos(double x, double c) { return exp(c * log(x)); }
+
+// 1/G^{-1}(eta) - 3 eta^2 - 1   with the Lindhard function of functionals.py:617-628
+__device__ __forceinline__ double lindhard_minus(double eta) {
+    double ginv;
+    if (eta == 0.0) ginv = 1.0;
+    else if (eta == 1.0) ginv = 0.5;
+    else ginv = 0.5 + ((1.0 - eta * eta) / (4.0 * eta)) * log(fabs((1.0 + eta) / (1.0 - eta)));
+    return 1.0 / ginv - 3.0 * eta * eta - 1.0;
+}
+
+__device__ __forceinline__ double kabs_of(double kx, double ky, double kz) {
+    const double k2 = kx * kx + ky * ky + kz * kz;
+    return k2 != 0.0 ? sqrt(k2) : 0.0;
+}
+
+template <int NRED, class F>
+void launch_ew(pad_plan* p, cudaStream_t s, F f) {
+    ew_kernel<NRED, F><<<pad_grid_for(p->N), PAD_THREADS, 0, s>>>(p->N, f, p->partials);
+}
+
+template <class F>
+void launch_ks(pad_plan* p, cudaStream_t s, F f) {
+    ks_kernel<F><<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, f);
+}
+
+void finalize(pad_plan* p, cudaStream_t s, int nterms, const double* coef, double* E_out, int accumulate,
+              double* sums_out = nullptr) {
+    FinalizeArgs a;
+    a.nblocks = pad_grid_for(p->N);
+    a.nterms = nterms;
+    a.accumulate = accumulate;
+    for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = t < nterms ? coef[t] : 0.0;
+    a.sums_out = sums_out;
+    a.E_out = E_out;
+    pad_launch_finalize(p, a, s);
+}
+
+int check_common(pad_plan* p, const double* den, const char* who) {
+    if (!p || !den) {
+        pad_set_error("%s: null plan or density pointer", who);
+        return PAD_ERR_ARG;
+    }
+    PAD_CUDA(cudaSetDevice(p->device));
+    return PAD_OK;
+}
+
+#define PAD_CHECK_LAUNCH() PAD_CUDA(cudaGetLastError())
+
+// ------------------------------- local pieces shared by several kernels -----------------------
+struct PZ {
+    double e, v;   // eps_c * n and d(eps_c n)/dn
+};
+__device__ __forceinline__ PZ pz_correlation(double n, double c13) {
+    // functionals.py:1515-1521 ; potential: tests/tools_for_tests.py:125-131
+    const double A = 0.0311, B = -0.048, C = 0.002, D = -0.0116;
+    const double ga = -0.1423, b1 = 1.0529, b2 = 0.3334;
+    const double rs = kRS13 / c13;
+    PZ r;
+    if (rs < 1.0) {
+        const double lr = log(rs);
+        r.e = n * (A * lr + B + C * rs * lr + D * rs);
+        r.v = lr * (A + (2.0 / 3.0) * C * rs) + (B - A / 3.0) + rs / 3.0 * (2.0 * D - C);
+    } else {
+        const double sr = sqrt(rs);
+        const double dn = 1.0 + b1 * sr + b2 * rs;
+        r.e = n * ga / dn;
+        r.v = ga * (1.0 + (7.0 / 6.0) * b1 * sr + (4.0 / 3.0) * b2 * rs) / (dn * dn);
+    }
+    return r;
+}
+
+}  // namespace
+
+// =============================================================================================
+//  IonElectron / ThomasFermi / lda_exchange / perdew_zunger_correlation  (one pass)
+// =============================================================================================
+extern "C" int pad_eval_local(pad_plan* p, const double* den, const double* v_ext, int terms, double* E_out,
+                              double* v_out, int accumulate, void* stream) {
+    PAD_TRY(check_common(p, den, "pad_eval_local"));
+    if ((terms & PAD_LOCAL_IONEL) && !v_ext) {
+        pad_set_error("pad_eval_local: IonElectron needs v_ext");
+        return PAD_ERR_ARG;
+    }
+    cudaStream_t s = as_stream(stream);
+    const bool tf = terms & PAD_LOCAL_TF, ldax = terms & PAD_LOCAL_LDAX, pzc = terms & PAD_LOCAL_PZC,
+               ion = terms & PAD_LOCAL_IONEL;
+    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
+        const double n = den[i];
+        double e = 0.0, v = 0.0;
+        if (tf || ldax || pzc) {
+            const double c = cbrt(n);
+            if (tf) { e += kCTF * n * c * c; v += (5.0 / 3.0) * kCTF * c * c; }
+            if (ldax) { e += kCX * n * c; v += (4.0 / 3.0) * kCX * c; }
+            if (pzc) { PZ r = pz_correlation(n, c); e += r.e; v += r.v; }
+        }
+        if (ion) { const double ve = v_ext[i]; e += n * ve; v += ve; }
+        acc[0] += e;
+        if (v_out) v_out[i] = accumulate ? v_out[i] + v : v;
+    });
+    PAD_CHECK_LAUNCH();
+    const double coef[1] = {p->dV};
+    if (E_out) finalize(p, s, 1, coef, E_out, accumulate);
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}
+
+// =============================================================================================
+//  Hartree (functionals.py:49-72): 2 FFTs
+// =============================================================================================
+extern "C" int pad_eval_hartree(pad_plan* p, const double* den, double* E_out, double* v_out, int accumulate,
+                                void* stream) {
+    PAD_TRY(check_common(p, den, "pad_eval_hartree"));
+    cudaStream_t s = as_stream(stream);
+    cufftDoubleComplex* C0;
+    double* R0;
+    PAD_TRY(pad_get_cbuf(p, 0, &C0));
+    PAD_TRY(pad_fft_forward(p, den, C0, s));
+    const double inv_n = p->geom.inv_n;
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+        const double m = inv_n * sym_even(k, [](double kx, double ky, double kz) {
+                             const double k2 = kx * kx + ky * ky + kz * kz;
+                             return k2 != 0.0 ? 4.0 * kPi / k2 : 0.0;
+                         });
+        cufftDoubleComplex c = C0[idx];
+        c.x *= m; c.y *= m;
+        C0[idx] = c;
+    });
+    PAD_CHECK_LAUNCH();
+    double* phi;
+    const bool direct = v_out && !accumulate;
+    if (direct) phi = v_out;
+    else { PAD_TRY(pad_get_rbuf(p, 0, &R0)); phi = R0; }
+    PAD_TRY(pad_fft_inverse(p, C0, phi, s));
+    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
+        const double ph = phi[i];
+        acc[0] += den[i] * ph;
+        if (v_out && !direct) v_out[i] += ph;
+    });
+    PAD_CHECK_LAUNCH();
+    const double coef[1] = {0.5 * p->dV};
+    if (E_out) finalize(p, s, 1, coef, E_out, accumulate);
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}
+
+// =============================================================================================
+//  spectral gradient / Laplacian (functional_tools.py:166-227)
+// =============================================================================================
+extern "C" int pad_laplacian(pad_plan* p, const double* f, double* out, void* stream) {
+    PAD_TRY(check_common(p, f, "pad_laplacian"));
+    cudaStream_t s = as_stream(stream);
+    cufftDoubleComplex* C0;
+    PAD_TRY(pad_get_cbuf(p, 0, &C0));
+    PAD_TRY(pad_fft_forward(p, f, C0, s));
+    const double inv_n = p->geom.inv_n;
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+        const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
+        cufftDoubleComplex c = C0[idx];
+        c.x *= m; c.y *= m;
+        C0[idx] = c;
+    });
+    PAD_CHECK_LAUNCH();
+    PAD_TRY(pad_fft_inverse(p, C0, out, s));
+    return PAD_OK;
+}
+
+// spectrum of f in C0 -> i k_c F / N in C1..C3
+static int spectral_gradient(pad_plan* p, cudaStream_t s, const cufftDoubleComplex* F, cufftDoubleComplex* Gx,
+                             cufftDoubleComplex* Gy, cufftDoubleComplex* Gz) {
+    const double inv_n = p->geom.inv_n;
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+        double kx, ky, kz;
+        sym_kvec(k, kx, ky, kz);
+        const cufftDoubleComplex c = F[idx];
+        const double a = c.x * inv_n, b = c.y * inv_n;
+        Gx[idx] = make_cuDoubleComplex(-b * kx, a * kx);
+        Gy[idx] = make_cuDoubleComplex(-b * ky, a * ky);
+        Gz[idx] = make_cuDoubleComplex(-b * kz, a * kz);
+    });
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}
+
+extern "C" int pad_gradient(pad_plan* p, const double* f, double* gx, double* gy, double* gz, void* stream) {
+    PAD_TRY(check_common(p, f, "pad_gradient"));
+    cudaStream_t s = as_stream(stream);
+    cufftDoubleComplex *C0, *C1, *C2, *C3;
+    PAD_TRY(pad_get_cbuf(p, 0, &C0)); PAD_TRY(pad_get_cbuf(p, 1, &C1));
+    PAD_TRY(pad_get_cbuf(p, 2, &C2)); PAD_TRY(pad_get_cbuf(p, 3, &C3));
+    PAD_TRY(pad_fft_forward(p, f, C0, s));
+    PAD_TRY(spectral_gradient(p, s, C0, C1, C2, C3));
+    PAD_TRY(pad_fft_inverse(p, C1, gx, s));
+    PAD_TRY(pad_fft_inverse(p, C2, gy, s));
+    PAD_TRY(pad_fft_inverse(p, C3, gz, s));
+    return PAD_OK;
+}
+
+// =============================================================================================
+//  Weizsaecker (functionals.py:227-246): chi = sqrt(n); E = -1/2 int chi lap(chi); v = -lap(chi)/(2 chi)
+//  (the 1/4 lap(n) term integrates to exactly zero: its k = 0 coefficient is -0 * n_hat(0))
+// =============================================================================================
+extern "C" int pad_eval_weizsaecker(pad_plan* p, const double* den, double* E_out, double* v_out, int accumulate,
+                                    void* stream) {
+    return pad_eval_wt(p, den, 1.0, 1.0, PAD_PART_VW, E_out, v_out, accumulate, stream);
+}
+
+// =============================================================================================
+//  Wang-Teter family (functionals.py:644-725): TF + vW + non-local term with the density-independent
+//  Lindhard kernel.  4 FFTs for alpha == beta, 6 otherwise.
+// =============================================================================================
+__global__ void wt_scalars_kernel(double* scal, double alpha, double beta, double inv_n) {
+    // n0 = N_elec / vol = mean(n)  (functionals.py:646-647; detached -> a plain number)
+    const double n0 = scal[S_SUM_RHO] * inv_n;
+    scal[S_N0] = n0;
+    const double kF = cbrt(k3Pi2 * n0);
+    scal[S_TMP0 + 0] = 1.0 / (2.0 * kF);
+    scal[S_TMP0 + 1] = 5.0 / (9.0 * alpha * beta * pow(n0, alpha + beta - 5.0 / 3.0));
+    scal[S_TMP0 + 2] = pow(n0, alpha);
+    scal[S_TMP0 + 3] = pow(n0, beta);
+}
+
+extern "C" int pad_eval_wt(pad_plan* p, const double* den, double alpha, double beta, int parts, double* E_out,
+                           double* v_out, int accumulate, void* stream) {
+    PAD_TRY(check_common(p, den, "pad_eval_wt"));
+    if (!(parts & PAD_PART_ALL)) { pad_set_error("pad_eval_wt: empty parts mask"); return PAD_ERR_ARG; }
+    cudaStream_t s = as_stream(stream);
+    const bool tf = parts & PAD_PART_TF, vw = parts & PAD_PART_VW, nl = parts & PAD_PART_NL;
+    const bool two = nl && (alpha != beta);
+    double *R0 = nullptr, *R1 = nullptr, *R2 = nullptr;
+    cufftDoubleComplex *C0 = nullptr, *C1 = nullptr, *C2 = nullptr;
+    double* scal = p->scal;
+    const double inv_n = p->geom.inv_n;
+
+    if (vw) { PAD_TRY(pad_get_rbuf(p, 0, &R0)); PAD_TRY(pad_get_cbuf(p, 0, &C0)); }
+    if (nl) { PAD_TRY(pad_get_rbuf(p, 1, &R1)); PAD_TRY(pad_get_cbuf(p, 1, &C1)); }
+    if (two) { PAD_TRY(pad_get_rbuf(p, 2, &R2)); PAD_TRY(pad_get_cbuf(p, 2, &C2)); }
+
+    if (nl) {
+        launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
+        PAD_CHECK_LAUNCH();
+        const double one[1] = {1.0};
+        finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
+        wt_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, inv_n);
+        PAD_CHECK_LAUNCH();
+    }
+    if (vw || nl) {
+        launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+            const double n = den[i];
+            if (vw) R0[i] = n != 0.0 ? sqrt(n) : 0.0;
+            if (nl) {
+                const double ln = log(n);
+                R1[i] = exp(beta * ln) - scal[S_TMP0 + 3];
+                if (two) R2[i] = exp(alpha * ln) - scal[S_TMP0 + 2];
+            }
+        });
+        PAD_CHECK_LAUNCH();
+        if (vw) PAD_TRY(pad_fft_forward(p, R0, C0, s));
+        if (nl) PAD_TRY(pad_fft_forward(p, R1, C1, s));
+        if (two) PAD_TRY(pad_fft_forward(p, R2, C2, s));
+        launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+            if (vw) {
+                const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
+                cufftDoubleComplex c = C0[idx];
+                c.x *= m; c.y *= m;
+                C0[idx] = c;
+            }
+            if (nl) {
+                const double inv2kF = scal[S_TMP0 + 0];
+                const double m = inv_n * scal[S_TMP0 + 1] * sym_even(k, [=](double kx, double ky, double kz) {
+                                     return lindhard_minus(kabs_of(kx, ky, kz) * inv2kF);
+                                 });
+                cufftDoubleComplex c = C1[idx];
+                c.x *= m; c.y *= m;
+                C1[idx] = c;
+                if (two) {
+                    cufftDoubleComplex d = C2[idx];
+                    d.x *= m; d.y *= m;
+                    C2[idx] = d;
+                }
+            }
+        });
+        PAD_CHECK_LAUNCH();
+        if (vw) PAD_TRY(pad_fft_inverse(p, C0, R0, s));      // lap(chi)
+        if (nl) PAD_TRY(pad_fft_inverse(p, C1, R1, s));      // K * n^beta
+        if (two) PAD_TRY(pad_fft_inverse(p, C2, R2, s));     // K * n^alpha
+    }
+    launch_ew<3>(p, s, [=] __device__(size_t i, double(&acc)[3]) {
+        const double n = den[i];
+        double v = 0.0;
+        if (tf) {
+            const double c = cbrt(n);
+            acc[0] += kCTF * n * c * c;
+            v += (5.0 / 3.0) * kCTF * c * c;
+        }
+        if (vw) {
+            const double chi = n != 0.0 ? sqrt(n) : 0.0;
+            const double lap = R0[i];
+            acc[1] += chi * lap;
+            if (n != 0.0) v += -0.5 * lap / chi;
+        }
+        if (nl) {
+            const double ln = log(n);
+            const double pb = exp(beta * ln);
+            const double pa = two ? exp(alpha * ln) : pb;
+            const double conv_b = R1[i];
+            const double conv_a = two ? R2[i] : conv_b;
+            acc[2] += (pa - scal[S_TMP0 + 2]) * conv_b;
+            v += kCTF * (alpha * pa * conv_b + beta * pb * conv_a) / n;
+        }
+        if (v_out) v_out[i] = accumulate ? v_out[i] + v : v;
+    });
+    PAD_CHECK_LAUNCH();
+    const double coef[3] = {p->dV, -0.5 * p->dV, kCTF * p->dV};
+    if (E_out) finalize(p, s, 3, coef, E_out, accumulate);
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}
+
+extern "C" int pad_eval_wt_components(pad_plan* p, const double* den, double alpha, double beta, double* E3_out,
+                                      double* v3_out, void* stream) {
+    if (!E3_out) { pad_set_error("pad_eval_wt_components: E3_out is null"); return PAD_ERR_ARG; }
+    const int parts[3] = {PAD_PART_TF, PAD_PART_VW, PAD_PART_NL};
+    for (int c = 0; c < 3; ++c) {
+        double* v = v3_out ? v3_out + (size_t)c * p->N : nullptr;
+        PAD_TRY(pad_eval_wt(p, den, alpha, beta, parts[c], E3_out + c, v, 0, stream));
+    }
+    return PAD_OK;
+}
+
+// =============================================================================================
+//  Wang-Govind-Carter 99 (functionals.py:787-985)
+// =============================================================================================
+#define WGC_TERMS 100
+struct WgcSeries {
+    double cA[WGC_TERMS];   // A_i / ((u + 2 i)^2 - v)    (eta > 1 branch)
+    double cB[WGC_TERMS];   // B_i / ((u - 2 i)^2 - v)    (eta <= 1 branch)
+    double u, v, c1, c2;
+    int vcase;              // +1: v > 0, 0: v == 0, -1: v < 0
+    double gamma;
+};
+__constant__ WgcSeries c_wgc;
+
+// w(eta), w'(eta), w''(eta) (unscaled), functionals.py:845-939
+__device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double& w2) {
+    const WgcSeries& S = c_wgc;
+    if (eta == 0.0) { w0 = w1 = w2 = 0.0; return; }
+    const bool inside = eta <= 1.0;
+    double C1, C2;
+    if (S.u >= 0.0) { C1 = inside ? S.c1 : 0.0; C2 = inside ? S.c2 : 0.0; }
+    else { C1 = inside ? 0.0 : S.c1; C2 = inside ? 0.0 : S.c2; }
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    if (C1 != 0.0 || C2 != 0.0) {
+        const double le = log(eta), u = S.u;
+        if (S.vcase > 0) {
+            const double rv = sqrt(S.v), x = u + rv, y = u - rv;
+            const double ex = exp(x * le), ey = exp(y * le);
+            h0 = C1 * ex + C2 * ey;
+            h1 = (C1 * x * ex + C2 * y * ey) / eta;
+            h2 = (C1 * x * (x - 1.0) * ex + C2 * y * (y - 1.0) * ey) / (eta * eta);
+        } else if (S.vcase == 0) {
+            const double eu = exp(u * le);
+            h0 = eu * (C2 * le + C1);
+            h1 = (C2 * eu * (1.0 + u * le) + C1 * u * eu) / eta;
+            h2 = (C2 * ((u - 1.0) * eu * (1.0 + u * le) + eu) + C1 * u * (u - 1.0) * eu) / (eta * eta);
+        } else {
+            const double sv = sqrt(-S.v), eu = exp(u * le);
+            double ts, tc;
+            sincos(sv * le, &ts, &tc);
+            const double p1 = u * tc - sv * ts, p2 = u * ts + sv * tc;
+            h0 = eu * (C1 * tc + C2 * ts);
+            h1 = eu / eta * (C1 * p1 + C2 * p2);
+            h2 = eu / (eta * eta) * ((u - 1.0) * (C1 * p1 + C2 * p2) + sv * (C2 * p1 - C1 * p2));
+        }
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (inside) {
+        const double x = eta * eta;
+        double pw = 1.0;
+        for (int i = 0; i < WGC_TERMS; ++i) {
+            const double t = S.cB[i] * pw, two_i = 2.0 * i;
+            s0 += t; s1 += t * two_i; s2 += t * two_i * (two_i - 1.0);
+            pw *= x;
+        }
+        w0 = h0 + s0; w1 = h1 + s1 / eta; w2 = h2 + s2 / x;
+    } else {
+        const double y = 1.0 / (eta * eta);
+        double pw = 1.0;
+        for (int i = 0; i < WGC_TERMS; ++i) {
+            const double t = S.cA[i] * pw, two_i = 2.0 * i;
+            s0 += t; s1 -= t * two_i; s2 += t * two_i * (two_i + 1.0);
+            pw *= y;
+        }
+        w0 = h0 + s0; w1 = h1 + s1 / eta; w2 = h2 + s2 * y;
+    }
+}
+
+__global__ void wgc_scalars_kernel(double* scal, double alpha, double beta, double kappa, double dV, double vol) {
+    // N_elec = round(mean(n) vol) (functionals.py:952; Python round = half-to-even = rint)
+    const double n_elec = rint(scal[S_SUM_RHO] * dV);
+    const double n_ref = kappa * n_elec / vol;
+    scal[S_NREF] = n_ref;
+    scal[S_TMP0 + 0] = 1.0 / (2.0 * cbrt(k3Pi2 * n_ref));
+    scal[S_TMP0 + 1] = 20.0 * pow(n_ref, 5.0 / 3.0 - alpha - beta);
+}
+
+// kern layout: [W0 | K1 | K2 | K3], each Nk doubles, pre-multiplied by 1/N
+__global__ void __launch_bounds__(PAD_THREADS) wgc_build_kernel(KGeom g, uint32_t nk, double* __restrict__ kern,
+                                                               double* scal, int force) {
+    const double n_ref = scal[S_NREF];
+    if (!force && n_ref == scal[S_NREF_KEY]) return;
+    const double inv2kF = scal[S_TMP0 + 0], T = scal[S_TMP0 + 1] * g.inv_n, gam = c_wgc.gamma;
+    const uint32_t stride = gridDim.x * PAD_THREADS;
+    for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
+        const KPoint k = make_kpoint(g, idx);
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        const int reps = k.special ? 2 : 1;
+        for (int r = 0; r < reps; ++r) {
+            const double eta = (r == 0 ? kabs_of(k.kx, k.ky, k.kz) : kabs_of(k.px, k.py, k.pz)) * inv2kF;
+            double w0, w1, w2;
+            wgc_w(eta, w0, w1, w2);
+            w0 *= T; w1 *= T; w2 *= T;
+            out[0] += w0;
+            out[1] += -eta * w1 / (6.0 * n_ref);
+            out[2] += (eta * eta * w2 + (7.0 - gam) * eta * w1) / (36.0 * n_ref * n_ref);
+            out[3] += (eta * eta * w2 + (1.0 + gam) * eta * w1) / (36.0 * n_ref * n_ref);
+        }
+        const double sc = k.special ? 0.5 : 1.0;
+        for (int c = 0; c < 4; ++c) kern[(size_t)c * nk + idx] = sc * out[c];
+    }
+}
+
+__global__ void wgc_key_kernel(double* scal) { scal[S_NREF_KEY] = scal[S_NREF]; }
+
+static void wgc_host_series(double alpha, double beta, double gamma, WgcSeries* S) {
+    // functionals.py:817-843 (coefficient recursions) and :853-875 (homogeneous-solution constants)
+    const int n = WGC_TERMS;
+    double a[WGC_TERMS + 1], b[WGC_TERMS];
+    a[0] = 3.0;
+    for (int idx = 1; idx <= n; ++idx) {
+        const int i = idx - 1;
+        double acc = 0.0;
+        for (int j = -1; j < i; ++j) acc += -3.0 * a[j + 1] / (4.0 * (double)(i - j + 1) * (double)(i - j + 1) - 1.0);
+        a[idx] = acc;
+    }
+    b[0] = 1.0;
+    for (int i = 1; i < n; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < i; ++j) acc += b[j] / (4.0 * (double)(i - j) * (double)(i - j) - 1.0);
+        b[i] = acc;
+    }
+    double A[WGC_TERMS], B[WGC_TERMS];
+    for (int i = 0; i < n; ++i) { A[i] = a[i + 1]; B[i] = b[i]; }
+    A[0] -= 1.0;
+    B[0] = 0.0;
+    B[1] = b[1] - 3.0;
+    const double u = 3.0 * (alpha + beta) - gamma / 2.0;
+    const double v = u * u - 36.0 * alpha * beta;
+    double Sd = 0.0, Ss = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double dA = (u + 2.0 * i) * (u + 2.0 * i) - v, dB = (u - 2.0 * i) * (u - 2.0 * i) - v;
+        S->cA[i] = A[i] / dA;
+        S->cB[i] = B[i] / dB;
+        Sd += S->cA[i] - S->cB[i];
+        Ss += (double)i * (S->cA[i] + S->cB[i]);
+    }
+    Ss *= -2.0;
+    const double sgn = (u > 0) - (u < 0);
+    if (v > 0) {
+        const double rv = sqrt(v);
+        S->c1 = sgn * ((rv - u) * Sd + Ss);
+        S->c2 = sgn * ((rv + u) * Sd - Ss) / (2.0 * rv);
+        S->vcase = 1;
+    } else if (v == 0) {
+        S->c1 = sgn * Sd;
+        S->c2 = sgn * (Ss - u * Sd);
+        S->vcase = 0;
+    } else {
+        S->c1 = sgn * Sd;
+        S->c2 = sgn * (Ss - u * Sd) / sqrt(-v);
+        S->vcase = -1;
+    }
+    S->u = u; S->v = v; S->gamma = gamma;
+}
+
+extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa,
+                              double* E_out, double* v_out, int accumulate, void* stream) {
+    PAD_TRY(check_common(p, den, "pad_eval_wgc99"));
+    cudaStream_t s = as_stream(stream);
+    double *R[4];
+    cufftDoubleComplex* C[4];
+    for (int i = 0; i < 4; ++i) { PAD_TRY(pad_get_rbuf(p, i, &R[i])); PAD_TRY(pad_get_cbuf(p, i, &C[i])); }
+    double* scal = p->scal;
+    const size_t nk = p->Nk;
+    const double inv_n = p->geom.inv_n;
+
+    // --- reference density and kernel -----------------------------------------------------------
+    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
+    PAD_CHECK_LAUNCH();
+    const double one[1] = {1.0};
+    finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
+    wgc_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, kappa, p->dV, p->vol);
+    PAD_CHECK_LAUNCH();
+    if (!p->wgc_kern) {
+        PAD_CUDA(cudaMalloc(&p->wgc_kern, sizeof(double) * 4 * nk));
+        p->bytes_allocated += sizeof(double) * 4 * nk;
+        p->wgc_key[5] = 0.0;
+    }
+    const bool same = p->wgc_key[5] == 1.0 && p->wgc_key[0] == alpha && p->wgc_key[1] == beta &&
+                      p->wgc_key[2] == gamma && p->wgc_key[3] == kappa && p->wgc_key[4] == (double)p->box_generation;
+    // the series coefficients live in one constant bank per device, shared by all plans
+    static double bank_key[64][3];
+    static bool bank_valid[64];
+    const int dv = p->device & 63;
+    if (!bank_valid[dv] || bank_key[dv][0] != alpha || bank_key[dv][1] != beta || bank_key[dv][2] != gamma) {
+        WgcSeries S;
+        wgc_host_series(alpha, beta, gamma, &S);
+        // stream-ordered: in-flight kernels of earlier calls on this stream finish first
+        PAD_CUDA(cudaMemcpyToSymbolAsync(c_wgc, &S, sizeof(S), 0, cudaMemcpyHostToDevice, s));
+        bank_key[dv][0] = alpha; bank_key[dv][1] = beta; bank_key[dv][2] = gamma;
+        bank_valid[dv] = true;
+    }
+    if (!same) {
+        p->wgc_key[0] = alpha; p->wgc_key[1] = beta; p->wgc_key[2] = gamma; p->wgc_key[3] = kappa;
+        p->wgc_key[4] = (double)p->box_generation; p->wgc_key[5] = 1.0;
+    }
+    double* kern = p->wgc_kern;
+    wgc_build_kernel<<<pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, scal, same ? 0 : 1);
+    PAD_CHECK_LAUNCH();
+    wgc_key_kernel<<<1, 1, 0, s>>>(scal);
+    PAD_CHECK_LAUNCH();
+    const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
+
+    // --- forward fields: a = n^beta, a theta, a theta^2 / 2, chi --------------------------------
+    double *Ra = R[0], *Rb = R[1], *Rc = R[2], *Rx = R[3];
+    launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+        const double n = den[i];
+        const double th = n - scal[S_NREF];
+        const double a = pow_pos(n, beta);
+        Ra[i] = a;
+        Rb[i] = a * th;
+        Rc[i] = 0.5 * a * th * th;
+        Rx[i] = n != 0.0 ? sqrt(n) : 0.0;
+    });
+    PAD_CHECK_LAUNCH();
+    for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    cufftDoubleComplex *CA = C[0], *CB = C[1], *CC = C[2], *CX = C[3];
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+        const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
+        const cufftDoubleComplex A = CA[idx], B = CB[idx], Cc = CC[idx];
+        CA[idx] = make_cuDoubleComplex(w0 * A.x + k1 * B.x + k2 * Cc.x, w0 * A.y + k1 * B.y + k2 * Cc.y);
+        CB[idx] = make_cuDoubleComplex(k1 * A.x + k3 * B.x, k1 * A.y + k3 * B.y);
+        CC[idx] = make_cuDoubleComplex(k2 * A.x, k2 * A.y);
+        const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
+        cufftDoubleComplex X = CX[idx];
+        X.x *= m; X.y *= m;
+        CX[idx] = X;
+    });
+    PAD_CHECK_LAUNCH();
+    for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // u1, u2, u3, lap(chi)
+
+    // --- energy densities, first half of the potential, fields for the adjoint convolutions -------
+    const bool want_v = v_out != nullptr;
+    launch_ew<3>(p, s, [=] __device__(size_t i, double(&acc)[3]) {
+        const double n = den[i];
+        const double th = n - scal[S_NREF];
+        const double ln = log(n);
+        const double P = exp(alpha * ln);
+        const double u1 = Ra[i], u2 = Rb[i], u3 = Rc[i], lap = Rx[i];
+        const double conv = u1 + th * (u2 + 0.5 * th * u3);
+        const double c = cbrt(n);
+        const double chi = n != 0.0 ? sqrt(n) : 0.0;
+        acc[0] += kCTF * n * c * c;
+        acc[1] += chi * lap;
+        acc[2] += P * conv;
+        if (want_v) {
+            double v = (5.0 / 3.0) * kCTF * c * c;
+            if (n != 0.0) v += -0.5 * lap / chi;
+            v += kCTF * (alpha * P / n * conv + P * (u2 + th * u3));
+            v_out[i] = accumulate ? v_out[i] + v : v;
+            Ra[i] = P;
+            Rb[i] = P * th;
+            Rc[i] = 0.5 * P * th * th;
+        }
+    });
+    PAD_CHECK_LAUNCH();
+    const double coef[3] = {p->dV, -0.5 * p->dV, kCTF * p->dV};
+    if (E_out) finalize(p, s, 3, coef, E_out, accumulate);
+    PAD_CHECK_LAUNCH();
+    if (!want_v) return PAD_OK;
+
+    // --- adjoint convolutions --------------------------------------------------------------------
+    for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint&) {
+        const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
+        const cufftDoubleComplex A = CA[idx], B = CB[idx], Cc = CC[idx];
+        CA[idx] = make_cuDoubleComplex(w0 * A.x + k1 * B.x + k2 * Cc.x, w0 * A.y + k1 * B.y + k2 * Cc.y);
+        CB[idx] = make_cuDoubleComplex(k1 * A.x + k3 * B.x, k1 * A.y + k3 * B.y);
+        CC[idx] = make_cuDoubleComplex(k2 * A.x, k2 * A.y);
+    });
+    PAD_CHECK_LAUNCH();
+    for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // g1, g2, g3
+    launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+        const double n = den[i];
+        const double th = n - scal[S_NREF];
+        const double a = pow_pos(n, beta);
+        const double da = beta * a / n;
+        v_out[i] += kCTF * (da * Ra[i] + (da * th + a) * Rb[i] + (0.5 * da * th * th + a * th) * Rc[i]);
+    });
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}
+
+// =============================================================================================
+//  PBE (functionals.py:1597-1635), 8 FFTs.  Potential = f_n - 2 div(f_sigma grad n)
+//  (tests/tools_for_tests.py:155-207), with the reference's +1e-30 guards kept.
+// =============================================================================================
+extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E_out, double* v_out, int accumulate,
+                            void* stream) {
+    PAD_TRY(check_common(p, den, "pad_eval_pbe"));
+    if (!(which & 3)) { pad_set_error("pad_eval_pbe: which must be 1, 2 or 3"); return PAD_ERR_ARG; }
+    cudaStream_t s = as_stream(stream);
+    double* R[4];
+    cufftDoubleComplex* C[4];
+    for (int i = 0; i < 4; ++i) { PAD_TRY(pad_get_rbuf(p, i, &R[i])); PAD_TRY(pad_get_cbuf(p, i, &C[i])); }
+    PAD_TRY(pad_fft_forward(p, den, C[0], s));
+    PAD_TRY(spectral_gradient(p, s, C[0], C[1], C[2], C[3]));
+    for (int c = 0; c < 3; ++c) PAD_TRY(pad_fft_inverse(p, C[c + 1], R[c], s));
+    double *Gx = R[0], *Gy = R[1], *Gz = R[2], *Fr = R[3];
+    const bool do_x = which & 1, do_c = which & 2, want_v = v_out != nullptr;
+    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
+        const double n = den[i];
+        const double gx = Gx[i], gy = Gy[i], gz = Gz[i];
+        const double sig = gx * gx + gy * gy + gz * gz;
+        const double c13 = cbrt(n);
+        double f = 0.0, f_rho = 0.0, f_sig = 0.0;
+        if (do_x) {
+            const double cs = 0.026121172985233605;       // (1/4)(3 pi^2)^(-2/3)
+            const double kap = 0.804, mu = 0.2195164512208958;
+            const double ex = kCX * n * c13;
+            const double r83 = n * n * c13 * c13;
+            const double s2 = cs * sig / r83;
+            const double q = 1.0 + mu / kap * s2;
+            const double Fx = 1.0 + kap - kap / q, dF = mu / (q * q);
+            f += Fx * ex;
+            f_rho += Fx * (4.0 / 3.0) * kCX * c13 + ex * dF * (-8.0 / 3.0) * s2 / n;
+            f_sig += ex * dF * cs / r83;
+        }
+        if (do_c) {
+            const double A1 = 0.0310907, a1 = 0.2137, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+            const double be = 0.066725, ga = 0.0310906908696549;   // (1 - ln 2) / pi^2
+            const double ct = 0.0634682060977037;                  // (1/16)(pi/3)^(1/3)
+            const double rs = kRS13 / c13;
+            const double sr = sqrt(rs);
+            const double Q = 2.0 * A1 * (b1 * sr + b2 * rs + b3 * rs * sr + b4 * rs * rs);
+            const double lg = log(1.0 + 1.0 / Q);
+            const double eps = -2.0 * A1 * (1.0 + a1 * rs) * lg;
+            const double dQ = A1 * (b1 / sr + 2.0 * b2 + 3.0 * b3 * sr + 4.0 * b4 * rs);
+            const double deps = (-2.0 * A1 * a1 * lg + 2.0 * A1 * (1.0 + a1 * rs) * dQ / (Q * (Q + 1.0))) * (-rs / (3.0 * n));
+            const double ee = exp(-eps / ga);
+            const double Aa = be / ga / (ee - 1.0 + 1e-30);
+            const double dAa = Aa * Aa / be * ee * deps;
+            const double r73 = n * n * c13 + 1e-30;
+            const double t2 = ct * sig / r73;
+            const double dt2_rho = -ct * sig * (7.0 / 3.0) * n * c13 / (r73 * r73);
+            const double dt2_sig = ct / r73;
+            const double X = Aa * t2;
+            const double num = 1.0 + X, dnm = 1.0 + X + X * X;
+            const double Rr = num / dnm;
+            const double dR = -X * (2.0 + X) / (dnm * dnm);
+            const double inner = 1.0 + be / ga * t2 * Rr;
+            const double H = ga * log(inner);
+            const double dH_rho = be / inner * (Rr * dt2_rho + t2 * dR * (Aa * dt2_rho + t2 * dAa));
+            const double dH_sig = be / inner * (Rr + t2 * dR * Aa) * dt2_sig;
+            f += n * (eps + H);
+            f_rho += eps + H + n * (deps + dH_rho);
+            f_sig += n * dH_sig;
+        }
+        acc[0] += f;
+        if (want_v) {
+            Fr[i] = f_rho;
+            const double w = 2.0 * f_sig;
+            Gx[i] = w * gx; Gy[i] = w * gy; Gz[i] = w * gz;
+        }
+    });
+    PAD_CHECK_LAUNCH();
+    const double coef[1] = {p->dV};
+    if (E_out) finalize(p, s, 1, coef, E_out, accumulate);
+    PAD_CHECK_LAUNCH();
+    if (!want_v) return PAD_OK;
+    for (int c = 0; c < 3; ++c) PAD_TRY(pad_fft_forward(p, R[c], C[c], s));
+    cufftDoubleComplex *C0 = C[0], *C1 = C[1], *C2 = C[2];
+    const double inv_n = p->geom.inv_n;
+    launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
+        double kx, ky, kz;
+        sym_kvec(k, kx, ky, kz);
+        const cufftDoubleComplex a = C0[idx], b = C1[idx], c = C2[idx];
+        const double re = kx * a.x + ky * b.x + kz * c.x, im = kx * a.y + ky * b.y + kz * c.y;
+        C0[idx] = make_cuDoubleComplex(-im * inv_n, re * inv_n);
+    });
+    PAD_CHECK_LAUNCH();
+    PAD_TRY(pad_fft_inverse(p, C0, R[0], s));
+    double* Dv = R[0];
+    launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+        const double v = Fr[i] - Dv[i];
+        v_out[i] = accumulate ? v_out[i] + v : v;
+    });
+    PAD_CHECK_LAUNCH();
+    return PAD_OK;
+}

@@ -1,0 +1,206 @@
+// Plan management, scratch memory, cuFFT wrappers and the deterministic second-stage reduction.
+// Replaces wavevecs() (functional_tools.py:135-162): the k-vectors are never materialised, the
+// reciprocal lattice (9 doubles) travels to every reciprocal-space kernel by value.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pad_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* pad_last_error(void) { return g_err; }
+extern "C" const char* pad_version(void) { return "professad_b200 0.1 (sm_100a, fp64)"; }
+
+static int invert3(const double* m, double* inv, double* det_out) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    *det_out = det;
+    if (det == 0.0 || !isfinite(det)) return 1;
+    const double id = 1.0 / det;
+    inv[0] = A * id;               inv[1] = -(b * i - c * h) * id; inv[2] = (b * f - c * e) * id;
+    inv[3] = B * id;               inv[4] = (a * i - c * g) * id;  inv[5] = -(a * f - c * d) * id;
+    inv[6] = C * id;               inv[7] = -(a * h - b * g) * id; inv[8] = (a * e - b * d) * id;
+    return 0;
+}
+
+static int set_box(pad_plan* p, const double* box) {
+    // b = 2 pi inv(box^T)  (functional_tools.py:149); rows of b are the reciprocal vectors
+    double bt[9], inv[9], det;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) bt[r * 3 + c] = box[c * 3 + r];
+    if (invert3(bt, inv, &det)) {
+        pad_set_error("Lattice vector matrix is not invertible.");
+        return PAD_ERR_ARG;
+    }
+    memcpy(p->box, box, sizeof(double) * 9);
+    for (int k = 0; k < 9; ++k) p->recip[k] = 2.0 * kPi * inv[k];
+    p->vol = fabs(det);
+    p->dV = p->vol / (double)p->N;
+    KGeom& g = p->geom;
+    g.n0 = p->n0; g.n1 = p->n1; g.n2 = p->n2; g.nzh = p->nzh;
+    g.e0 = (p->n0 % 2 == 0); g.e1 = (p->n1 % 2 == 0); g.e2 = (p->n2 % 2 == 0);
+    memcpy(g.b, p->recip, sizeof(double) * 9);
+    g.inv_n = 1.0 / (double)p->N;
+    p->box_generation++;
+    return PAD_OK;
+}
+
+extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* shape, int device) {
+    if (!out || !box || !shape) {
+        pad_set_error("pad_plan_create: null argument");
+        return PAD_ERR_ARG;
+    }
+    if (shape[0] < 1 || shape[1] < 1 || shape[2] < 1) {
+        pad_set_error("pad_plan_create: bad shape (%d,%d,%d)", shape[0], shape[1], shape[2]);
+        return PAD_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        pad_set_error("professad_b200 needs a CUDA device (sm_100a); none is visible (%s). There is no CPU fallback.",
+                      cudaGetErrorString(ce));
+        return PAD_ERR_CUDA;
+    }
+    PAD_CUDA(cudaSetDevice(device));
+    pad_plan* p = new pad_plan();
+    memset(p, 0, sizeof(pad_plan));
+    p->n0 = shape[0]; p->n1 = shape[1]; p->n2 = shape[2]; p->nzh = shape[2] / 2 + 1;
+    p->N = (size_t)p->n0 * p->n1 * p->n2;
+    p->Nk = (size_t)p->n0 * p->n1 * p->nzh;
+    p->device = device;
+    if (p->Nk >= 0xffffffffull) {
+        pad_set_error("grid too large for one device plan (%zu half-spectrum points)", p->Nk);
+        delete p;
+        return PAD_ERR_ARG;
+    }
+    int rc = set_box(p, box);
+    if (rc != PAD_OK) { delete p; return rc; }
+    PAD_CUDA(cudaMalloc(&p->partials, sizeof(double) * PAD_MAX_RED * PAD_MAX_BLOCKS));
+    PAD_CUDA(cudaMalloc(&p->scal, sizeof(double) * PAD_N_SCAL));
+    PAD_CUDA(cudaMemset(p->scal, 0, sizeof(double) * PAD_N_SCAL));
+    p->bytes_allocated = sizeof(double) * (PAD_MAX_RED * PAD_MAX_BLOCKS + PAD_N_SCAL);
+    *out = p;
+    return PAD_OK;
+}
+
+extern "C" int pad_plan_set_box(pad_plan* p, const double* box) {
+    if (!p || !box) { pad_set_error("pad_plan_set_box: null argument"); return PAD_ERR_ARG; }
+    return set_box(p, box);
+}
+
+extern "C" size_t pad_plan_workspace_bytes(const pad_plan* p) { return p ? p->bytes_allocated : 0; }
+
+extern "C" int pad_plan_destroy(pad_plan* p) {
+    if (!p) return PAD_OK;
+    cudaSetDevice(p->device);
+    if (p->fft_ready) { cufftDestroy(p->d2z); cufftDestroy(p->z2d); }
+    if (p->fft_work) cudaFree(p->fft_work);
+    for (int i = 0; i < PAD_N_RBUF; ++i) if (p->rbuf[i]) cudaFree(p->rbuf[i]);
+    for (int i = 0; i < PAD_N_CBUF; ++i) if (p->cbuf[i]) cudaFree(p->cbuf[i]);
+    if (p->wgc_kern) cudaFree(p->wgc_kern);
+    cudaFree(p->partials);
+    cudaFree(p->scal);
+    delete p;
+    return PAD_OK;
+}
+
+int pad_get_rbuf(pad_plan* p, int i, double** out) {
+    if (i < 0 || i >= PAD_N_RBUF) { pad_set_error("rbuf index %d", i); return PAD_ERR_ARG; }
+    if (!p->rbuf[i]) {
+        PAD_CUDA(cudaMalloc(&p->rbuf[i], sizeof(double) * p->N));
+        p->bytes_allocated += sizeof(double) * p->N;
+    }
+    *out = p->rbuf[i];
+    return PAD_OK;
+}
+
+int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out) {
+    if (i < 0 || i >= PAD_N_CBUF) { pad_set_error("cbuf index %d", i); return PAD_ERR_ARG; }
+    if (!p->cbuf[i]) {
+        PAD_CUDA(cudaMalloc(&p->cbuf[i], sizeof(cufftDoubleComplex) * p->Nk));
+        p->bytes_allocated += sizeof(cufftDoubleComplex) * p->Nk;
+    }
+    *out = p->cbuf[i];
+    return PAD_OK;
+}
+
+static int ensure_fft(pad_plan* p, cudaStream_t s) {
+    if (!p->fft_ready) {
+        size_t w1 = 0, w2 = 0;
+        PAD_CUFFT(cufftCreate(&p->d2z));
+        PAD_CUFFT(cufftCreate(&p->z2d));
+        PAD_CUFFT(cufftSetAutoAllocation(p->d2z, 0));
+        PAD_CUFFT(cufftSetAutoAllocation(p->z2d, 0));
+        PAD_CUFFT(cufftMakePlan3d(p->d2z, p->n0, p->n1, p->n2, CUFFT_D2Z, &w1));
+        PAD_CUFFT(cufftMakePlan3d(p->z2d, p->n0, p->n1, p->n2, CUFFT_Z2D, &w2));
+        size_t w = w1 > w2 ? w1 : w2;
+        if (w > 0) {
+            PAD_CUDA(cudaMalloc(&p->fft_work, w));
+            p->bytes_allocated += w;
+        }
+        p->fft_work_bytes = w;
+        PAD_CUFFT(cufftSetWorkArea(p->d2z, p->fft_work));
+        PAD_CUFFT(cufftSetWorkArea(p->z2d, p->fft_work));
+        p->fft_ready = true;
+        p->fft_stream = (cudaStream_t)(-1);
+    }
+    if (p->fft_stream != s) {
+        PAD_CUFFT(cufftSetStream(p->d2z, s));
+        PAD_CUFFT(cufftSetStream(p->z2d, s));
+        p->fft_stream = s;
+    }
+    return PAD_OK;
+}
+
+int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s) {
+    PAD_TRY(ensure_fft(p, s));
+    PAD_CUFFT(cufftExecD2Z(p->d2z, const_cast<double*>(in), out));
+    return PAD_OK;
+}
+
+int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
+    PAD_TRY(ensure_fft(p, s));
+    PAD_CUFFT(cufftExecZ2D(p->z2d, in, out));
+    return PAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+//  second-stage reduction: one CTA sums the per-block partials in a fixed order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAD_THREADS) finalize_kernel(const double* __restrict__ partials, FinalizeArgs a) {
+    __shared__ double sm[PAD_THREADS / 32];
+    __shared__ double total[PAD_MAX_RED];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = 0; t < a.nterms; ++t) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < a.nblocks; b += PAD_THREADS) v += partials[(size_t)t * PAD_MAX_BLOCKS + b];
+        v = warp_sum(v);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double w = lane < PAD_THREADS / 32 ? sm[lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) total[t] = w;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int t = 0; t < a.nterms; ++t) {
+            if (a.sums_out) a.sums_out[t] = total[t];
+            e += a.coef[t] * total[t];
+        }
+        if (a.E_out) a.E_out[0] = (a.accumulate ? a.E_out[0] : 0.0) + e;
+    }
+}
+
+void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s) {
+    finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, a);
+}

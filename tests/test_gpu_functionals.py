@@ -1,0 +1,117 @@
+"""GPU parity: every native functional (through the C ABI) vs the golden vectors produced by the
+unmodified reference, and vs the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): energies <= 1e-8 Ha/atom -- we hold |dE| <= 1e-10 * max(1, |E|);
+potentials <= 1e-9 relative max-abs."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-10
+V_RTOL = 1e-9
+
+CASES = ['rough_even', 'rough_odd', 'rough_mixed', 'smooth16']
+
+
+def _native_functionals(v_ext):
+    import profess_ad_b200.functionals as F
+    return {
+        'IonElectron': lambda b, n: F.IonElectron(b, n, v_ext),
+        'Hartree': F.Hartree, 'ThomasFermi': F.ThomasFermi, 'Weizsaecker': F.Weizsaecker,
+        'WangTeter': F.WangTeter, 'Perrot': F.Perrot, 'SmargiassiMadden': F.SmargiassiMadden,
+        'WangGovindCarter98': F.WangGovindCarter98,
+        'WangGovindCarter99': F.WangGovindCarter99().forward,
+        'WangGovindCarter99_g3k12': F.WangGovindCarter99((0.9, 0.7, 3.0, 1.2)).forward,
+        'WangTeterStyle': F.WangTeterStyleFunctional((0.8, 0.7, lambda x: 1 + x + 0.1 * x * x)).forward,
+        'lda_exchange': F.lda_exchange, 'perdew_zunger_correlation': F.perdew_zunger_correlation,
+        'PerdewZunger': F.PerdewZunger,
+        'pbe_exchange': F.pbe_exchange, 'pbe_correlation': F.pbe_correlation,
+        'PerdewBurkeErnzerhof': F.PerdewBurkeErnzerhof,
+    }
+
+
+def _compare(name, E, V, E_ref, V_ref):
+    dE = abs(E - E_ref)
+    dV = np.abs(V - V_ref).max() / np.abs(V_ref).max()
+    assert dE <= E_RTOL * max(1.0, abs(E_ref)), f'{name}: |dE| = {dE:.3e} (E_ref = {E_ref:.12e})'
+    assert dV <= V_RTOL, f'{name}: max|dV|/max|V| = {dV:.3e}'
+    return dE, dV
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_functionals_match_reference_golden(case, golden_dir):
+    from profess_ad_b200.functionals import energy_and_potential
+    g = np.load(os.path.join(golden_dir, f'functionals_{case}.npz'))
+    dev = torch.device('cuda:0')
+    box = torch.from_numpy(g['box']).to(dev)
+    den = torch.from_numpy(g['den']).to(dev)
+    v_ext = torch.from_numpy(g['v_ext']).to(dev)
+    for name, f in _native_functionals(v_ext).items():
+        E, V = energy_and_potential(box, den, f)
+        _compare(f'{case}/{name}', E.item(), V.cpu().numpy(), g['E_' + name].item(), g['V_' + name])
+
+
+@pytest.mark.parametrize('shape,seed', [((32, 30, 28), 11), ((27, 25, 33), 12), ((40, 40, 40), 13), ((17, 32, 24), 14)])
+def test_functionals_match_oracle_rough(shape, seed):
+    """Skewed cell + white-noise density: every Nyquist / self-conjugate-plane corner is exercised."""
+    from oracle import ofdft_oracle as orc
+    from profess_ad_b200.functionals import energy_and_potential
+    box, den = orc.synth_rough(shape, seed=seed)
+    gen = torch.Generator().manual_seed(seed)
+    v_ext = -0.5 + 0.2 * torch.rand(*shape, dtype=torch.double, generator=gen)
+    dev = torch.device('cuda:0')
+    oracle_f = {
+        'IonElectron': lambda b, n: orc.IonElectron(b, n, v_ext),
+        'Hartree': orc.Hartree, 'ThomasFermi': orc.ThomasFermi, 'Weizsaecker': orc.Weizsaecker,
+        'WangTeter': orc.WangTeter, 'Perrot': orc.Perrot, 'SmargiassiMadden': orc.SmargiassiMadden,
+        'WangGovindCarter98': orc.WangGovindCarter98, 'WangGovindCarter99': orc.WangGovindCarter99(),
+        'WangGovindCarter99_g3k12': orc.WangGovindCarter99(0.9, 0.7, 3.0, 1.2),
+        'PerdewZunger': orc.PerdewZunger, 'PerdewBurkeErnzerhof': orc.PerdewBurkeErnzerhof,
+    }
+    native = _native_functionals(v_ext.to(dev))
+    for name, fo in oracle_f.items():
+        E_ref, V_ref = orc.energy_and_potential(box, den, fo)
+        E, V = energy_and_potential(box.to(dev), den.to(dev), native[name])
+        _compare(f'{shape}/{name}', E.item(), V.cpu().numpy(), E_ref.item(), V_ref.numpy())
+
+
+def test_smooth_known_answers_64():
+    """BASELINE.md section 4 known answers for synth(n, side=4) (reference CPU values, agree across n to 1e-10)."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    box, den = orc.synth_smooth(64, 4)
+    dev = torch.device('cuda:0')
+    box, den = box.to(dev), den.to(dev)
+    known = {
+        'ThomasFermi': (F.ThomasFermi, 1.986207932281e+02), 'Hartree': (F.Hartree, 7.336599600805e-01),
+        'PerdewZunger': (F.PerdewZunger, -2.042240137136e+02),
+        'PerdewBurkeErnzerhof': (F.PerdewBurkeErnzerhof, -2.039708854110e+02),
+        'WangTeter': (F.WangTeter, 1.991658266842e+02), 'WangGovindCarter98': (F.WangGovindCarter98, 1.991645908341e+02),
+    }
+    for name, (f, val) in known.items():
+        E = f(box, den).item()
+        assert abs(E - val) <= 2e-10 * abs(val) + 1e-10, f'{name}: {E!r} vs {val!r}'
+
+
+def test_energy_only_path_and_errors():
+    import profess_ad_b200.functionals as F
+    from oracle import ofdft_oracle as orc
+    box, den = orc.synth_rough((12, 10, 14), seed=0)
+    dev = torch.device('cuda:0')
+    b, d = box.to(dev), den.to(dev)
+    wgc = F.WangGovindCarter99()
+    e1 = wgc.forward(b, d).item()                       # energy only: no potential buffers
+    d2 = d.clone().requires_grad_(True)
+    e2 = wgc.forward(b, d2)
+    e2.backward()
+    assert abs(e1 - e2.item()) <= 1e-13 * abs(e1)
+    assert d2.grad is not None and torch.isfinite(d2.grad).all()
+    with pytest.raises(RuntimeError):
+        F.Hartree(box, den)                             # CPU tensors: loud failure, no fallback
+    with pytest.raises(NotImplementedError):
+        F.Hartree(b.clone().requires_grad_(True), d)    # stress path is out of scope
