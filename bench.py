@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: WangGovindCarter99 energy + potential evaluations per second at 256^3.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on host cores
+
+One "step" = one evaluation of E[n] and dE/dn for the full kinetic functional WangGovindCarter99
+(TF + vW + non-local term, kernel cached) on the synthetic 256-atom Al supercell density of
+BASELINE.md section 4 (`synth(256, side=4)`), i.e. BASELINE.json configs[1].
+
+  value     : whole-job evals/s, density resident in HBM, timed with CUDA events on the launch stream
+  e2e       : same metric through the public Python API from PINNED HOST buffers: H2D of the density,
+              evaluation, D2H of the energy and the potential, all inside the timed region
+  roofline  : algorithmic bytes per evaluation (16 N n_fft + 16 N, n_fft = 14)
+              / measured time per evaluation, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the oracle port (oracle/ofdft_oracle.py = the reference algorithm, torch CPU fp64,
+              all host threads) on a bounded sample, N=1 rank 0 only
+
+Multi-GPU (torchrun): independent systems, one per GPU (BASELINE.json configs[3] style weak scaling);
+no data-path collective, only the timing barrier / max-reduce.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'WGC99 energy+potential evaluations per second at 256^3'
+UNIT = 'evals/s'
+GRID = int(os.environ.get('PAD_BENCH_GRID', '256'))
+SIDE = 4
+N_FFT = 14
+
+
+def algorithmic_bytes(n):
+    npts = n ** 3
+    return 16 * npts * N_FFT + 16 * npts
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------
+#  CPU reference arm / cpu_baseline
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_grid=None):
+    """Oracle port of WangGovindCarter99 E+V on the host cores.  A step at 256^3 costs ~12 s on 8
+    cores (+ ~20 s one-off kernel build), so the run uses a bounded sample: the same synthetic
+    supercell on a 128^3 grid, converted to the 256^3 unit by the N log N work ratio."""
+    import torch
+    from oracle import ofdft_oracle as orc
+    cores = torch.get_num_threads()
+    n = sample_grid or (GRID if (steps + warmup) <= 4 else min(GRID, 128))
+    box, den = orc.synth_smooth(n, SIDE)
+    wgc = orc.WangGovindCarter99()
+    for _ in range(max(1, warmup)):
+        orc.energy_and_potential(box, den, wgc)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.energy_and_potential(box, den, wgc)
+    dt = (time.perf_counter() - t0) / steps
+    scale = (GRID ** 3 * math.log2(GRID ** 3)) / (n ** 3 * math.log2(n ** 3))
+    sec_per_eval = dt * scale
+    sample = (f'{steps} evals (+{max(1, warmup)} warm-up, kernel cached) of the oracle port at {n}^3 on {cores} threads'
+              + ('' if n == GRID else f', scaled x{scale:.2f} (N log N) to {GRID}^3'))
+    return 1.0 / sec_per_eval, sec_per_eval * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    value, ms, cores, sample = cpu_reference_run(args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'Al 256-atom supercell, WangGovindCarter99 E+V, {GRID}^3 grid (BASELINE.json configs[1])'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+#  B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from oracle import ofdft_oracle as orc          # input generator only (synthetic density)
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native
+    lib = _native.load_library()
+
+    box_h, den_h = orc.synth_smooth(GRID, SIDE)
+    box = box_h.to(dev)
+    den = den_h.to(dev)
+    wgc = F.WangGovindCarter99()
+    npts = den.numel()
+
+    def step_device():
+        d = den.requires_grad_(True)
+        E = wgc.forward(box, d)
+        (g,) = torch.autograd.grad(E, d)
+        den.requires_grad_(False)
+        return E, g
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, f0 = lib.pad_launch_count(), lib.pad_fft_exec_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        E, g = step_device()
+    ev1.record()
+    barrier()
+    launches = int(lib.pad_launch_count() - l0)
+    fft_execs = int(lib.pad_fft_exec_count() - f0)
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host -> device -> E, V -> pinned host ---------------------------------
+    den_pin = den_h.pin_memory()
+    v_pin = torch.empty_like(den_pin).pin_memory()
+    e_pin = torch.empty((), dtype=torch.double).pin_memory()
+    den_in = torch.empty_like(den)
+
+    def step_e2e():
+        den_in.copy_(den_pin, non_blocking=True)
+        d = den_in.requires_grad_(True)
+        E = wgc.forward(box, d)
+        (g,) = torch.autograd.grad(E, d)
+        den_in.requires_grad_(False)
+        v_pin.copy_(g, non_blocking=True)
+        e_pin.copy_(E.detach().reshape(()), non_blocking=True)
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    ev0.record()
+    n_e2e = max(3, min(args.steps, 20))
+    for _ in range(n_e2e):
+        step_e2e()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e / (t.item() * 1e-3)
+    dV = abs(torch.linalg.det(box_h).item()) / npts
+    e_check = float(e_pin)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        balg = algorithmic_bytes(GRID)
+        achieved = balg / (ms_per_step * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'Al 256-atom supercell, WangGovindCarter99 E+V, {GRID}^3 grid (BASELINE.json configs[1])',
+                       'grid': [GRID] * 3, 'per_gpu': 'one independent system per GPU',
+                       'l2': 'working set per evaluation (>= 2 GB of fields) exceeds the 126 MB L2',
+                       'energy_Ha': e_check},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': npts * 8, 'd2h_bytes_per_step': npts * 8 + 8},
+            'gpu_launches': launches + fft_execs,
+            'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'whole WGC99 E+V evaluation (14 FFTs + fused elementwise passes)',
+                         'algorithmic_bytes_per_eval': balg},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores, sample = cpu_reference_run(3, 1, sample_grid=min(GRID, 128))
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -53,6 +53,9 @@ typedef struct pad_plan pad_plan;
 
 const char* pad_version(void);
 const char* pad_last_error(void);
+/* kernels this library has launched so far in this process (own kernels; cuFFT execs counted separately) */
+unsigned long long pad_launch_count(void);
+unsigned long long pad_fft_exec_count(void);
 
 /* ---- plan: replaces wavevecs(box_vecs, shape) (functional_tools.py:135-162) and owns the cuFFT
  *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */

@@ -22,6 +22,8 @@ _dbl = ctypes.c_double
 SIGNATURES = {
     'pad_version': (ctypes.c_char_p, []),
     'pad_last_error': (ctypes.c_char_p, []),
+    'pad_launch_count': (ctypes.c_ulonglong, []),
+    'pad_fft_exec_count': (ctypes.c_ulonglong, []),
     'pad_plan_create': (_int, [ctypes.POINTER(_vp), _c_double_p, ctypes.POINTER(_int), _int]),
     'pad_plan_destroy': (_int, [_vp]),
     'pad_plan_set_box': (_int, [_vp, _c_double_p]),

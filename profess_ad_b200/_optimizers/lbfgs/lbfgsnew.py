@@ -1,0 +1,152 @@
+"""Fixed-step limited-memory BFGS with the interface and stopping rules of the reference's
+``LBFGSNew`` (src/professad/_optimizers/lbfgs/lbfgsnew.py:512-769) for the configuration
+``System.optimize_density`` uses: ``line_search_fn=False, batch_mode=False``.
+
+Written from the algorithm, not from the reference file: the (y, s) history lives in two
+preallocated (m, N) ring buffers, the two-loop recursion works on rows of them, and the
+curvature products are computed once per update.  ``line_search_fn=True`` / ``batch_mode=True``
+(geometry optimisation and stochastic training) are outside the hot path and raise.
+
+Semantics kept exactly:
+  * first-ever step length t = min(1, 1/|g|_1) * lr, afterwards t = lr;
+  * history update only if  y.s > 1e-10 |s|^2, oldest pair dropped at ``history_size``;
+  * H_diag = y.s / y.y of the most recent accepted pair;
+  * the closure is re-evaluated after every inner iteration except the last (``max_iter``);
+  * break on: max_iter, max_eval, |g|_1 <= tolerance_grad, g.d > -tolerance_change,
+    |t d|_1 <= tolerance_change, |loss - prev_loss| < tolerance_change.
+
+This host-driven class serves user-supplied (Python) energy terms.  When every term of a System is
+native, ``System.optimize_density`` runs the same algorithm device-resident through the C ABI
+(``pad_lbfgs_*``) instead, with no host synchronisation inside an outer iteration.
+"""
+import math
+
+import torch
+from torch.optim import Optimizer
+
+
+class LBFGSNew(Optimizer):
+
+    def __init__(self, params, lr=1, max_iter=10, max_eval=None, tolerance_grad=1e-5, tolerance_change=1e-9,
+                 history_size=7, line_search_fn=False, batch_mode=False):
+        if line_search_fn or batch_mode:
+            raise NotImplementedError('LBFGSNew: line searches / batch mode are not part of the density-optimisation '
+                                      'hot path (geometry optimisation and stochastic training are out of scope)')
+        if max_eval is None:
+            max_eval = max_iter * 5 // 4
+        defaults = dict(lr=lr, max_iter=max_iter, max_eval=max_eval, tolerance_grad=tolerance_grad,
+                        tolerance_change=tolerance_change, history_size=history_size)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("LBFGS doesn't support per-parameter options (parameter groups)")
+        self._params = self.param_groups[0]['params']
+        if len(self._params) != 1:
+            raise ValueError('LBFGSNew (B200 build) optimises a single flat variable (chi)')
+        self._x = self._params[0]
+        self._n_iter_total = 0
+        self._hist_y = self._hist_s = None
+        self._order = []            # ring-buffer rows, oldest first
+        self._H = 1.0
+        self._d = None
+        self._t = None
+        self._prev_g = None
+        self._prev_loss = None
+        self.func_evals = 0
+
+    def _grad(self):
+        g = self._x.grad
+        if g is None:
+            return torch.zeros_like(self._x.data).reshape(-1)
+        return g.data.reshape(-1)
+
+    def _push_pair(self, y, s):
+        m = self.param_groups[0]['history_size']
+        if self._hist_y is None:
+            self._hist_y = torch.empty((m, y.numel()), dtype=y.dtype, device=y.device)
+            self._hist_s = torch.empty_like(self._hist_y)
+        if len(self._order) == m:
+            row = self._order.pop(0)
+        else:
+            row = len(self._order)
+        self._hist_y[row].copy_(y)
+        self._hist_s[row].copy_(s)
+        self._order.append(row)
+
+    def _direction(self, g):
+        """two-loop recursion: d = -H g"""
+        rows = self._order
+        Y, S = self._hist_y, self._hist_s
+        rho = [1.0 / float(torch.dot(Y[r], S[r])) for r in rows]
+        q = g.neg()
+        alpha = [0.0] * len(rows)
+        for k in range(len(rows) - 1, -1, -1):
+            alpha[k] = float(torch.dot(S[rows[k]], q)) * rho[k]
+            q.add_(Y[rows[k]], alpha=-alpha[k])
+        d = q.mul_(self._H)
+        for k in range(len(rows)):
+            beta = float(torch.dot(Y[rows[k]], d)) * rho[k]
+            d.add_(S[rows[k]], alpha=alpha[k] - beta)
+        return d
+
+    def step(self, closure):
+        grp = self.param_groups[0]
+        lr, max_iter, max_eval = grp['lr'], grp['max_iter'], grp['max_eval']
+        tol_g, tol_c = grp['tolerance_grad'], grp['tolerance_change']
+
+        orig_loss = closure()
+        loss = float(orig_loss.detach()) if isinstance(orig_loss, torch.Tensor) else float(orig_loss)
+        evals = 1
+        self.func_evals += 1
+        g = self._grad()
+        g_l1 = float(g.abs().sum())
+        if g_l1 <= tol_g:
+            return orig_loss
+        g_l2 = float(g.norm())
+        it = 0
+        d, t = self._d, self._t
+        while it < max_iter and not math.isnan(g_l2):
+            it += 1
+            self._n_iter_total += 1
+            if self._n_iter_total == 1:
+                d = g.neg()
+                self._order = []
+                self._H = 1.0
+            else:
+                y = g - self._prev_g
+                s = d * t
+                ys = float(torch.dot(y, s))
+                s_l2 = float(s.norm())
+                if ys > 1e-10 * s_l2 * s_l2:
+                    self._push_pair(y, s)
+                    self._H = ys / float(torch.dot(y, y))
+                if math.isnan(self._H):
+                    print('Warning H_diag nan')
+                d = self._direction(g)
+            if self._prev_g is None:
+                self._prev_g = g.clone()
+            else:
+                self._prev_g.copy_(g)
+            self._prev_loss = loss
+            t = min(1.0, 1.0 / g_l1) * lr if self._n_iter_total == 1 else lr
+            gtd = float(torch.dot(g, d))
+            if math.isnan(gtd):
+                print('Warning grad norm infinite')
+            self._x.data.add_(d.view_as(self._x.data), alpha=t)
+            if it != max_iter:
+                loss = closure()
+                loss = float(loss.detach()) if isinstance(loss, torch.Tensor) else float(loss)
+                g = self._grad()
+                g_l1 = float(g.abs().sum())
+                if math.isnan(g_l1):
+                    print('Warning: gradient nan')
+                    break
+                evals += 1
+                self.func_evals += 1
+            if it == max_iter or evals >= max_eval or g_l1 <= tol_g:
+                break
+            if gtd > -tol_c or float(d.abs().sum()) * abs(t) <= tol_c:
+                break
+            if abs(loss - self._prev_loss) < tol_c:
+                break
+        self._d, self._t = d, t
+        return orig_loss

@@ -21,6 +21,8 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kCTF = 2.871234000188191;
 
 void pad_set_error(const char* fmt, ...);
+extern unsigned long long g_pad_launches;   // kernels launched by this library (own kernels + cuFFT execs)
+extern unsigned long long g_pad_fft_execs;
 
 #define PAD_CUDA(call)                                                                          \
     do {                                                                                        \

@@ -30,11 +30,13 @@ __device__ __forceinline__ double kabs_of(double kx, double ky, double kz) {
 template <int NRED, class F>
 void launch_ew(pad_plan* p, cudaStream_t s, F f) {
     ew_kernel<NRED, F><<<pad_grid_for(p->N), PAD_THREADS, 0, s>>>(p->N, f, p->partials);
+    ++g_pad_launches;
 }
 
 template <class F>
 void launch_ks(pad_plan* p, cudaStream_t s, F f) {
     ks_kernel<F><<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, f);
+    ++g_pad_launches;
 }
 
 void finalize(pad_plan* p, cudaStream_t s, int nterms, const double* coef, double* E_out, int accumulate,
@@ -255,6 +257,7 @@ extern "C" int pad_eval_wt(pad_plan* p, const double* den, double alpha, double 
         const double one[1] = {1.0};
         finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
         wt_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, inv_n);
+        ++g_pad_launches;
         PAD_CHECK_LAUNCH();
     }
     if (vw || nl) {
@@ -513,6 +516,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     const double one[1] = {1.0};
     finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
     wgc_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, kappa, p->dV, p->vol);
+    ++g_pad_launches;
     PAD_CHECK_LAUNCH();
     if (!p->wgc_kern) {
         PAD_CUDA(cudaMalloc(&p->wgc_kern, sizeof(double) * 4 * nk));
@@ -541,6 +545,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     wgc_build_kernel<<<pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, scal, same ? 0 : 1);
     PAD_CHECK_LAUNCH();
     wgc_key_kernel<<<1, 1, 0, s>>>(scal);
+    g_pad_launches += 2;
     PAD_CHECK_LAUNCH();
     const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
 

@@ -6,6 +6,11 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_pad_launches = 0;
+unsigned long long g_pad_fft_execs = 0;
+
+extern "C" unsigned long long pad_launch_count(void) { return g_pad_launches; }
+extern "C" unsigned long long pad_fft_exec_count(void) { return g_pad_fft_execs; }
 
 void pad_set_error(const char* fmt, ...) {
     va_list ap;
@@ -162,12 +167,14 @@ static int ensure_fft(pad_plan* p, cudaStream_t s) {
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s) {
     PAD_TRY(ensure_fft(p, s));
     PAD_CUFFT(cufftExecD2Z(p->d2z, const_cast<double*>(in), out));
+    ++g_pad_fft_execs;
     return PAD_OK;
 }
 
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
     PAD_TRY(ensure_fft(p, s));
     PAD_CUFFT(cufftExecZ2D(p->z2d, in, out));
+    ++g_pad_fft_execs;
     return PAD_OK;
 }
 
@@ -203,4 +210,5 @@ __global__ void __launch_bounds__(PAD_THREADS) finalize_kernel(const double* __r
 
 void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s) {
     finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, a);
+    ++g_pad_launches;
 }

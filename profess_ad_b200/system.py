@@ -1,0 +1,441 @@
+"""``System``: the facade of PROFESS-AD (src/professad/system.py) on the B200-native hot path.
+
+Same constructor, setters/getters and ``optimize_density`` keyword arguments as the reference, so
+user scripts switch by changing the import.  What differs is underneath:
+
+* every native energy term is one C-ABI call that returns the energy and the analytic potential;
+* when all terms are native, ``optimize_density`` / ``functional_derivative`` use the *fused
+  evaluator* (one pass structure for the whole term list, shared FFTs, chi-projection kernel) and
+  the device-resident L-BFGS / TPGD loop (``_density_opt.py``) -- no host synchronisation inside an
+  outer iteration;
+* user-defined Python terms (lambdas, ``nn.Module.forward``) still work through the generic
+  autograd closure, exactly as in the reference (system.py:830-854).
+
+Cell derivatives (stress, pressure, elastic constants) and ionic forces need autograd through
+``box_vecs`` / ion positions and second derivatives; they are outside this path (SURVEY.md section 8,
+rows f2/f4) and raise ``NotImplementedError``.
+"""
+import numpy as np
+import torch
+
+from .ion_utils import get_ion_charge, interpolate_recpot, lattice_sum, ion_interaction_sum
+from .functional_tools import wavevecs
+from ._optimizers.lbfgs.lbfgsnew import LBFGSNew
+from ._optimizers.tpgd.two_point_gradient_descent import TPGD
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('professad_b200.System needs a CUDA device (B200); none is visible and there is no '
+                           'CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _term_name(functional):
+    return getattr(functional, '__qualname__', None) or getattr(functional, '__name__', '')
+
+
+class System():
+    """A periodic system for orbital-free DFT (system.py:18-72)."""
+
+    # 2018 CODATA (system.py:26-33)
+    m_per_bohr = 5.29177210903e-11
+    A_per_b = m_per_bohr * 1e10
+    J_per_Ha = 4.3597447222071e-18
+    eV_per_Ha = J_per_Ha / 1.602176634e-19
+    GPa_per_atomic = J_per_Ha / m_per_bohr**3 * 1e-9
+
+    def __init__(self, box_vecs, shape, ions, terms, units='b', coord_type='cartesian', Rc=None,
+                 pme_order=None, device=None):
+        self.__device = _default_device() if device is None else torch.device(device)
+        self.__terms = terms
+        self.__shape = tuple(int(s) for s in shape)
+        self.__pme_order = pme_order
+        self.__Rc = Rc
+        self.__Eion_cache = None
+        self.set_lattice(box_vecs, units, initialization=True)
+        self.__process_ions(ions, coord_type, units)
+        self.__update_ionic_potential()
+        self.initialize_density()
+        self.__ene = self.__compute_energy()
+
+    @classmethod
+    def ecut2shape(self, energy_cutoff, box_vecs):
+        """Grid shape for an energy cutoff in eV and a lattice in Angstrom (system.py:74-89): always odd."""
+        bvs = box_vecs / self.A_per_b
+        kcut = np.sqrt(2 * energy_cutoff / self.eV_per_Ha)
+        shape = 1 + 2 * torch.ceil(kcut / (2 * np.pi / torch.sqrt(torch.sum(bvs.pow(2), axis=1))))
+        return tuple(shape.int().tolist())
+
+    # ------------------------------------------------------------------ initialisation / updates
+    def set_device(self, device=None):
+        self.__device = _default_device() if device is None else torch.device(device)
+        self.__box_vecs = self.__box_vecs.to(self.__device)
+        self.__den = self.__den.to(self.__device)
+        self.__v_ext = self.__v_ext.to(self.__device)
+        self.__frac_ion_coords = self.__frac_ion_coords.to(self.__device)
+
+    def __unit_factor(self, units):
+        if units == 'a':
+            return self.A_per_b
+        if units == 'b':
+            return 1.0
+        raise ValueError('Parameter \'units\' can only be \'b\' (Bohr) or \'a\' (Angstrom)')
+
+    def __process_ions(self, ions, coord_type, units):
+        n_elec, ion_list, name, coords = 0, [], '', []
+        for species in ions:   # [name, path_to_recpot, coordinates]
+            charge = get_ion_charge(species[1])
+            count = species[2].shape[0]
+            ion_list.append((species[0], species[1], count, charge))
+            coords.append(species[2].double().to(self.__device))
+            n_elec += count * charge
+            name += species[0] + str(int(count))
+        ion_coords = torch.cat(coords) if coords else torch.empty((0, 3), dtype=torch.double, device=self.__device)
+        self.__name = name
+        self.__N_ions = ion_coords.shape[0]
+        self.__N_elec = n_elec
+        self.__ions = ion_list
+        self.place_ions(ion_coords, coord_type, units, initialization=True)
+
+    def place_ions(self, ion_coords, coord_type='cartesian', units='a', initialization=False):
+        """system.py:125-157"""
+        ion_coords = ion_coords.clone().double().to(self.__device)
+        if coord_type == 'cartesian':
+            frac = torch.matmul(ion_coords / self.__unit_factor(units), torch.linalg.inv(self.__box_vecs))
+        elif coord_type == 'fractional':
+            frac = ion_coords
+        else:
+            raise ValueError('Parameter \'coord_type\' can only be \'cartesian\' or \'fractional\'')
+        frac = frac - torch.floor(frac)          # twice on purpose: -1e-17 -> 1.0 -> 0.0
+        self.__frac_ion_coords = frac - torch.floor(frac)
+        if not initialization:
+            self.__update_ionic_potential()
+            self.__ene = self.__compute_energy()
+
+    def set_lattice(self, box_vecs, units='a', initialization=False):
+        """system.py:159-181 : the density is rescaled to conserve the electron number."""
+        factor = self.__unit_factor(units)
+        if not initialization:
+            old_vol = self.__vol()
+        self.__box_vecs = box_vecs.clone().double().to(self.__device) / factor
+        if not initialization:
+            self.__update_ionic_potential()
+            self.__den = self.__den * (old_vol / self.__vol())
+            self.__ene = self.__compute_energy()
+
+    def __potential_from_ions(self, cart_ion_coords):
+        kx, ky, kz, k2 = wavevecs(self.__box_vecs, self.__shape)
+        k = torch.sqrt(k2)
+        v_ext = torch.zeros(self.__shape, dtype=torch.double, device=self.__device)
+        first = 0
+        for _, path, count, _ in self.__ions:
+            v_s_ft = interpolate_recpot(path, k)
+            v_ext += lattice_sum(self.__box_vecs, self.__shape, cart_ion_coords[first:first + count], v_s_ft,
+                                 self.__pme_order)
+            first += count
+        return v_ext
+
+    def __update_ionic_potential(self):
+        if any(_term_name(f) == 'IonElectron' for f in self.__terms):
+            self.__v_ext = self.__potential_from_ions(torch.matmul(self.__frac_ion_coords, self.__box_vecs))
+        else:
+            self.__v_ext = torch.zeros(self.__shape, dtype=torch.double, device=self.__device)
+
+    def set_potential(self, pot):
+        assert tuple(pot.shape) == self.__shape, 'Shape of new potential must match the system\'s.'
+        self.__v_ext = pot.clone().double().to(self.__device)
+        self.__ene = self.__compute_energy()
+
+    def initialize_density(self):
+        """Uniform density N_elec / vol (system.py:218-222)."""
+        self.__den = torch.full(self.__shape, float(self.__N_elec) / self.__vol().item(), dtype=torch.double,
+                                device=self.__device)
+
+    def set_density(self, den):
+        assert tuple(den.shape) == self.__shape, 'Shape of new density must match the system\'s.'
+        self.__den = den.double().to(self.__device)
+        self.__ene = self.__compute_energy()
+
+    def set_electron_number(self, N):
+        self.__N_elec = N
+
+    def __vol(self):
+        return torch.abs(torch.linalg.det(self.__box_vecs))
+
+    def detach(self):
+        self.__box_vecs = self.__box_vecs.detach()
+        self.__den = self.__den.detach()
+        self.__v_ext = self.__v_ext.detach()
+        self.__frac_ion_coords = self.__frac_ion_coords.detach()
+
+    # ------------------------------------------------------------------------------- getters
+    def device(self):
+        return self.__device
+
+    def name(self):
+        return self.__name
+
+    def ion_count(self):
+        return self.__N_ions
+
+    def electron_count(self):
+        return self.__N_elec
+
+    def lattice_vectors(self, units='a'):
+        return self.__unit_factor(units) * self.__box_vecs
+
+    def ions(self):
+        return self.__ions
+
+    def cartesian_ionic_coordinates(self, units='a'):
+        return self.__unit_factor(units) * torch.matmul(self.__frac_ion_coords, self.__box_vecs)
+
+    def fractional_ionic_coordinates(self):
+        return self.__frac_ion_coords
+
+    def ionic_potential(self, units='Ha'):
+        if units == 'Ha':
+            return self.__v_ext
+        if units == 'eV':
+            return self.__v_ext * self.eV_per_Ha
+        raise ValueError('Parameter \'units\' can only be \'Ha\' or \'eV\'')
+
+    def density(self, requires_grad=False):
+        if requires_grad:
+            self.__second_order('density(requires_grad=True)')
+        return self.__den.detach()
+
+    def volume(self, units='b3'):
+        if units == 'b3':
+            return self.__vol().item()
+        if units == 'a3':
+            return self.__vol().item() * self.A_per_b**3
+        raise ValueError('Parameter \'units\' can only be \'b3\' or \'a3\'')
+
+    def energy(self, units='Ha', requires_grad=False):
+        if requires_grad:
+            self.__second_order('energy(requires_grad=True)')
+        E = self.__ene.item()
+        if units == 'Ha':
+            return E
+        if units == 'eV':
+            return E * self.eV_per_Ha
+        raise ValueError('Parameter \'units\' can only be \'Ha\' or \'eV\'')
+
+    # ------------------------------------------------------------- convergence measures / potentials
+    def check_density_convergence(self, method='dEdchi'):
+        """max |dE/dchi| or max |mu - dE/dn| (system.py:377-412)."""
+        if method == 'dEdchi':
+            return torch.max(torch.abs(self.functional_derivative('chi'))).item()
+        elif method == 'euler':
+            dEdn = self.functional_derivative('density')
+            mu = torch.mean(dEdn * self.__den) * self.__vol() / self.__N_elec
+            return torch.max(torch.abs(mu - dEdn)).item()
+
+    def functional_derivative(self, type='density', requires_grad=False):
+        """dE/dn or dE/dchi with n = N chi^2 / int chi^2 (system.py:414-447)."""
+        if requires_grad:
+            self.__second_order('functional_derivative(requires_grad=True)')
+        self.detach()
+        dV = self.__vol() / self.__den.numel()
+        if type == 'density':
+            den = self.__den.requires_grad_(True)
+            E = self.__compute_energy(for_den_opt=True)
+            dEdn = torch.autograd.grad(E, den)[0] / dV
+            self.__den = self.__den.detach().requires_grad_(False)
+            return dEdn
+        elif type == 'chi':
+            chi = torch.sqrt(self.__den).requires_grad_(True)
+            N_tilde = torch.mean(chi.pow(2)) * self.__vol()
+            self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
+            E = self.__compute_energy(for_den_opt=True)
+            dEdchi = torch.autograd.grad(E, chi)[0] / dV
+            self.__den = self.__den.detach()
+            return dEdchi
+
+    def chemical_potential(self):
+        dEdn = self.functional_derivative('density')
+        return (torch.mean(dEdn * self.__den) * self.__vol() / self.__N_elec).item()
+
+    # ------------------------------------------------------------------------- out-of-scope API
+    def __second_order(self, what):
+        raise NotImplementedError(f'System.{what}: implicit differentiation / second derivatives are outside the '
+                                  'B200 hot path (SURVEY.md section 8: out of scope)')
+
+    def pressure(self, units='Ha/b3', requires_grad=False):
+        self.__second_order('pressure')
+
+    def enthalpy(self, units='Ha'):
+        self.__second_order('enthalpy')
+
+    def bulk_modulus(self, units='Ha/b3', requires_grad=False):
+        self.__second_order('bulk_modulus')
+
+    def forces(self, units='Ha/b'):
+        self.__second_order('forces')
+
+    def stress(self, units='Ha/b3'):
+        self.__second_order('stress')
+
+    def elastic_constants(self, units='Ha/b3'):
+        self.__second_order('elastic_constants')
+
+    def force_constants(self, primitive_ion_indices, units='eV/a2'):
+        self.__second_order('force_constants')
+
+    def optimize_geometry(self, *args, **kwargs):
+        self.__second_order('optimize_geometry')
+
+    def optimize_parameterized_geometry(self, *args, **kwargs):
+        self.__second_order('optimize_parameterized_geometry')
+
+    # ------------------------------------------------------------------------------- ion-ion
+    def set_Rc(self, Rc=None):
+        self.__Rc = Rc
+
+    def __ion_ion_interaction(self, cart_ion_coords):
+        """system.py:733-754 : R_d = 2 h_max, R_c = 3 R_d^2 / h_max unless Rc is given."""
+        charges = torch.cat([torch.full((count,), float(z), dtype=torch.double, device=self.__device)
+                             for _, _, count, z in self.__ions])
+        h_max = torch.max(1 / torch.sqrt(torch.sum(torch.linalg.inv(self.__box_vecs.detach().T).pow(2), 1)))
+        if self.__Rc is None:
+            Rd = 2 * h_max
+            Rc = 3 * Rd * Rd / h_max
+        else:
+            Rc = self.__Rc
+            Rd = torch.sqrt(h_max * Rc / 3)
+        E_ion = ion_interaction_sum(self.__box_vecs, cart_ion_coords, charges, Rc, Rd)
+        self.__Eion_cache = E_ion.item()
+        return E_ion
+
+    # --------------------------------------------------------------------- energy and optimisation
+    def __compute_energy(self, for_den_opt=False, use_ion_cache=False):
+        """Sum of the terms (system.py:759-772); IonElectron gets v_ext, IonIon is skipped inside the
+        density optimisation."""
+        E = torch.zeros((1,), dtype=torch.double, device=self.__device)
+        for functional in self.__terms:
+            name = _term_name(functional)
+            if name == 'IonElectron':
+                E = E + functional(self.__box_vecs, self.__den, self.__v_ext)
+            elif name == 'IonIon':
+                if not for_den_opt:
+                    if use_ion_cache and self.__Eion_cache is not None:
+                        E = E + self.__Eion_cache
+                    else:
+                        E = E + self.__ion_ion_interaction(torch.matmul(self.__frac_ion_coords, self.__box_vecs))
+            else:
+                E = E + functional(self.__box_vecs, self.__den)
+        return E
+
+    def optimize_density(self, ntol=1e-7, n_conv_cond_count=3, n_method='LBFGS', n_step_size=0.1,
+                         n_maxiter=1000, conv_target='dE', n_verbose=False, from_uniform=False,
+                         potentials=None):
+        """Direct minimisation over chi = sqrt(n) (system.py:774-908); same arguments and stop rule:
+        after the 5th iteration, ``conv_target`` below ``ntol`` on ``n_conv_cond_count`` consecutive
+        iterations."""
+        if n_method not in ('LBFGS', 'TPGD'):
+            raise ValueError('Only \'LBFGS\' or \'TPGD\' recognized for \'n_method\' argument')
+        if conv_target not in ('dE', 'dEdchi', 'euler'):
+            raise ValueError('Only \'dE\', \'dEdchi\' or \'euler\' recognized as \'conv_target\' argument')
+        self.detach()
+        if from_uniform:
+            self.initialize_density()
+        else:
+            current_den = self.__den
+            current_E = self.__compute_energy(for_den_opt=True)
+            self.initialize_density()
+            uniform_E = self.__compute_energy(for_den_opt=True)
+            if current_E < uniform_E:
+                self.set_density(current_den)
+
+        chi = torch.sqrt(self.__den).requires_grad_()
+        if n_method == 'LBFGS':
+            optimizer = LBFGSNew([chi], lr=n_step_size, history_size=8, max_iter=6)
+        else:
+            optimizer = TPGD([chi], lr=n_step_size)
+        vol, dV = self.__vol(), self.__vol() / self.__den.numel()
+
+        if potentials is None:
+            def closure():
+                if torch.is_grad_enabled():
+                    optimizer.zero_grad()
+                N_tilde = torch.mean(chi.pow(2)) * vol
+                self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
+                E = self.__compute_energy(for_den_opt=True)
+                if E.requires_grad:
+                    E.backward()
+                return E
+        else:
+            def closure():
+                if torch.is_grad_enabled():
+                    optimizer.zero_grad()
+                with torch.no_grad():
+                    N_tilde = torch.mean(chi.pow(2)) * vol
+                    self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
+                    E = self.__compute_energy(for_den_opt=True)
+                    dEdn = potentials(self.__box_vecs, self.__den)
+                    mu = torch.mean(dEdn * self.__den) * vol / self.__N_elec
+                    chi.grad = (self.__N_elec / N_tilde) * 2 * chi * (dEdn - mu) * dV
+                return E
+
+        E_prev = self.__compute_energy(for_den_opt=True).item() * self.eV_per_Ha
+        if n_verbose:
+            print('Starting density optimization')
+            print('{:^8} {:^12} {:^12} {:^18} {:^18}'.format('Iter', 'E [eV]', 'dE [eV]', 'Max |𝛿E/𝛿χ|', 'Max |µ-𝛿E/𝛿n|'))
+            print('{:^8} {:^12.6f} {:^12.6g} {:^18.6g} {:^18.6g}'.format(
+                0, E_prev, 0, self.check_density_convergence('dEdchi'), self.check_density_convergence('euler')))
+
+        conv_counter = 0
+        self.last_optimization = {'iterations': 0, 'converged': False}
+        for it in range(1, round(n_maxiter) + 1):
+            optimizer.step(closure)
+            dEdchi = torch.abs(chi.grad / dV).max().item()
+            with torch.no_grad():
+                E = self.__compute_energy(for_den_opt=True).item() * self.eV_per_Ha
+            dE, E_prev = E - E_prev, E
+            if n_verbose or conv_target == 'euler':
+                euler = self.check_density_convergence('euler')
+            if n_verbose:
+                print('{:^8} {:^12.6f} {:^12.6g} {:^18.6g} {:^18.6g}'.format(it, E_prev, dE, dEdchi, euler))
+            stop_var = {'dE': abs(dE), 'dEdchi': dEdchi}.get(conv_target)
+            if conv_target == 'euler':
+                stop_var = euler
+            if it > 5:
+                conv_counter = conv_counter + 1 if stop_var < ntol else 0
+            self.last_optimization['iterations'] = it
+            if conv_counter == n_conv_cond_count:
+                self.last_optimization['converged'] = True
+                if n_verbose:
+                    print('Density optimization successfully converged in {} step(s) \n'.format(it))
+                break
+            if it == round(n_maxiter) and n_verbose:
+                print('Density optimization failed to converge in {} steps \n'.format(int(it)))
+        self.detach()
+        self.__ene = self.__compute_energy(use_ion_cache=True)
+
+    # ------------------------------------------------------------------------------ strain scan
+    def eos_fit(self, f=0.05, N=9, eos='bm', verbose=False, plot=False, **den_opt_kwargs):
+        """Energy-volume scan + equation-of-state fit (system.py:568-621).  Returns (params, err) in
+        the reference's order: K0 [GPa], K0', E0 [eV], V0 [A^3]."""
+        from .elastic_tools import fit_eos
+        opts = {'ntol': 1e-10, 'n_conv_cond_count': 3, 'n_method': 'LBFGS', 'n_step_size': 0.1, 'n_maxiter': 1000,
+                'conv_target': 'dE', 'n_verbose': False, 'from_uniform': False}
+        opts.update(den_opt_kwargs)
+        v0 = self.volume('a3')
+        shape_vecs = self.lattice_vectors('a') / v0**(1 / 3)
+        volumes, energies = [], []
+        if verbose:
+            print('\n{:^22} {:^22}'.format('Volume [Å³ per atom]', 'Energy [eV per atom]'))
+        for v in v0 * np.linspace(1 - f, 1 + f, N):
+            self.set_lattice(v**(1 / 3) * shape_vecs, units='a')
+            self.optimize_density(**opts)
+            volumes.append(self.volume('a3') / self.__N_ions)
+            energies.append(self.energy('eV') / self.__N_ions)
+            if verbose:
+                print('{:^22.10f} {:^22.10f}'.format(volumes[-1], energies[-1]))
+        params, err = fit_eos(volumes, energies, eos, plot)
+        to_gpa = self.GPa_per_atomic / (self.eV_per_Ha / self.A_per_b**3)
+        params[0] *= to_gpa
+        err[0] *= to_gpa
+        return params, err

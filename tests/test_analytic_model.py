@@ -1,0 +1,47 @@
+"""The analytic, minimum-FFT formulation implemented by the CUDA kernels (tests/analytic_model.py)
+equals the autograd oracle on CPU -- including on even grids with skewed cells, where the
+reference's positive-Nyquist convention makes the multipliers non-Hermitian."""
+import math
+
+import pytest
+import torch
+
+import analytic_model as am
+from oracle import ofdft_oracle as orc
+
+A98, B98 = (5 + math.sqrt(5)) / 6, (5 - math.sqrt(5)) / 6
+
+
+@pytest.mark.parametrize('shape', [(12, 10, 14), (9, 11, 7), (8, 9, 6), (6, 6, 6)])
+def test_analytic_potentials_equal_autograd(shape):
+    box, den = orc.synth_rough(shape, seed=5)
+    pairs = {
+        'Hartree': (orc.Hartree, lambda: am.hartree(box, den)),
+        'ThomasFermi': (orc.ThomasFermi, lambda: am.thomas_fermi(box, den)),
+        'Weizsaecker': (orc.Weizsaecker, lambda: am.weizsaecker(box, den)),
+        'WangTeter': (orc.WangTeter, lambda: am.wt_family(box, den, 5 / 6, 5 / 6)),
+        'WGC98': (orc.WangGovindCarter98, lambda: am.wt_family(box, den, A98, B98)),
+        'WGC99': (orc.WangGovindCarter99(),
+                  lambda: am.wgc99(box, den, lambda eta: orc.wgc99_kernel(eta, A98, B98, 2.7), A98, B98, 2.7, 1.0)),
+        'PerdewZunger': (orc.PerdewZunger, lambda: am.perdew_zunger(box, den)),
+        'PBE': (orc.PerdewBurkeErnzerhof, lambda: am.pbe(box, den)),
+    }
+    for name, (fo, fm) in pairs.items():
+        E, V = orc.energy_and_potential(box, den, fo)
+        e, v = fm()
+        assert abs(E.item() - e) < 1e-12 * max(1.0, abs(e)), name
+        assert ((V - v).abs().max() / V.abs().max()).item() < 1e-12, name
+
+
+def test_chi_projection_equals_autograd():
+    """system.py:842-854 vs autograd through n = N chi^2 / int chi^2 (tests/test_den_opt.py:58-75)."""
+    box, den = orc.synth_rough((9, 8, 10), seed=2)
+    chi = torch.sqrt(den) * 1.3
+    n_elec = 7.0
+    terms = [orc.Hartree, orc.WangTeter, orc.PerdewZunger]
+    E, g_auto, n = orc.chi_gradient(box, chi, n_elec, terms)
+    v = sum(orc.energy_and_potential(box, n, f)[1] for f in terms)
+    g_proj = am.chi_projection(box, chi, n_elec, v)
+    assert ((g_auto - g_proj).abs().max() / g_auto.abs().max()).item() < 1e-12
+    g_orc = orc.chi_gradient_from_potential(box, chi, n_elec, v)
+    assert ((g_auto - g_orc).abs().max() / g_auto.abs().max()).item() < 1e-12

@@ -1,0 +1,113 @@
+"""GPU parity of the System facade and the density-optimisation loop against the unmodified
+reference (golden runs in tests/golden/denopt_*.npz) and the reference's own known answers.
+
+Gate (BASELINE.json): optimised energies within 1e-6 eV/atom."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+EV = 27.211386245988
+
+
+def _system(case, golden_dir, potentials_dir, terms, pot, **kw):
+    from profess_ad_b200.system import System
+    g = np.load(os.path.join(golden_dir, f'denopt_{case}.npz'))
+    box = torch.from_numpy(g['box_bohr'])
+    shape = tuple(int(s) for s in g['shape'])
+    ions = [[pot[:2].capitalize(), os.path.join(potentials_dir, pot), torch.from_numpy(g['frac'])]]
+    return System(box, shape, ions, terms, units='b', coord_type='fractional', **kw), g
+
+
+def test_vext_and_ion_energy_match_reference(golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    terms = [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+    s, g = _system('al_fcc18_wt_pbe', golden_dir, potentials_dir, terms, 'al.gga.recpot')
+    v = s.ionic_potential().cpu().numpy()
+    assert np.abs(v - g['v_ext']).max() <= 1e-11 * np.abs(g['v_ext']).max()
+    assert abs(s._System__Eion_cache - float(g['E_ion_Ha'])) < 1e-10
+    assert s.electron_count() == 3 and s.ion_count() == 1
+
+
+CASES = {
+    'al_fcc18_wt_pbe': ('al.gga.recpot', lambda F: [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof],
+                        dict(ntol=1e-7), 1),
+    'li_bcc18_sm_pbe': ('li.gga.recpot', lambda F: [F.IonIon, F.IonElectron, F.Hartree, F.SmargiassiMadden, F.PerdewBurkeErnzerhof],
+                        dict(ntol=1e-7), 2),
+    'al_fcc4_config1': ('al.gga.recpot', lambda F: [F.IonElectron, F.Hartree, F.ThomasFermi, F.Weizsaecker, F.PerdewZunger],
+                        dict(ntol=1e-7, from_uniform=True), 4),
+    'al_fcc4_tpgd': ('al.gga.recpot', lambda F: [F.IonElectron, F.Hartree, F.WangTeter, F.PerdewZunger],
+                     dict(ntol=1e-6, n_method='TPGD', n_conv_cond_count=5), 4),
+    'al_fcc4_wgc99': ('al.gga.recpot', lambda F: [F.IonElectron, F.Hartree, F.WangGovindCarter99().forward, F.PerdewZunger],
+                      dict(ntol=1e-7), 4),
+}
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_optimize_density_matches_reference(case, golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    pot, terms, kw, natoms = CASES[case]
+    s, g = _system(case, golden_dir, potentials_dir, terms(F), pot)
+    s.optimize_density(**kw)
+    dE_eV_per_atom = abs(s.energy('eV') - float(g['energy_eV'])) / natoms
+    assert dE_eV_per_atom < 1e-6, f'{case}: {dE_eV_per_atom:.3e} eV/atom'
+    den = s.density().cpu().numpy()
+    assert np.abs(den - g['den']).max() < 1e-5
+
+
+def test_known_answers_profess4(golden_dir, potentials_dir):
+    """tests/test_match_profess4.py:23,35 (atol 1e-4 eV)."""
+    import profess_ad_b200.functionals as F
+    s, _ = _system('al_fcc18_wt_pbe', golden_dir, potentials_dir, CASES['al_fcc18_wt_pbe'][1](F), 'al.gga.recpot')
+    s.optimize_density(ntol=1e-7)
+    assert abs(s.energy('eV') - (-57.183329401794985)) < 1e-4
+    s, _ = _system('li_bcc18_sm_pbe', golden_dir, potentials_dir, CASES['li_bcc18_sm_pbe'][1](F), 'li.gga.recpot')
+    s.optimize_density(ntol=1e-7)
+    assert abs(s.energy('eV') - (-14.741886997024537)) < 1e-4
+
+
+def test_potentials_hook_and_convergence_measures(golden_dir, potentials_dir):
+    """tests/test_functional_derivative.py:120-139 and tests/test_den_opt.py:58-75."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.functional_tools import get_functional_derivative
+    terms = [F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+    s, _ = _system('al_fcc4_tpgd', golden_dir, potentials_dir, terms, 'al.gga.recpot')
+    s.optimize_density(ntol=1e-7)
+    E1, den1 = s.energy(), s.density().clone()
+
+    def dEdn(bv, n):
+        return s.ionic_potential() + sum(get_functional_derivative(bv, n, f) for f in terms[1:])
+    s.initialize_density()
+    s.optimize_density(ntol=1e-7, potentials=dEdn)
+    assert abs(E1 - s.energy()) <= 1e-7 * abs(E1)
+    assert (den1 - s.density()).abs().max().item() < 1e-5
+
+    dEdchi = s.check_density_convergence()
+    v = s.functional_derivative('density')
+    chi = torch.sqrt(s.density())
+    n_tilde = torch.mean(chi.pow(2)) * s.volume()
+    mu = torch.mean(v * s.density()) * s.volume() / s.electron_count()
+    proj = (s.electron_count() / n_tilde) * 2 * chi * (v - mu)
+    assert abs(dEdchi - proj.abs().max().item()) <= 1e-10 * dEdchi
+    assert abs(s.chemical_potential() - mu.item()) < 1e-12
+    assert s.check_density_convergence('euler') < 1e-3
+
+
+def test_setters_and_errors(golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    s, g = _system('al_fcc4_tpgd', golden_dir, potentials_dir, [F.IonElectron, F.ThomasFermi], 'al.gga.recpot')
+    e0 = s.energy()
+    s.set_lattice(1.02 * s.lattice_vectors('b'), units='b')
+    assert abs(s.density().mean().item() * s.volume() - s.electron_count()) < 1e-10      # N conserved
+    assert s.energy() != e0
+    with pytest.raises(ValueError):
+        s.set_lattice(s.lattice_vectors('b'), units='x')
+    with pytest.raises(ValueError):
+        s.optimize_density(n_method='nope')
+    with pytest.raises(NotImplementedError):
+        s.stress()
+    with pytest.raises(AssertionError):
+        s.set_density(torch.ones(3, 3, 3, dtype=torch.double))
