@@ -93,6 +93,59 @@ int pad_eval_pbe(pad_plan* plan, const double* den, int which, double* E_out, do
 int pad_gradient(pad_plan* plan, const double* f, double* gx, double* gy, double* gz, void* stream);
 int pad_laplacian(pad_plan* plan, const double* f, double* out, void* stream);
 
+/* ---- fused evaluation of a whole term list: replaces System.__compute_energy + autograd
+ *      (system.py:759-772, 830-838).  E_out = sum of terms, v_out = total dE/dn. ---------------- */
+typedef struct pad_terms {
+    int local_mask;      /* PAD_LOCAL_* bits (IonElectron needs v_ext)                       */
+    int hartree;         /* 0/1                                                              */
+    int kinetic;         /* 0 none, 1 Wang-Teter family (alpha, beta, kinetic_parts), 2 WGC99 */
+    int kinetic_parts;   /* PAD_PART_* mask for kinetic == 1 (e.g. PAD_PART_VW alone = Weizsaecker) */
+    int pbe;             /* 0 none, 1 exchange, 2 correlation, 3 both                        */
+    double alpha, beta, gamma, kappa;
+} pad_terms;
+int pad_eval_total(pad_plan* plan, const pad_terms* terms, const double* den, const double* v_ext,
+                   double* E_out, double* v_out, void* stream);
+
+/* ---- chi-parametrisation (system.py:830-854): n = N chi^2 / int chi^2 and the projected gradient
+ *      dE/dchi_ijk = dV (N/Ntilde) 2 chi (v - mu), mu = int v n / N.  grad_out = N doubles. -------- */
+int pad_chi_to_density(pad_plan* plan, const double* chi, double n_elec, double* den_out, void* stream);
+int pad_chi_project(pad_plan* plan, const double* chi, const double* den, const double* v, double n_elec,
+                    double* grad_out, double* stats_out /* device, 4: |g|_1, g.g, max|dE/dchi|, max|mu - v| */,
+                    void* stream);
+
+/* ---- device-resident density optimisation: replaces the loop of System.optimize_density
+ *      (system.py:866-901) driving LBFGSNew.step (lbfgsnew.py:512-769, fixed step) or TPGD.step
+ *      (two_point_gradient_descent.py:25-65).  The host only enqueues work and polls a pinned
+ *      status word a few evaluations behind the GPU; there is no synchronisation inside an outer
+ *      iteration. ------------------------------------------------------------------------------ */
+typedef struct pad_denopt pad_denopt;
+typedef struct pad_denopt_params {
+    double n_elec;             /* electrons in the cell                                         */
+    double ntol;               /* optimize_density(ntol)                                        */
+    int n_conv_cond_count;
+    int method;                /* 0 = LBFGS, 1 = TPGD                                           */
+    double step_size;          /* n_step_size (lr)                                              */
+    int n_maxiter;
+    int conv_target;           /* 0 = dE [eV], 1 = max|dE/dchi|, 2 = max|mu - dE/dn|            */
+    int history;               /* L-BFGS history (reference: 8); <= 8                           */
+    int max_iter;              /* L-BFGS inner iterations per step (reference: 6)               */
+    double tolerance_grad;     /* 1e-5 */
+    double tolerance_change;   /* 1e-9 */
+} pad_denopt_params;
+typedef struct pad_denopt_result {
+    int iterations;            /* outer iterations executed                                     */
+    int converged;             /* 1 if the stop rule fired, 0 if n_maxiter was reached          */
+    int closures;              /* energy+potential evaluations                                  */
+    double energy;             /* functional energy (without ion-ion) of the final density [Ha] */
+    double last_dE_eV, last_dEdchi, last_euler;
+} pad_denopt_result;
+int pad_denopt_create(pad_denopt** opt, pad_plan* plan, const pad_terms* terms, const pad_denopt_params* params);
+/* den_inout: initial density in, optimised density out (device).  trace_host (may be NULL) receives
+ * 4 doubles per outer iteration: E [eV], dE [eV], max|dE/dchi|, max|mu - dE/dn|. Blocks until done. */
+int pad_denopt_run(pad_denopt* opt, double* den_inout, const double* v_ext, pad_denopt_result* result_host,
+                   double* trace_host, void* stream);
+int pad_denopt_destroy(pad_denopt* opt);
+
 #ifdef __cplusplus
 }
 #endif

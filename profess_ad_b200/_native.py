@@ -37,6 +37,13 @@ SIGNATURES = {
     'pad_eval_pbe': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
     'pad_gradient': (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     'pad_laplacian': (_int, [_vp, _vp, _vp, _vp]),
+    # struct pointers (pad_terms*, pad_denopt_params*, pad_denopt_result*) are passed with ctypes.byref
+    'pad_eval_total': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'pad_chi_to_density': (_int, [_vp, _vp, _dbl, _vp, _vp]),
+    'pad_chi_project': (_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
+    'pad_denopt_create': (_int, [ctypes.POINTER(_vp), _vp, _vp, _vp]),
+    'pad_denopt_run': (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    'pad_denopt_destroy': (_int, [_vp]),
 }
 
 PART_TF, PART_VW, PART_NL, PART_ALL = 1, 2, 4, 7

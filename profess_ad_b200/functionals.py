@@ -307,3 +307,23 @@ def pbe_correlation(box_vecs, den):
 def PerdewBurkeErnzerhof(box_vecs, den):
     """PBE exchange-correlation (functionals.py:1621-1635): 8 FFTs, gradient shared by x and c."""
     return _evaluate(box_vecs, den, _L_PBE)
+
+
+# ----------------------------------------------------------------------------------------------
+#  descriptors for the fused evaluator / device-resident optimiser (see _density_opt.describe_terms)
+# ----------------------------------------------------------------------------------------------
+IonElectron._pad_term = ('local', _native.LOCAL_IONEL)
+ThomasFermi._pad_term = ('local', _native.LOCAL_TF)
+lda_exchange._pad_term = ('local', _native.LOCAL_LDAX)
+perdew_zunger_correlation._pad_term = ('local', _native.LOCAL_PZC)
+PerdewZunger._pad_term = ('local', _native.LOCAL_LDAX | _native.LOCAL_PZC)
+Hartree._pad_term = ('hartree',)
+Weizsaecker._pad_term = ('wt', 1.0, 1.0, _native.PART_VW)
+WangTeter._pad_term = ('wt', 5 / 6, 5 / 6, _native.PART_ALL)
+Perrot._pad_term = ('wt', 1.0, 1.0, _native.PART_ALL)
+SmargiassiMadden._pad_term = ('wt', 0.5, 0.5, _native.PART_ALL)
+WangGovindCarter98._pad_term = ('wt', _A98, _B98, _native.PART_ALL)
+pbe_exchange._pad_term = ('pbe', 1)
+pbe_correlation._pad_term = ('pbe', 2)
+PerdewBurkeErnzerhof._pad_term = ('pbe', 3)
+WangGovindCarter99._pad_term_of = lambda self: ('wgc99',) + self._args

@@ -22,6 +22,7 @@ from .ion_utils import get_ion_charge, interpolate_recpot, lattice_sum, ion_inte
 from .functional_tools import wavevecs
 from ._optimizers.lbfgs.lbfgsnew import LBFGSNew
 from ._optimizers.tpgd.two_point_gradient_descent import TPGD
+from . import _density_opt
 
 
 def _default_device():
@@ -44,6 +45,9 @@ class System():
     J_per_Ha = 4.3597447222071e-18
     eV_per_Ha = J_per_Ha / 1.602176634e-19
     GPa_per_atomic = J_per_Ha / m_per_bohr**3 * 1e-9
+
+    # set to False to force the generic host-driven optimiser even when every term is native
+    use_native_optimizer = True
 
     def __init__(self, box_vecs, shape, ions, terms, units='b', coord_type='cartesian', Rc=None,
                  pme_order=None, device=None):
@@ -349,6 +353,12 @@ class System():
             if current_E < uniform_E:
                 self.set_density(current_den)
 
+        T = _density_opt.describe_terms(self.__terms) if (potentials is None and self.use_native_optimizer) else None
+        if T is not None:
+            self.__optimize_density_native(T, ntol, n_conv_cond_count, n_method, n_step_size, n_maxiter, conv_target,
+                                           n_verbose)
+            return
+
         chi = torch.sqrt(self.__den).requires_grad_()
         if n_method == 'LBFGS':
             optimizer = LBFGSNew([chi], lr=n_step_size, history_size=8, max_iter=6)
@@ -370,13 +380,15 @@ class System():
             def closure():
                 if torch.is_grad_enabled():
                     optimizer.zero_grad()
-                with torch.no_grad():
-                    N_tilde = torch.mean(chi.pow(2)) * vol
-                    self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
-                    E = self.__compute_energy(for_den_opt=True)
-                    dEdn = potentials(self.__box_vecs, self.__den)
-                    mu = torch.mean(dEdn * self.__den) * vol / self.__N_elec
-                    chi.grad = (self.__N_elec / N_tilde) * 2 * chi * (dEdn - mu) * dV
+                chi.requires_grad = False       # user potentials may use autograd themselves
+                N_tilde = torch.mean(chi.pow(2)) * vol
+                self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
+                E = self.__compute_energy(for_den_opt=True)
+                dEdn = potentials(self.__box_vecs, self.__den)
+                mu = torch.mean(dEdn * self.__den) * vol / self.__N_elec
+                grad = (self.__N_elec / N_tilde) * 2 * chi * (dEdn - mu) * dV
+                chi.requires_grad = True
+                chi.grad = grad
                 return E
 
         E_prev = self.__compute_energy(for_den_opt=True).item() * self.eV_per_Ha
@@ -411,6 +423,32 @@ class System():
                 break
             if it == round(n_maxiter) and n_verbose:
                 print('Density optimization failed to converge in {} steps \n'.format(int(it)))
+        self.detach()
+        self.__ene = self.__compute_energy(use_ion_cache=True)
+
+    def __optimize_density_native(self, T, ntol, n_conv_cond_count, n_method, n_step_size, n_maxiter, conv_target,
+                                  n_verbose):
+        """Every term is native: run the whole loop on the device (pad_denopt_run).  Same iterates and
+        stop rule as the generic path; the per-iteration table is printed once the loop has finished
+        because the host never waits on an individual iteration."""
+        if n_verbose:
+            print('Starting density optimization')
+            print('{:^8} {:^12} {:^12} {:^18} {:^18}'.format('Iter', 'E [eV]', 'dE [eV]', 'Max |𝛿E/𝛿χ|', 'Max |µ-𝛿E/𝛿n|'))
+            E0 = self.__compute_energy(for_den_opt=True).item() * self.eV_per_Ha
+            print('{:^8} {:^12.6f} {:^12.6g} {:^18.6g} {:^18.6g}'.format(
+                0, E0, 0, self.check_density_convergence('dEdchi'), self.check_density_convergence('euler')))
+        den = self.__den.detach().clone().contiguous()
+        res, trace = _density_opt.run(self.__box_vecs, den, self.__v_ext, T, self.__N_elec, ntol, n_conv_cond_count,
+                                      n_method, n_step_size, n_maxiter, conv_target)
+        self.__den = den
+        self.last_optimization = dict(res, trace=trace, native=True)
+        if n_verbose:
+            for i, row in enumerate(trace.tolist(), start=1):
+                print('{:^8} {:^12.6f} {:^12.6g} {:^18.6g} {:^18.6g}'.format(i, *row))
+            if res['converged']:
+                print('Density optimization successfully converged in {} step(s) \n'.format(res['iterations']))
+            else:
+                print('Density optimization failed to converge in {} steps \n'.format(res['iterations']))
         self.detach()
         self.__ene = self.__compute_energy(use_ion_cache=True)
 

@@ -46,12 +46,17 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize('native', [True, False], ids=['device_resident', 'host_driven'])
 @pytest.mark.parametrize('case', list(CASES))
-def test_optimize_density_matches_reference(case, golden_dir, potentials_dir):
+def test_optimize_density_matches_reference(case, native, golden_dir, potentials_dir, monkeypatch):
     import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    monkeypatch.setattr(System, 'use_native_optimizer', native)
     pot, terms, kw, natoms = CASES[case]
     s, g = _system(case, golden_dir, potentials_dir, terms(F), pot)
     s.optimize_density(**kw)
+    if native:
+        assert s.last_optimization.get('native') and s.last_optimization['converged']
     dE_eV_per_atom = abs(s.energy('eV') - float(g['energy_eV'])) / natoms
     assert dE_eV_per_atom < 1e-6, f'{case}: {dE_eV_per_atom:.3e} eV/atom'
     den = s.density().cpu().numpy()
@@ -111,3 +116,43 @@ def test_setters_and_errors(golden_dir, potentials_dir):
         s.stress()
     with pytest.raises(AssertionError):
         s.set_density(torch.ones(3, 3, 3, dtype=torch.double))
+
+
+def test_fused_evaluator_and_projection_match_oracle():
+    """pad_eval_total (whole term list in one call) and pad_chi_project vs the autograd oracle."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _density_opt as D
+    dev = torch.device('cuda:0')
+    for shape, seed in (((16, 18, 20), 3), ((15, 17, 13), 4)):
+        box, den = orc.synth_rough(shape, seed=seed)
+        gen = torch.Generator().manual_seed(seed)
+        v_ext = -0.5 + 0.2 * torch.rand(*shape, dtype=torch.double, generator=gen)
+        chi = torch.sqrt(den) * (1 + 0.1 * torch.rand(*shape, dtype=torch.double, generator=gen))
+        n_elec = 11.0
+        combos = [
+            ([F.IonElectron, F.Hartree, F.WangGovindCarter99().forward, F.PerdewZunger],
+             [orc.IonElectron, orc.Hartree, orc.WangGovindCarter99(), orc.PerdewZunger]),
+            ([F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof],
+             [orc.IonElectron, orc.Hartree, orc.WangTeter, orc.PerdewBurkeErnzerhof]),
+            ([F.IonElectron, F.Hartree, F.ThomasFermi, F.Weizsaecker, F.PerdewZunger],
+             [orc.IonElectron, orc.Hartree, orc.ThomasFermi, orc.Weizsaecker, orc.PerdewZunger]),
+        ]
+        for native_terms, oracle_terms in combos:
+            T = D.describe_terms(native_terms)
+            assert T is not None
+            E_ref, g_ref, n_ref = orc.chi_gradient(box, chi, n_elec, oracle_terms, v_ext)
+            b, c = box.to(dev), chi.to(dev)
+            n = D.chi_to_density(b, c, n_elec)
+            assert ((n.cpu() - n_ref).abs().max() / n_ref.abs().max()).item() < 1e-13
+            E, v = D.eval_total(b, n, v_ext.to(dev), T)
+            assert abs(E.item() - E_ref.item()) <= 1e-10 * abs(E_ref.item())
+            g, stats = D.chi_project(b, c, n, v, n_elec)
+            assert ((g.cpu() - g_ref).abs().max() / g_ref.abs().max()).item() < 1e-9
+            stats = stats.cpu()
+            dV = abs(torch.linalg.det(box).item()) / chi.numel()
+            assert abs(stats[0].item() - g_ref.abs().sum().item()) <= 1e-9 * g_ref.abs().sum().item()
+            assert abs(stats[1].item() - (g_ref * g_ref).sum().item()) <= 1e-9 * (g_ref * g_ref).sum().item()
+            assert abs(stats[2].item() - (g_ref / dV).abs().max().item()) <= 1e-9 * (g_ref / dV).abs().max().item()
+    assert D.describe_terms([F.Hartree, lambda b, n: F.ThomasFermi(b, n)]) is None      # user term -> generic path
+    assert D.describe_terms([F.ThomasFermi, F.ThomasFermi]) is None
