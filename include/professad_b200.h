@@ -89,6 +89,16 @@ int pad_eval_wgc99(pad_plan* plan, const double* den, double alpha, double beta,
 /* PerdewBurkeErnzerhof (functionals.py:1597-1635); `which`: 1 = exchange, 2 = correlation, 3 = both */
 int pad_eval_pbe(pad_plan* plan, const double* den, int which, double* E_out, double* v_out, int accumulate, void* stream);
 
+/* HuangCarter.forward (variant 0: p0 = lambda) / RevisedHuangCarter.forward (variant 1: p0 = a, p1 = b)
+ * (functionals.py:1232-1269, 1331-1365) with field_dependent_convolution + interpolate_kernel +
+ * interpolate (functional_tools.py:292-423) fused into node-wise convolutions and a per-voxel
+ * 4-node Hermite gather.  table_dev: DEVICE pointer to 2*n_eta doubles [eta | omega(eta)], eta uniform
+ * from 0.  geometric != 0 selects the geometric node progression (what HC/revHC use), else arithmetic.
+ * Does one device->host read (min/max of xi), as the reference does.  n_nodes_out (host, may be NULL). */
+int pad_eval_hc(pad_plan* plan, const double* den, int variant, double p0, double p1, double beta, double kappa,
+                int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out, int accumulate,
+                int* n_nodes_out, void* stream);
+
 /* ---- spectral tools (functional_tools.py:166-227) ------------------------------------------ */
 int pad_gradient(pad_plan* plan, const double* f, double* gx, double* gy, double* gz, void* stream);
 int pad_laplacian(pad_plan* plan, const double* f, double* out, void* stream);

@@ -191,6 +191,12 @@ struct pad_plan {
     double* wgc_kern;
     double wgc_key[6];           // alpha, beta, gamma, kappa, + box generation, valid flag
     uint64_t box_generation;
+    // Huang-Carter scratch: xi-node list (+ min/max words), table slopes, n_xi convolution fields
+    double* hc_scratch;
+    double* hc_slopes;
+    int hc_slopes_n;
+    double* hc_conv;
+    int hc_conv_nodes;
     size_t bytes_allocated;
 };
 

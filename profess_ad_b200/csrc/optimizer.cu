@@ -561,11 +561,12 @@ extern "C" int pad_denopt_create(pad_denopt** out, pad_plan* plan, const pad_ter
     const size_t N = plan->N, vb = sizeof(double) * N;
     const int nvec = 6 + (P.method == 0 ? 2 * OPT_SLOTS : 1);
     double* pool = nullptr;
-    PAD_CUDA(cudaMalloc(&pool, vb * nvec));
+    const size_t Np = (N + 31) & ~(size_t)31;      // 256-byte aligned vectors: den / v are cuFFT operands
+    PAD_CUDA(cudaMalloc(&pool, vb * nvec + sizeof(double) * 32 * 8));
     o->bytes = vb * nvec;
-    o->chi = pool; o->g = pool + N; o->prev_g = pool + 2 * N; o->d = pool + 3 * N; o->den = pool + 4 * N; o->v = pool + 5 * N;
-    if (P.method == 0) { o->Sh = pool + 6 * N; o->Yh = o->Sh + (size_t)OPT_SLOTS * N; o->x_prev = nullptr; }
-    else { o->x_prev = pool + 6 * N; }
+    o->chi = pool; o->g = pool + Np; o->prev_g = pool + 2 * Np; o->d = pool + 3 * Np; o->den = pool + 4 * Np; o->v = pool + 5 * Np;
+    if (P.method == 0) { o->Sh = pool + 6 * Np; o->Yh = o->Sh + (size_t)OPT_SLOTS * N; o->x_prev = nullptr; }
+    else { o->x_prev = pool + 6 * Np; }
     PAD_CUDA(cudaMalloc(&o->partials, sizeof(double) * OPT_NACC * PAD_MAX_BLOCKS));
     PAD_CUDA(cudaMalloc(&o->st, sizeof(OptState)));
     PAD_CUDA(cudaMalloc(&o->trace, sizeof(double) * 4 * (size_t)(prm->n_maxiter > 0 ? prm->n_maxiter : 1)));

@@ -37,6 +37,8 @@ class _NativeEnergy(torch.autograd.Function):
         d = den.detach()
         if not d.is_contiguous():
             d = d.contiguous()
+        if d.data_ptr() % 16:           # views at odd offsets: cuFFT operands need 16-byte alignment
+            d = d.clone()
         plan = _native.get_plan(box_vecs, d)
         need_v = ctx.needs_input_grad[0]
         E = torch.empty((), dtype=torch.double, device=d.device)
@@ -327,3 +329,108 @@ pbe_exchange._pad_term = ('pbe', 1)
 pbe_correlation._pad_term = ('pbe', 2)
 PerdewBurkeErnzerhof._pad_term = ('pbe', 3)
 WangGovindCarter99._pad_term_of = lambda self: ('wgc99',) + self._args
+
+
+# ----------------------------------------------------------------------------------------------
+#  Huang-Carter family (functionals.py:1176-1365): field-dependent kernel by a spline over xi
+# ----------------------------------------------------------------------------------------------
+def huang_carter_kernel_table(beta, eta_max=50, N_eta=10000, rtol=1e-12, atol=1e-14):
+    """omega(eta) on linspace(0, eta_max, N_eta) (functionals.py:1204-1230): the ODE
+    w' = -[(5/3)(1/Ginv - 3 eta^2 - 1) - (5 - 3 beta) beta w] / (beta eta) integrated from eta_max
+    down to the first grid point with w(eta_max) = -(8/3)/((5 - 3 beta) beta); omega(0) = 0.
+    The reference integrates with xitorch.solve_ivp defaults (un-pinned dependency); here an
+    8th-order Dormand-Prince integrator at tight tolerance is used (parity unpinned at
+    this boundary -- for parity runs inject the same table into both sides via ``.kernel``)."""
+    from scipy.integrate import solve_ivp
+
+    def lind(e):
+        if e == 0:
+            return 1.0
+        if e == 1:
+            return 2.0
+        return 1.0 / (0.5 + (1 - e * e) / (4 * e) * math.log(abs((1 + e) / (1 - e))))
+
+    def rhs(e, w):
+        return [-((5.0 / 3.0) * (lind(e) - 3 * e * e - 1) - (5 - 3 * beta) * beta * w[0]) / beta / e]
+    etas = np.linspace(0.0, float(eta_max), int(N_eta))
+    w_inf = -(8.0 / 3.0) / ((5 - 3 * beta) * beta)
+    sol = solve_ivp(rhs, (etas[-1], etas[1]), [w_inf], t_eval=etas[1:][::-1], method='DOP853', rtol=rtol, atol=atol)
+    w = np.concatenate([[0.0], sol.y[0][::-1]])
+    return torch.from_numpy(np.stack([etas, w]))
+
+
+class _HuangCarterFamily(KineticFunctional):
+    mode = 'geometric'
+    _variant = 0
+
+    def generate_kernel(self, eta_max=50, N_eta=10000):
+        self.kernel = huang_carter_kernel_table(float(self.beta.item()), eta_max, N_eta)
+
+    def _params(self):
+        raise NotImplementedError
+
+    def forward(self, box_vecs, den):
+        p0, p1 = self._params()
+        beta, kappa, variant = float(self.beta.item()), float(self.kappa), self._variant
+        geometric = 1 if self.mode == 'geometric' else 0
+        if self.mode not in ('geometric', 'arithmetic'):
+            raise ValueError('Parameter \'mode\' can only be \'arithmetic\' or \'geometric\'')
+        if geometric:
+            assert kappa > 1, 'κ > 1 for geometric progression based spline for field_dependent_convolution'
+        table = self.kernel
+        if table.device != den.device or table.dtype != torch.double or not table.is_contiguous():
+            table = table.to(device=den.device, dtype=torch.double).contiguous()
+            self.kernel = table
+        n_eta = int(table.shape[1])
+        owner = self
+
+        def launch(plan, d, _, E, v, stream):
+            n_nodes = ctypes.c_int(0)
+            check(plan.lib.pad_eval_hc(plan.handle, ptr(d), variant, p0, p1, beta, kappa, geometric, ptr(table), n_eta,
+                                       ptr(E), ptr(v), 0, ctypes.byref(n_nodes), stream))
+            owner.last_n_nodes = n_nodes.value
+        return _evaluate(box_vecs, den, launch).reshape(1)
+
+
+class HuangCarter(_HuangCarterFamily):
+    """Huang-Carter functional (functionals.py:1176-1269), init_args = (lambda, beta, kappa).
+    xi = 2 kF(n) (1 + lambda |grad n|^2 / n^{8/3})."""
+    _variant = 0
+
+    def __init__(self, init_args, kernel=None):
+        super().__init__()
+        lamb, beta, kappa = init_args
+        self.lamb = torch.nn.Parameter(torch.tensor([lamb], dtype=torch.double))
+        self.beta = torch.nn.Parameter(torch.tensor([beta], dtype=torch.double))
+        self.kappa = kappa
+        self.debug = False          # the reference forgets to set this (functionals.py:1247)
+        self.initialize()
+        if kernel is None:
+            self.generate_kernel()
+        else:
+            self.kernel = kernel
+
+    def _params(self):
+        return float(self.lamb.item()), 0.0
+
+
+class RevisedHuangCarter(_HuangCarterFamily):
+    """revised Huang-Carter functional (functionals.py:1272-1365), init_args = (a, b, beta, kappa).
+    xi = 2 kF(n) (1 + a s^2 / (1 + b s^2)) with s the reduced gradient."""
+    _variant = 1
+
+    def __init__(self, init_args, kernel=None):
+        super().__init__()
+        a, b, beta, kappa = init_args
+        self.a = torch.nn.Parameter(torch.tensor([a], dtype=torch.double))
+        self.b = torch.nn.Parameter(torch.tensor([b], dtype=torch.double))
+        self.beta = torch.nn.Parameter(torch.tensor([beta], dtype=torch.double))
+        self.kappa = kappa
+        self.initialize()
+        if kernel is None:
+            self.generate_kernel()
+        else:
+            self.kernel = kernel
+
+    def _params(self):
+        return float(self.a.item()), float(self.b.item())

@@ -115,3 +115,35 @@ def test_energy_only_path_and_errors():
         F.Hartree(box, den)                             # CPU tensors: loud failure, no fallback
     with pytest.raises(NotImplementedError):
         F.Hartree(b.clone().requires_grad_(True), d)    # stress path is out of scope
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_huang_carter_family_matches_reference_golden(case, golden_dir):
+    """HC / revHC with the SAME omega(eta) table injected on both sides (the table itself comes from an
+    ODE solve with xitorch in the reference: parity unpinned at that boundary)."""
+    import profess_ad_b200.functionals as F
+    g = np.load(os.path.join(golden_dir, f'functionals_{case}.npz'))
+    tab = np.load(os.path.join(golden_dir, 'hc_table.npz'))
+    dev = torch.device('cuda:0')
+    box = torch.from_numpy(g['box']).to(dev)
+    den = torch.from_numpy(g['den']).to(dev)
+    hc = F.HuangCarter((0.01177, 0.7143, 1.2), kernel=torch.from_numpy(tab['hc']))
+    rev = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15), kernel=torch.from_numpy(tab['revhc']))
+    for name, f in (('HuangCarter', hc), ('RevisedHuangCarter', rev)):
+        E, V = F.energy_and_potential(box, den, f.forward)
+        _compare(f'{case}/{name}', E.item(), V.cpu().numpy(), g['E_' + name].item(), g['V_' + name])
+        assert f.last_n_nodes >= 7
+
+
+def test_huang_carter_vs_oracle_larger_grid(golden_dir):
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    tab = np.load(os.path.join(golden_dir, 'hc_table.npz'))
+    dev = torch.device('cuda:0')
+    for shape, seed in (((24, 20, 22), 21), ((21, 25, 19), 22)):
+        box, den = orc.synth_rough(shape, seed=seed)
+        t = torch.from_numpy(tab['revhc'])
+        E_ref, V_ref = orc.energy_and_potential(box, den, orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=t))
+        f = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15), kernel=t.clone())
+        E, V = F.energy_and_potential(box.to(dev), den.to(dev), f.forward)
+        _compare(f'{shape}/revHC', E.item(), V.cpu().numpy(), E_ref.item(), V_ref.numpy())
