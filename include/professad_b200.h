@@ -56,6 +56,9 @@ const char* pad_last_error(void);
 /* kernels this library has launched so far in this process (own kernels; cuFFT execs counted separately) */
 unsigned long long pad_launch_count(void);
 unsigned long long pad_fft_exec_count(void);
+/* 1 (default): use the hand-written fused z-pass FFT pipeline where the grid allows (n2 in 128/256/512);
+ * 0: plain cuFFT 3-D transforms + separate elementwise kernels.  Returns the previous setting. */
+int pad_set_fast_fft(int on);
 
 /* ---- plan: replaces wavevecs(box_vecs, shape) (functional_tools.py:135-162) and owns the cuFFT
  *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */
@@ -102,6 +105,12 @@ int pad_eval_hc(pad_plan* plan, const double* den, int variant, double p0, doubl
 /* ---- spectral tools (functional_tools.py:166-227) ------------------------------------------ */
 int pad_gradient(pad_plan* plan, const double* f, double* gx, double* gy, double* gz, void* stream);
 int pad_laplacian(pad_plan* plan, const double* f, double* out, void* stream);
+
+/* ---- hand-written 3-D real FFT (z passes own, (x,y) batched cuFFT) over the padded half-spectrum layout
+ *      (n0, n1, nzp = n2/2 + 8) complex; unnormalised like cuFFT.  Exposed for tests and profiling. -------- */
+int pad_fast_fft_supported(const pad_plan* plan);
+int pad_rfft3_fast(pad_plan* plan, const double* in, double* out_cplx_padded, int* nzp_out, void* stream);
+int pad_irfft3_fast(pad_plan* plan, double* in_cplx_padded /* destroyed */, double* out, void* stream);
 
 /* ---- fused evaluation of a whole term list: replaces System.__compute_energy + autograd
  *      (system.py:759-772, 830-838).  E_out = sum of terms, v_out = total dE/dn. ---------------- */

@@ -36,6 +36,10 @@ SIGNATURES = {
     'pad_eval_wgc99': (_int, [_vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _int, _vp]),
     'pad_eval_pbe': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
     'pad_eval_hc': (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _dbl, _int, _vp, _int, _vp, _vp, _int, _vp, _vp]),
+    'pad_set_fast_fft': (_int, [_int]),
+    'pad_fast_fft_supported': (_int, [_vp]),
+    'pad_rfft3_fast': (_int, [_vp, _vp, _vp, _vp, _vp]),
+    'pad_irfft3_fast': (_int, [_vp, _vp, _vp, _vp]),
     'pad_gradient': (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     'pad_laplacian': (_int, [_vp, _vp, _vp, _vp]),
     # struct pointers (pad_terms*, pad_denopt_params*, pad_denopt_result*) are passed with ctypes.byref

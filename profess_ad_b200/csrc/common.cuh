@@ -197,6 +197,13 @@ struct pad_plan {
     int hc_slopes_n;
     double* hc_conv;
     int hc_conv_nodes;
+    // fused z-pass pipeline (fftz.cu): padded half-spectrum buffers and the batched 2-D (x, y) cuFFT plan
+    int nzp;
+    cufftHandle xy;
+    bool xy_ready;
+    void* xy_work;
+    cudaStream_t xy_stream;
+    cufftDoubleComplex* zbuf[4];
     size_t bytes_allocated;
 };
 
@@ -214,6 +221,10 @@ int pad_get_rbuf(pad_plan* p, int i, double** out);
 int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
+extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
+int pad_wgc99_fast_supported(const pad_plan* p);
+int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,
+                   double* v_out, int accumulate, cudaStream_t s);
 
 // finalize: E_out (+)= sum_t coef[t] * (sum over blocks of partials[t]); optionally store raw sums
 struct FinalizeArgs {

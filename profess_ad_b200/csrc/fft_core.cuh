@@ -1,0 +1,161 @@
+// Register-level fp64 FFT building blocks for the hand-written transform passes (sm_100a).
+//
+//  * fft_reg<R, DIR>: R-point complex FFT (R = 2, 4, 8, 16) entirely in registers, radix-4/2
+//    decimation; the output with natural index k ends up in register slot fft_slot<R>(k).
+//  * line_fft<M, TPL, DIR>: M-point complex FFT of one line shared by TPL consecutive lanes of a
+//    warp (M / TPL elements per lane), four-step: radix-(M/TPL) in registers, twiddle, one
+//    shared-memory exchange (warp-synchronous, no block barrier), radix-TPL in registers.
+//  * real <-> half-complex post/pre-processing for lines of 2M reals packed as M complex numbers.
+//
+// DIR = -1: forward (exp(-i...)), DIR = +1: inverse, both unnormalised.
+#pragma once
+#include <cuda_runtime.h>
+
+struct cd {
+    double x, y;
+};
+__device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cd cmul(cd a, cd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cd cconj(cd a) { return {a.x, -a.y}; }
+__device__ __forceinline__ cd cscale(cd a, double s) { return {a.x * s, a.y * s}; }
+
+// multiply by DIR * i  (forward butterflies need -i)
+template <int DIR>
+__device__ __forceinline__ cd mul_i(cd a) {
+    return DIR < 0 ? cd{a.y, -a.x} : cd{-a.y, a.x};
+}
+
+// twiddle table: c_tw[j] = exp(-2 pi i j / FFT_TW_N), j < FFT_TW_N; forward sign, conjugate for inverse
+// (defined here: the header is included by exactly one translation unit, fftz.cu -- the library is built
+//  without relocatable device code, so device symbols cannot be shared across .cu files)
+#define FFT_TW_N 2048
+__device__ double2 g_fft_tw[FFT_TW_N];
+
+template <int DIR>
+__device__ __forceinline__ cd twiddle(int num, int den_log2_shift /* FFT_TW_N / den */) {
+    const double2 w = g_fft_tw[(num * den_log2_shift) & (FFT_TW_N - 1)];
+    return DIR < 0 ? cd{w.x, w.y} : cd{w.x, -w.y};
+}
+
+template <int DIR>
+__device__ __forceinline__ void fft2(cd& a, cd& b) {
+    const cd t = a - b;
+    a = a + b;
+    b = t;
+}
+
+template <int DIR>
+__device__ __forceinline__ void fft4(cd& a0, cd& a1, cd& a2, cd& a3) {
+    const cd t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = mul_i<DIR>(a1 - a3);
+    a0 = t0 + t2;
+    a1 = t1 + t3;
+    a2 = t0 - t2;
+    a3 = t1 - t3;
+}
+
+// constant twiddles exp(DIR * 2 pi i m / 16)
+template <int DIR>
+__device__ __forceinline__ cd w16(int m) {
+    constexpr double c1 = 0.92387953251128674, s1 = 0.38268343236508977, h = 0.70710678118654752;
+    double c, s;
+    switch (m & 15) {
+        case 0: c = 1; s = 0; break;
+        case 1: c = c1; s = s1; break;
+        case 2: c = h; s = h; break;
+        case 3: c = s1; s = c1; break;
+        case 4: c = 0; s = 1; break;
+        case 5: c = -s1; s = c1; break;
+        case 6: c = -h; s = h; break;
+        case 7: c = -c1; s = s1; break;
+        case 8: c = -1; s = 0; break;
+        case 9: c = -c1; s = -s1; break;
+        case 10: c = -h; s = -h; break;
+        case 11: c = -s1; s = -c1; break;
+        case 12: c = 0; s = -1; break;
+        case 13: c = s1; s = -c1; break;
+        case 14: c = h; s = -h; break;
+        default: c = c1; s = -s1; break;
+    }
+    return cd{c, DIR < 0 ? -s : s};
+}
+
+// register slot that holds natural output index k after fft_reg<R>
+template <int R>
+__device__ __forceinline__ constexpr int fft_slot(int k) {
+    return R == 16 ? (k >> 2) + 4 * (k & 3) : R == 8 ? (k >> 2) + 2 * (k & 3) : k;
+}
+// natural output index held by register slot r (inverse of fft_slot)
+template <int R>
+__device__ __forceinline__ constexpr int fft_nat(int r) {
+    return R == 16 ? (r >> 2) + 4 * (r & 3) : R == 8 ? (r >> 1) + 4 * (r & 1) : r;
+}
+
+template <int R, int DIR>
+__device__ __forceinline__ void fft_reg(cd* v) {
+    if constexpr (R == 2) {
+        fft2<DIR>(v[0], v[1]);
+    } else if constexpr (R == 4) {
+        fft4<DIR>(v[0], v[1], v[2], v[3]);
+    } else if constexpr (R == 8) {
+        // n = n1 + 2 n2 ; k = k2 + 4 k1
+#pragma unroll
+        for (int n1 = 0; n1 < 2; ++n1) fft4<DIR>(v[n1], v[n1 + 2], v[n1 + 4], v[n1 + 6]);
+        v[3] = cmul(v[3], w16<DIR>(2));      // W8^1
+        v[5] = mul_i<DIR>(v[5]);             // W8^2
+        v[7] = cmul(v[7], w16<DIR>(6));      // W8^3
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) fft2<DIR>(v[2 * k2], v[2 * k2 + 1]);
+    } else {
+        static_assert(R == 16, "fft_reg: R must be 2, 4, 8 or 16");
+        // n = n1 + 4 n2 ; k = k2 + 4 k1
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) fft4<DIR>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+#pragma unroll
+        for (int n1 = 1; n1 < 4; ++n1)
+#pragma unroll
+            for (int k2 = 1; k2 < 4; ++k2) v[n1 + 4 * k2] = cmul(v[n1 + 4 * k2], w16<DIR>(n1 * k2));
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) fft4<DIR>(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+//  M-point complex FFT of one line spread over TPL lanes.  On entry lane t holds
+//  v[j] = z[t + TPL j], j < EPT = M / TPL.  On exit v[g * TPL + r] = Z[k] with
+//  k = (t + TPL g) + EPT * fft_nat<TPL>(r),  g < EPT / TPL.
+//  S: shared scratch of the line, M * (1 + 1/TPL) complex (padded rows of TPL + 1).
+// ---------------------------------------------------------------------------------------------
+template <int M, int TPL, int DIR>
+__device__ __forceinline__ void line_fft(cd* v, cd* S, int t) {
+    constexpr int EPT = M / TPL;
+    constexpr int G = EPT / TPL;
+    static_assert(EPT % TPL == 0, "line_fft: M / TPL must be a multiple of TPL");
+    fft_reg<EPT, DIR>(v);
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const int k1 = fft_nat<EPT>(r);
+        cd a = v[r];
+        if (k1 != 0) a = cmul(a, twiddle<DIR>(t * k1, FFT_TW_N / M));
+        S[k1 * (TPL + 1) + t] = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int k1 = t + TPL * g;
+        cd u[TPL];
+#pragma unroll
+        for (int t2 = 0; t2 < TPL; ++t2) u[t2] = S[k1 * (TPL + 1) + t2];
+        fft_reg<TPL, DIR>(u);
+#pragma unroll
+        for (int r = 0; r < TPL; ++r) v[g * TPL + r] = u[r];
+    }
+    __syncwarp();
+}
+
+template <int M, int TPL>
+__device__ __forceinline__ int line_fft_out_index(int t, int slot) {
+    constexpr int EPT = M / TPL;
+    const int g = slot / TPL, r = slot % TPL;
+    return (t + TPL * g) + EPT * fft_nat<TPL>(r);
+}

@@ -548,6 +548,8 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     g_pad_launches += 2;
     PAD_CHECK_LAUNCH();
     const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
+    if (g_pad_fast_fft && pad_wgc99_fast_supported(p))
+        return pad_wgc99_fast(p, den, alpha, beta, kern, E_out, v_out, accumulate, s);
 
     // --- forward fields: a = n^beta, a theta, a theta^2 / 2, chi --------------------------------
     double *Ra = R[0], *Rb = R[1], *Rc = R[2], *Rx = R[3];

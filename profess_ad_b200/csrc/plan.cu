@@ -11,6 +11,8 @@ unsigned long long g_pad_fft_execs = 0;
 
 extern "C" unsigned long long pad_launch_count(void) { return g_pad_launches; }
 extern "C" unsigned long long pad_fft_exec_count(void) { return g_pad_fft_execs; }
+int g_pad_fast_fft = 1;
+extern "C" int pad_set_fast_fft(int on) { const int old = g_pad_fast_fft; g_pad_fast_fft = on ? 1 : 0; return old; }
 
 void pad_set_error(const char* fmt, ...) {
     va_list ap;
@@ -80,6 +82,7 @@ extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* sha
     p->N = (size_t)p->n0 * p->n1 * p->n2;
     p->Nk = (size_t)p->n0 * p->n1 * p->nzh;
     p->device = device;
+    p->nzp = p->n2 / 2 + 8;      // padded row length of the fused pipeline (multiple of 8 complex)
     if (p->Nk >= 0xffffffffull) {
         pad_set_error("grid too large for one device plan (%zu half-spectrum points)", p->Nk);
         delete p;
@@ -113,6 +116,9 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     if (p->hc_scratch) cudaFree(p->hc_scratch);
     if (p->hc_slopes) cudaFree(p->hc_slopes);
     if (p->hc_conv) cudaFree(p->hc_conv);
+    if (p->xy_ready) cufftDestroy(p->xy);
+    if (p->xy_work) cudaFree(p->xy_work);
+    for (int i = 0; i < 4; ++i) if (p->zbuf[i]) cudaFree(p->zbuf[i]);
     cudaFree(p->partials);
     cudaFree(p->scal);
     delete p;

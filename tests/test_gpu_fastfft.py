@@ -1,0 +1,62 @@
+"""The hand-written fused z-pass FFT pipeline (csrc/fftz.cu) vs library FFTs and vs the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan(box, den):
+    from profess_ad_b200 import _native
+    return _native.get_plan(box, den), _native
+
+
+@pytest.mark.parametrize('shape', [(6, 10, 128), (12, 9, 256), (5, 4, 512), (16, 16, 128)])
+def test_fast_rfft3_matches_library(shape):
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(sum(shape))
+    f = torch.rand(*shape, dtype=torch.double, generator=gen).to(dev)
+    box = torch.eye(3, dtype=torch.double, device=dev) * 7.0
+    plan, nat = _plan(box, f)
+    assert plan.lib.pad_fast_fft_supported(plan.handle) == 1
+    nzp = shape[2] // 2 + 8
+    spec = torch.zeros(shape[0], shape[1], nzp, dtype=torch.complex128, device=dev)
+    nzp_out = ctypes.c_int(0)
+    nat.check(plan.lib.pad_rfft3_fast(plan.handle, nat.ptr(f), nat.ptr(spec), ctypes.byref(nzp_out), nat.stream_ptr(dev)))
+    assert nzp_out.value == nzp
+    ref = torch.fft.rfftn(f)
+    nzh = shape[2] // 2 + 1
+    err = (spec[:, :, :nzh] - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-14, err
+    assert spec[:, :, nzh:].abs().max().item() == 0.0
+    out = torch.empty_like(f)
+    nat.check(plan.lib.pad_irfft3_fast(plan.handle, nat.ptr(spec), nat.ptr(out), nat.stream_ptr(dev)))
+    err = (out / f.numel() - f).abs().max().item()
+    assert err < 1e-14, err
+
+
+@pytest.mark.parametrize('shape,seed', [((10, 12, 128), 31), ((9, 8, 256), 32), ((4, 6, 512), 33)])
+def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native
+    lib = _native.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=seed, L=9.0)
+    E_ref, V_ref = orc.energy_and_potential(box, den, orc.WangGovindCarter99())
+    b, d = box.to(dev), den.to(dev)
+    results = {}
+    for fast in (1, 0):
+        old = lib.pad_set_fast_fft(fast)
+        try:
+            E, V = F.energy_and_potential(b, d, F.WangGovindCarter99().forward)
+            e_only = F.WangGovindCarter99().forward(b, d).item()
+        finally:
+            lib.pad_set_fast_fft(old)
+        results[fast] = (E.item(), V.cpu())
+        assert abs(E.item() - E_ref.item()) <= 1e-10 * abs(E_ref.item()), (fast, E.item(), E_ref.item())
+        assert ((V.cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9, fast
+        assert abs(e_only - E.item()) <= 1e-13 * abs(E.item())
+    assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
