@@ -126,8 +126,15 @@ __device__ __forceinline__ void fft_reg(cd* v) {
 //  k = (t + TPL g) + EPT * fft_nat<TPL>(r),  g < EPT / TPL.
 //  S: shared scratch of the line, M * (1 + 1/TPL) complex (padded rows of TPL + 1).
 // ---------------------------------------------------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ cd tw_dir(cd w) {
+    return DIR < 0 ? w : cd{w.x, -w.y};
+}
+
+// tw1: table in SHARED memory, tw1[e] = exp(-2 pi i e / M), e < M (global-memory twiddles stall the
+// FFT on L2 latency: with most of the L1 carved out as shared memory the table does not stay resident)
 template <int M, int TPL, int DIR>
-__device__ __forceinline__ void line_fft(cd* v, cd* S, int t) {
+__device__ __forceinline__ void line_fft(cd* v, cd* S, int t, const cd* __restrict__ tw1) {
     constexpr int EPT = M / TPL;
     constexpr int G = EPT / TPL;
     static_assert(EPT % TPL == 0, "line_fft: M / TPL must be a multiple of TPL");
@@ -136,7 +143,7 @@ __device__ __forceinline__ void line_fft(cd* v, cd* S, int t) {
     for (int r = 0; r < EPT; ++r) {
         const int k1 = fft_nat<EPT>(r);
         cd a = v[r];
-        if (k1 != 0) a = cmul(a, twiddle<DIR>(t * k1, FFT_TW_N / M));
+        if (k1 != 0) a = cmul(a, tw_dir<DIR>(tw1[t * k1]));
         S[k1 * (TPL + 1) + t] = a;
     }
     __syncwarp();
@@ -158,4 +165,41 @@ __device__ __forceinline__ int line_fft_out_index(int t, int slot) {
     constexpr int EPT = M / TPL;
     const int g = slot / TPL, r = slot % TPL;
     return (t + TPL * g) + EPT * fft_nat<TPL>(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+//  8-elements-per-lane variant: M = 64 (TPL = 8) or M = 128 (TPL = 16).  On entry lane t holds
+//  v[j] = z[t + TPL j], j < 8; on exit slot r holds Z[t + TPL * fft_nat<8>(r)]: the output is
+//  distributed over the lanes exactly like the input, so real-space data never needs re-staging.
+//  For M = 128 the second stage is a 16-point FFT per k1 shared by the two lanes (k1, h):
+//  lane h computes the outputs k2 = 2 m + h as an 8-point FFT of (y[t'] +- y[t' + 8]) W16^{t' h}.
+//  S: shared scratch of the line, 8 rows of TPL + 1 complex.
+// ---------------------------------------------------------------------------------------------
+template <int M, int TPL, int DIR>
+__device__ __forceinline__ void line_fft8(cd* v, cd* S, int t, const cd* __restrict__ tw1) {
+    static_assert((M == 64 && TPL == 8) || (M == 128 && TPL == 16), "line_fft8: (M, TPL) must be (64, 8) or (128, 16)");
+    fft_reg<8, DIR>(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int k1 = fft_nat<8>(r);
+        cd a = v[r];
+        if (k1 != 0) a = cmul(a, tw_dir<DIR>(tw1[t * k1]));
+        S[k1 * (TPL + 1) + t] = a;
+    }
+    __syncwarp();
+    if constexpr (TPL == 8) {
+#pragma unroll
+        for (int t2 = 0; t2 < 8; ++t2) v[t2] = S[t * (TPL + 1) + t2];
+    } else {
+        const int k1 = t & 7, h = t >> 3;
+#pragma unroll
+        for (int t2 = 0; t2 < 8; ++t2) {
+            const cd lo = S[k1 * (TPL + 1) + t2], hi = S[k1 * (TPL + 1) + t2 + 8];
+            cd u = h ? lo - hi : lo + hi;
+            if (h && t2 != 0) u = cmul(u, w16<DIR>(t2));
+            v[t2] = u;
+        }
+    }
+    fft_reg<8, DIR>(v);
+    __syncwarp();
 }

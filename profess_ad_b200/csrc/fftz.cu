@@ -43,109 +43,153 @@ int ensure_twiddles(int device) {
 }
 
 // ------------------------------------------------------------------------------------------------
-//  shared-memory carving: per line  [ stage: NST * 2M doubles | S: M + M/TPL complex ]
+//  z-pass kernels.  TPL lanes share a line; each lane owns the 8 packed-complex points
+//  n = t + TPL j (j < 8) of the line -- as FFT input AND as FFT output (line_fft8), so everything
+//  that is per real-space point (staged inputs, the NF inverse results) lives in registers.
+//  Shared memory per block: [ tw1: M cd | tw2: M/2 + 2 cd ] + per line one scratch of kScratch cd.
 // ------------------------------------------------------------------------------------------------
-template <int M, int TPL, int NST>
+template <int M, int TPL>
 struct ZLayout {
-    static constexpr int kStageDoubles = NST * 2 * M;
-    static constexpr int kScratchCplx = M + M / TPL + 1;           // also holds M + 1 natural-order values
-    static constexpr int kLineBytes = kStageDoubles * 8 + kScratchCplx * 16;
+    static constexpr int kTwBytes = (M + M / 2 + 2) * 16;
+    static constexpr int kScratch = (8 * (TPL + 1) > M + 1 ? 8 * (TPL + 1) : M + 1) + 1;
+    static constexpr int kLineBytes = kScratch * 16;
     static constexpr int kLinesPerWarp = 32 / TPL;
 };
 
-// forward: NF fields generated from staged per-point values, r2c along z, written as padded half-spectra
-//   Gen::NST                      staged doubles per point
-//   gen.stage(gidx, out[NST])     values to keep for the point with global index gidx
-//   gen.field(f, st[NST])         value of field f at a point
+template <int M>
+__device__ __forceinline__ void load_twiddles(cd* tw1, cd* tw2) {
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        const double2 w = g_fft_tw[e * (FFT_TW_N / M)];
+        tw1[e] = cd{w.x, w.y};
+    }
+    for (int e = threadIdx.x; e <= M / 2; e += blockDim.x) {
+        const double2 w = g_fft_tw[e * (FFT_TW_N / (2 * M))];
+        tw2[e] = cd{w.x, w.y};
+    }
+    __syncthreads();
+}
+
+// forward: field F generated from the staged values, packed FFT, real post-processing, store
+template <int M, int TPL, int F, class Gen>
+__device__ __forceinline__ void zfwd_field(const Gen& gen, const double (&sa)[Gen::NST][8], const double (&sb)[Gen::NST][8],
+                                           cd* S, const cd* tw1, const cd* tw2, int t, cd* __restrict__ out, bool live) {
+    constexpr int NST = Gen::NST;
+    cd v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double a[NST], b[NST];
+#pragma unroll
+        for (int s = 0; s < NST; ++s) { a[s] = sa[s][j]; b[s] = sb[s][j]; }
+        v[j] = cd{gen.template field<F>(a), gen.template field<F>(b)};
+    }
+    line_fft8<M, TPL, -1>(v, S, t, tw1);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) S[t + TPL * fft_nat<8>(r)] = v[r];      // natural order
+    __syncwarp();
+    // X[k] = Ev + w^k Od, X[M-k] = conj(Ev - w^k Od);  Ev = (Z[k] + conj Z[M-k])/2, Od = -i (Z[k] - conj Z[M-k])/2
+#pragma unroll
+    for (int i = 0; i < (M / 2 + TPL) / TPL; ++i) {
+        const int k = t + TPL * i;
+        if (k <= M / 2) {
+            const cd A = S[k], B = cconj(S[(M - k) & (M - 1)]);
+            const cd Ev = cscale(A + B, 0.5);
+            const cd D = A - B;
+            const cd Od = cd{0.5 * D.y, -0.5 * D.x};
+            const cd T = cmul(Od, tw2[k]);
+            if (live) {
+                if (k == 0) {
+                    out[0] = cd{A.x + A.y, 0.0};
+                    out[M] = cd{A.x - A.y, 0.0};
+                } else {
+                    out[k] = Ev + T;
+                    out[M - k] = cconj(Ev - T);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+//   Gen::NST                        staged doubles per point
+//   gen.stage(g, a[NST], b[NST])    values to keep for the points g and g + 1 (one 16-byte load each input)
+//   gen.field<F>(st[NST])           value of field F at a point
 template <int M, int TPL, int NF, class Gen>
 __global__ void __launch_bounds__(128) zfwd_kernel(Gen gen, cd* __restrict__ o0, cd* __restrict__ o1, cd* __restrict__ o2,
                                                   cd* __restrict__ o3, int nlines, int nzp) {
-    using L = ZLayout<M, TPL, Gen::NST>;
-    constexpr int EPT = M / TPL, LPW = L::kLinesPerWarp, NST = Gen::NST;
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tw1 = reinterpret_cast<cd*>(smem_raw);
+    cd* tw2 = tw1 + M;
+    load_twiddles<M>(tw1, tw2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
-    unsigned char* mine = smem_raw + (size_t)(warp * LPW + sub) * L::kLineBytes;
-    double* st = reinterpret_cast<double*>(mine);
-    cd* S = reinterpret_cast<cd*>(mine + L::kStageDoubles * 8);
-    cd* outs[4] = {o0, o1, o2, o3};
+    cd* S = reinterpret_cast<cd*>(smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * L::kLineBytes);
 
     for (int line0 = (blockIdx.x * wpb + warp) * LPW; line0 < nlines; line0 += gridDim.x * wpb * LPW) {
         const int line = line0 + sub;
         const bool live = line < nlines;
-        const size_t base = (size_t)line * (2 * M);
-        // ---- load the line once, stage the per-point values
-        if (live) {
+        const size_t base = (size_t)(live ? line : 0) * (2 * M);
+        double sa[NST][8], sb[NST][8];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const int z = 2 * (t + TPL * j);
-                double a[NST], b[NST];
-                gen.stage(base + z, base + z + 1, a, b);
+        for (int j = 0; j < 8; ++j) {
+            double a[NST], b[NST];
+            gen.stage(base + 2 * (t + TPL * j), a, b);
 #pragma unroll
-                for (int s = 0; s < NST; ++s) {
-                    st[s * 2 * M + z] = a[s];
-                    st[s * 2 * M + z + 1] = b[s];
-                }
-            }
+            for (int s = 0; s < NST; ++s) { sa[s][j] = a[s]; sb[s][j] = b[s]; }
         }
-        __syncwarp();
-#pragma unroll 1
-        for (int f = 0; f < NF; ++f) {
-            cd v[EPT];
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const int z = 2 * (t + TPL * j);
-                double a[NST], b[NST];
-#pragma unroll
-                for (int s = 0; s < NST; ++s) {
-                    a[s] = st[s * 2 * M + z];
-                    b[s] = st[s * 2 * M + z + 1];
-                }
-                v[j] = cd{gen.field(f, a), gen.field(f, b)};
-            }
-            line_fft<M, TPL, -1>(v, S, t);
-            // natural order into S (all stage-2 reads are done after line_fft's trailing __syncwarp)
-#pragma unroll
-            for (int sl = 0; sl < EPT; ++sl) S[line_fft_out_index<M, TPL>(t, sl)] = v[sl];
-            __syncwarp();
-            // real post-processing: X[k] = Ev + w^k Od, X[M-k] = conj(Ev - w^k Od)
-            cd* out = outs[f] + (size_t)line * nzp;
-            for (int k = t; k <= M / 2; k += TPL) {
-                const cd A = S[k], B = cconj(S[(M - k) & (M - 1)]);
-                const cd Ev = cscale(A + B, 0.5);
-                const cd D = A - B;                          // 2 i Od
-                const cd Od = cd{0.5 * D.y, -0.5 * D.x};     // -i/2 * D
-                const cd T = cmul(Od, twiddle<-1>(k, FFT_TW_N / (2 * M)));
-                if (live) {
-                    if (k == 0) {
-                        out[0] = cd{A.x + A.y, 0.0};
-                        out[M] = cd{A.x - A.y, 0.0};
-                    } else {
-                        out[k] = Ev + T;
-                        out[M - k] = cconj(Ev - T);
-                    }
-                }
-            }
-            __syncwarp();
-        }
+        const size_t orow = (size_t)(live ? line : 0) * nzp;
+        zfwd_field<M, TPL, 0>(gen, sa, sb, S, tw1, tw2, t, o0 + orow, live);
+        if constexpr (NF > 1) zfwd_field<M, TPL, 1>(gen, sa, sb, S, tw1, tw2, t, o1 + orow, live);
+        if constexpr (NF > 2) zfwd_field<M, TPL, 2>(gen, sa, sb, S, tw1, tw2, t, o2 + orow, live);
+        if constexpr (NF > 3) zfwd_field<M, TPL, 3>(gen, sa, sb, S, tw1, tw2, t, o3 + orow, live);
     }
 }
 
-// inverse: NF padded half-spectra -> c2r along z -> post(gidx, values[NF], acc)
-//   post.apply(gidx0, gidx1, u0[NF], u1[NF], acc)   for the two points of a packed pair
+// inverse of one field: half-spectrum line -> packed complex Z -> inverse FFT; slot r of `res` then holds
+// the real pair (f[2n], f[2n+1]) for n = t + TPL fft_nat<8>(r), scaled like an unnormalised c2r of length 2M
+template <int M, int TPL>
+__device__ __forceinline__ void zinv_field(const cd* __restrict__ in, cd* res, cd* S, const cd* tw1, const cd* tw2, int t) {
+    // Z[k] = Ev + i Od, Z[M-k] = conj(Ev - i Od);  Ev = (X[k] + conj X[M-k])/2,  w^k Od = (X[k] - conj X[M-k])/2.
+    // Imaginary parts of X[0], X[M] are ignored (c2r semantics).
+#pragma unroll
+    for (int i = 0; i < (M / 2 + TPL) / TPL; ++i) {
+        const int k = t + TPL * i;
+        if (k <= M / 2) {
+            cd Xa = in[k], Xb = in[M - k];
+            if (k == 0) { Xa.y = 0.0; Xb.y = 0.0; }
+            const cd B = cconj(Xb);
+            const cd Ev = cscale(Xa + B, 0.5);
+            const cd T = cscale(Xa - B, 0.5);
+            const cd Od = cmul(T, cconj(tw2[k]));
+            const cd iOd = cd{-Od.y, Od.x};
+            S[k] = Ev + iOd;
+            if (k != 0 && k != M - k) S[M - k] = cconj(Ev - iOd);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res[j] = S[t + TPL * j];
+    __syncwarp();
+    line_fft8<M, TPL, +1>(res, S, t, tw1);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) res[r] = cscale(res[r], 2.0);
+}
+
+//   post.apply(g, u0[NF], u1[NF], acc)   for the points g and g + 1
 template <int M, int TPL, int NF, int NRED, class Post>
 __global__ void __launch_bounds__(128) zinv_kernel(Post post, const cd* __restrict__ i0, const cd* __restrict__ i1,
                                                   const cd* __restrict__ i2, const cd* __restrict__ i3, int nlines, int nzp,
                                                   double* __restrict__ partials) {
-    using L = ZLayout<M, TPL, NF>;
-    constexpr int EPT = M / TPL, LPW = L::kLinesPerWarp;
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tw1 = reinterpret_cast<cd*>(smem_raw);
+    cd* tw2 = tw1 + M;
+    load_twiddles<M>(tw1, tw2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
-    unsigned char* mine = smem_raw + (size_t)(warp * LPW + sub) * L::kLineBytes;
-    double* st = reinterpret_cast<double*>(mine);
-    cd* S = reinterpret_cast<cd*>(mine + L::kStageDoubles * 8);
-    const cd* ins[4] = {i0, i1, i2, i3};
+    cd* S = reinterpret_cast<cd*>(smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * L::kLineBytes);
     double acc[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
@@ -154,54 +198,23 @@ __global__ void __launch_bounds__(128) zinv_kernel(Post post, const cd* __restri
         const int line = line0 + sub;
         const bool live = line < nlines;
         const size_t base = (size_t)line * (2 * M);
-#pragma unroll 1
-        for (int f = 0; f < NF; ++f) {
-            const cd* in = ins[f] + (size_t)(live ? line : 0) * nzp;
-            // pre-processing: Z[k] = Ev + i Od, Z[M-k] = conj(Ev - i Od);  Ev = (X[k] + conj X[M-k])/2,
-            // w^k Od = (X[k] - conj X[M-k])/2.  Imaginary parts of X[0], X[M] are ignored (c2r semantics).
-            for (int k = t; k <= M / 2; k += TPL) {
-                cd Xa = in[k], Xb = in[M - k];
-                if (k == 0) { Xa.y = 0.0; Xb.y = 0.0; }
-                const cd B = cconj(Xb);
-                const cd Ev = cscale(Xa + B, 0.5);
-                const cd T = cscale(Xa - B, 0.5);
-                const cd Od = cmul(T, twiddle<+1>(k, FFT_TW_N / (2 * M)));      // conj(w^k) T
-                const cd iOd = cd{-Od.y, Od.x};
-                S[k] = Ev + iOd;
-                if (k != 0 && k != M - k) S[M - k] = cconj(Ev - iOd);
-            }
-            __syncwarp();
-            cd v[EPT];
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) v[j] = S[t + TPL * j];
-            __syncwarp();
-            line_fft<M, TPL, +1>(v, S, t);
-            // packed complex n -> reals 2n, 2n+1; factor 2 makes it the unnormalised c2r of length 2M
-#pragma unroll
-            for (int sl = 0; sl < EPT; ++sl) {
-                const int n = line_fft_out_index<M, TPL>(t, sl);
-                st[f * 2 * M + 2 * n] = 2.0 * v[sl].x;
-                st[f * 2 * M + 2 * n + 1] = 2.0 * v[sl].y;
-            }
-            __syncwarp();
-        }
+        const size_t irow = (size_t)(live ? line : 0) * nzp;
+        cd res[NF][8];
+        zinv_field<M, TPL>(i0 + irow, res[0], S, tw1, tw2, t);
+        if constexpr (NF > 1) zinv_field<M, TPL>(i1 + irow, res[1], S, tw1, tw2, t);
+        if constexpr (NF > 2) zinv_field<M, TPL>(i2 + irow, res[2], S, tw1, tw2, t);
+        if constexpr (NF > 3) zinv_field<M, TPL>(i3 + irow, res[3], S, tw1, tw2, t);
         if (live) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const int z = 2 * (t + TPL * j);
+            for (int r = 0; r < 8; ++r) {
                 double u0[NF], u1[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    u0[f] = st[f * 2 * M + z];
-                    u1[f] = st[f * 2 * M + z + 1];
-                }
-                post.apply(base + z, base + z + 1, u0, u1, acc);
+                for (int f = 0; f < NF; ++f) { u0[f] = res[f][r].x; u1[f] = res[f][r].y; }
+                post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), u0, u1, acc);
             }
         }
-        __syncwarp();
     }
     if constexpr (NRED > 0) {
-        // 128-thread block reduction (4 warps)
         __shared__ double red[NRED][4];
 #pragma unroll
         for (int r = 0; r < NRED; ++r) {
@@ -217,9 +230,9 @@ __global__ void __launch_bounds__(128) zinv_kernel(Post post, const cd* __restri
     }
 }
 
-template <int M, int TPL, int NST>
+template <int M, int TPL>
 constexpr int zsmem_bytes(int warps) {
-    return warps * ZLayout<M, TPL, NST>::kLinesPerWarp * ZLayout<M, TPL, NST>::kLineBytes;
+    return ZLayout<M, TPL>::kTwBytes + warps * ZLayout<M, TPL>::kLinesPerWarp * ZLayout<M, TPL>::kLineBytes;
 }
 
 inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
@@ -233,17 +246,10 @@ inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
 template <int M, int TPL, int NF, class Gen>
 int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, cd* o0, cd* o1, cd* o2, cd* o3) {
     constexpr int warps = 4;
-    constexpr int smem = zsmem_bytes<M, TPL, Gen::NST>(warps);
-    static bool attr = false;
+    constexpr int smem = zsmem_bytes<M, TPL>(warps);
     auto kern = zfwd_kernel<M, TPL, NF, Gen>;
-    if (!attr) {
-        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
     const int nlines = p->n0 * p->n1;
-    const int lpb = warps * (32 / TPL);
-    const int bps = smem > 0 ? (227 * 1024) / smem : 4;
-    kern<<<zgrid(nlines, lpb, bps < 1 ? 1 : bps), warps * 32, smem, s>>>(gen, o0, o1, o2, o3, nlines, p->nzp);
+    kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, o0, o1, o2, o3, nlines, p->nzp);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
@@ -252,17 +258,10 @@ int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, cd* o0, cd* o1, cd* o2, cd
 template <int M, int TPL, int NF, int NRED, class Post>
 int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3, int* grid_out) {
     constexpr int warps = 4;
-    constexpr int smem = zsmem_bytes<M, TPL, NF>(warps);
-    static bool attr = false;
+    constexpr int smem = zsmem_bytes<M, TPL>(warps);
     auto kern = zinv_kernel<M, TPL, NF, NRED, Post>;
-    if (!attr) {
-        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
     const int nlines = p->n0 * p->n1;
-    const int lpb = warps * (32 / TPL);
-    const int bps = (227 * 1024) / smem;
-    const int grid = zgrid(nlines, lpb, bps < 1 ? 1 : bps);
+    const int grid = zgrid(nlines, warps * (32 / TPL), 4);
     kern<<<grid, warps * 32, smem, s>>>(post, i0, i1, i2, i3, nlines, p->nzp, p->partials);
     ++g_pad_launches;
     if (grid_out) *grid_out = grid;
@@ -316,14 +315,13 @@ int get_zbuf(pad_plan* p, int i, cd** out) {
     return PAD_OK;
 }
 
-bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256 || p->n2 == 512; }
+bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256; }
 
-// dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 8), (256, 16)}
+// dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16)}
 #define ZDISPATCH(p, CALL)                                             \
     do {                                                               \
-        if ((p)->n2 == 256) { constexpr int M = 128, TPL = 8; CALL; }  \
-        else if ((p)->n2 == 128) { constexpr int M = 64, TPL = 8; CALL; } \
-        else { constexpr int M = 256, TPL = 16; CALL; }                \
+        if ((p)->n2 == 256) { constexpr int M = 128, TPL = 16; CALL; } \
+        else { constexpr int M = 64, TPL = 8; CALL; }                  \
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -332,15 +330,18 @@ bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256 || p->n
 struct GenCopy {                       // plain r2c of one real field
     static constexpr int NST = 1;
     const double* f;
-    __device__ void stage(size_t g0, size_t g1, double* a, double* b) const { a[0] = f[g0]; b[0] = f[g1]; }
-    __device__ double field(int, const double* s) const { return s[0]; }
+    __device__ void stage(size_t g, double* a, double* b) const {
+        const double2 v = *reinterpret_cast<const double2*>(f + g);
+        a[0] = v.x; b[0] = v.y;
+    }
+    template <int F>
+    __device__ double field(const double* s) const { return s[0]; }
 };
 
 struct PostStore {                     // plain c2r of one real field
     double* out;
-    __device__ void apply(size_t g0, size_t g1, const double* u0, const double* u1, double*) const {
-        out[g0] = u0[0];
-        out[g1] = u1[0];
+    __device__ void apply(size_t g, const double* u0, const double* u1, double*) const {
+        *reinterpret_cast<double2*>(out + g) = make_double2(u0[0], u1[0]);
     }
 };
 
@@ -350,18 +351,18 @@ struct GenWgcA {
     const double* den;
     const double* scal;
     double beta;
-    __device__ void stage(size_t g0, size_t g1, double* a, double* b) const {
-        const double n0 = den[g0], n1 = den[g1];
-        a[0] = n0; a[1] = exp(beta * log(n0));
-        b[0] = n1; b[1] = exp(beta * log(n1));
+    __device__ void stage(size_t g, double* a, double* b) const {
+        const double2 n = *reinterpret_cast<const double2*>(den + g);
+        a[0] = n.x; a[1] = exp(beta * log(n.x));
+        b[0] = n.y; b[1] = exp(beta * log(n.y));
     }
-    __device__ double field(int f, const double* s) const {
-        const double th = s[0] - scal[S_NREF];
-        switch (f) {
-            case 0: return s[1];
-            case 1: return s[1] * th;
-            case 2: return 0.5 * s[1] * th * th;
-            default: return s[0] != 0.0 ? sqrt(s[0]) : 0.0;
+    template <int F>
+    __device__ double field(const double* s) const {
+        if constexpr (F == 0) return s[1];
+        else if constexpr (F == 3) return s[0] != 0.0 ? sqrt(s[0]) : 0.0;
+        else {
+            const double th = s[0] - scal[S_NREF];
+            return F == 1 ? s[1] * th : 0.5 * s[1] * th * th;
         }
     }
 };
@@ -372,13 +373,19 @@ struct GenWgcP {
     const double* den;
     const double* P;
     const double* scal;
-    __device__ void stage(size_t g0, size_t g1, double* a, double* b) const {
-        a[0] = den[g0]; a[1] = P[g0];
-        b[0] = den[g1]; b[1] = P[g1];
+    __device__ void stage(size_t g, double* a, double* b) const {
+        const double2 n = *reinterpret_cast<const double2*>(den + g);
+        const double2 q = *reinterpret_cast<const double2*>(P + g);
+        a[0] = n.x; a[1] = q.x;
+        b[0] = n.y; b[1] = q.y;
     }
-    __device__ double field(int f, const double* s) const {
-        const double th = s[0] - scal[S_NREF];
-        return f == 0 ? s[1] : (f == 1 ? s[1] * th : 0.5 * s[1] * th * th);
+    template <int F>
+    __device__ double field(const double* s) const {
+        if constexpr (F == 0) return s[1];
+        else {
+            const double th = s[0] - scal[S_NREF];
+            return F == 1 ? s[1] * th : 0.5 * s[1] * th * th;
+        }
     }
 };
 
@@ -390,27 +397,30 @@ struct PostWgcMid {
     double* P_out;
     double alpha;
     int accumulate, want_v;
-    __device__ void one(size_t g, const double* u, double* acc) const {
-        const double n = den[g];
+    __device__ void one(double n, double vold, const double* u, double* acc, double& v, double& P) const {
         const double th = n - scal[S_NREF];
-        const double P = exp(alpha * log(n));
+        P = exp(alpha * log(n));
         const double conv = u[0] + th * (u[1] + 0.5 * th * u[2]);
         const double c = cbrt(n);
         const double chi = n != 0.0 ? sqrt(n) : 0.0;
         acc[0] += kCTF * n * c * c;
         acc[1] += chi * u[3];
         acc[2] += P * conv;
-        if (want_v) {
-            double v = (5.0 / 3.0) * kCTF * c * c;
-            if (n != 0.0) v += -0.5 * u[3] / chi;
-            v += kCTF * (alpha * P / n * conv + P * (u[1] + th * u[2]));
-            v_out[g] = accumulate ? v_out[g] + v : v;
-            P_out[g] = P;
-        }
+        v = vold + (5.0 / 3.0) * kCTF * c * c;
+        if (n != 0.0) v += -0.5 * u[3] / chi;
+        v += kCTF * (alpha * P / n * conv + P * (u[1] + th * u[2]));
     }
-    __device__ void apply(size_t g0, size_t g1, const double* u0, const double* u1, double* acc) const {
-        one(g0, u0, acc);
-        one(g1, u1, acc);
+    __device__ void apply(size_t g, const double* u0, const double* u1, double* acc) const {
+        const double2 n = *reinterpret_cast<const double2*>(den + g);
+        double2 vo = make_double2(0.0, 0.0);
+        if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+        double v0, v1, P0, P1;
+        one(n.x, vo.x, u0, acc, v0, P0);
+        one(n.y, vo.y, u1, acc, v1, P1);
+        if (want_v) {
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(P_out + g) = make_double2(P0, P1);
+        }
     }
 };
 
@@ -420,16 +430,18 @@ struct PostWgcFin {
     const double* scal;
     double* v_out;
     double beta;
-    __device__ void one(size_t g, const double* u) const {
-        const double n = den[g];
+    __device__ double one(double n, const double* u) const {
         const double th = n - scal[S_NREF];
         const double a = exp(beta * log(n));
         const double da = beta * a / n;
-        v_out[g] += kCTF * (da * u[0] + (da * th + a) * u[1] + (0.5 * da * th * th + a * th) * u[2]);
+        return kCTF * (da * u[0] + (da * th + a) * u[1] + (0.5 * da * th * th + a * th) * u[2]);
     }
-    __device__ void apply(size_t g0, size_t g1, const double* u0, const double* u1, double*) const {
-        one(g0, u0);
-        one(g1, u1);
+    __device__ void apply(size_t g, const double* u0, const double* u1, double*) const {
+        const double2 n = *reinterpret_cast<const double2*>(den + g);
+        double2 v = *reinterpret_cast<const double2*>(v_out + g);
+        v.x += one(n.x, u0);
+        v.y += one(n.y, u1);
+        *reinterpret_cast<double2*>(v_out + g) = v;
     }
 };
 
@@ -460,7 +472,7 @@ extern "C" int pad_fast_fft_supported(const pad_plan* p) { return p && fast_shap
 // out: padded half-spectrum (n0, n1, nzp) complex; returns nzp through *nzp_out
 extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_padded, int* nzp_out, void* stream) {
     if (!p || !in || !out_cplx_padded) { pad_set_error("pad_rfft3_fast: null argument"); return PAD_ERR_ARG; }
-    if (!fast_shape(p)) { pad_set_error("pad_rfft3_fast: n2 = %d not supported (128, 256, 512)", p->n2); return PAD_ERR_ARG; }
+    if (!fast_shape(p)) { pad_set_error("pad_rfft3_fast: n2 = %d not supported (128, 256)", p->n2); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
@@ -476,7 +488,7 @@ extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_pa
 // in: padded half-spectrum (destroyed); out: real field, unnormalised (N x the inverse)
 extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out, void* stream) {
     if (!p || !in_cplx_padded || !out) { pad_set_error("pad_irfft3_fast: null argument"); return PAD_ERR_ARG; }
-    if (!fast_shape(p)) { pad_set_error("pad_irfft3_fast: n2 = %d not supported (128, 256, 512)", p->n2); return PAD_ERR_ARG; }
+    if (!fast_shape(p)) { pad_set_error("pad_irfft3_fast: n2 = %d not supported (128, 256)", p->n2); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
