@@ -59,6 +59,10 @@ unsigned long long pad_fft_exec_count(void);
 /* 1: use the hand-written fused z-pass FFT pipeline where the grid allows (n2 in 128/256); default 0 for now;
  * 0: plain cuFFT 3-D transforms + separate elementwise kernels.  Returns the previous setting. */
 int pad_set_fast_fft(int on);
+/* tuning switches (process-wide): "fast_fft" (as above), "own_xy" (1: hand-written strided x/y passes with the
+ * reciprocal-space multiply fused into the x pass; 0: batched 2-D cuFFT), "zgroup" (z chunks of 8 columns per
+ * L2-blocked group of the y / x-multiply-x / y passes; 0 = whole grid).  Returns the previous value, -1 on error. */
+int pad_set_option(const char* name, int value);
 
 /* ---- plan: replaces wavevecs(box_vecs, shape) (functional_tools.py:135-162) and owns the cuFFT
  *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */
@@ -111,6 +115,9 @@ int pad_laplacian(pad_plan* plan, const double* f, double* out, void* stream);
 int pad_fast_fft_supported(const pad_plan* plan);
 int pad_rfft3_fast(pad_plan* plan, const double* in, double* out_cplx_padded, int* nzp_out, void* stream);
 int pad_irfft3_fast(pad_plan* plan, double* in_cplx_padded /* destroyed */, double* out, void* stream);
+/* one strided pass on its own: in-place complex FFT of a padded half-spectrum along axis 0 or 1 (length 64/128/256),
+ * dir = -1 forward, +1 inverse, unnormalised (torch.fft.fft / ifft * n along that axis) */
+int pad_fft_axis_fast(pad_plan* plan, double* cplx_padded, int axis, int dir, void* stream);
 
 /* ---- fused evaluation of a whole term list: replaces System.__compute_energy + autograd
  *      (system.py:759-772, 830-838).  E_out = sum of terms, v_out = total dE/dn. ---------------- */

@@ -37,6 +37,8 @@ SIGNATURES = {
     'pad_eval_pbe': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
     'pad_eval_hc': (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _dbl, _int, _vp, _int, _vp, _vp, _int, _vp, _vp]),
     'pad_set_fast_fft': (_int, [_int]),
+    'pad_set_option': (_int, [ctypes.c_char_p, _int]),
+    'pad_fft_axis_fast': (_int, [_vp, _vp, _int, _int, _vp]),
     'pad_fast_fft_supported': (_int, [_vp]),
     'pad_rfft3_fast': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'pad_irfft3_fast': (_int, [_vp, _vp, _vp, _vp]),
@@ -74,6 +76,9 @@ def load_library():
             fn = getattr(lib, name)       # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
+        for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy'), ('PAD_ZGROUP', b'zgroup')):
+            if os.environ.get(env, '').lstrip('-').isdigit():
+                lib.pad_set_option(opt, int(os.environ[env]))
         _lib = lib
     return _lib
 

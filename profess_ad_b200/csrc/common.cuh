@@ -65,12 +65,9 @@ struct KPoint {
     int j0, j1, j2;
 };
 
-__device__ __forceinline__ KPoint make_kpoint(const KGeom& g, uint32_t idx) {
+__device__ __forceinline__ KPoint make_kpoint_at(const KGeom& g, int j0, int j1, int j2) {
     KPoint p;
-    uint32_t row = idx / (uint32_t)g.nzh;
-    p.j2 = (int)(idx - row * (uint32_t)g.nzh);
-    p.j0 = (int)(row / (uint32_t)g.n1);
-    p.j1 = (int)(row - (uint32_t)p.j0 * (uint32_t)g.n1);
+    p.j0 = j0; p.j1 = j1; p.j2 = j2;
     const double f0 = (double)(p.j0 <= g.n0 / 2 ? p.j0 : p.j0 - g.n0);
     const double f1 = (double)(p.j1 <= g.n1 / 2 ? p.j1 : p.j1 - g.n1);
     const double f2 = (double)p.j2;
@@ -91,6 +88,14 @@ __device__ __forceinline__ KPoint make_kpoint(const KGeom& g, uint32_t idx) {
         p.pz = q0 * g.b[2] + q1 * g.b[5] + f2 * g.b[8];
     }
     return p;
+}
+
+__device__ __forceinline__ KPoint make_kpoint(const KGeom& g, uint32_t idx) {
+    const uint32_t row = idx / (uint32_t)g.nzh;
+    const int j2 = (int)(idx - row * (uint32_t)g.nzh);
+    const int j0 = (int)(row / (uint32_t)g.n1);
+    const int j1 = (int)(row - (uint32_t)j0 * (uint32_t)g.n1);
+    return make_kpoint_at(g, j0, j1, j2);
 }
 
 // Effective real multiplier M(|k|^2-like even function) on the half spectrum: on special points the
@@ -221,6 +226,7 @@ int pad_get_rbuf(pad_plan* p, int i, double** out);
 int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
+extern int g_pad_own_xy, g_pad_zgroup;
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,

@@ -14,6 +14,7 @@
 // Conventions match cuFFT: forward and inverse are unnormalised (the 1/N lives in the multipliers).
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft_strided.cuh"
 
 namespace {
 
@@ -315,6 +316,120 @@ int get_zbuf(pad_plan* p, int i, cd** out) {
     return PAD_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+//  own strided passes (fft_strided.cuh): launchers
+// ------------------------------------------------------------------------------------------------
+inline bool spass_len_ok(int n) { return n == 64 || n == 128 || n == 256; }
+bool own_xy_shape(const pad_plan* p) { return spass_len_ok(p->n0) && spass_len_ok(p->n1); }
+
+SPassGeom spass_geom(const pad_plan* p, int axis, int zc0, int nzc) {
+    SPassGeom g;
+    const long long row = p->nzp, plane = (long long)p->n1 * p->nzp;
+    g.axis_stride = axis == 0 ? plane : row;
+    g.outer_stride = axis == 0 ? row : plane;
+    g.n_outer = axis == 0 ? p->n1 : p->n0;
+    g.zc0 = zc0;
+    g.nzc = nzc;
+    g.nzh = p->nzh;
+    return g;
+}
+
+inline int spass_nzc_total(const pad_plan* p) { return (p->nzh + 7) / 8; }
+
+template <int L, int DIR>
+int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, const SPassGeom& g) {
+    auto kern = spass_kernel<L, DIR>;
+    constexpr int smem = spass_smem_bytes<L>(0);
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const long long tiles = (long long)nf * g.n_outer * g.nzc;
+    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    if (grid > (1 << 20)) grid = 1 << 20;
+    kern<<<(unsigned)grid, 128, smem, s>>>(f, nf, g);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+// in-place FFT of nf padded half-spectra along axis 0 (x) or 1 (y), z chunks [zc0, zc0 + nzc)
+int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf, int zc0, int nzc) {
+    SPassFields f;
+    for (int i = 0; i < 4; ++i) f.f[i] = i < nf ? fields[i] : nullptr;
+    const SPassGeom g = spass_geom(p, axis, zc0, nzc);
+    const int L = axis == 0 ? p->n0 : p->n1;
+#define SPASS_CASE(LL)                                                        \
+    case LL:                                                                  \
+        return dir < 0 ? launch_spass_L<LL, -1>(p, s, f, nf, g) : launch_spass_L<LL, +1>(p, s, f, nf, g);
+    switch (L) {
+        SPASS_CASE(64)
+        SPASS_CASE(128)
+        SPASS_CASE(256)
+    }
+#undef SPASS_CASE
+    pad_set_error("strided FFT pass: length %d not supported", L);
+    return PAD_ERR_ARG;
+}
+
+template <int L, int NF, class Mix>
+int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix) {
+    auto kern = xmix_kernel<L, NF, Mix>;
+    constexpr int smem = spass_smem_bytes<L>(NF - 1);
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const long long tiles = (long long)g.n_outer * g.nzc;
+    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    if (grid > (1 << 20)) grid = 1 << 20;
+    kern<<<(unsigned)grid, 128, smem, s>>>(f, g, p->geom, mix);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+// spec_f <- IFFT_x( mix( FFT_x(spec_0..NF-1) ) ) for z chunks [zc0, zc0 + nzc)
+template <int NF, class Mix>
+int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, int zc0, int nzc, Mix mix) {
+    SPassFields f;
+    for (int i = 0; i < 4; ++i) f.f[i] = i < NF ? fields[i] : nullptr;
+    const SPassGeom g = spass_geom(p, 0, zc0, nzc);
+    switch (p->n0) {
+        case 64: return launch_xmix_L<64, NF>(p, s, f, g, mix);
+        case 128: return launch_xmix_L<128, NF>(p, s, f, g, mix);
+        case 256: return launch_xmix_L<256, NF>(p, s, f, g, mix);
+    }
+    pad_set_error("fused x pass: length %d not supported", p->n0);
+    return PAD_ERR_ARG;
+}
+
+// reciprocal-space multipliers for the fused x pass
+struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:968-981), kernels pre-scaled by 1/N
+    const double *W0, *K1, *K2, *K3;
+    __device__ void operator()(const KPoint&, uint32_t idx, cd* q) const {
+        const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
+        const cd A = q[0], B = q[1], C = q[2];
+        q[0] = cd{w0 * A.x + k1 * B.x + k2 * C.x, w0 * A.y + k1 * B.y + k2 * C.y};
+        q[1] = cd{k1 * A.x + k3 * B.x, k1 * A.y + k3 * B.y};
+        q[2] = cd{k2 * A.x, k2 * A.y};
+    }
+};
+struct MixLaplace {                    // -k^2 / N   (functional_tools.py:209-227)
+    double inv_n;
+    __device__ void operator()(const KPoint& k, uint32_t, cd* q) const {
+        const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
+        q[0] = cd{q[0].x * m, q[0].y * m};
+    }
+};
+struct MixScale {                      // plain 1/N (round-trip tests)
+    double m;
+    __device__ void operator()(const KPoint&, uint32_t, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
+};
+
 bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256; }
 
 // dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16)}
@@ -462,6 +577,48 @@ void launch_ksp(pad_plan* p, cudaStream_t s, F f) {
     ++g_pad_launches;
 }
 
+
+// (x, y) transform of nf padded half-spectra, in place: own strided passes where the shape allows, else cuFFT
+int xy_transform(pad_plan* p, cudaStream_t s, cd* const* B, int nf, int dir) {
+    if (g_pad_own_xy && own_xy_shape(p)) {
+        const int nzc = spass_nzc_total(p);
+        if (dir < 0) {
+            PAD_TRY(launch_spass(p, s, 1, -1, B, nf, 0, nzc));
+            PAD_TRY(launch_spass(p, s, 0, -1, B, nf, 0, nzc));
+        } else {
+            PAD_TRY(launch_spass(p, s, 0, +1, B, nf, 0, nzc));
+            PAD_TRY(launch_spass(p, s, 1, +1, B, nf, 0, nzc));
+        }
+        return PAD_OK;
+    }
+    for (int i = 0; i < nf; ++i) PAD_TRY(xy_exec(p, s, B[i], dir));
+    return PAD_OK;
+}
+
+// y forward, fused x-forward/multiply/x-inverse, y inverse for the coupled fields B[0..NF-1] and,
+// if lap != null, the independent field lap (multiplied by -k^2/N).  z chunks are processed in groups
+// of g_pad_zgroup so that the three passes of a group find their tiles in L2.
+template <int NF, class Mix>
+int xy_convolve_own(pad_plan* p, cudaStream_t s, cd* const* B, cd* lap, Mix mix) {
+    const int nzc = spass_nzc_total(p);
+    const int group = g_pad_zgroup > 0 ? g_pad_zgroup : nzc;
+    cd* all[4];
+    int nall = 0;
+    for (int i = 0; i < NF; ++i) all[nall++] = B[i];
+    if (lap) all[nall++] = lap;
+    for (int z0 = 0; z0 < nzc; z0 += group) {
+        const int nz = z0 + group <= nzc ? group : nzc - z0;
+        PAD_TRY(launch_spass(p, s, 1, -1, all, nall, z0, nz));
+        PAD_TRY((launch_xmix<NF>(p, s, B, z0, nz, mix)));
+        if (lap) {
+            cd* one[1] = {lap};
+            PAD_TRY((launch_xmix<1>(p, s, one, z0, nz, MixLaplace{p->geom.inv_n})));
+        }
+        PAD_TRY(launch_spass(p, s, 1, +1, all, nall, z0, nz));
+    }
+    return PAD_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -476,12 +633,12 @@ extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_pa
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
-    PAD_TRY(ensure_xy(p, s));
     if (nzp_out) *nzp_out = p->nzp;
     cd* o = reinterpret_cast<cd*>(out_cplx_padded);
     GenCopy gen{in};
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, gen, o, nullptr, nullptr, nullptr))));
-    PAD_TRY(xy_exec(p, s, o, -1));
+    cd* one[1] = {o};
+    PAD_TRY(xy_transform(p, s, one, 1, -1));
     return PAD_OK;
 }
 
@@ -493,7 +650,8 @@ extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out,
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
     cd* i = reinterpret_cast<cd*>(in_cplx_padded);
-    PAD_TRY(xy_exec(p, s, i, +1));
+    cd* one[1] = {i};
+    PAD_TRY(xy_transform(p, s, one, 1, +1));
     PostStore post{out};
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, post, i, nullptr, nullptr, nullptr, nullptr))));
     return PAD_OK;
@@ -507,7 +665,7 @@ int pad_wgc99_fast_supported(const pad_plan* p) { return fast_shape(p) ? 1 : 0; 
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,
                    double* v_out, int accumulate, cudaStream_t s) {
     PAD_TRY(ensure_twiddles(p->device));
-    PAD_TRY(ensure_xy(p, s));
+    if (!(g_pad_own_xy && own_xy_shape(p))) PAD_TRY(ensure_xy(p, s));
     cd* B[4];
     for (int i = 0; i < 4; ++i) PAD_TRY(get_zbuf(p, i, &B[i]));
     double* Pbuf;
@@ -520,22 +678,24 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
 
     GenWgcA genA{den, scal, beta};
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, B[0], B[1], B[2], B[3]))));
-    for (int i = 0; i < 4; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
-    {
+    const bool own = g_pad_own_xy && own_xy_shape(p);
+    const MixWgc mixw{W0, K1, K2, K3};
+    if (own) {
+        PAD_TRY((xy_convolve_own<3>(p, s, B, B[3], mixw)));
+    } else {
+        for (int i = 0; i < 4; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
         cd *CA = B[0], *CB = B[1], *CC = B[2], *CX = B[3];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
-            const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
-            const cd A = CA[pidx], Bb = CB[pidx], Cc = CC[pidx];
-            CA[pidx] = cd{w0 * A.x + k1 * Bb.x + k2 * Cc.x, w0 * A.y + k1 * Bb.y + k2 * Cc.y};
-            CB[pidx] = cd{k1 * A.x + k3 * Bb.x, k1 * A.y + k3 * Bb.y};
-            CC[pidx] = cd{k2 * A.x, k2 * A.y};
+            cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
+            mixw(k, idx, q);
+            CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
             const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
             const cd X = CX[pidx];
             CX[pidx] = cd{X.x * m, X.y * m};
         });
         PAD_CUDA(cudaGetLastError());
+        for (int i = 0; i < 4; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     }
-    for (int i = 0; i < 4; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     int grid = 1;
     PostWgcMid mid{den, scal, v_out, Pbuf, alpha, accumulate, want_v ? 1 : 0};
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 4, 3>(p, s, mid, B[0], B[1], B[2], B[3], &grid))));
@@ -552,20 +712,33 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
 
     GenWgcP genP{den, Pbuf, scal};
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, genP, B[0], B[1], B[2], nullptr))));
-    for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
-    {
+    if (own) {
+        PAD_TRY((xy_convolve_own<3>(p, s, B, nullptr, mixw)));
+    } else {
+        for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
         cd *CA = B[0], *CB = B[1], *CC = B[2];
-        launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint&) {
-            const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
-            const cd A = CA[pidx], Bb = CB[pidx], Cc = CC[pidx];
-            CA[pidx] = cd{w0 * A.x + k1 * Bb.x + k2 * Cc.x, w0 * A.y + k1 * Bb.y + k2 * Cc.y};
-            CB[pidx] = cd{k1 * A.x + k3 * Bb.x, k1 * A.y + k3 * Bb.y};
-            CC[pidx] = cd{k2 * A.x, k2 * A.y};
+        launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
+            cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
+            mixw(k, idx, q);
+            CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
         });
         PAD_CUDA(cudaGetLastError());
+        for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     }
-    for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     PostWgcFin fin{den, scal, v_out, beta};
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, fin, B[0], B[1], B[2], nullptr, nullptr))));
     return PAD_OK;
+}
+
+// in-place complex FFT of one padded half-spectrum along axis 0 or 1 (own strided pass); unnormalised
+extern "C" int pad_fft_axis_fast(pad_plan* p, double* cplx_padded, int axis, int dir, void* stream) {
+    if (!p || !cplx_padded || (axis != 0 && axis != 1)) { pad_set_error("pad_fft_axis_fast: bad argument"); return PAD_ERR_ARG; }
+    if (!spass_len_ok(axis == 0 ? p->n0 : p->n1)) {
+        pad_set_error("pad_fft_axis_fast: axis length %d not supported (64, 128, 256)", axis == 0 ? p->n0 : p->n1);
+        return PAD_ERR_ARG;
+    }
+    PAD_CUDA(cudaSetDevice(p->device));
+    PAD_TRY(ensure_twiddles(p->device));
+    cd* one[1] = {reinterpret_cast<cd*>(cplx_padded)};
+    return launch_spass(p, (cudaStream_t)stream, axis, dir, one, 1, 0, spass_nzc_total(p));
 }

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+python bench.py > gpurun_out/bench_cufft.json 2> gpurun_out/bench_cufft.err
+PAD_FAST_FFT=1 python bench.py --no-cpu-baseline > gpurun_out/bench_fast.json 2> gpurun_out/bench_fast.err
+PAD_FAST_FFT=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_fast.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fast.log 2>&1
+tail -3 gpurun_out/pytest.log; cat gpurun_out/bench_cufft.json gpurun_out/bench_fast.json

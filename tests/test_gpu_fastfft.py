@@ -37,7 +37,55 @@ def test_fast_rfft3_matches_library(shape):
     assert err < 1e-14, err
 
 
-@pytest.mark.parametrize('shape,seed', [((10, 12, 128), 31), ((9, 8, 256), 32), ((4, 6, 256), 33)])
+@pytest.mark.parametrize('shape,axis', [((64, 128, 128), 0), ((64, 128, 128), 1), ((256, 64, 128), 0), ((128, 256, 256), 1),
+                                        ((128, 64, 256), 0), ((64, 64, 128), 1)])
+def test_strided_axis_pass_matches_library(shape, axis):
+    """Own strided x / y pass (csrc/fft_strided.cuh) against torch.fft on the live columns; padding untouched."""
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(7 + sum(shape) + axis)
+    nzh, nzp = shape[2] // 2 + 1, shape[2] // 2 + 8
+    spec = torch.zeros(shape[0], shape[1], nzp, dtype=torch.complex128, device=dev)
+    live = torch.view_as_complex(torch.rand(shape[0], shape[1], nzh, 2, dtype=torch.double, generator=gen) - 0.5).to(dev)
+    spec[:, :, :nzh] = live
+    spec[:, :, nzh:] = 123.0            # sentinel: the pass must not touch padding columns
+    box = torch.eye(3, dtype=torch.double, device=dev) * 7.0
+    f = torch.empty(*shape, dtype=torch.double, device=dev)
+    plan, nat = _plan(box, f)
+    for direction, ref in ((-1, torch.fft.fft(live, dim=axis)), (+1, torch.fft.ifft(live, dim=axis) * shape[axis])):
+        work = spec.clone()
+        nat.check(plan.lib.pad_fft_axis_fast(plan.handle, nat.ptr(work), axis, direction, nat.stream_ptr(dev)))
+        err = (work[:, :, :nzh] - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-14, (direction, err)
+        assert (work[:, :, nzh:] == 123.0).all()
+
+
+@pytest.mark.parametrize('shape', [(64, 64, 128), (128, 64, 256), (64, 128, 128)])
+@pytest.mark.parametrize('zgroup', [0, 3])
+def test_fast_rfft3_own_xy(shape, zgroup):
+    """Full own 3-D transform (z pass + strided y and x passes), with and without z-chunk grouping."""
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(sum(shape))
+    f = torch.rand(*shape, dtype=torch.double, generator=gen).to(dev)
+    box = torch.eye(3, dtype=torch.double, device=dev) * 7.0
+    plan, nat = _plan(box, f)
+    nzh, nzp = shape[2] // 2 + 1, shape[2] // 2 + 8
+    spec = torch.zeros(shape[0], shape[1], nzp, dtype=torch.complex128, device=dev)
+    old = plan.lib.pad_set_option(b'zgroup', zgroup)
+    try:
+        nat.check(plan.lib.pad_rfft3_fast(plan.handle, nat.ptr(f), nat.ptr(spec), None, nat.stream_ptr(dev)))
+        ref = torch.fft.rfftn(f)
+        err = (spec[:, :, :nzh] - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-14, err
+        out = torch.empty_like(f)
+        nat.check(plan.lib.pad_irfft3_fast(plan.handle, nat.ptr(spec), nat.ptr(out), nat.stream_ptr(dev)))
+        err = (out / f.numel() - f).abs().max().item()
+        assert err < 1e-14, err
+    finally:
+        plan.lib.pad_set_option(b'zgroup', old)
+
+
+@pytest.mark.parametrize('shape,seed', [((10, 12, 128), 31), ((9, 8, 256), 32), ((4, 6, 256), 33),
+                                        ((64, 64, 128), 34), ((64, 128, 256), 35), ((128, 64, 128), 36)])
 def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     from oracle import ofdft_oracle as orc
     import profess_ad_b200.functionals as F
@@ -60,3 +108,29 @@ def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
         assert ((V.cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9, fast
         assert abs(e_only - E.item()) <= 1e-13 * abs(E.item())
     assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
+
+
+def test_wgc99_zgroup_blocking_is_equivalent():
+    """L2-blocked scheduling of the (y, x-multiply-x, y) passes must not change the result."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native
+    lib = _native.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough((64, 64, 256), seed=41, L=9.0)
+    b, d = box.to(dev), den.to(dev)
+    old_fast = lib.pad_set_fast_fft(1)
+    res = {}
+    try:
+        for zg in (0, 1, 5):
+            old = lib.pad_set_option(b'zgroup', zg)
+            try:
+                E, V = F.energy_and_potential(b, d, F.WangGovindCarter99().forward)
+                res[zg] = (E.item(), V.clone())
+            finally:
+                lib.pad_set_option(b'zgroup', old)
+    finally:
+        lib.pad_set_fast_fft(old_fast)
+    for zg in (1, 5):
+        assert res[zg][0] == res[0][0]
+        assert torch.equal(res[zg][1], res[0][1])
