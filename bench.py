@@ -171,12 +171,12 @@ def run_gpu(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
 
-    from oracle import ofdft_oracle as orc          # input generator only (synthetic density)
     import profess_ad_b200.functionals as F
+    from profess_ad_b200.synthetic import smooth_supercell
     from profess_ad_b200 import _native
     lib = _native.load_library()
 
-    box_h, den_h = orc.synth_smooth(GRID, SIDE)
+    box_h, den_h = smooth_supercell(GRID, SIDE)
     box = box_h.to(dev)
     den = den_h.to(dev)
     wgc = F.WangGovindCarter99()
