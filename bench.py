@@ -44,6 +44,23 @@ def algorithmic_bytes(n):
     return 16 * npts * N_FFT + 16 * npts
 
 
+def stage_bytes(name, n, ns):
+    """Bytes one launch of a pipeline stage has to move (its own inputs and outputs once): n real points
+    (8 B), ns live half-spectrum points (16 B)."""
+    table = {
+        'sum(n) -> n_ref, kernel cache check': 8 * n,
+        'gen a,a.th,a.th2,chi + z-r2c (4 fields)': 8 * n + 4 * 16 * ns,
+        'y-fwd (4 fields)': 2 * 4 * 16 * ns, 'y-inv (4 fields)': 2 * 4 * 16 * ns,
+        'y-fwd (3 fields)': 2 * 3 * 16 * ns, 'y-inv (3 fields)': 2 * 3 * 16 * ns,
+        'x-fwd * kernel-mix * x-inv (3 fields)': 2 * 3 * 16 * ns + 32 * ns,
+        'x-fwd * (-k^2) * x-inv (1 field)': 2 * 16 * ns,
+        'z-c2r (4 fields) + energy/v1/P': 4 * 16 * ns + 8 * n + 16 * n,
+        'gen P,P.th,P.th2 + z-r2c (3 fields)': 16 * n + 3 * 16 * ns,
+        'z-c2r (3 fields) + v2': 3 * 16 * ns + 8 * n + 16 * n,
+    }
+    return table.get(name)
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -54,56 +71,54 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons sampled every ~5 ms through NVML while the timed region runs
+    (nvidia-smi polling is too slow for a sub-second region)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.mask = 0
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+        self.max_mhz = None
+        self.power = []
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(',')]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith('active'):
-                    reasons.add(nm)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + str(self.err)]}
+        sm = sorted(self.samples)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_min_mhz': sm[0], 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(v for k, v in self.REASONS.items() if self.mask & k),
+                'power_w_max': max(self.power) if self.power else None, 'samples': len(sm)}
 
 
 def dist_env():
@@ -220,6 +235,33 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
 
+    # ---- live per-kernel timing (CUDA events on the launch stream between the pipeline stages) ----
+    stages = []
+    if rank == 0:
+        import ctypes
+        lib.pad_profile_begin()
+        for _ in range(5):
+            step_device()
+        torch.cuda.synchronize(dev)
+        names = ctypes.create_string_buffer(48 * 256)
+        ms = (ctypes.c_double * 256)()
+        n_st, n_ev = ctypes.c_int(0), ctypes.c_int(0)
+        lib.pad_profile_end(names, ms, 256, ctypes.byref(n_st), ctypes.byref(n_ev))
+        agg = {}
+        for i in range(n_st.value):
+            nm = names.raw[48 * i:48 * i + 48].split(b'\0')[0].decode()
+            a = agg.setdefault(nm, [0.0, 0])
+            a[0] += ms[i]
+            a[1] += 1
+        ns = GRID * GRID * (GRID // 2 + 1)
+        for nm, (t_ms, cnt) in agg.items():
+            b = stage_bytes(nm, npts, ns)
+            if b and nm.startswith('x-fwd * kernel-mix'):
+                b *= 2          # both convolutions of an evaluation run this stage over the whole grid
+            stages.append({'stage': nm, 'launches_per_eval': cnt, 'ms_per_eval': t_ms,
+                           'alg_bytes_per_eval': b,
+                           'GBps': (b / (t_ms * 1e-3) / 1e9) if b and t_ms > 0 else None})
+
     # ---- end to end: pinned host -> device -> E, V -> pinned host ---------------------------------
     den_pin = den_h.pin_memory()
     v_pin = torch.empty_like(den_pin).pin_memory()
@@ -270,8 +312,15 @@ def run_gpu(args):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': None, 'peak_source': peak_src,
                          'kernel': 'whole WGC99 E+V evaluation (14 FFTs + fused elementwise passes)',
-                         'algorithmic_bytes_per_eval': balg},
+                         'algorithmic_bytes_per_eval': balg,
+                         'kernels': stages},
         }
+        if stages:
+            dom = max(stages, key=lambda r: r['ms_per_eval'])
+            line['roofline']['dominant_kernel'] = {
+                'stage': dom['stage'], 'ms_per_eval': dom['ms_per_eval'], 'achieved': dom['GBps'],
+                'frac': (dom['GBps'] / peak) if dom['GBps'] else None,
+                'note': 'CUDA events on the launch stream around this stage, mean of 5 evaluations'}
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = cpu_reference_run(3, 1, sample_grid=min(GRID, 128))
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
@@ -283,7 +332,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -63,6 +63,12 @@ int pad_set_fast_fft(int on);
  * reciprocal-space multiply fused into the x pass; 0: batched 2-D cuFFT), "zgroup" (z chunks of 8 columns per
  * L2-blocked group of the y / x-multiply-x / y passes; 0 = whole grid).  Returns the previous value, -1 on error. */
 int pad_set_option(const char* name, int value);
+/* Live per-stage device timing (CUDA events on the launch stream between the kernels of the fused WGC99
+ * pipeline).  pad_profile_begin() switches it on and clears the sums; pad_profile_end() switches it off and
+ * returns, for each stage i < *n_out (at most cap), the mean milliseconds per evaluation in ms_out[i] and its
+ * name in names_out[i * 48 ...] (NUL-terminated).  Used by bench.py for the dominant-kernel roofline. */
+int pad_profile_begin(void);
+int pad_profile_end(char* names_out, double* ms_out, int cap, int* n_out, int* evals_out);
 
 /* ---- plan: replaces wavevecs(box_vecs, shape) (functional_tools.py:135-162) and owns the cuFFT
  *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */

@@ -38,6 +38,8 @@ SIGNATURES = {
     'pad_eval_hc': (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _dbl, _int, _vp, _int, _vp, _vp, _int, _vp, _vp]),
     'pad_set_fast_fft': (_int, [_int]),
     'pad_set_option': (_int, [ctypes.c_char_p, _int]),
+    'pad_profile_begin': (_int, []),
+    'pad_profile_end': (_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     'pad_fft_axis_fast': (_int, [_vp, _vp, _int, _int, _vp]),
     'pad_fast_fft_supported': (_int, [_vp]),
     'pad_rfft3_fast': (_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -56,6 +56,7 @@ struct KGeom {
     int e0, e1, e2;          // axis length even?
     double b[9];             // reciprocal lattice, rows = b_i = 2 pi inv(box^T)[i]
     double inv_n;            // 1 / (n0 n1 n2): cuFFT transforms are unnormalised
+    int nzp_pad;             // padded row length (complex) of the fused-pipeline spectra: n2/2 + 8
 };
 
 struct KPoint {
@@ -194,6 +195,7 @@ struct pad_plan {
     double* scal;                // PAD_N_SCAL device scalars
     // WGC99 kernel cache: 4 half-spectrum real arrays W0, K1, K2, K3 and the key they were built for
     double* wgc_kern;
+    double* wgc_kern4;           // same kernels, interleaved (W0,K1,K2,K3) per k-point over the PADDED half-spectrum layout
     double wgc_key[6];           // alpha, beta, gamma, kappa, + box generation, valid flag
     uint64_t box_generation;
     // Huang-Carter scratch: xi-node list (+ min/max words), table slopes, n_xi convolution fields
@@ -227,6 +229,9 @@ int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
 extern int g_pad_own_xy, g_pad_zgroup;
+extern int g_pad_profile;          // 1: record CUDA events between pipeline stages (pad_profile_begin/end)
+void pad_stage_begin(cudaStream_t s);
+void pad_stage_mark(const char* name, cudaStream_t s);
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,

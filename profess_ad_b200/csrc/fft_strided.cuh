@@ -128,12 +128,37 @@ __global__ void __launch_bounds__(128) spass_kernel(SPassFields fields, int nf, 
 }
 
 // ------------------------------------------------------------------------------------------------
-//  x pass with fused multiply:  NF coupled fields.  mix(kpoint, idx, f[NF]) edits the NF spectral
-//  values of one k-point in place; idx = (kx n1 + ky) nzh + kz is the unpadded half-spectrum index.
-//  The transformed axis is axis 0, the outer axis is axis 1.
+//  asynchronous global -> shared copies (LDGSTS): each thread copies the elements it will read itself,
+//  so a cp.async.wait_group is all the synchronisation the consumer needs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
+
+// ------------------------------------------------------------------------------------------------
+//  x pass with fused multiply:  NF coupled fields.  The transformed axis is axis 0, the outer axis is
+//  axis 1.  Mix concept:
+//      typename Mix::Coef
+//      Coef  fetch(kg, kx, ky, z, pidx)     multiplier data of one k-point (pidx = padded index (kx n1 + ky) nzp + z)
+//      void  hint(pidx)                     optional L2 prefetch of that data
+//      void  apply(coef, q[NF])             edits the NF spectral values in place
+//
+//  Per tile every field has one shared-memory buffer B[f] of L x 8 complex.  It is, in turn, the landing
+//  zone of the asynchronous loads (thread-owned rows t + TPL j), the exchange scratch of the forward
+//  transform, the parking place of the spectrum until its partners are ready (same thread-owned rows),
+//  and the exchange scratch of the inverse transform.  As soon as the inverse transform of field f has
+//  left the buffer, the loads of field f of the CTA's NEXT tile are issued into it, so they fly during
+//  the remaining inverse transforms, the stores and the next tile's first forward transforms.
 // ------------------------------------------------------------------------------------------------
 template <int L, int NF, class Mix>
-__global__ void __launch_bounds__(128) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
+__global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -141,68 +166,108 @@ __global__ void __launch_bounds__(128) xmix_kernel(SPassFields fields, SPassGeom
     const int tile_in_cta = threadIdx.x / P::TILE_THREADS;
     const int tid = threadIdx.x % P::TILE_THREADS;
     const int t = tid / P::ZC, c = tid % P::ZC;
-    cd* S = tw + L + (size_t)tile_in_cta * P::TILE_CD;
-    // park[f][slot][thread]: thread-private, conflict-free (consecutive threads -> consecutive 16-byte words)
-    cd* park = tw + L + (size_t)P::TPC * P::TILE_CD + threadIdx.x;
-    constexpr int PARK_FIELD = P::EPT * P::THREADS;
+    cd* B0 = tw + L + (size_t)tile_in_cta * (NF * P::TILE_CD);          // B[f] = B0 + f * TILE_CD
+    cd* own = B0 + t * P::ZC + c;                                       // own[f * TILE_CD + (TPL j) * ZC]: row t + TPL j
+    constexpr int ROWSTEP = P::TPL * P::ZC;
     const long long total = (long long)geo.n_outer * geo.nzc;
-    for (long long w0 = (long long)blockIdx.x * P::TPC; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
+    const uint32_t xs = (uint32_t)geo.axis_stride;                      // < 2^32 elements for every supported shape
+
+    struct TileAt {
+        bool live;
+        int o, z;
+        long long off;
+    };
+    auto locate = [&](long long w0) {
+        TileAt a;
         const long long w = w0 + tile_in_cta;
         const bool live_tile = w < total;
         const int rem = (int)(live_tile ? w : 0);
-        const int o = rem / geo.nzc;
-        const int z = (geo.zc0 + (rem - o * geo.nzc)) * P::ZC + c;
-        const bool live = live_tile && z < geo.nzh;
-        const long long off = (long long)o * geo.outer_stride + z;
+        a.o = rem / geo.nzc;
+        a.z = (geo.zc0 + (rem - a.o * geo.nzc)) * P::ZC + c;
+        a.live = live_tile && a.z < geo.nzh;
+        a.off = (long long)a.o * geo.outer_stride + a.z;
+        return a;
+    };
+    auto issue = [&](int f, const TileAt& a) {
+        if (a.live) {
+            const cd* base = fields.f[f] + a.off + (size_t)t * xs;
+#pragma unroll
+            for (int j = 0; j < P::EPT; ++j) cp_async16(own + f * P::TILE_CD + j * ROWSTEP, base + (size_t)(P::TPL * j) * xs);
+        }
+        cp_async_commit();
+    };
+
+    long long w0 = (long long)blockIdx.x * P::TPC;
+    TileAt cur = locate(w0);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) issue(f, cur);
+
+    for (; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
+        const TileAt nxt = locate(w0 + (long long)gridDim.x * P::TPC);
+        const size_t prow = ((size_t)cur.o) * kg.nzp_pad + cur.z;         // + kx n1 nzp
+        const size_t kxs = (size_t)kg.n1 * kg.nzp_pad;
+        if (cur.live) {
+#pragma unroll
+            for (int s = 0; s < P::EPT; ++s) mix.hint(prow + (size_t)spass_out_index<L>(t, s) * kxs);
+        }
         cd v[P::EPT];
-        // forward transforms; fields NF-1 .. 1 are parked, field 0 stays in registers
-#pragma unroll
-        for (int f = NF - 1; f >= 0; --f) {
-            const cd* base = fields.f[f] + off;
-#pragma unroll
-            for (int j = 0; j < P::EPT; ++j) v[j] = live ? base[(long long)(t + P::TPL * j) * geo.axis_stride] : cd{0.0, 0.0};
-            tile_fft<L, -1>(v, S, t, c, tw);
-            if (f > 0) {
-#pragma unroll
-                for (int s = 0; s < P::EPT; ++s) park[(f - 1) * PARK_FIELD + s * P::THREADS] = v[s];
-            }
-        }
-        // multiply
-#pragma unroll
-        for (int s = 0; s < P::EPT; ++s) {
-            cd q[NF];
-            q[0] = v[s];
-#pragma unroll
-            for (int f = 1; f < NF; ++f) q[f] = park[(f - 1) * PARK_FIELD + s * P::THREADS];
-            if (live) {
-                const int kx = spass_out_index<L>(t, s);
-                const KPoint kp = make_kpoint_at(kg, kx, o, z);
-                mix(kp, ((uint32_t)kx * (uint32_t)kg.n1 + (uint32_t)o) * (uint32_t)kg.nzh + (uint32_t)z, q);
-            }
-            v[s] = q[0];
-#pragma unroll
-            for (int f = 1; f < NF; ++f) park[(f - 1) * PARK_FIELD + s * P::THREADS] = q[f];
-        }
-        // inverse transforms
+        // forward transforms; every spectrum but the last is parked in its thread-owned rows
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            cd u[P::EPT];
+            if (f == 0) cp_async_wait<NF - 1>();
+            else if (f == 1) cp_async_wait<(NF > 2 ? NF - 2 : 0)>();
+            else if (f == 2) cp_async_wait<(NF > 3 ? NF - 3 : 0)>();
+            else cp_async_wait<0>();
+            cd* Bf = own + f * P::TILE_CD;
 #pragma unroll
-            for (int j = 0; j < P::EPT; ++j) {
-                const int s = spass_slot_of_input<L>(j);
-                u[j] = (f == 0) ? v[s] : park[(f - 1) * PARK_FIELD + s * P::THREADS];
-            }
-            tile_fft<L, +1>(u, S, t, c, tw);
-            if (live) {
-                cd* base = fields.f[f] + off;
+            for (int j = 0; j < P::EPT; ++j) v[j] = cur.live ? Bf[j * ROWSTEP] : cd{0.0, 0.0};
+            tile_fft<L, -1>(v, B0 + f * P::TILE_CD, t, c, tw);
+            if (f < NF - 1) {
 #pragma unroll
-                for (int s = 0; s < P::EPT; ++s) base[(long long)spass_out_index<L>(t, s) * geo.axis_stride] = u[s];
+                for (int s = 0; s < P::EPT; ++s) Bf[s * ROWSTEP] = v[s];
             }
         }
+        // multiply; all mixed spectra go back to the parking rows
+        {
+            typename Mix::Coef coef = mix.fetch(kg, spass_out_index<L>(t, 0), cur.o, cur.z, prow + (size_t)spass_out_index<L>(t, 0) * kxs, cur.live);
+#pragma unroll
+            for (int s = 0; s < P::EPT; ++s) {
+                typename Mix::Coef cnext = coef;
+                if (s + 1 < P::EPT) {
+                    const int kxn = spass_out_index<L>(t, s + 1 < P::EPT ? s + 1 : s);
+                    cnext = mix.fetch(kg, kxn, cur.o, cur.z, prow + (size_t)kxn * kxs, cur.live);
+                }
+                cd q[NF];
+#pragma unroll
+                for (int f = 0; f < NF - 1; ++f) q[f] = own[f * P::TILE_CD + s * ROWSTEP];
+                q[NF - 1] = v[s];
+                if (cur.live) mix.apply(coef, q);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) own[f * P::TILE_CD + s * ROWSTEP] = q[f];
+                coef = cnext;
+            }
+        }
+        // inverse transforms; the buffer of field f is refilled with the next tile as soon as it is free
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            cd* Bf = own + f * P::TILE_CD;
+            cd u[P::EPT];
+#pragma unroll
+            for (int j = 0; j < P::EPT; ++j) u[j] = Bf[spass_slot_of_input<L>(j) * ROWSTEP];
+            tile_fft<L, +1>(u, B0 + f * P::TILE_CD, t, c, tw);
+            issue(f, nxt);
+            if (cur.live) {
+                cd* base = fields.f[f] + cur.off;
+#pragma unroll
+                for (int s = 0; s < P::EPT; ++s) base[(size_t)spass_out_index<L>(t, s) * xs] = u[s];
+            }
+        }
+        cur = nxt;
     }
+    cp_async_wait<0>();
 }
 
 template <int L>
-constexpr int spass_smem_bytes(int parked_fields) {
-    return (L + SPass<L>::TPC * SPass<L>::TILE_CD + parked_fields * SPass<L>::EPT * SPass<L>::THREADS) * 16;
+constexpr int spass_smem_bytes(int tile_buffers) {
+    return (L + SPass<L>::TPC * SPass<L>::TILE_CD * tile_buffers) * 16;
 }

@@ -47,25 +47,32 @@ int ensure_twiddles(int device) {
 //  z-pass kernels.  TPL lanes share a line; each lane owns the 8 packed-complex points
 //  n = t + TPL j (j < 8) of the line -- as FFT input AND as FFT output (line_fft8), so everything
 //  that is per real-space point (staged inputs, the NF inverse results) lives in registers.
-//  Shared memory per block: [ tw1: M cd | tw2: M/2 + 2 cd ] + per line one scratch of kScratch cd.
+//
+//  Every line slot (32 / TPL per warp) has its own shared-memory landing zone; the global inputs of the
+//  slot's NEXT line are copied into it with cp.async as soon as the current line has consumed the
+//  corresponding part, so the HBM latency is off the critical path although only 8 warps fit on an SM.
+//  Steady state: G groups in flight per thread, the oldest one is the item needed next => wait_group<G-1>.
+//
+//  Shared memory per block: [ tw1: M cd | tw2: M cd ] + per line slot [ FFT scratch | landing zone ].
 // ------------------------------------------------------------------------------------------------
 template <int M, int TPL>
 struct ZLayout {
-    static constexpr int kTwBytes = (M + M / 2 + 2) * 16;
-    static constexpr int kScratch = (8 * (TPL + 1) > M + 1 ? 8 * (TPL + 1) : M + 1) + 1;
-    static constexpr int kLineBytes = kScratch * 16;
+    static constexpr int kTwBytes = 2 * M * 16;
+    static constexpr int kScratch = 8 * (TPL + 1);                    // cd, line_fft8 exchange
+    static constexpr int kSpecLine = M + 2;                           // cd per staged half-spectrum line (M + 1 used)
     static constexpr int kLinesPerWarp = 32 / TPL;
+    __host__ __device__ static constexpr int inv_line_bytes(int nf, int nreal) { return (kScratch + nf * kSpecLine) * 16 + nreal * 2 * M * 8; }
+    __host__ __device__ static constexpr int fwd_line_bytes(int nin) { return (kScratch > M + 1 ? kScratch : M + 2) * 16 + nin * 2 * M * 8; }
 };
 
+// tw1[e] = exp(-2 pi i e / M), tw2[e] = exp(-2 pi i e / (2 M)), e < M
 template <int M>
 __device__ __forceinline__ void load_twiddles(cd* tw1, cd* tw2) {
     for (int e = threadIdx.x; e < M; e += blockDim.x) {
         const double2 w = g_fft_tw[e * (FFT_TW_N / M)];
         tw1[e] = cd{w.x, w.y};
-    }
-    for (int e = threadIdx.x; e <= M / 2; e += blockDim.x) {
-        const double2 w = g_fft_tw[e * (FFT_TW_N / (2 * M))];
-        tw2[e] = cd{w.x, w.y};
+        const double2 w2 = g_fft_tw[e * (FFT_TW_N / (2 * M))];
+        tw2[e] = cd{w2.x, w2.y};
     }
     __syncthreads();
 }
@@ -111,110 +118,183 @@ __device__ __forceinline__ void zfwd_field(const Gen& gen, const double (&sa)[Ge
     __syncwarp();
 }
 
-//   Gen::NST                        staged doubles per point
-//   gen.stage(g, a[NST], b[NST])    values to keep for the points g and g + 1 (one 16-byte load each input)
+//   Gen::NST, Gen::NIN              staged doubles per point; real input fields (<= 2) read per point
+//   gen.stage(in[NIN] (double2 each: the points g, g + 1), a[NST], b[NST])
 //   gen.field<F>(st[NST])           value of field F at a point
+struct ZIn {
+    const double* f[2];
+};
+
 template <int M, int TPL, int NF, class Gen>
-__global__ void __launch_bounds__(128) zfwd_kernel(Gen gen, cd* __restrict__ o0, cd* __restrict__ o1, cd* __restrict__ o2,
+__global__ void __launch_bounds__(128) zfwd_kernel(Gen gen, ZIn in, cd* __restrict__ o0, cd* __restrict__ o1, cd* __restrict__ o2,
                                                   cd* __restrict__ o3, int nlines, int nzp) {
     using L = ZLayout<M, TPL>;
-    constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST;
+    constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST, NIN = Gen::NIN;
+    constexpr int kLineBytes = L::fwd_line_bytes(NIN);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw1 = reinterpret_cast<cd*>(smem_raw);
     cd* tw2 = tw1 + M;
     load_twiddles<M>(tw1, tw2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
-    cd* S = reinterpret_cast<cd*>(smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * L::kLineBytes);
+    unsigned char* slot = smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * kLineBytes;
+    cd* S = reinterpret_cast<cd*>(slot);
+    double2* land = reinterpret_cast<double2*>(slot + (L::kScratch > M + 1 ? L::kScratch : M + 2) * 16);   // [NIN][M] pairs
+    const int stride = gridDim.x * wpb * LPW;
 
-    for (int line0 = (blockIdx.x * wpb + warp) * LPW; line0 < nlines; line0 += gridDim.x * wpb * LPW) {
+    // chunk t + TPL j of a line is copied AND read by lane t: no cross-lane hazard on the landing zone
+    auto issue = [&](int line) {
+        if (line < nlines) {
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) {
+                const double2* src = reinterpret_cast<const double2*>(in.f[q] + (size_t)line * (2 * M)) + t;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cp_async16(land + q * M + t + TPL * j, src + TPL * j);
+            }
+        }
+        cp_async_commit();
+    };
+    int line0 = (blockIdx.x * wpb + warp) * LPW;
+    issue(line0 + sub);
+    for (; line0 < nlines; line0 += stride) {
         const int line = line0 + sub;
         const bool live = line < nlines;
-        const size_t base = (size_t)(live ? line : 0) * (2 * M);
+        cp_async_wait<0>();
         double sa[NST][8], sb[NST][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            double2 pin[NIN];
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) pin[q] = live ? land[q * M + t + TPL * j] : make_double2(1.0, 1.0);
             double a[NST], b[NST];
-            gen.stage(base + 2 * (t + TPL * j), a, b);
+            gen.stage(pin, a, b);
 #pragma unroll
             for (int s = 0; s < NST; ++s) { sa[s][j] = a[s]; sb[s][j] = b[s]; }
         }
+        issue(line + stride);
         const size_t orow = (size_t)(live ? line : 0) * nzp;
         zfwd_field<M, TPL, 0>(gen, sa, sb, S, tw1, tw2, t, o0 + orow, live);
         if constexpr (NF > 1) zfwd_field<M, TPL, 1>(gen, sa, sb, S, tw1, tw2, t, o1 + orow, live);
         if constexpr (NF > 2) zfwd_field<M, TPL, 2>(gen, sa, sb, S, tw1, tw2, t, o2 + orow, live);
         if constexpr (NF > 3) zfwd_field<M, TPL, 3>(gen, sa, sb, S, tw1, tw2, t, o3 + orow, live);
     }
+    cp_async_wait<0>();
 }
 
-// inverse of one field: half-spectrum line -> packed complex Z -> inverse FFT; slot r of `res` then holds
-// the real pair (f[2n], f[2n+1]) for n = t + TPL fft_nat<8>(r), scaled like an unnormalised c2r of length 2M
+// inverse of one field from its staged half-spectrum line X[0..M]: packed complex Z, inverse FFT; slot r of
+// `res` then holds the real pair (f[2n], f[2n+1]) for n = t + TPL fft_nat<8>(r), scaled like an unnormalised
+// c2r of length 2M.   Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k]),  w = exp(-i pi / M);
+// every lane builds the 8 inputs of its own FFT directly (no exchange); Im X[0], Im X[M] are ignored (c2r).
 template <int M, int TPL>
-__device__ __forceinline__ void zinv_field(const cd* __restrict__ in, cd* res, cd* S, const cd* tw1, const cd* tw2, int t) {
-    // Z[k] = Ev + i Od, Z[M-k] = conj(Ev - i Od);  Ev = (X[k] + conj X[M-k])/2,  w^k Od = (X[k] - conj X[M-k])/2.
-    // Imaginary parts of X[0], X[M] are ignored (c2r semantics).
+__device__ __forceinline__ void zinv_field(const cd* X, cd* res, cd* S, const cd* tw1, const cd* tw2, int t) {
 #pragma unroll
-    for (int i = 0; i < (M / 2 + TPL) / TPL; ++i) {
-        const int k = t + TPL * i;
-        if (k <= M / 2) {
-            cd Xa = in[k], Xb = in[M - k];
-            if (k == 0) { Xa.y = 0.0; Xb.y = 0.0; }
-            const cd B = cconj(Xb);
-            const cd Ev = cscale(Xa + B, 0.5);
-            const cd T = cscale(Xa - B, 0.5);
-            const cd Od = cmul(T, cconj(tw2[k]));
-            const cd iOd = cd{-Od.y, Od.x};
-            S[k] = Ev + iOd;
-            if (k != 0 && k != M - k) S[M - k] = cconj(Ev - iOd);
-        }
+    for (int j = 0; j < 8; ++j) {
+        const int k = t + TPL * j;
+        cd Xa = X[k], Xb = X[M - k];
+        if (k == 0) { Xa.y = 0.0; Xb.y = 0.0; }
+        const cd B = cconj(Xb);
+        const cd Ev = Xa + B;
+        const cd Od = cmul(Xa - B, cconj(tw2[k]));
+        res[j] = cd{Ev.x - Od.y, Ev.y + Od.x};
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) res[j] = S[t + TPL * j];
-    __syncwarp();
     line_fft8<M, TPL, +1>(res, S, t, tw1);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) res[r] = cscale(res[r], 2.0);
 }
 
-//   post.apply(g, u0[NF], u1[NF], acc)   for the points g and g + 1
+struct ZSpec {
+    const cd* f[4];
+};
+
+//   Post::kDen / Post::kVin          the post-op reads the density / the previous potential at its points
+//   post.apply(g, n, vold, u0[NF], u1[NF], acc)    for the points g and g + 1 (n, vold: double2)
 template <int M, int TPL, int NF, int NRED, class Post>
-__global__ void __launch_bounds__(128) zinv_kernel(Post post, const cd* __restrict__ i0, const cd* __restrict__ i1,
-                                                  const cd* __restrict__ i2, const cd* __restrict__ i3, int nlines, int nzp,
-                                                  double* __restrict__ partials) {
+__global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, ZSpec in, const double* __restrict__ den,
+                                                     const double* __restrict__ vin, int nlines, int nzp,
+                                                     double* __restrict__ partials) {
     using L = ZLayout<M, TPL>;
     constexpr int LPW = L::kLinesPerWarp;
+    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
+    constexpr int G = NF + NREAL;                              // cp.async groups per line
+    constexpr int kLineBytes = L::inv_line_bytes(NF, NREAL);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw1 = reinterpret_cast<cd*>(smem_raw);
     cd* tw2 = tw1 + M;
     load_twiddles<M>(tw1, tw2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
-    cd* S = reinterpret_cast<cd*>(smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * L::kLineBytes);
+    unsigned char* slot = smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * kLineBytes;
+    cd* S = reinterpret_cast<cd*>(slot);
+    cd* spec = S + L::kScratch;                                // [NF][kSpecLine]
+    double2* rland = reinterpret_cast<double2*>(spec + NF * L::kSpecLine);   // [NREAL][M] pairs
+    const int stride = gridDim.x * wpb * LPW;
     double acc[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
 
-    for (int line0 = (blockIdx.x * wpb + warp) * LPW; line0 < nlines; line0 += gridDim.x * wpb * LPW) {
+    auto issue_spec = [&](int f, int line) {
+        if (line < nlines) {
+            const cd* src = in.f[f] + (size_t)line * nzp + t;
+            cd* dst = spec + f * L::kSpecLine + t;
+#pragma unroll
+            for (int i = 0; i < (M + TPL) / TPL; ++i)
+                if (t + TPL * i <= M) cp_async16(dst + TPL * i, src + TPL * i);
+        }
+        cp_async_commit();
+    };
+    auto issue_real = [&](int q, const double* base, int line) {
+        if (line < nlines) {
+            const double2* src = reinterpret_cast<const double2*>(base + (size_t)line * (2 * M)) + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async16(rland + q * M + t + TPL * j, src + TPL * j);
+        }
+        cp_async_commit();
+    };
+    auto issue_all = [&](int line) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) issue_spec(f, line);
+        if constexpr (Post::kDen) issue_real(0, den, line);
+        if constexpr (Post::kVin) issue_real(Post::kDen ? 1 : 0, vin, line);
+    };
+
+    int line0 = (blockIdx.x * wpb + warp) * LPW;
+    issue_all(line0 + sub);
+    for (; line0 < nlines; line0 += stride) {
         const int line = line0 + sub;
         const bool live = line < nlines;
+        const int next = line + stride;
         const size_t base = (size_t)line * (2 * M);
-        const size_t irow = (size_t)(live ? line : 0) * nzp;
         cd res[NF][8];
-        zinv_field<M, TPL>(i0 + irow, res[0], S, tw1, tw2, t);
-        if constexpr (NF > 1) zinv_field<M, TPL>(i1 + irow, res[1], S, tw1, tw2, t);
-        if constexpr (NF > 2) zinv_field<M, TPL>(i2 + irow, res[2], S, tw1, tw2, t);
-        if constexpr (NF > 3) zinv_field<M, TPL>(i3 + irow, res[3], S, tw1, tw2, t);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            cp_async_wait<G - 1>();
+            __syncwarp();                                      // the line was copied by all lanes of its group
+            zinv_field<M, TPL>(spec + f * L::kSpecLine, res[f], S, tw1, tw2, t);   // ends with __syncwarp: all reads of spec[f] done
+            issue_spec(f, next);
+        }
+        double2 nn[8], vv[8];
+        if constexpr (Post::kDen) {
+            cp_async_wait<G - 1>();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) nn[r] = rland[t + TPL * fft_nat<8>(r)];      // own chunks
+            issue_real(0, den, next);
+        }
+        if constexpr (Post::kVin) {
+            cp_async_wait<G - 1>();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) vv[r] = rland[(Post::kDen ? M : 0) + t + TPL * fft_nat<8>(r)];
+            issue_real(Post::kDen ? 1 : 0, vin, next);
+        }
         if (live) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 double u0[NF], u1[NF];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) { u0[f] = res[f][r].x; u1[f] = res[f][r].y; }
-                post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), u0, u1, acc);
+                post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), Post::kDen ? nn[r] : make_double2(0.0, 0.0),
+                           Post::kVin ? vv[r] : make_double2(0.0, 0.0), u0, u1, acc);
             }
         }
     }
+    cp_async_wait<0>();
     if constexpr (NRED > 0) {
         __shared__ double red[NRED][4];
 #pragma unroll
@@ -231,11 +311,6 @@ __global__ void __launch_bounds__(128) zinv_kernel(Post post, const cd* __restri
     }
 }
 
-template <int M, int TPL>
-constexpr int zsmem_bytes(int warps) {
-    return ZLayout<M, TPL>::kTwBytes + warps * ZLayout<M, TPL>::kLinesPerWarp * ZLayout<M, TPL>::kLineBytes;
-}
-
 inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
     int b = (nlines + lines_per_block - 1) / lines_per_block;
     const int cap = 148 * blocks_per_sm;
@@ -245,25 +320,42 @@ inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
 }
 
 template <int M, int TPL, int NF, class Gen>
-int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, cd* o0, cd* o1, cd* o2, cd* o3) {
+int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3) {
     constexpr int warps = 4;
-    constexpr int smem = zsmem_bytes<M, TPL>(warps);
+    using L = ZLayout<M, TPL>;
+    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::fwd_line_bytes(Gen::NIN);
     auto kern = zfwd_kernel<M, TPL, NF, Gen>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
     const int nlines = p->n0 * p->n1;
-    kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, o0, o1, o2, o3, nlines, p->nzp);
+    ZIn in{{in0, in1}};
+    kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, in, o0, o1, o2, o3, nlines, p->nzp);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
 }
 
 template <int M, int TPL, int NF, int NRED, class Post>
-int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3, int* grid_out) {
+int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
+                const double* den, const double* vin, int* grid_out) {
     constexpr int warps = 4;
-    constexpr int smem = zsmem_bytes<M, TPL>(warps);
+    using L = ZLayout<M, TPL>;
+    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
+    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::inv_line_bytes(NF, NREAL);
     auto kern = zinv_kernel<M, TPL, NF, NRED, Post>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
     const int nlines = p->n0 * p->n1;
-    const int grid = zgrid(nlines, warps * (32 / TPL), 4);
-    kern<<<grid, warps * 32, smem, s>>>(post, i0, i1, i2, i3, nlines, p->nzp, p->partials);
+    constexpr int by_smem = (227 * 1024) / (smem + 1024);
+    const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < 2 ? by_smem : 2);
+    ZSpec in{{i0, i1, i2, i3}};
+    kern<<<grid, warps * 32, smem, s>>>(post, in, den, vin, nlines, p->nzp, p->partials);
     ++g_pad_launches;
     if (grid_out) *grid_out = grid;
     PAD_CUDA(cudaGetLastError());
@@ -340,7 +432,7 @@ inline int spass_nzc_total(const pad_plan* p) { return (p->nzh + 7) / 8; }
 template <int L, int DIR>
 int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, const SPassGeom& g) {
     auto kern = spass_kernel<L, DIR>;
-    constexpr int smem = spass_smem_bytes<L>(0);
+    constexpr int smem = spass_smem_bytes<L>(1);
     static bool attr_done[64] = {false};
     if (!attr_done[p->device & 63]) {
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -377,15 +469,19 @@ int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fiel
 template <int L, int NF, class Mix>
 int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix) {
     auto kern = xmix_kernel<L, NF, Mix>;
-    constexpr int smem = spass_smem_bytes<L>(NF - 1);
+    constexpr int smem = spass_smem_bytes<L>(NF);
     static bool attr_done[64] = {false};
     if (!attr_done[p->device & 63]) {
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done[p->device & 63] = true;
     }
+    // persistent CTAs: the kernel prefetches its next tile while it finishes the current one
+    constexpr int by_smem = (227 * 1024) / (smem + 1024);
+    constexpr int per_sm = (L >= 128) ? (by_smem < 2 ? by_smem : 2) : (by_smem < 3 ? by_smem : 3);
+    static_assert(per_sm >= 1, "fused x pass: tile buffers do not fit in shared memory");
     const long long tiles = (long long)g.n_outer * g.nzc;
     long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
-    if (grid > (1 << 20)) grid = 1 << 20;
+    if (grid > 148 * per_sm) grid = 148 * per_sm;
     kern<<<(unsigned)grid, 128, smem, s>>>(f, g, p->geom, mix);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
@@ -407,11 +503,19 @@ int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, int zc0, int nzc
     return PAD_ERR_ARG;
 }
 
-// reciprocal-space multipliers for the fused x pass
+// reciprocal-space multipliers for the fused x pass (Mix concept: fft_strided.cuh)
 struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:968-981), kernels pre-scaled by 1/N
-    const double *W0, *K1, *K2, *K3;
-    __device__ void operator()(const KPoint&, uint32_t idx, cd* q) const {
-        const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
+    const double2* K4;                 // [(kx n1 + ky) nzp + z][2]: (W0, K1), (K2, K3)
+    struct Coef { double2 a, b; };
+    __device__ __forceinline__ Coef fetch(const KGeom&, int, int, int, size_t pidx, bool live) const {
+        Coef c;
+        c.a = c.b = make_double2(0.0, 0.0);
+        if (live) { c.a = __ldcs(K4 + 2 * pidx); c.b = __ldcs(K4 + 2 * pidx + 1); }
+        return c;
+    }
+    __device__ __forceinline__ void hint(size_t pidx) const { prefetch_l2(K4 + 2 * pidx); }
+    __device__ __forceinline__ void apply(const Coef& k, cd* q) const {
+        const double w0 = k.a.x, k1 = k.a.y, k2 = k.b.x, k3 = k.b.y;
         const cd A = q[0], B = q[1], C = q[2];
         q[0] = cd{w0 * A.x + k1 * B.x + k2 * C.x, w0 * A.y + k1 * B.y + k2 * C.y};
         q[1] = cd{k1 * A.x + k3 * B.x, k1 * A.y + k3 * B.y};
@@ -420,14 +524,21 @@ struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:9
 };
 struct MixLaplace {                    // -k^2 / N   (functional_tools.py:209-227)
     double inv_n;
-    __device__ void operator()(const KPoint& k, uint32_t, cd* q) const {
-        const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
-        q[0] = cd{q[0].x * m, q[0].y * m};
+    typedef double Coef;
+    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+        if (!live) return 0.0;
+        const KPoint k = make_kpoint_at(g, kx, ky, z);
+        return -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
     }
+    __device__ __forceinline__ void hint(size_t) const {}
+    __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
 };
 struct MixScale {                      // plain 1/N (round-trip tests)
     double m;
-    __device__ void operator()(const KPoint&, uint32_t, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
+    typedef double Coef;
+    __device__ __forceinline__ Coef fetch(const KGeom&, int, int, int, size_t, bool) const { return m; }
+    __device__ __forceinline__ void hint(size_t) const {}
+    __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 
 bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256; }
@@ -443,33 +554,28 @@ bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256; }
 //  functors
 // ------------------------------------------------------------------------------------------------
 struct GenCopy {                       // plain r2c of one real field
-    static constexpr int NST = 1;
-    const double* f;
-    __device__ void stage(size_t g, double* a, double* b) const {
-        const double2 v = *reinterpret_cast<const double2*>(f + g);
-        a[0] = v.x; b[0] = v.y;
-    }
+    static constexpr int NST = 1, NIN = 1;
+    __device__ void stage(const double2* in, double* a, double* b) const { a[0] = in[0].x; b[0] = in[0].y; }
     template <int F>
     __device__ double field(const double* s) const { return s[0]; }
 };
 
 struct PostStore {                     // plain c2r of one real field
+    static constexpr bool kDen = false, kVin = false;
     double* out;
-    __device__ void apply(size_t g, const double* u0, const double* u1, double*) const {
+    __device__ void apply(size_t g, double2, double2, const double* u0, const double* u1, double*) const {
         *reinterpret_cast<double2*>(out + g) = make_double2(u0[0], u1[0]);
     }
 };
 
 // WGC99, first forward pass: a = n^beta, a theta, a theta^2 / 2, chi = sqrt(n)   (functionals.py:974-981, :242-243)
 struct GenWgcA {
-    static constexpr int NST = 2;      // n, n^beta
-    const double* den;
+    static constexpr int NST = 2, NIN = 1;      // staged: n, n^beta;  input: density
     const double* scal;
     double beta;
-    __device__ void stage(size_t g, double* a, double* b) const {
-        const double2 n = *reinterpret_cast<const double2*>(den + g);
-        a[0] = n.x; a[1] = exp(beta * log(n.x));
-        b[0] = n.y; b[1] = exp(beta * log(n.y));
+    __device__ void stage(const double2* in, double* a, double* b) const {
+        a[0] = in[0].x; a[1] = exp(beta * log(in[0].x));
+        b[0] = in[0].y; b[1] = exp(beta * log(in[0].y));
     }
     template <int F>
     __device__ double field(const double* s) const {
@@ -484,15 +590,11 @@ struct GenWgcA {
 
 // WGC99, second forward pass: P = n^alpha (stored by the mid pass), P theta, P theta^2 / 2
 struct GenWgcP {
-    static constexpr int NST = 2;      // n, P
-    const double* den;
-    const double* P;
+    static constexpr int NST = 2, NIN = 2;      // staged: n, P;  inputs: density, P
     const double* scal;
-    __device__ void stage(size_t g, double* a, double* b) const {
-        const double2 n = *reinterpret_cast<const double2*>(den + g);
-        const double2 q = *reinterpret_cast<const double2*>(P + g);
-        a[0] = n.x; a[1] = q.x;
-        b[0] = n.y; b[1] = q.y;
+    __device__ void stage(const double2* in, double* a, double* b) const {
+        a[0] = in[0].x; a[1] = in[1].x;
+        b[0] = in[0].y; b[1] = in[1].y;
     }
     template <int F>
     __device__ double field(const double* s) const {
@@ -506,7 +608,7 @@ struct GenWgcP {
 
 // WGC99 mid pass: u1, u2, u3, lap(chi) -> energy densities, first half of the potential, P
 struct PostWgcMid {
-    const double* den;
+    static constexpr bool kDen = true, kVin = false;
     const double* scal;
     double* v_out;
     double* P_out;
@@ -525,8 +627,7 @@ struct PostWgcMid {
         if (n != 0.0) v += -0.5 * u[3] / chi;
         v += kCTF * (alpha * P / n * conv + P * (u[1] + th * u[2]));
     }
-    __device__ void apply(size_t g, const double* u0, const double* u1, double* acc) const {
-        const double2 n = *reinterpret_cast<const double2*>(den + g);
+    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc) const {
         double2 vo = make_double2(0.0, 0.0);
         if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
         double v0, v1, P0, P1;
@@ -541,7 +642,7 @@ struct PostWgcMid {
 
 // WGC99 final pass: g1, g2, g3 -> second half of the potential
 struct PostWgcFin {
-    const double* den;
+    static constexpr bool kDen = true, kVin = true;
     const double* scal;
     double* v_out;
     double beta;
@@ -551,9 +652,7 @@ struct PostWgcFin {
         const double da = beta * a / n;
         return kCTF * (da * u[0] + (da * th + a) * u[1] + (0.5 * da * th * th + a * th) * u[2]);
     }
-    __device__ void apply(size_t g, const double* u0, const double* u1, double*) const {
-        const double2 n = *reinterpret_cast<const double2*>(den + g);
-        double2 v = *reinterpret_cast<const double2*>(v_out + g);
+    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double*) const {
         v.x += one(n.x, u0);
         v.y += one(n.y, u1);
         *reinterpret_cast<double2*>(v_out + g) = v;
@@ -609,12 +708,16 @@ int xy_convolve_own(pad_plan* p, cudaStream_t s, cd* const* B, cd* lap, Mix mix)
     for (int z0 = 0; z0 < nzc; z0 += group) {
         const int nz = z0 + group <= nzc ? group : nzc - z0;
         PAD_TRY(launch_spass(p, s, 1, -1, all, nall, z0, nz));
+        pad_stage_mark(lap ? "y-fwd (4 fields)" : "y-fwd (3 fields)", s);
         PAD_TRY((launch_xmix<NF>(p, s, B, z0, nz, mix)));
+        pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
         if (lap) {
             cd* one[1] = {lap};
             PAD_TRY((launch_xmix<1>(p, s, one, z0, nz, MixLaplace{p->geom.inv_n})));
+            pad_stage_mark("x-fwd * (-k^2) * x-inv (1 field)", s);
         }
         PAD_TRY(launch_spass(p, s, 1, +1, all, nall, z0, nz));
+        pad_stage_mark(lap ? "y-inv (4 fields)" : "y-inv (3 fields)", s);
     }
     return PAD_OK;
 }
@@ -635,8 +738,8 @@ extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_pa
     PAD_TRY(ensure_twiddles(p->device));
     if (nzp_out) *nzp_out = p->nzp;
     cd* o = reinterpret_cast<cd*>(out_cplx_padded);
-    GenCopy gen{in};
-    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, gen, o, nullptr, nullptr, nullptr))));
+    GenCopy gen{};
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, gen, in, nullptr, o, nullptr, nullptr, nullptr))));
     cd* one[1] = {o};
     PAD_TRY(xy_transform(p, s, one, 1, -1));
     return PAD_OK;
@@ -653,7 +756,7 @@ extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out,
     cd* one[1] = {i};
     PAD_TRY(xy_transform(p, s, one, 1, +1));
     PostStore post{out};
-    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, post, i, nullptr, nullptr, nullptr, nullptr))));
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, post, i, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))));
     return PAD_OK;
 }
 
@@ -671,15 +774,15 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     double* Pbuf;
     PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
     const double* scal = p->scal;
-    const size_t nk = p->Nk;
     const double inv_n = p->geom.inv_n;
-    const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
+    const KGeom geom = p->geom;
     const bool want_v = v_out != nullptr;
 
-    GenWgcA genA{den, scal, beta};
-    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, B[0], B[1], B[2], B[3]))));
+    GenWgcA genA{scal, beta};
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, den, nullptr, B[0], B[1], B[2], B[3]))));
+    pad_stage_mark("gen a,a.th,a.th2,chi + z-r2c (4 fields)", s);
     const bool own = g_pad_own_xy && own_xy_shape(p);
-    const MixWgc mixw{W0, K1, K2, K3};
+    const MixWgc mixw{reinterpret_cast<const double2*>(kern)};
     if (own) {
         PAD_TRY((xy_convolve_own<3>(p, s, B, B[3], mixw)));
     } else {
@@ -687,7 +790,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         cd *CA = B[0], *CB = B[1], *CC = B[2], *CX = B[3];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw(k, idx, q);
+            mixw.apply(mixw.fetch(geom, 0, 0, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
             const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
             const cd X = CX[pidx];
@@ -697,8 +800,9 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         for (int i = 0; i < 4; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     }
     int grid = 1;
-    PostWgcMid mid{den, scal, v_out, Pbuf, alpha, accumulate, want_v ? 1 : 0};
-    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 4, 3>(p, s, mid, B[0], B[1], B[2], B[3], &grid))));
+    PostWgcMid mid{scal, v_out, Pbuf, alpha, accumulate, want_v ? 1 : 0};
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 4, 3>(p, s, mid, B[0], B[1], B[2], B[3], den, nullptr, &grid))));
+    pad_stage_mark("z-c2r (4 fields) + energy/v1/P", s);
     if (E_out) {
         FinalizeArgs a;
         a.nblocks = grid; a.nterms = 3; a.accumulate = accumulate;
@@ -710,8 +814,9 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     }
     if (!want_v) return PAD_OK;
 
-    GenWgcP genP{den, Pbuf, scal};
-    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, genP, B[0], B[1], B[2], nullptr))));
+    GenWgcP genP{scal};
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, genP, den, Pbuf, B[0], B[1], B[2], nullptr))));
+    pad_stage_mark("gen P,P.th,P.th2 + z-r2c (3 fields)", s);
     if (own) {
         PAD_TRY((xy_convolve_own<3>(p, s, B, nullptr, mixw)));
     } else {
@@ -719,14 +824,15 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         cd *CA = B[0], *CB = B[1], *CC = B[2];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw(k, idx, q);
+            mixw.apply(mixw.fetch(geom, 0, 0, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
         });
         PAD_CUDA(cudaGetLastError());
         for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     }
-    PostWgcFin fin{den, scal, v_out, beta};
-    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, fin, B[0], B[1], B[2], nullptr, nullptr))));
+    PostWgcFin fin{scal, v_out, beta};
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, fin, B[0], B[1], B[2], nullptr, den, v_out, nullptr))));
+    pad_stage_mark("z-c2r (3 fields) + v2", s);
     return PAD_OK;
 }
 

@@ -422,7 +422,7 @@ __global__ void wgc_scalars_kernel(double* scal, double alpha, double beta, doub
 
 // kern layout: [W0 | K1 | K2 | K3], each Nk doubles, pre-multiplied by 1/N
 __global__ void __launch_bounds__(PAD_THREADS) wgc_build_kernel(KGeom g, uint32_t nk, double* __restrict__ kern,
-                                                               double* scal, int force) {
+                                                               double* __restrict__ kern4, double* scal, int force) {
     const double n_ref = scal[S_NREF];
     if (!force && n_ref == scal[S_NREF_KEY]) return;
     const double inv2kF = scal[S_TMP0 + 0], T = scal[S_TMP0 + 1] * g.inv_n, gam = c_wgc.gamma;
@@ -443,6 +443,11 @@ __global__ void __launch_bounds__(PAD_THREADS) wgc_build_kernel(KGeom g, uint32_
         }
         const double sc = k.special ? 0.5 : 1.0;
         for (int c = 0; c < 4; ++c) kern[(size_t)c * nk + idx] = sc * out[c];
+        if (kern4) {     // interleaved copy over the padded layout for the fused x pass (fft_strided.cuh)
+            double2* o = reinterpret_cast<double2*>(kern4) + 2 * (((size_t)k.j0 * g.n1 + k.j1) * g.nzp_pad + k.j2);
+            o[0] = make_double2(sc * out[0], sc * out[1]);
+            o[1] = make_double2(sc * out[2], sc * out[3]);
+        }
     }
 }
 
@@ -511,6 +516,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     const double inv_n = p->geom.inv_n;
 
     // --- reference density and kernel -----------------------------------------------------------
+    pad_stage_begin(s);
     launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
     PAD_CHECK_LAUNCH();
     const double one[1] = {1.0};
@@ -521,6 +527,13 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     if (!p->wgc_kern) {
         PAD_CUDA(cudaMalloc(&p->wgc_kern, sizeof(double) * 4 * nk));
         p->bytes_allocated += sizeof(double) * 4 * nk;
+        p->wgc_key[5] = 0.0;
+    }
+    if (!p->wgc_kern4 && pad_wgc99_fast_supported(p)) {
+        const size_t bytes = sizeof(double) * 4 * (size_t)p->n0 * p->n1 * p->nzp;
+        PAD_CUDA(cudaMalloc(&p->wgc_kern4, bytes));
+        PAD_CUDA(cudaMemsetAsync(p->wgc_kern4, 0, bytes, s));
+        p->bytes_allocated += bytes;
         p->wgc_key[5] = 0.0;
     }
     const bool same = p->wgc_key[5] == 1.0 && p->wgc_key[0] == alpha && p->wgc_key[1] == beta &&
@@ -542,14 +555,15 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         p->wgc_key[4] = (double)p->box_generation; p->wgc_key[5] = 1.0;
     }
     double* kern = p->wgc_kern;
-    wgc_build_kernel<<<pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, scal, same ? 0 : 1);
+    wgc_build_kernel<<<pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, p->wgc_kern4, scal, same ? 0 : 1);
     PAD_CHECK_LAUNCH();
     wgc_key_kernel<<<1, 1, 0, s>>>(scal);
     g_pad_launches += 2;
     PAD_CHECK_LAUNCH();
     const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
+    pad_stage_mark("sum(n) -> n_ref, kernel cache check", s);
     if (g_pad_fast_fft && pad_wgc99_fast_supported(p))
-        return pad_wgc99_fast(p, den, alpha, beta, kern, E_out, v_out, accumulate, s);
+        return pad_wgc99_fast(p, den, alpha, beta, p->wgc_kern4, E_out, v_out, accumulate, s);
 
     // --- forward fields: a = n^beta, a theta, a theta^2 / 2, chi --------------------------------
     double *Ra = R[0], *Rb = R[1], *Rc = R[2], *Rx = R[3];
@@ -563,7 +577,9 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         Rx[i] = n != 0.0 ? sqrt(n) : 0.0;
     });
     PAD_CHECK_LAUNCH();
+    pad_stage_mark("gen a,a.th,a.th2,chi", s);
     for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    pad_stage_mark("cuFFT D2Z x4", s);
     cufftDoubleComplex *CA = C[0], *CB = C[1], *CC = C[2], *CX = C[3];
     launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
         const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
@@ -577,7 +593,9 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         CX[idx] = X;
     });
     PAD_CHECK_LAUNCH();
+    pad_stage_mark("kernel mix + (-k^2)", s);
     for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // u1, u2, u3, lap(chi)
+    pad_stage_mark("cuFFT Z2D x4", s);
 
     // --- energy densities, first half of the potential, fields for the adjoint convolutions -------
     const bool want_v = v_out != nullptr;
@@ -607,10 +625,12 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     const double coef[3] = {p->dV, -0.5 * p->dV, kCTF * p->dV};
     if (E_out) finalize(p, s, 3, coef, E_out, accumulate);
     PAD_CHECK_LAUNCH();
+    pad_stage_mark("energy/v1/P fields", s);
     if (!want_v) return PAD_OK;
 
     // --- adjoint convolutions --------------------------------------------------------------------
     for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    pad_stage_mark("cuFFT D2Z x3", s);
     launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint&) {
         const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
         const cufftDoubleComplex A = CA[idx], B = CB[idx], Cc = CC[idx];
@@ -619,7 +639,9 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         CC[idx] = make_cuDoubleComplex(k2 * A.x, k2 * A.y);
     });
     PAD_CHECK_LAUNCH();
+    pad_stage_mark("kernel mix", s);
     for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // g1, g2, g3
+    pad_stage_mark("cuFFT Z2D x3", s);
     launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
         const double n = den[i];
         const double th = n - scal[S_NREF];
@@ -628,6 +650,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         v_out[i] += kCTF * (da * Ra[i] + (da * th + a) * Rb[i] + (0.5 * da * th * th + a * th) * Rc[i]);
     });
     PAD_CHECK_LAUNCH();
+    pad_stage_mark("v2", s);
     return PAD_OK;
 }
 

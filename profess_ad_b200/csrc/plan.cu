@@ -27,6 +27,77 @@ extern "C" int pad_set_option(const char* name, int value) {
     return old;
 }
 
+// ---- live per-stage timing ------------------------------------------------------------------------
+int g_pad_profile = 0;
+namespace {
+constexpr int kMaxStages = 256;
+struct StageProf {
+    cudaEvent_t ev[kMaxStages + 1];
+    const char* name[kMaxStages + 1];
+    int n = 0;                 // events recorded in the evaluation in flight
+    bool created = false;
+    double sum_ms[kMaxStages + 1];
+    const char* sum_name[kMaxStages + 1];
+    int n_stages = 0, evals = 0;
+} g_prof;
+
+void prof_flush() {
+    StageProf& P = g_prof;
+    if (P.n < 2) { P.n = 0; return; }
+    cudaEventSynchronize(P.ev[P.n - 1]);
+    for (int i = 1; i < P.n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, P.ev[i - 1], P.ev[i]);
+        if (P.evals == 0) { P.sum_ms[i - 1] = 0.0; P.sum_name[i - 1] = P.name[i]; }
+        P.sum_ms[i - 1] += ms;
+    }
+    if (P.evals == 0) P.n_stages = P.n - 1;
+    ++P.evals;
+    P.n = 0;
+}
+}  // namespace
+
+void pad_stage_begin(cudaStream_t s) {
+    if (!g_pad_profile) return;
+    StageProf& P = g_prof;
+    if (!P.created) {
+        for (int i = 0; i <= kMaxStages; ++i) cudaEventCreate(&P.ev[i]);
+        P.created = true;
+    }
+    prof_flush();
+    cudaEventRecord(P.ev[0], s);
+    P.name[0] = "begin";
+    P.n = 1;
+}
+
+void pad_stage_mark(const char* name, cudaStream_t s) {
+    if (!g_pad_profile) return;
+    StageProf& P = g_prof;
+    if (P.n < 1 || P.n > kMaxStages) return;
+    cudaEventRecord(P.ev[P.n], s);
+    P.name[P.n] = name;
+    ++P.n;
+}
+
+extern "C" int pad_profile_begin(void) {
+    g_prof.n = 0; g_prof.n_stages = 0; g_prof.evals = 0;
+    g_pad_profile = 1;
+    return PAD_OK;
+}
+
+extern "C" int pad_profile_end(char* names_out, double* ms_out, int cap, int* n_out, int* evals_out) {
+    prof_flush();
+    g_pad_profile = 0;
+    const int n = g_prof.n_stages < cap ? g_prof.n_stages : cap;
+    for (int i = 0; i < n; ++i) {
+        if (ms_out) ms_out[i] = g_prof.evals ? g_prof.sum_ms[i] / g_prof.evals : 0.0;
+        if (names_out) { strncpy(names_out + 48 * i, g_prof.sum_name[i], 47); names_out[48 * i + 47] = 0; }
+    }
+    if (n_out) *n_out = n;
+    if (evals_out) *evals_out = g_prof.evals;
+    return PAD_OK;
+}
+
 void pad_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -68,6 +139,7 @@ static int set_box(pad_plan* p, const double* box) {
     g.e0 = (p->n0 % 2 == 0); g.e1 = (p->n1 % 2 == 0); g.e2 = (p->n2 % 2 == 0);
     memcpy(g.b, p->recip, sizeof(double) * 9);
     g.inv_n = 1.0 / (double)p->N;
+    g.nzp_pad = p->n2 / 2 + 8;
     p->box_generation++;
     return PAD_OK;
 }
@@ -126,6 +198,7 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     for (int i = 0; i < PAD_N_RBUF; ++i) if (p->rbuf[i]) cudaFree(p->rbuf[i]);
     for (int i = 0; i < PAD_N_CBUF; ++i) if (p->cbuf[i]) cudaFree(p->cbuf[i]);
     if (p->wgc_kern) cudaFree(p->wgc_kern);
+    if (p->wgc_kern4) cudaFree(p->wgc_kern4);
     if (p->hc_scratch) cudaFree(p->hc_scratch);
     if (p->hc_slopes) cudaFree(p->hc_slopes);
     if (p->hc_conv) cudaFree(p->hc_conv);
