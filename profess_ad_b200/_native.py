@@ -38,6 +38,7 @@ SIGNATURES = {
     'pad_eval_hc': (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _dbl, _int, _vp, _int, _vp, _vp, _int, _vp, _vp]),
     'pad_set_fast_fft': (_int, [_int]),
     'pad_set_option': (_int, [ctypes.c_char_p, _int]),
+    'pad_dbg_fastmath': (_int, [_vp, ctypes.c_size_t, _dbl, _vp, _vp, _vp]),
     'pad_profile_begin': (_int, []),
     'pad_profile_end': (_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     'pad_fft_axis_fast': (_int, [_vp, _vp, _int, _int, _vp]),
@@ -78,7 +79,7 @@ def load_library():
             fn = getattr(lib, name)       # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy'), ('PAD_ZGROUP', b'zgroup')):
+        for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy')):
             if os.environ.get(env, '').lstrip('-').isdigit():
                 lib.pad_set_option(opt, int(os.environ[env]))
         _lib = lib

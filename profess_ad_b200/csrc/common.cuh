@@ -228,7 +228,7 @@ int pad_get_rbuf(pad_plan* p, int i, double** out);
 int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
-extern int g_pad_own_xy, g_pad_zgroup;
+extern int g_pad_own_xy;
 extern int g_pad_profile;          // 1: record CUDA events between pipeline stages (pad_profile_begin/end)
 void pad_stage_begin(cudaStream_t s);
 void pad_stage_mark(const char* name, cudaStream_t s);

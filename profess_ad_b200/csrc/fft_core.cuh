@@ -11,7 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-struct cd {
+struct __align__(16) cd {
     double x, y;
 };
 __device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }

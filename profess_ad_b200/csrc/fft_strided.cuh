@@ -81,11 +81,46 @@ __device__ __forceinline__ void spass_load_twiddles(cd* tw) {
 
 struct SPassGeom {
     long long axis_stride;     // complex elements between consecutive points of a line
-    long long outer_stride;    // complex elements between consecutive lines groups (the non-transformed, non-z axis)
+    long long outer_stride;    // complex elements between consecutive line groups (the non-transformed, non-z axis)
     int n_outer;               // extent of that axis
-    int zc0, nzc;              // first z chunk and number of z chunks handled by this launch
     int nzh;                   // live z columns (n2/2 + 1); columns >= nzh are padding and are not touched
 };
+
+// Tiles of one field.  A regular tile is one outer index x 8 consecutive z columns.  nzh = 8 m + 1 for every
+// supported n2, so the last (Nyquist) column would cost a whole tile per outer index with 1 lane in 8 live;
+// instead the Nyquist column of 8 consecutive outer indices is packed into one tile (16-byte row segments,
+// but only 1 / nzh of the data).
+__host__ __device__ inline bool spass_packed_tail(const SPassGeom& g) { return (g.nzh % 8) == 1; }
+__host__ __device__ inline int spass_chunks(const SPassGeom& g) { return spass_packed_tail(g) ? g.nzh / 8 : (g.nzh + 7) / 8; }
+__host__ __device__ inline long long spass_tiles(const SPassGeom& g) {
+    return (long long)g.n_outer * spass_chunks(g) + (spass_packed_tail(g) ? (g.n_outer + 7) / 8 : 0);
+}
+
+struct TileAt {
+    bool live;
+    int o, z;
+    long long off;             // element offset of (o, z) inside a field
+};
+// thread column c of tile w (w < spass_tiles, else dead)
+__device__ __forceinline__ TileAt spass_locate(const SPassGeom& g, long long w, long long tiles, int c) {
+    TileAt a;
+    const int chunks = spass_chunks(g);
+    const long long regular = (long long)g.n_outer * chunks;
+    const bool in_range = w < tiles;
+    const long long ww = in_range ? w : 0;
+    if (ww < regular) {
+        a.o = (int)(ww / chunks);
+        a.z = (int)(ww - (long long)a.o * chunks) * 8 + c;
+        a.live = in_range && a.z < g.nzh;
+    } else {
+        a.o = (int)(ww - regular) * 8 + c;
+        a.z = g.nzh - 1;
+        a.live = in_range && a.o < g.n_outer;
+        if (!a.live) a.o = 0;
+    }
+    a.off = (long long)a.o * g.outer_stride + a.z;
+    return a;
+}
 
 struct SPassFields {
     cd* f[4];
@@ -95,7 +130,7 @@ struct SPassFields {
 //  plain pass: in-place FFT along the strided axis for nf fields
 // ------------------------------------------------------------------------------------------------
 template <int L, int DIR>
-__global__ void __launch_bounds__(128) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
+__global__ void __launch_bounds__(128, 4) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -104,23 +139,18 @@ __global__ void __launch_bounds__(128) spass_kernel(SPassFields fields, int nf, 
     const int tid = threadIdx.x % P::TILE_THREADS;
     const int t = tid / P::ZC, c = tid % P::ZC;
     cd* S = tw + L + (size_t)tile_in_cta * P::TILE_CD;
-    const long long per_field = (long long)geo.n_outer * geo.nzc;
+    const long long per_field = spass_tiles(geo);
     const long long total = per_field * nf;
     for (long long w0 = (long long)blockIdx.x * P::TPC; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
         const long long w = w0 + tile_in_cta;
-        const bool live_tile = w < total;
-        const long long wf = live_tile ? w : 0;
-        const int fi = (int)(wf / per_field);
-        const int rem = (int)(wf - (long long)fi * per_field);
-        const int o = rem / geo.nzc;
-        const int z = (geo.zc0 + (rem - o * geo.nzc)) * P::ZC + c;
-        const bool live = live_tile && z < geo.nzh;
-        cd* base = fields.f[fi] + (long long)o * geo.outer_stride + z;
+        const int fi = w < total ? (int)(w / per_field) : 0;
+        const TileAt a = spass_locate(geo, w < total ? w - (long long)fi * per_field : per_field, per_field, c);
+        cd* base = fields.f[fi] + a.off;
         cd v[P::EPT];
 #pragma unroll
-        for (int j = 0; j < P::EPT; ++j) v[j] = live ? base[(long long)(t + P::TPL * j) * geo.axis_stride] : cd{0.0, 0.0};
+        for (int j = 0; j < P::EPT; ++j) v[j] = a.live ? base[(long long)(t + P::TPL * j) * geo.axis_stride] : cd{0.0, 0.0};
         tile_fft<L, DIR>(v, S, t, c, tw);
-        if (live) {
+        if (a.live) {
 #pragma unroll
             for (int s = 0; s < P::EPT; ++s) base[(long long)spass_out_index<L>(t, s) * geo.axis_stride] = v[s];
         }
@@ -169,25 +199,9 @@ __global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFiel
     cd* B0 = tw + L + (size_t)tile_in_cta * (NF * P::TILE_CD);          // B[f] = B0 + f * TILE_CD
     cd* own = B0 + t * P::ZC + c;                                       // own[f * TILE_CD + (TPL j) * ZC]: row t + TPL j
     constexpr int ROWSTEP = P::TPL * P::ZC;
-    const long long total = (long long)geo.n_outer * geo.nzc;
+    const long long total = spass_tiles(geo);
     const uint32_t xs = (uint32_t)geo.axis_stride;                      // < 2^32 elements for every supported shape
-
-    struct TileAt {
-        bool live;
-        int o, z;
-        long long off;
-    };
-    auto locate = [&](long long w0) {
-        TileAt a;
-        const long long w = w0 + tile_in_cta;
-        const bool live_tile = w < total;
-        const int rem = (int)(live_tile ? w : 0);
-        a.o = rem / geo.nzc;
-        a.z = (geo.zc0 + (rem - a.o * geo.nzc)) * P::ZC + c;
-        a.live = live_tile && a.z < geo.nzh;
-        a.off = (long long)a.o * geo.outer_stride + a.z;
-        return a;
-    };
+    auto locate = [&](long long w0) { return spass_locate(geo, w0 + tile_in_cta, total, c); };
     auto issue = [&](int f, const TileAt& a) {
         if (a.live) {
             const cd* base = fields.f[f] + a.off + (size_t)t * xs;
@@ -227,15 +241,22 @@ __global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFiel
                 for (int s = 0; s < P::EPT; ++s) Bf[s * ROWSTEP] = v[s];
             }
         }
-        // multiply; all mixed spectra go back to the parking rows
+        // multiply; all mixed spectra go back to the parking rows.  The multiplier data comes from global
+        // memory (L2 after the hints above): keep PF slots of it in flight.
         {
-            typename Mix::Coef coef = mix.fetch(kg, spass_out_index<L>(t, 0), cur.o, cur.z, prow + (size_t)spass_out_index<L>(t, 0) * kxs, cur.live);
+            constexpr int PF = 4;
+            typename Mix::Coef ring[PF];
+#pragma unroll
+            for (int s = 0; s < PF; ++s) {
+                const int kx = spass_out_index<L>(t, s);
+                ring[s] = mix.fetch(kg, kx, cur.o, cur.z, prow + (size_t)kx * kxs, cur.live);
+            }
 #pragma unroll
             for (int s = 0; s < P::EPT; ++s) {
-                typename Mix::Coef cnext = coef;
-                if (s + 1 < P::EPT) {
-                    const int kxn = spass_out_index<L>(t, s + 1 < P::EPT ? s + 1 : s);
-                    cnext = mix.fetch(kg, kxn, cur.o, cur.z, prow + (size_t)kxn * kxs, cur.live);
+                const typename Mix::Coef coef = ring[s % PF];
+                if (s + PF < P::EPT) {
+                    const int kxn = spass_out_index<L>(t, s + PF < P::EPT ? s + PF : s);
+                    ring[s % PF] = mix.fetch(kg, kxn, cur.o, cur.z, prow + (size_t)kxn * kxs, cur.live);
                 }
                 cd q[NF];
 #pragma unroll
@@ -244,7 +265,6 @@ __global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFiel
                 if (cur.live) mix.apply(coef, q);
 #pragma unroll
                 for (int f = 0; f < NF; ++f) own[f * P::TILE_CD + s * ROWSTEP] = q[f];
-                coef = cnext;
             }
         }
         // inverse transforms; the buffer of field f is refilled with the next tile as soon as it is free

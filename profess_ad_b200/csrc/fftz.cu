@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "fft_strided.cuh"
+#include "fastmath.cuh"
 
 namespace {
 
@@ -39,6 +40,18 @@ int ensure_twiddles(int device) {
     host[FFT_TW_N / 2] = {-1.0, 0.0};
     host[3 * FFT_TW_N / 4] = {0.0, 1.0};
     PAD_CUDA(cudaMemcpyToSymbol(g_fft_tw, host, sizeof(host)));
+    // fastmath.cuh tables, evaluated in long double
+    static double2 hlog[128];
+    static double hexp[64];
+    for (int i = 0; i < 128; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+        const double inv = (double)(1.0L / c);
+        hlog[i].x = inv;
+        hlog[i].y = (double)(-logl((long double)inv));
+    }
+    for (int j = 0; j < 64; ++j) hexp[j] = (double)exp2l((long double)j / 64.0L);
+    PAD_CUDA(cudaMemcpyToSymbol(g_fm_log, hlog, sizeof(hlog)));
+    PAD_CUDA(cudaMemcpyToSymbol(g_fm_exp, hexp, sizeof(hexp)));
     g_tw_ready[device & 63] = true;
     return PAD_OK;
 }
@@ -126,7 +139,7 @@ struct ZIn {
 };
 
 template <int M, int TPL, int NF, class Gen>
-__global__ void __launch_bounds__(128) zfwd_kernel(Gen gen, ZIn in, cd* __restrict__ o0, cd* __restrict__ o1, cd* __restrict__ o2,
+__global__ void __launch_bounds__(128, 4) zfwd_kernel(Gen gen, ZIn in, cd* __restrict__ o0, cd* __restrict__ o1, cd* __restrict__ o2,
                                                   cd* __restrict__ o3, int nlines, int nzp) {
     using L = ZLayout<M, TPL>;
     constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST, NIN = Gen::NIN;
@@ -415,19 +428,15 @@ int get_zbuf(pad_plan* p, int i, cd** out) {
 inline bool spass_len_ok(int n) { return n == 64 || n == 128 || n == 256; }
 bool own_xy_shape(const pad_plan* p) { return spass_len_ok(p->n0) && spass_len_ok(p->n1); }
 
-SPassGeom spass_geom(const pad_plan* p, int axis, int zc0, int nzc) {
+SPassGeom spass_geom(const pad_plan* p, int axis) {
     SPassGeom g;
     const long long row = p->nzp, plane = (long long)p->n1 * p->nzp;
     g.axis_stride = axis == 0 ? plane : row;
     g.outer_stride = axis == 0 ? row : plane;
     g.n_outer = axis == 0 ? p->n1 : p->n0;
-    g.zc0 = zc0;
-    g.nzc = nzc;
     g.nzh = p->nzh;
     return g;
 }
-
-inline int spass_nzc_total(const pad_plan* p) { return (p->nzh + 7) / 8; }
 
 template <int L, int DIR>
 int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, const SPassGeom& g) {
@@ -438,7 +447,7 @@ int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, co
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done[p->device & 63] = true;
     }
-    const long long tiles = (long long)nf * g.n_outer * g.nzc;
+    const long long tiles = (long long)nf * spass_tiles(g);
     long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
     if (grid > (1 << 20)) grid = 1 << 20;
     kern<<<(unsigned)grid, 128, smem, s>>>(f, nf, g);
@@ -447,11 +456,11 @@ int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, co
     return PAD_OK;
 }
 
-// in-place FFT of nf padded half-spectra along axis 0 (x) or 1 (y), z chunks [zc0, zc0 + nzc)
-int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf, int zc0, int nzc) {
+// in-place FFT of nf padded half-spectra along axis 0 (x) or 1 (y)
+int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf) {
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < nf ? fields[i] : nullptr;
-    const SPassGeom g = spass_geom(p, axis, zc0, nzc);
+    const SPassGeom g = spass_geom(p, axis);
     const int L = axis == 0 ? p->n0 : p->n1;
 #define SPASS_CASE(LL)                                                        \
     case LL:                                                                  \
@@ -479,7 +488,7 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     constexpr int by_smem = (227 * 1024) / (smem + 1024);
     constexpr int per_sm = (L >= 128) ? (by_smem < 2 ? by_smem : 2) : (by_smem < 3 ? by_smem : 3);
     static_assert(per_sm >= 1, "fused x pass: tile buffers do not fit in shared memory");
-    const long long tiles = (long long)g.n_outer * g.nzc;
+    const long long tiles = spass_tiles(g);
     long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
     if (grid > 148 * per_sm) grid = 148 * per_sm;
     kern<<<(unsigned)grid, 128, smem, s>>>(f, g, p->geom, mix);
@@ -488,12 +497,12 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     return PAD_OK;
 }
 
-// spec_f <- IFFT_x( mix( FFT_x(spec_0..NF-1) ) ) for z chunks [zc0, zc0 + nzc)
+// spec_f <- IFFT_x( mix( FFT_x(spec_0..NF-1) ) )
 template <int NF, class Mix>
-int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, int zc0, int nzc, Mix mix) {
+int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < NF ? fields[i] : nullptr;
-    const SPassGeom g = spass_geom(p, 0, zc0, nzc);
+    const SPassGeom g = spass_geom(p, 0);
     switch (p->n0) {
         case 64: return launch_xmix_L<64, NF>(p, s, f, g, mix);
         case 128: return launch_xmix_L<128, NF>(p, s, f, g, mix);
@@ -568,20 +577,28 @@ struct PostStore {                     // plain c2r of one real field
     }
 };
 
+// n^e for the first forward pass
+__device__ __noinline__ double pow_pos_ool(double n, double e) {
+    if (fm_ok(n)) return fm_exp(e * fm_log(n));
+    return exp(e * log(n));
+}
+
 // WGC99, first forward pass: a = n^beta, a theta, a theta^2 / 2, chi = sqrt(n)   (functionals.py:974-981, :242-243)
 struct GenWgcA {
     static constexpr int NST = 2, NIN = 1;      // staged: n, n^beta;  input: density
     const double* scal;
     double beta;
     __device__ void stage(const double2* in, double* a, double* b) const {
-        a[0] = in[0].x; a[1] = exp(beta * log(in[0].x));
-        b[0] = in[0].y; b[1] = exp(beta * log(in[0].y));
+        a[0] = in[0].x; a[1] = pow_pos_ool(in[0].x, beta);
+        b[0] = in[0].y; b[1] = pow_pos_ool(in[0].y, beta);
     }
     template <int F>
     __device__ double field(const double* s) const {
         if constexpr (F == 0) return s[1];
-        else if constexpr (F == 3) return s[0] != 0.0 ? sqrt(s[0]) : 0.0;
-        else {
+        else if constexpr (F == 3) {
+            if (fm_ok(s[0])) return fm_sqrt_from_rsqrt(s[0], fm_rsqrt(s[0]));
+            return s[0] != 0.0 ? sqrt(s[0]) : 0.0;
+        } else {
             const double th = s[0] - scal[S_NREF];
             return F == 1 ? s[1] * th : 0.5 * s[1] * th * th;
         }
@@ -607,6 +624,40 @@ struct GenWgcP {
 };
 
 // WGC99 mid pass: u1, u2, u3, lap(chi) -> energy densities, first half of the potential, P
+struct MidOut {
+    double v, P, e_tf, e_vw, e_nl;
+};
+// kept out of line: inlined 16 times per line the transcendental code alone overflows the instruction cache
+__device__ __noinline__ MidOut wgc_mid_point(double n, double n_ref, double alpha, double u1, double u2, double u3, double lap) {
+    MidOut o;
+    const double th = n - n_ref;
+    const double conv = u1 + th * (u2 + 0.5 * th * u3);
+    if (fm_ok(n)) {
+        // one log, two table exps and one rsqrt give n^alpha, n^(2/3), sqrt(n), 1/sqrt(n), 1/n
+        const double l = fm_log(n);
+        o.P = fm_exp(alpha * l);
+        const double c2 = fm_exp((2.0 / 3.0) * l);
+        const double y = fm_rsqrt(n);
+        const double chi = fm_sqrt_from_rsqrt(n, y);
+        o.e_tf = kCTF * n * c2;
+        o.e_vw = chi * lap;
+        o.e_nl = o.P * conv;
+        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * o.P * (y * y) * conv + o.P * (u2 + th * u3));
+        return o;
+    }
+    o.P = exp(alpha * log(n));
+    const double c = cbrt(n);
+    const double chi = n != 0.0 ? sqrt(n) : 0.0;
+    o.e_tf = kCTF * n * c * c;
+    o.e_vw = chi * lap;
+    o.e_nl = o.P * conv;
+    double v = (5.0 / 3.0) * kCTF * c * c;
+    if (n != 0.0) v += -0.5 * lap / chi;
+    v += kCTF * (alpha * o.P / n * conv + o.P * (u2 + th * u3));
+    o.v = v;
+    return o;
+}
+
 struct PostWgcMid {
     static constexpr bool kDen = true, kVin = false;
     const double* scal;
@@ -614,47 +665,45 @@ struct PostWgcMid {
     double* P_out;
     double alpha;
     int accumulate, want_v;
-    __device__ void one(double n, double vold, const double* u, double* acc, double& v, double& P) const {
-        const double th = n - scal[S_NREF];
-        P = exp(alpha * log(n));
-        const double conv = u[0] + th * (u[1] + 0.5 * th * u[2]);
-        const double c = cbrt(n);
-        const double chi = n != 0.0 ? sqrt(n) : 0.0;
-        acc[0] += kCTF * n * c * c;
-        acc[1] += chi * u[3];
-        acc[2] += P * conv;
-        v = vold + (5.0 / 3.0) * kCTF * c * c;
-        if (n != 0.0) v += -0.5 * u[3] / chi;
-        v += kCTF * (alpha * P / n * conv + P * (u[1] + th * u[2]));
-    }
     __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc) const {
         double2 vo = make_double2(0.0, 0.0);
         if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
-        double v0, v1, P0, P1;
-        one(n.x, vo.x, u0, acc, v0, P0);
-        one(n.y, vo.y, u1, acc, v1, P1);
+        const double n_ref = scal[S_NREF];
+        const MidOut a = wgc_mid_point(n.x, n_ref, alpha, u0[0], u0[1], u0[2], u0[3]);
+        const MidOut b = wgc_mid_point(n.y, n_ref, alpha, u1[0], u1[1], u1[2], u1[3]);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
         if (want_v) {
-            *reinterpret_cast<double2*>(v_out + g) = make_double2(v0, v1);
-            *reinterpret_cast<double2*>(P_out + g) = make_double2(P0, P1);
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+            *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
         }
     }
 };
 
 // WGC99 final pass: g1, g2, g3 -> second half of the potential
+__device__ __noinline__ double wgc_fin_point(double n, double n_ref, double beta, double g1, double g2, double g3) {
+    const double th = n - n_ref;
+    double a, da;
+    if (fm_ok(n)) {
+        const double l = fm_log(n);
+        a = fm_exp(beta * l);
+        da = beta * fm_exp((beta - 1.0) * l);
+    } else {
+        a = exp(beta * log(n));
+        da = beta * a / n;
+    }
+    return kCTF * (da * g1 + (da * th + a) * g2 + (0.5 * da * th * th + a * th) * g3);
+}
+
 struct PostWgcFin {
     static constexpr bool kDen = true, kVin = true;
     const double* scal;
     double* v_out;
     double beta;
-    __device__ double one(double n, const double* u) const {
-        const double th = n - scal[S_NREF];
-        const double a = exp(beta * log(n));
-        const double da = beta * a / n;
-        return kCTF * (da * u[0] + (da * th + a) * u[1] + (0.5 * da * th * th + a * th) * u[2]);
-    }
     __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double*) const {
-        v.x += one(n.x, u0);
-        v.y += one(n.y, u1);
+        const double n_ref = scal[S_NREF];
+        v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]);
+        v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]);
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
 };
@@ -680,13 +729,12 @@ void launch_ksp(pad_plan* p, cudaStream_t s, F f) {
 // (x, y) transform of nf padded half-spectra, in place: own strided passes where the shape allows, else cuFFT
 int xy_transform(pad_plan* p, cudaStream_t s, cd* const* B, int nf, int dir) {
     if (g_pad_own_xy && own_xy_shape(p)) {
-        const int nzc = spass_nzc_total(p);
         if (dir < 0) {
-            PAD_TRY(launch_spass(p, s, 1, -1, B, nf, 0, nzc));
-            PAD_TRY(launch_spass(p, s, 0, -1, B, nf, 0, nzc));
+            PAD_TRY(launch_spass(p, s, 1, -1, B, nf));
+            PAD_TRY(launch_spass(p, s, 0, -1, B, nf));
         } else {
-            PAD_TRY(launch_spass(p, s, 0, +1, B, nf, 0, nzc));
-            PAD_TRY(launch_spass(p, s, 1, +1, B, nf, 0, nzc));
+            PAD_TRY(launch_spass(p, s, 0, +1, B, nf));
+            PAD_TRY(launch_spass(p, s, 1, +1, B, nf));
         }
         return PAD_OK;
     }
@@ -695,30 +743,27 @@ int xy_transform(pad_plan* p, cudaStream_t s, cd* const* B, int nf, int dir) {
 }
 
 // y forward, fused x-forward/multiply/x-inverse, y inverse for the coupled fields B[0..NF-1] and,
-// if lap != null, the independent field lap (multiplied by -k^2/N).  z chunks are processed in groups
-// of g_pad_zgroup so that the three passes of a group find their tiles in L2.
+// if lap != null, the independent field lap (multiplied by -k^2/N).
+// (Blocking these passes over z-chunk groups so that a group stays in L2 was measured and dropped: the B200 L2
+//  keeps ~64 MB between kernels at ~9 TB/s, a group of that size is 2 of 17 chunks, and launches that small
+//  lose more to their tails than the L2 hits win; see DESIGN.md.)
 template <int NF, class Mix>
 int xy_convolve_own(pad_plan* p, cudaStream_t s, cd* const* B, cd* lap, Mix mix) {
-    const int nzc = spass_nzc_total(p);
-    const int group = g_pad_zgroup > 0 ? g_pad_zgroup : nzc;
     cd* all[4];
     int nall = 0;
     for (int i = 0; i < NF; ++i) all[nall++] = B[i];
     if (lap) all[nall++] = lap;
-    for (int z0 = 0; z0 < nzc; z0 += group) {
-        const int nz = z0 + group <= nzc ? group : nzc - z0;
-        PAD_TRY(launch_spass(p, s, 1, -1, all, nall, z0, nz));
-        pad_stage_mark(lap ? "y-fwd (4 fields)" : "y-fwd (3 fields)", s);
-        PAD_TRY((launch_xmix<NF>(p, s, B, z0, nz, mix)));
-        pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
-        if (lap) {
-            cd* one[1] = {lap};
-            PAD_TRY((launch_xmix<1>(p, s, one, z0, nz, MixLaplace{p->geom.inv_n})));
-            pad_stage_mark("x-fwd * (-k^2) * x-inv (1 field)", s);
-        }
-        PAD_TRY(launch_spass(p, s, 1, +1, all, nall, z0, nz));
-        pad_stage_mark(lap ? "y-inv (4 fields)" : "y-inv (3 fields)", s);
+    PAD_TRY(launch_spass(p, s, 1, -1, all, nall));
+    pad_stage_mark(lap ? "y-fwd (4 fields)" : "y-fwd (3 fields)", s);
+    PAD_TRY((launch_xmix<NF>(p, s, B, mix)));
+    pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
+    if (lap) {
+        cd* one[1] = {lap};
+        PAD_TRY((launch_xmix<1>(p, s, one, MixLaplace{p->geom.inv_n})));
+        pad_stage_mark("x-fwd * (-k^2) * x-inv (1 field)", s);
     }
+    PAD_TRY(launch_spass(p, s, 1, +1, all, nall));
+    pad_stage_mark(lap ? "y-inv (4 fields)" : "y-inv (3 fields)", s);
     return PAD_OK;
 }
 
@@ -836,6 +881,29 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     return PAD_OK;
 }
 
+// fastmath.cuh against the library functions: out[0..n) = fm_exp(e * fm_log(x)), out[n..2n) = sqrt via fm_rsqrt,
+// out[2n..3n) = fm_rsqrt(x)^2 (used as 1/x); ref[...] the same from exp/log, sqrt and division
+__global__ void fastmath_probe_kernel(const double* x, size_t n, double e, double* out, double* ref) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        const double y = fm_rsqrt(v);
+        out[i] = fm_exp(e * fm_log(v));
+        out[n + i] = fm_sqrt_from_rsqrt(v, y);
+        out[2 * n + i] = y * y;
+        ref[i] = pow(v, e);
+        ref[n + i] = sqrt(v);
+        ref[2 * n + i] = 1.0 / v;
+    }
+}
+extern "C" int pad_dbg_fastmath(const double* x, size_t n, double e, double* out3n, double* ref3n, void* stream) {
+    int dev = 0;
+    PAD_CUDA(cudaGetDevice(&dev));
+    PAD_TRY(ensure_twiddles(dev));
+    fastmath_probe_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(x, n, e, out3n, ref3n);
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
 // in-place complex FFT of one padded half-spectrum along axis 0 or 1 (own strided pass); unnormalised
 extern "C" int pad_fft_axis_fast(pad_plan* p, double* cplx_padded, int axis, int dir, void* stream) {
     if (!p || !cplx_padded || (axis != 0 && axis != 1)) { pad_set_error("pad_fft_axis_fast: bad argument"); return PAD_ERR_ARG; }
@@ -846,5 +914,5 @@ extern "C" int pad_fft_axis_fast(pad_plan* p, double* cplx_padded, int axis, int
     PAD_CUDA(cudaSetDevice(p->device));
     PAD_TRY(ensure_twiddles(p->device));
     cd* one[1] = {reinterpret_cast<cd*>(cplx_padded)};
-    return launch_spass(p, (cudaStream_t)stream, axis, dir, one, 1, 0, spass_nzc_total(p));
+    return launch_spass(p, (cudaStream_t)stream, axis, dir, one, 1);
 }

@@ -14,13 +14,11 @@ extern "C" unsigned long long pad_fft_exec_count(void) { return g_pad_fft_execs;
 int g_pad_fast_fft = 0;      // opt-in until the (x, y) passes are hand-written too: batched 2-D cuFFT over the padded layout is 2.4x slower than inside a 3-D plan
 extern "C" int pad_set_fast_fft(int on) { const int old = g_pad_fast_fft; g_pad_fast_fft = on ? 1 : 0; return old; }
 int g_pad_own_xy = 1;        // hand-written strided (x, y) passes with the fused multiply (n0, n1 in 64/128/256)
-int g_pad_zgroup = 0;        // z chunks (of 8 columns) per L2-blocked group of the (y, x, y) passes; 0 = whole grid
 extern "C" int pad_set_option(const char* name, int value) {
     int* slot = nullptr;
     if (!name) { pad_set_error("pad_set_option: null name"); return -1; }
     if (!strcmp(name, "fast_fft")) slot = &g_pad_fast_fft;
     else if (!strcmp(name, "own_xy")) slot = &g_pad_own_xy;
-    else if (!strcmp(name, "zgroup")) slot = &g_pad_zgroup;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }
     const int old = *slot;
     *slot = value;

@@ -59,10 +59,9 @@ def test_strided_axis_pass_matches_library(shape, axis):
         assert (work[:, :, nzh:] == 123.0).all()
 
 
-@pytest.mark.parametrize('shape', [(64, 64, 128), (128, 64, 256), (64, 128, 128)])
-@pytest.mark.parametrize('zgroup', [0, 3])
-def test_fast_rfft3_own_xy(shape, zgroup):
-    """Full own 3-D transform (z pass + strided y and x passes), with and without z-chunk grouping."""
+@pytest.mark.parametrize('shape', [(64, 64, 128), (128, 64, 256), (64, 128, 128), (256, 128, 128), (64, 256, 256)])
+def test_fast_rfft3_own_xy(shape):
+    """Full own 3-D transform (z pass + strided y and x passes, Nyquist column packed 8 lines per tile)."""
     dev = torch.device('cuda:0')
     gen = torch.Generator().manual_seed(sum(shape))
     f = torch.rand(*shape, dtype=torch.double, generator=gen).to(dev)
@@ -70,18 +69,15 @@ def test_fast_rfft3_own_xy(shape, zgroup):
     plan, nat = _plan(box, f)
     nzh, nzp = shape[2] // 2 + 1, shape[2] // 2 + 8
     spec = torch.zeros(shape[0], shape[1], nzp, dtype=torch.complex128, device=dev)
-    old = plan.lib.pad_set_option(b'zgroup', zgroup)
-    try:
-        nat.check(plan.lib.pad_rfft3_fast(plan.handle, nat.ptr(f), nat.ptr(spec), None, nat.stream_ptr(dev)))
-        ref = torch.fft.rfftn(f)
-        err = (spec[:, :, :nzh] - ref).abs().max().item() / ref.abs().max().item()
-        assert err < 1e-14, err
-        out = torch.empty_like(f)
-        nat.check(plan.lib.pad_irfft3_fast(plan.handle, nat.ptr(spec), nat.ptr(out), nat.stream_ptr(dev)))
-        err = (out / f.numel() - f).abs().max().item()
-        assert err < 1e-14, err
-    finally:
-        plan.lib.pad_set_option(b'zgroup', old)
+    nat.check(plan.lib.pad_rfft3_fast(plan.handle, nat.ptr(f), nat.ptr(spec), None, nat.stream_ptr(dev)))
+    ref = torch.fft.rfftn(f)
+    err = (spec[:, :, :nzh] - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-14, err
+    assert spec[:, :, nzh:].abs().max().item() == 0.0
+    out = torch.empty_like(f)
+    nat.check(plan.lib.pad_irfft3_fast(plan.handle, nat.ptr(spec), nat.ptr(out), nat.stream_ptr(dev)))
+    err = (out / f.numel() - f).abs().max().item()
+    assert err < 1e-14, err
 
 
 @pytest.mark.parametrize('shape,seed', [((10, 12, 128), 31), ((9, 8, 256), 32), ((4, 6, 256), 33),
@@ -110,27 +106,25 @@ def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
 
 
-def test_wgc99_zgroup_blocking_is_equivalent():
-    """L2-blocked scheduling of the (y, x-multiply-x, y) passes must not change the result."""
-    from oracle import ofdft_oracle as orc
-    import profess_ad_b200.functionals as F
-    from profess_ad_b200 import _native
-    lib = _native.load_library()
+@pytest.mark.parametrize('expo', [(5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6, 2.0 / 3.0, -0.5393])
+def test_fast_math_accuracy(expo):
+    """Table-driven pow / sqrt / reciprocal (csrc/fastmath.cuh) against torch fp64 over 60 decades."""
+    from profess_ad_b200 import _native as nat
+    lib = nat.load_library()
     dev = torch.device('cuda:0')
-    box, den = orc.synth_rough((64, 64, 256), seed=41, L=9.0)
-    b, d = box.to(dev), den.to(dev)
-    old_fast = lib.pad_set_fast_fft(1)
-    res = {}
-    try:
-        for zg in (0, 1, 5):
-            old = lib.pad_set_option(b'zgroup', zg)
-            try:
-                E, V = F.energy_and_potential(b, d, F.WangGovindCarter99().forward)
-                res[zg] = (E.item(), V.clone())
-            finally:
-                lib.pad_set_option(b'zgroup', old)
-    finally:
-        lib.pad_set_fast_fft(old_fast)
-    for zg in (1, 5):
-        assert res[zg][0] == res[0][0]
-        assert torch.equal(res[zg][1], res[0][1])
+    gen = torch.Generator().manual_seed(11)
+    n = 1 << 20
+    x = torch.pow(10.0, 60.0 * torch.rand(n, dtype=torch.double, generator=gen) - 40.0).to(dev)
+    x[:8] = torch.tensor([1.0, 2.0, 0.5, 1.0 - 2 ** -53, 1.0 + 2 ** -52, 0.0301, 1e-30, 7.3e19], dtype=torch.double)
+    out = torch.empty(3 * n, dtype=torch.double, device=dev)
+    ref = torch.empty(3 * n, dtype=torch.double, device=dev)
+    nat.check(lib.pad_dbg_fastmath(nat.ptr(x), n, expo, nat.ptr(out), nat.ptr(ref), nat.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    exact = torch.cat([torch.pow(x, expo), torch.sqrt(x), 1.0 / x])
+    # exp(e log x) in plain fp64 (what the kernels replaced) is conditioned by |e log x|: weigh the pow error by it
+    cond = torch.cat([1.0 + (expo * torch.log(x)).abs(), torch.ones(2 * n, dtype=torch.double, device=dev)])
+    err = ((out - exact).abs() / exact.abs() / cond).view(3, n).max(dim=1).values.tolist()
+    err_lib = ((ref - exact).abs() / exact.abs()).view(3, n).max(dim=1).values.tolist()
+    assert err[0] < 4e-16, (err, err_lib)
+    assert err[1] < 2.5e-16, (err, err_lib)        # sqrt: correctly rounded or 1 ulp
+    assert err[2] < 7e-16, (err, err_lib)          # 1/x as rsqrt^2
