@@ -56,7 +56,7 @@ const char* pad_last_error(void);
 /* kernels this library has launched so far in this process (own kernels; cuFFT execs counted separately) */
 unsigned long long pad_launch_count(void);
 unsigned long long pad_fft_exec_count(void);
-/* 1: use the hand-written fused z-pass FFT pipeline where the grid allows (n2 in 128/256); default 0 for now;
+/* 1 (default): use the hand-written fused FFT pipeline where the grid allows (n2 in 128/256);
  * 0: plain cuFFT 3-D transforms + separate elementwise kernels.  Returns the previous setting. */
 int pad_set_fast_fft(int on);
 /* tuning switches (process-wide): "fast_fft" (as above), "own_xy" (1: hand-written strided x/y passes with the

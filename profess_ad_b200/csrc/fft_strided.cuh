@@ -177,7 +177,6 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 //  axis 1.  Mix concept:
 //      typename Mix::Coef
 //      Coef  fetch(kg, kx, ky, z, pidx)     multiplier data of one k-point (pidx = padded index (kx n1 + ky) nzp + z)
-//      void  hint(pidx)                     optional L2 prefetch of that data
 //      void  apply(coef, q[NF])             edits the NF spectral values in place
 //
 //  Per tile every field has one shared-memory buffer B[f] of L x 8 complex.  It is, in turn, the landing
@@ -220,10 +219,6 @@ __global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFiel
         const TileAt nxt = locate(w0 + (long long)gridDim.x * P::TPC);
         const size_t prow = ((size_t)cur.o) * kg.nzp_pad + cur.z;         // + kx n1 nzp
         const size_t kxs = (size_t)kg.n1 * kg.nzp_pad;
-        if (cur.live) {
-#pragma unroll
-            for (int s = 0; s < P::EPT; ++s) mix.hint(prow + (size_t)spass_out_index<L>(t, s) * kxs);
-        }
         cd v[P::EPT];
         // forward transforms; every spectrum but the last is parked in its thread-owned rows
 #pragma unroll
@@ -242,9 +237,9 @@ __global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFiel
             }
         }
         // multiply; all mixed spectra go back to the parking rows.  The multiplier data comes from global
-        // memory (L2 after the hints above): keep PF slots of it in flight.
+        // memory: keep PF slots of it in flight.
         {
-            constexpr int PF = 4;
+            constexpr int PF = 8;      // measured at 256^3: 8 in flight, no L2 hints: 269 us; 4 + prefetch.L2 hints: 283 us
             typename Mix::Coef ring[PF];
 #pragma unroll
             for (int s = 0; s < PF; ++s) {

@@ -522,7 +522,6 @@ struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:9
         if (live) { c.a = __ldcs(K4 + 2 * pidx); c.b = __ldcs(K4 + 2 * pidx + 1); }
         return c;
     }
-    __device__ __forceinline__ void hint(size_t pidx) const { prefetch_l2(K4 + 2 * pidx); }
     __device__ __forceinline__ void apply(const Coef& k, cd* q) const {
         const double w0 = k.a.x, k1 = k.a.y, k2 = k.b.x, k3 = k.b.y;
         const cd A = q[0], B = q[1], C = q[2];
@@ -539,14 +538,12 @@ struct MixLaplace {                    // -k^2 / N   (functional_tools.py:209-22
         const KPoint k = make_kpoint_at(g, kx, ky, z);
         return -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
     }
-    __device__ __forceinline__ void hint(size_t) const {}
     __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
 };
 struct MixScale {                      // plain 1/N (round-trip tests)
     double m;
     typedef double Coef;
     __device__ __forceinline__ Coef fetch(const KGeom&, int, int, int, size_t, bool) const { return m; }
-    __device__ __forceinline__ void hint(size_t) const {}
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 

@@ -1,7 +1,7 @@
 """Deterministic synthetic inputs for benchmarks.
 
 No files, no reference code: a smooth Al-like density on a cubic supercell.  bench.py uses this for
-the B200 arm; the CPU oracle has its own, independent generator for the baseline arm and the tests.
+the B200 arm; the CPU baseline arm and the tests generate their inputs independently.
 """
 import math
 
