@@ -73,6 +73,25 @@ int pad_profile_end(char* names_out, double* ms_out, int cap, int* n_out, int* e
  *      plans, scratch fields and cached reciprocal-space kernels for one (box, shape, device). ---- */
 int pad_plan_create(pad_plan** plan, const double* box_host, const int* shape_host, int device);
 int pad_plan_destroy(pad_plan* plan);
+
+/* ---- slab plan: one large grid split over `world` ranks (one process per GPU).  Real space is split along
+ *      axis 0 (n0 / world planes per rank), the half spectrum along axis 1 (n1 / world rows, all of axis 0);
+ *      every 3-D transform is a local batched 2-D (y, z) cuFFT, ONE all-to-all, and a local strided 1-D (x)
+ *      cuFFT.  The library does not link a communication library: the caller supplies `fn`, which must, on
+ *      `stream`'s device and ordered with `stream`,
+ *        op == PAD_COMM_ALL_TO_ALL : exchange send_buf -> recv_buf, `count` complex128 per peer (peer r's block
+ *                                    is send_buf[r * count ...]; block r of recv_buf comes from peer r)
+ *        op == PAD_COMM_ALL_REDUCE : sum comm_scratch[0 .. count) over the ranks, in place
+ *      and return 0.  Python binds it to torch.distributed (NCCL over NVLink).  Every functional entry point
+ *      below then takes LOCAL slabs (den, v: n0/world x n1 x n2) and returns GLOBAL energies on every rank.
+ *      Not available on slab plans: the fused FFT pipeline, pad_eval_hc, pad_denopt_*, pad_chi_project. ---- */
+#define PAD_COMM_ALL_TO_ALL 0
+#define PAD_COMM_ALL_REDUCE 1
+#define PAD_COMM_SCRATCH 16
+typedef int (*pad_comm_fn)(void* user, int op, long long count, void* stream);
+int pad_plan_create_slab(pad_plan** plan, const double* box_host, const int* global_shape_host, int device,
+                         int rank, int world, void* send_buf, void* recv_buf, double* comm_scratch,
+                         pad_comm_fn fn, void* user);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
 size_t pad_plan_workspace_bytes(const pad_plan* plan);
 

@@ -17,6 +17,8 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
 _dbl = ctypes.c_double
+# pad_comm_fn (include/professad_b200.h): int fn(void* user, int op, long long count, void* stream)
+COMM_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p)
 
 # name -> (restype, argtypes); must list every symbol include/professad_b200.h declares
 SIGNATURES = {
@@ -25,6 +27,7 @@ SIGNATURES = {
     'pad_launch_count': (ctypes.c_ulonglong, []),
     'pad_fft_exec_count': (ctypes.c_ulonglong, []),
     'pad_plan_create': (_int, [ctypes.POINTER(_vp), _c_double_p, ctypes.POINTER(_int), _int]),
+    'pad_plan_create_slab': (_int, [ctypes.POINTER(_vp), ctypes.POINTER(_dbl), ctypes.POINTER(_int), _int, _int, _int, _vp, _vp, _vp, COMM_FN, _vp]),
     'pad_plan_destroy': (_int, [_vp]),
     'pad_plan_set_box': (_int, [_vp, _c_double_p]),
     'pad_plan_workspace_bytes': (ctypes.c_size_t, [_vp]),
@@ -175,10 +178,15 @@ def box_to_host(box_vecs):
 
 
 def get_plan(box_vecs, den):
-    """Plan for (den.shape, den.device), with its lattice updated to ``box_vecs``."""
+    """Plan for (den.shape, den.device), with its lattice updated to ``box_vecs``.  Inside a
+    ``parallel.slab(...)`` context: the rank's slab plan of the global grid."""
     require_cuda(den)
     if den.dim() != 3:
         raise ValueError('den must be a 3-D grid')
+    from . import parallel
+    ctx = parallel.current()
+    if ctx is not None:
+        return ctx.plan_for(box_vecs, den)
     dev = den.device.index if den.device.index is not None else torch.cuda.current_device()
     key = (tuple(den.shape), dev)
     host = box_to_host(box_vecs)

@@ -57,6 +57,8 @@ struct KGeom {
     double b[9];             // reciprocal lattice, rows = b_i = 2 pi inv(box^T)[i]
     double inv_n;            // 1 / (n0 n1 n2): cuFFT transforms are unnormalised
     int nzp_pad;             // padded row length (complex) of the fused-pipeline spectra: n2/2 + 8
+    int n1_loc, j1_off;      // half-spectrum rows held by this plan: (n0, n1_loc, nzh), j1 = local index + j1_off
+                             // (single-GPU plans: n1_loc = n1, j1_off = 0; slab plans: the rank's y range)
 };
 
 struct KPoint {
@@ -94,8 +96,8 @@ __device__ __forceinline__ KPoint make_kpoint_at(const KGeom& g, int j0, int j1,
 __device__ __forceinline__ KPoint make_kpoint(const KGeom& g, uint32_t idx) {
     const uint32_t row = idx / (uint32_t)g.nzh;
     const int j2 = (int)(idx - row * (uint32_t)g.nzh);
-    const int j0 = (int)(row / (uint32_t)g.n1);
-    const int j1 = (int)(row - (uint32_t)j0 * (uint32_t)g.n1);
+    const int j0 = (int)(row / (uint32_t)g.n1_loc);
+    const int j1 = (int)(row - (uint32_t)j0 * (uint32_t)g.n1_loc) + g.j1_off;
     return make_kpoint_at(g, j0, j1, j2);
 }
 
@@ -212,6 +214,16 @@ struct pad_plan {
     cudaStream_t xy_stream;
     cufftDoubleComplex* zbuf[4];
     size_t bytes_allocated;
+    // slab decomposition over `world` ranks (plan.cu, "slab plans"): real space is split along axis 0
+    // (n0_loc planes per rank), reciprocal space along axis 1 (n1_loc rows per rank, all of axis 0).
+    // N and Nk above are then the LOCAL point counts; dV, vol, geom.inv_n stay global.
+    bool dist;
+    int rank, world, n0_loc, n1_loc;
+    cufftHandle d2z_yz, z2d_yz, z2z_x;
+    void *send_buf, *recv_buf;   // Nk complex each, owned by the caller
+    double* comm_scratch;        // PAD_COMM_SCRATCH doubles, owned by the caller
+    pad_comm_fn comm_fn;
+    void* comm_user;
 };
 
 // scalar slots (device doubles in plan->scal)

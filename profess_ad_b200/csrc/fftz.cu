@@ -547,7 +547,7 @@ struct MixScale {                      // plain 1/N (round-trip tests)
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 
-bool fast_shape(const pad_plan* p) { return p->n2 == 128 || p->n2 == 256; }
+bool fast_shape(const pad_plan* p) { return !p->dist && (p->n2 == 128 || p->n2 == 256); }
 
 // dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16)}
 #define ZDISPATCH(p, CALL)                                             \

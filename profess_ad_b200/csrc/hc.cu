@@ -172,6 +172,7 @@ __device__ __forceinline__ NodeWeights node_weights(const double* __restrict__ x
 extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa,
                            int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out,
                            int accumulate, int* n_nodes_out, void* stream) {
+    if (p && p->dist) { pad_set_error("pad_eval_hc: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !den || !table_dev) { pad_set_error("pad_eval_hc: null argument"); return PAD_ERR_ARG; }
     if (variant != 0 && variant != 1) { pad_set_error("pad_eval_hc: variant must be 0 (HC) or 1 (revHC)"); return PAD_ERR_ARG; }
     if (n_eta < 3) { pad_set_error("pad_eval_hc: kernel table too short"); return PAD_ERR_ARG; }

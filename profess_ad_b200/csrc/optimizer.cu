@@ -436,6 +436,7 @@ static void finalize_sums(pad_plan* p, cudaStream_t s, int nterms, double* sums_
 }
 
 extern "C" int pad_chi_to_density(pad_plan* p, const double* chi, double n_elec, double* den_out, void* stream) {
+    if (p && p->dist) { pad_set_error("pad_chi_to_density: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !chi || !den_out) { pad_set_error("pad_chi_to_density: null argument"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -508,6 +509,7 @@ __global__ void k_pack_stats(const double* partials_sums, const unsigned long lo
 
 extern "C" int pad_chi_project(pad_plan* p, const double* chi, const double* den, const double* v, double n_elec,
                                double* grad_out, double* stats_out, void* stream) {
+    if (p && p->dist) { pad_set_error("pad_chi_project: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !chi || !den || !v || !grad_out) { pad_set_error("pad_chi_project: null argument"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -544,6 +546,7 @@ struct pad_denopt {
 };
 
 extern "C" int pad_denopt_create(pad_denopt** out, pad_plan* plan, const pad_terms* terms, const pad_denopt_params* prm) {
+    if (plan && plan->dist) { pad_set_error("pad_denopt_create: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!out || !plan || !terms || !prm) { pad_set_error("pad_denopt_create: null argument"); return PAD_ERR_ARG; }
     if (prm->method != 0 && prm->method != 1) { pad_set_error("pad_denopt_create: method must be 0 (LBFGS) or 1 (TPGD)"); return PAD_ERR_ARG; }
     if (prm->history < 1 || prm->history > OPT_M) { pad_set_error("pad_denopt_create: history must be in 1..%d", OPT_M); return PAD_ERR_ARG; }

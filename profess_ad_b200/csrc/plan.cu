@@ -131,18 +131,22 @@ static int set_box(pad_plan* p, const double* box) {
     memcpy(p->box, box, sizeof(double) * 9);
     for (int k = 0; k < 9; ++k) p->recip[k] = 2.0 * kPi * inv[k];
     p->vol = fabs(det);
-    p->dV = p->vol / (double)p->N;
+    const double n_global = (double)p->n0 * (double)p->n1 * (double)p->n2;      // p->N is the local count on slab plans
+    p->dV = p->vol / n_global;
     KGeom& g = p->geom;
     g.n0 = p->n0; g.n1 = p->n1; g.n2 = p->n2; g.nzh = p->nzh;
     g.e0 = (p->n0 % 2 == 0); g.e1 = (p->n1 % 2 == 0); g.e2 = (p->n2 % 2 == 0);
     memcpy(g.b, p->recip, sizeof(double) * 9);
-    g.inv_n = 1.0 / (double)p->N;
+    g.inv_n = 1.0 / n_global;
     g.nzp_pad = p->n2 / 2 + 8;
+    g.n1_loc = p->dist ? p->n1_loc : p->n1;
+    g.j1_off = p->dist ? p->rank * p->n1_loc : 0;
     p->box_generation++;
     return PAD_OK;
 }
 
-extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* shape, int device) {
+static int plan_create_common(pad_plan** out, const double* box, const int* shape, int device, int rank, int world,
+                              void* send_buf, void* recv_buf, double* comm_scratch, pad_comm_fn fn, void* user) {
     if (!out || !box || !shape) {
         pad_set_error("pad_plan_create: null argument");
         return PAD_ERR_ARG;
@@ -150,6 +154,18 @@ extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* sha
     if (shape[0] < 1 || shape[1] < 1 || shape[2] < 1) {
         pad_set_error("pad_plan_create: bad shape (%d,%d,%d)", shape[0], shape[1], shape[2]);
         return PAD_ERR_ARG;
+    }
+    const bool dist = world > 0;
+    if (dist) {
+        if (rank < 0 || rank >= world || !send_buf || !recv_buf || !comm_scratch || !fn) {
+            pad_set_error("pad_plan_create_slab: bad rank/world (%d/%d) or null buffer / callback", rank, world);
+            return PAD_ERR_ARG;
+        }
+        if (shape[0] % world || shape[1] % world) {
+            pad_set_error("pad_plan_create_slab: n0 = %d and n1 = %d must be multiples of the world size %d",
+                          shape[0], shape[1], world);
+            return PAD_ERR_ARG;
+        }
     }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -162,8 +178,18 @@ extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* sha
     pad_plan* p = new pad_plan();
     memset(p, 0, sizeof(pad_plan));
     p->n0 = shape[0]; p->n1 = shape[1]; p->n2 = shape[2]; p->nzh = shape[2] / 2 + 1;
-    p->N = (size_t)p->n0 * p->n1 * p->n2;
-    p->Nk = (size_t)p->n0 * p->n1 * p->nzh;
+    p->dist = dist;
+    if (dist) {
+        p->rank = rank; p->world = world;
+        p->n0_loc = p->n0 / world; p->n1_loc = p->n1 / world;
+        p->send_buf = send_buf; p->recv_buf = recv_buf; p->comm_scratch = comm_scratch;
+        p->comm_fn = fn; p->comm_user = user;
+        p->N = (size_t)p->n0_loc * p->n1 * p->n2;
+        p->Nk = (size_t)p->n0 * p->n1_loc * p->nzh;
+    } else {
+        p->N = (size_t)p->n0 * p->n1 * p->n2;
+        p->Nk = (size_t)p->n0 * p->n1 * p->nzh;
+    }
     p->device = device;
     p->nzp = p->n2 / 2 + 8;      // padded row length of the fused pipeline (multiple of 8 complex)
     if (p->Nk >= 0xffffffffull) {
@@ -181,6 +207,17 @@ extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* sha
     return PAD_OK;
 }
 
+extern "C" int pad_plan_create(pad_plan** out, const double* box, const int* shape, int device) {
+    return plan_create_common(out, box, shape, device, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int pad_plan_create_slab(pad_plan** out, const double* box, const int* global_shape, int device, int rank,
+                                    int world, void* send_buf, void* recv_buf, double* comm_scratch, pad_comm_fn fn,
+                                    void* user) {
+    if (world < 1) { pad_set_error("pad_plan_create_slab: world must be >= 1"); return PAD_ERR_ARG; }
+    return plan_create_common(out, box, global_shape, device, rank, world, send_buf, recv_buf, comm_scratch, fn, user);
+}
+
 extern "C" int pad_plan_set_box(pad_plan* p, const double* box) {
     if (!p || !box) { pad_set_error("pad_plan_set_box: null argument"); return PAD_ERR_ARG; }
     return set_box(p, box);
@@ -191,7 +228,8 @@ extern "C" size_t pad_plan_workspace_bytes(const pad_plan* p) { return p ? p->by
 extern "C" int pad_plan_destroy(pad_plan* p) {
     if (!p) return PAD_OK;
     cudaSetDevice(p->device);
-    if (p->fft_ready) { cufftDestroy(p->d2z); cufftDestroy(p->z2d); }
+    if (p->fft_ready && !p->dist) { cufftDestroy(p->d2z); cufftDestroy(p->z2d); }
+    if (p->fft_ready && p->dist) { cufftDestroy(p->d2z_yz); cufftDestroy(p->z2d_yz); cufftDestroy(p->z2z_x); }
     if (p->fft_work) cudaFree(p->fft_work);
     for (int i = 0; i < PAD_N_RBUF; ++i) if (p->rbuf[i]) cudaFree(p->rbuf[i]);
     for (int i = 0; i < PAD_N_CBUF; ++i) if (p->cbuf[i]) cudaFree(p->cbuf[i]);
@@ -257,7 +295,98 @@ static int ensure_fft(pad_plan* p, cudaStream_t s) {
     return PAD_OK;
 }
 
+// ---- slab plans: 3-D transform = batched 2-D (y, z) cuFFT + all-to-all + strided 1-D (x) cuFFT ------------
+static int ensure_fft_slab(pad_plan* p, cudaStream_t s) {
+    if (!p->fft_ready) {
+        size_t w[3] = {0, 0, 0};
+        PAD_CUFFT(cufftCreate(&p->d2z_yz));
+        PAD_CUFFT(cufftCreate(&p->z2d_yz));
+        PAD_CUFFT(cufftCreate(&p->z2z_x));
+        PAD_CUFFT(cufftSetAutoAllocation(p->d2z_yz, 0));
+        PAD_CUFFT(cufftSetAutoAllocation(p->z2d_yz, 0));
+        PAD_CUFFT(cufftSetAutoAllocation(p->z2z_x, 0));
+        int nyz[2] = {p->n1, p->n2};
+        PAD_CUFFT(cufftMakePlanMany(p->d2z_yz, 2, nyz, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, p->n0_loc, &w[0]));
+        PAD_CUFFT(cufftMakePlanMany(p->z2d_yz, 2, nyz, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, p->n0_loc, &w[1]));
+        int nx[1] = {p->n0};
+        const int lines = p->n1_loc * p->nzh;             // (n0, n1_loc, nzh): x has stride `lines`, lines are contiguous
+        PAD_CUFFT(cufftMakePlanMany(p->z2z_x, 1, nx, nx, lines, 1, nx, lines, 1, CUFFT_Z2Z, lines, &w[2]));
+        size_t wmax = w[0] > w[1] ? w[0] : w[1];
+        if (w[2] > wmax) wmax = w[2];
+        if (wmax > 0) {
+            PAD_CUDA(cudaMalloc(&p->fft_work, wmax));
+            p->bytes_allocated += wmax;
+        }
+        p->fft_work_bytes = wmax;
+        PAD_CUFFT(cufftSetWorkArea(p->d2z_yz, p->fft_work));
+        PAD_CUFFT(cufftSetWorkArea(p->z2d_yz, p->fft_work));
+        PAD_CUFFT(cufftSetWorkArea(p->z2z_x, p->fft_work));
+        p->fft_ready = true;
+        p->fft_stream = (cudaStream_t)(-1);
+    }
+    if (p->fft_stream != s) {
+        PAD_CUFFT(cufftSetStream(p->d2z_yz, s));
+        PAD_CUFFT(cufftSetStream(p->z2d_yz, s));
+        PAD_CUFFT(cufftSetStream(p->z2z_x, s));
+        p->fft_stream = s;
+    }
+    return PAD_OK;
+}
+
+// (n0_loc, n1, nzh) <-> (world, n0_loc, n1_loc, nzh): block r holds the y range of rank r
+__global__ void __launch_bounds__(PAD_THREADS) slab_permute_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                                   int n0_loc, int n1, int n1_loc, int nzh, int to_blocks) {
+    const size_t total = (size_t)n0_loc * n1 * nzh;
+    for (size_t e = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * PAD_THREADS) {
+        const int k = (int)(e % nzh);
+        const size_t row = e / nzh;
+        const int j = (int)(row % n1);
+        const int i = (int)(row / n1);
+        const int r = j / n1_loc, jl = j - r * n1_loc;
+        const size_t blocked = (((size_t)r * n0_loc + i) * n1_loc + jl) * nzh + k;
+        if (to_blocks) dst[blocked] = src[e];
+        else dst[e] = src[blocked];
+    }
+}
+
+static int slab_comm(pad_plan* p, int op, long long count, cudaStream_t s) {
+    const int rc = p->comm_fn(p->comm_user, op, count, (void*)s);
+    if (rc != 0) {
+        pad_set_error("slab plan: the communication callback failed (op %d, rc %d)", op, rc);
+        return PAD_ERR_NCCL;
+    }
+    return PAD_OK;
+}
+
+static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s) {
+    PAD_TRY(ensure_fft_slab(p, s));
+    PAD_CUFFT(cufftExecD2Z(p->d2z_yz, const_cast<double*>(in), out));                       // (n0_loc, n1, nzh)
+    slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(out),
+        reinterpret_cast<double2*>(p->send_buf), p->n0_loc, p->n1, p->n1_loc, p->nzh, 1);
+    PAD_CUDA(cudaGetLastError());
+    PAD_TRY(slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (n0, n1_loc, nzh)
+    PAD_CUFFT(cufftExecZ2Z(p->z2z_x, reinterpret_cast<cufftDoubleComplex*>(p->recv_buf), out, CUFFT_FORWARD));
+    g_pad_fft_execs += 2;
+    ++g_pad_launches;
+    return PAD_OK;
+}
+
+static int fft_inverse_slab(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
+    PAD_TRY(ensure_fft_slab(p, s));
+    // x inverse into the send buffer: (n0, n1_loc, nzh) is already blocked by x range
+    PAD_CUFFT(cufftExecZ2Z(p->z2z_x, in, reinterpret_cast<cufftDoubleComplex*>(p->send_buf), CUFFT_INVERSE));
+    PAD_TRY(slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (world, n0_loc, n1_loc, nzh)
+    slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(p->recv_buf),
+        reinterpret_cast<double2*>(in), p->n0_loc, p->n1, p->n1_loc, p->nzh, 0);
+    PAD_CUDA(cudaGetLastError());
+    PAD_CUFFT(cufftExecZ2D(p->z2d_yz, in, out));
+    g_pad_fft_execs += 2;
+    ++g_pad_launches;
+    return PAD_OK;
+}
+
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s) {
+    if (p->dist) return fft_forward_slab(p, in, out, s);
     PAD_TRY(ensure_fft(p, s));
     PAD_CUFFT(cufftExecD2Z(p->d2z, const_cast<double*>(in), out));
     ++g_pad_fft_execs;
@@ -265,6 +394,7 @@ int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cuda
 }
 
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
+    if (p->dist) return fft_inverse_slab(p, in, out, s);
     PAD_TRY(ensure_fft(p, s));
     PAD_CUFFT(cufftExecZ2D(p->z2d, in, out));
     ++g_pad_fft_execs;
@@ -301,7 +431,27 @@ __global__ void __launch_bounds__(PAD_THREADS) finalize_kernel(const double* __r
     }
 }
 
+// slab plans: the raw sums go through the caller's all-reduce before they are combined
+__global__ void finalize_apply_kernel(const double* __restrict__ totals, FinalizeArgs a) {
+    double e = 0.0;
+    for (int t = 0; t < a.nterms; ++t) {
+        if (a.sums_out) a.sums_out[t] = totals[t];
+        e += a.coef[t] * totals[t];
+    }
+    if (a.E_out) a.E_out[0] = (a.accumulate ? a.E_out[0] : 0.0) + e;
+}
+
 void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s) {
-    finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, a);
-    ++g_pad_launches;
+    if (!p->dist) {
+        finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, a);
+        ++g_pad_launches;
+        return;
+    }
+    FinalizeArgs raw = a;
+    raw.sums_out = p->comm_scratch;
+    raw.E_out = nullptr;
+    finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, raw);
+    if (slab_comm(p, PAD_COMM_ALL_REDUCE, a.nterms, s) != PAD_OK) return;      // error text is set; the caller's next CUDA check reports
+    finalize_apply_kernel<<<1, 1, 0, s>>>(p->comm_scratch, a);
+    g_pad_launches += 2;
 }

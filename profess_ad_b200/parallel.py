@@ -1,0 +1,221 @@
+"""One large grid over several GPUs: slab-decomposed evaluation of the native functionals.
+
+Real space is split along axis 0 (each rank holds ``n0 / world`` planes of the density), the half
+spectrum along axis 1.  Every 3-D transform inside the C library becomes a local batched 2-D (y, z)
+cuFFT, ONE all-to-all and a local strided 1-D (x) cuFFT (``csrc/plan.cu``, "slab plans"); energies and
+the scalars the functionals need mid-evaluation (sum of n for n0 / n_ref) are all-reduced.  The library
+itself does not link a communication library: it calls back into this module, which uses
+``torch.distributed`` (NCCL over NVLink / NVSwitch) on the caller's current stream.
+
+Usage (one process per GPU, ``torch.distributed`` initialised, the same script on every rank)::
+
+    from profess_ad_b200 import parallel
+    from profess_ad_b200.functionals import WangGovindCarter99, Hartree
+    with parallel.slab(global_shape=(512, 512, 512)):
+        den_local = parallel.local_slab(den_global)            # (n0 / world, n1, n2), or build it locally
+        den_local.requires_grad_(True)
+        E = WangGovindCarter99().forward(box_vecs, den_local)  # the GLOBAL energy, identical on every rank
+        (g,) = torch.autograd.grad(E, den_local)               # this rank's slab of dE/dn * dV
+
+Inside the context the ordinary functional callables take LOCAL slabs.  Not available on slabs yet:
+HuangCarter, the device-resident optimiser (System.optimize_density) -- they raise.
+
+There is no analogue in the reference (single process).
+"""
+import contextlib
+import ctypes
+import threading
+
+import torch
+
+from . import _native
+
+_COMM_FN = _native.COMM_FN
+COMM_SCRATCH = 16
+_state = threading.local()
+
+
+class TorchDistComm:
+    """Communication through ``torch.distributed`` (backend nccl for CUDA tensors)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_to_all(self, recv, send):
+        self.dist.all_to_all_single(recv, send, group=self.group)
+
+    def all_reduce(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+
+class SingleComm:
+    """world = 1: the exchange is a copy (exercises the slab code path on one GPU)."""
+    rank, world = 0, 1
+
+    def all_to_all(self, recv, send):
+        recv.copy_(send)
+
+    def all_reduce(self, t):
+        pass
+
+
+class ThreadComm:
+    """`world` ranks as threads of ONE process sharing one GPU -- a test double for NCCL.
+
+    Every rank runs its evaluation in its own thread and its own CUDA stream; the collectives meet at a
+    ``threading.Barrier`` after synchronising the streams.  Used by tests/test_gpu_parallel.py to check
+    world = 2, 4 slab results on the single-GPU test box."""
+
+    class Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.send = [None] * world
+            self.vals = [None] * world
+
+    def __init__(self, shared, rank):
+        self.shared, self.rank, self.world = shared, rank, shared.world
+
+    def all_to_all(self, recv, send):
+        sh = self.shared
+        torch.cuda.current_stream(send.device).synchronize()
+        sh.send[self.rank] = send
+        sh.barrier.wait()
+        n = send.numel() // self.world
+        for r in range(self.world):
+            recv[r * n:(r + 1) * n].copy_(sh.send[r][self.rank * n:(self.rank + 1) * n])
+        torch.cuda.current_stream(send.device).synchronize()
+        sh.barrier.wait()
+
+    def all_reduce(self, t):
+        sh = self.shared
+        torch.cuda.current_stream(t.device).synchronize()
+        sh.vals[self.rank] = t.clone()
+        sh.barrier.wait()
+        total = sh.vals[0].clone()
+        for r in range(1, self.world):      # fixed order: every rank gets bit-identical sums
+            total += sh.vals[r]
+        sh.barrier.wait()
+        t.copy_(total)
+
+
+class SlabPlan(_native.Plan):
+    """``pad_plan`` for this rank's slab of a global grid."""
+
+    def __init__(self, box_host, global_shape, device_index, comm):
+        self.lib = _native.load_library()
+        self.comm = comm
+        self.global_shape = tuple(int(s) for s in global_shape)
+        n0, n1, n2 = self.global_shape
+        if n0 % comm.world or n1 % comm.world:
+            raise ValueError(f'slab decomposition needs n0 = {n0} and n1 = {n1} to be multiples of the world size {comm.world}')
+        self.shape = (n0 // comm.world, n1, n2)                  # the local real-space slab
+        self.device_index = device_index
+        dev = torch.device('cuda', device_index)
+        nk_loc = n0 * (n1 // comm.world) * (n2 // 2 + 1)
+        self.send = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+        self.recv = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+        self.scratch = torch.zeros(COMM_SCRATCH, dtype=torch.double, device=dev)
+        self.error = None
+
+        def callback(_user, op, count, _stream):
+            try:
+                if op == 0:
+                    self.comm.all_to_all(self.recv, self.send)
+                else:
+                    self.comm.all_reduce(self.scratch[:count])
+                return 0
+            except BaseException as e:      # noqa: BLE001 -- must not propagate through the C frame
+                self.error = e
+                return 1
+
+        self._callback = _COMM_FN(callback)                      # keep alive as long as the plan
+        self.handle = ctypes.c_void_p()
+        self.box = None
+        box_arr = (ctypes.c_double * 9)(*box_host)
+        shp = (ctypes.c_int * 3)(*self.global_shape)
+        _native.check(self.lib.pad_plan_create_slab(ctypes.byref(self.handle), box_arr, shp, device_index, comm.rank,
+                                                    comm.world, _native.ptr(self.send), _native.ptr(self.recv),
+                                                    _native.ptr(self.scratch), self._callback, None))
+        self.box = tuple(box_host)
+        self._set_geometry()
+
+    def _set_geometry(self):
+        super()._set_geometry()
+        n0, n1, n2 = self.global_shape
+        self.npts = n0 * n1 * n2                                 # dV is the GLOBAL volume element
+        self.dV = self.vol / self.npts
+
+
+class _SlabContext:
+    def __init__(self, global_shape, comm):
+        self.global_shape = tuple(int(s) for s in global_shape)
+        self.comm = comm
+        self.plans = {}
+
+    @property
+    def local_shape(self):
+        n0, n1, n2 = self.global_shape
+        return (n0 // self.comm.world, n1, n2)
+
+    def plan_for(self, box_vecs, den):
+        if tuple(den.shape) != self.local_shape:
+            raise ValueError(f'inside parallel.slab(global_shape={self.global_shape}) rank {self.comm.rank} of '
+                             f'{self.comm.world} expects a density slab of shape {self.local_shape}, got {tuple(den.shape)}')
+        dev = den.device.index if den.device.index is not None else torch.cuda.current_device()
+        host = _native.box_to_host(box_vecs)
+        plan = self.plans.get(dev)
+        if plan is None:
+            plan = SlabPlan(host, self.global_shape, dev, self.comm)
+            self.plans[dev] = plan
+        else:
+            plan.set_box(host)
+        return plan
+
+    def close(self):
+        for p in self.plans.values():
+            p.close()
+        self.plans.clear()
+
+
+def current():
+    """The active slab context of this thread, or None."""
+    return getattr(_state, 'ctx', None)
+
+
+@contextlib.contextmanager
+def slab(global_shape, comm=None, group=None):
+    """Evaluate native functionals on this rank's slab of a ``global_shape`` grid (see the module docstring)."""
+    if comm is None:
+        import torch.distributed as dist
+        comm = TorchDistComm(group) if dist.is_available() and dist.is_initialized() else SingleComm()
+    ctx = _SlabContext(global_shape, comm)
+    prev = current()
+    _state.ctx = ctx
+    try:
+        yield ctx
+    finally:
+        _state.ctx = prev
+        ctx.close()
+
+
+def slab_bounds(n0, rank, world):
+    """[lo, hi) planes of axis 0 owned by ``rank``."""
+    if n0 % world:
+        raise ValueError(f'n0 = {n0} is not a multiple of the world size {world}')
+    m = n0 // world
+    return rank * m, (rank + 1) * m
+
+
+def local_slab(field_global, comm=None):
+    """This rank's contiguous slab (a copy) of a full (n0, n1, n2) field."""
+    ctx = current()
+    comm = comm or (ctx.comm if ctx else None)
+    if comm is None:
+        raise RuntimeError('local_slab needs an active parallel.slab(...) context or an explicit comm')
+    lo, hi = slab_bounds(field_global.shape[0], comm.rank, comm.world)
+    return field_global[lo:hi].contiguous()
