@@ -8,10 +8,11 @@ import math
 import torch
 
 
-def smooth_supercell(n, side, device='cpu'):
+def smooth_supercell(n, side, device='cpu', x_range=None):
     """(box_vecs, den): cubic cell of side*a (a = 4.05 A in bohr), 4*side^3 Al atoms, 3 e-/atom, n^3 grid.
 
     den = n0 (1 + 0.3 cos(kX) cos(kY) cos(kZ) + 0.05 cos(2kX) cos(2kY)), k = 2 pi side, x = i / n.
+    ``x_range=(lo, hi)`` returns only the planes lo <= i < hi of axis 0 (a rank's slab, see parallel.py).
     """
     dt = torch.double
     a = 4.05 / 0.529177210903
@@ -21,6 +22,8 @@ def smooth_supercell(n, side, device='cpu'):
     k = 2 * math.pi * side
     c1, c2 = torch.cos(k * x), torch.cos(2 * k * x)
     n0 = 12 * side ** 3 / L ** 3
-    den = n0 * (1 + 0.3 * c1[:, None, None] * c1[None, :, None] * c1[None, None, :]
-                + 0.05 * (c2[:, None, None] * c2[None, :, None]).expand(n, n, n))
+    lo, hi = x_range if x_range is not None else (0, n)
+    c1x, c2x = c1[lo:hi], c2[lo:hi]
+    den = n0 * (1 + 0.3 * c1x[:, None, None] * c1[None, :, None] * c1[None, None, :]
+                + 0.05 * (c2x[:, None, None] * c2[None, :, None]).expand(hi - lo, n, n))
     return box, den.contiguous()
