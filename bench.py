@@ -133,24 +133,24 @@ def dist_env():
 #  CPU reference arm / cpu_baseline
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, sample_grid=None):
-    """Oracle port of WangGovindCarter99 E+V on the host cores.  A step at 256^3 costs ~12 s on 8
-    cores (+ ~20 s one-off kernel build), so the run uses a bounded sample: the same synthetic
-    supercell on a 128^3 grid, converted to the 256^3 unit by the N log N work ratio."""
+    """Oracle port of WangGovindCarter99 E+V (the reference algorithm: torch CPU fp64, autograd potential, all host
+    threads) on the SAME 256^3 workload.  Bounded sample: at most 5 timed evaluations (about 1 s each on 16
+    threads) after one warm-up that also builds and caches the kernel (~10-20 s, not timed, as on the GPU)."""
     import torch
     from oracle import ofdft_oracle as orc
     cores = torch.get_num_threads()
-    n = sample_grid or (GRID if (steps + warmup) <= 4 else min(GRID, 128))
+    n = sample_grid or GRID
+    n_timed = max(1, min(steps, 5))
     box, den = orc.synth_smooth(n, SIDE)
     wgc = orc.WangGovindCarter99()
-    for _ in range(max(1, warmup)):
-        orc.energy_and_potential(box, den, wgc)
+    orc.energy_and_potential(box, den, wgc)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(n_timed):
         orc.energy_and_potential(box, den, wgc)
-    dt = (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / n_timed
     scale = (GRID ** 3 * math.log2(GRID ** 3)) / (n ** 3 * math.log2(n ** 3))
     sec_per_eval = dt * scale
-    sample = (f'{steps} evals (+{max(1, warmup)} warm-up, kernel cached) of the oracle port at {n}^3 on {cores} threads'
+    sample = (f'{n_timed} evals (+1 warm-up, kernel cached) of the oracle port at {n}^3 on {cores} threads'
               + ('' if n == GRID else f', scaled x{scale:.2f} (N log N) to {GRID}^3'))
     return 1.0 / sec_per_eval, sec_per_eval * 1e3, cores, sample
 
@@ -343,12 +343,47 @@ def run_gpu(args):
                 'stage': dom['stage'], 'ms_per_eval': dom['ms_per_eval'], 'achieved': dom['GBps'],
                 'frac': (dom['GBps'] / peak) if dom['GBps'] else None,
                 'note': 'CUDA events on the launch stream around this stage, mean of 5 evaluations'}
+        if world == 1 and not args.no_denopt:
+            line['density_optimization'] = density_optimization_leg(dev)
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores, sample = cpu_reference_run(3, 1, sample_grid=min(GRID, 128))
+            v, ms, cores, sample = cpu_reference_run(3, 1)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def density_optimization_leg(dev):
+    """BASELINE.json metric 2, "s per density optimisation": System.optimize_density(ntol=1e-7, LBFGS, from uniform)
+    for a 256-atom fcc Al supercell with [IonElectron, Hartree, WangGovindCarter99, PerdewZunger] and the
+    tests/potentials/al.gga.recpot local pseudopotential; wall clock around the public call, second of two runs."""
+    import torch
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.synthetic import fcc_supercell
+    from profess_ad_b200.system import System
+    pot = os.path.join(ROOT, 'tests', 'potentials', 'al.gga.recpot')
+    out = []
+    for grid in (128, 256):
+        try:
+            box, frac = fcc_supercell(4)
+            terms = [F.IonElectron, F.Hartree, F.WangGovindCarter99().forward, F.PerdewZunger]
+            s = System(box, (grid,) * 3, [['Al', pot, frac]], terms, units='b', coord_type='fractional', device=dev)
+            dt = None
+            for _ in range(2):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                s.optimize_density(ntol=1e-7, n_method='LBFGS', from_uniform=True)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+            info = s.last_optimization
+            out.append({'workload': f'Al 256-atom fcc supercell, {grid}^3 grid, IonElectron + Hartree + WGC99 + PZ',
+                        'seconds': dt, 'iterations': info.get('iterations'), 'closures': info.get('closures'),
+                        'converged': bool(info.get('converged')), 'energy_eV_per_atom': s.energy('eV') / 256,
+                        'optimizer': 'device-resident L-BFGS' if info.get('native') else 'host-driven L-BFGS'})
+            del s
+        except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
+            out.append({'workload': f'{grid}^3', 'error': repr(e)})
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -427,6 +462,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-denopt', action='store_true', help='skip the density-optimisation timing leg')
     ap.add_argument('--slab-grid', type=int, default=0,
                     help='strong-scaling mode: ONE n^3 grid slab-decomposed over the --gpus ranks (e.g. 512)')
     args = ap.parse_args()

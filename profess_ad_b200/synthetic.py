@@ -27,3 +27,14 @@ def smooth_supercell(n, side, device='cpu', x_range=None):
     den = n0 * (1 + 0.3 * c1x[:, None, None] * c1[None, :, None] * c1[None, None, :]
                 + 0.05 * (c2x[:, None, None] * c2[None, :, None]).expand(hi - lo, n, n))
     return box, den.contiguous()
+
+
+def fcc_supercell(side, a_angstrom=4.05):
+    """(box_vecs in bohr, fractional coordinates): side^3 conventional fcc cells, 4 side^3 atoms."""
+    dt = torch.double
+    a = a_angstrom / 0.529177210903
+    basis = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.5]], dtype=dt)
+    r = torch.arange(side, dtype=dt)
+    cells = torch.stack(torch.meshgrid(r, r, r, indexing='ij'), dim=-1).reshape(-1, 1, 3)
+    frac = ((cells + basis[None]) / side).reshape(-1, 3)
+    return side * a * torch.eye(3, dtype=dt), frac
