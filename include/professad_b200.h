@@ -82,12 +82,15 @@ int pad_plan_destroy(pad_plan* plan);
  *        op == PAD_COMM_ALL_TO_ALL : exchange send_buf -> recv_buf, `count` complex128 per peer (peer r's block
  *                                    is send_buf[r * count ...]; block r of recv_buf comes from peer r)
  *        op == PAD_COMM_ALL_REDUCE : sum comm_scratch[0 .. count) over the ranks, in place
+ *        op == PAD_COMM_ALL_REDUCE_MAX : maximum of comm_scratch[0 .. count) over the ranks, in place
  *      and return 0.  Python binds it to torch.distributed (NCCL over NVLink).  Every functional entry point
- *      below then takes LOCAL slabs (den, v: n0/world x n1 x n2) and returns GLOBAL energies on every rank.
- *      Not available on slab plans: the fused FFT pipeline, pad_eval_hc, pad_denopt_*, pad_chi_project. ---- */
+ *      below then takes LOCAL slabs (den, v: n0/world x n1 x n2) and returns GLOBAL energies on every rank;
+ *      pad_denopt_* keeps each rank's slab of chi, the gradient and the L-BFGS history and all-reduces the
+ *      inner products of an iteration in one batch.  Not available on slab plans: the fused FFT pipeline. ---- */
 #define PAD_COMM_ALL_TO_ALL 0
 #define PAD_COMM_ALL_REDUCE 1
-#define PAD_COMM_SCRATCH 16
+#define PAD_COMM_ALL_REDUCE_MAX 2
+#define PAD_COMM_SCRATCH 64
 typedef int (*pad_comm_fn)(void* user, int op, long long count, void* stream);
 int pad_plan_create_slab(pad_plan** plan, const double* box_host, const int* global_shape_host, int device,
                          int rank, int world, void* send_buf, void* recv_buf, double* comm_scratch,
@@ -144,6 +147,29 @@ int pad_irfft3_fast(pad_plan* plan, double* in_cplx_padded /* destroyed */, doub
 int pad_fft_axis_fast(pad_plan* plan, double* cplx_padded, int axis, int dir, void* stream);
 /* test hook: the table-driven pow / sqrt / reciprocal of csrc/fastmath.cuh next to the CUDA library results */
 int pad_dbg_fastmath(const double* x, size_t n, double e, double* out3n, double* ref3n, void* stream);
+
+/* ---- ionic potential and ion-electron forces: replaces System.__potential_from_ions (system.py:183-205) ->
+ *      interpolate_recpot (ion_utils.py:49-81) -> lattice_sum (ion_utils.py:88-118) -> structure_factor
+ *      (ion_utils.py:121-137), and the IonElectron part of System.__compute_forces (system.py:913-925).
+ *      Exact structure factor, O(N_k N_ion) complex multiply-adds from per-ion 1-D phase tables; no N_k x N_ion
+ *      temporary.  Works on slab plans (v_ext_out is then the local slab; forces_out holds this rank's PARTIAL
+ *      sums, which the caller adds over the ranks). ---- */
+typedef struct pad_species {
+    const double* table_dev;   /* DEVICE, 2 * n_table doubles [k | v(k)]: k uniform from 0 to k_max (1/bohr), v the
+                                  tabulated local pseudopotential (Ha bohr^3) with the Coulomb tail -4 pi z / k^2
+                                  ADDED BACK (the smooth part the reference interpolates, ion_utils.py:62-66)      */
+    int n_table;
+    double k_max;
+    double z;                  /* ion charge: the tail is removed again after the interpolation                  */
+    const double* frac_dev;    /* DEVICE, n_ions x 3 fractional coordinates                                      */
+    int n_ions;
+} pad_species;
+/* v_ext(r) = irfftn(sum_s v_s(|k|) S_s(k)) / vol over the plan's grid; v_ext_out: N doubles */
+int pad_ionic_potential(pad_plan* plan, const pad_species* species, int n_species, double* v_ext_out, void* stream);
+/* F_I = -d/dR_I of IonElectron(den, v_ext[R]) at fixed density, Cartesian, Ha/bohr; forces_out: DEVICE,
+ * 3 * (total number of ions) doubles in species order */
+int pad_ion_forces(pad_plan* plan, const pad_species* species, int n_species, const double* den, double* forces_out,
+                   void* stream);
 
 /* ---- fused evaluation of a whole term list: replaces System.__compute_energy + autograd
  *      (system.py:759-772, 830-838).  E_out = sum of terms, v_out = total dE/dn. ---------------- */

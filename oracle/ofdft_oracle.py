@@ -688,6 +688,90 @@ def optimize_density(box, den0, n_elec, terms, v_ext=None, ntol=1e-7, n_conv_con
 
 
 # ----------------------------------------------------------------------------------------------
+#  ionic rows: local pseudopotential, structure factor, forces, stress
+# ----------------------------------------------------------------------------------------------
+_BOHR = 0.529177208607388                   # ion_utils.py:8-10 (the reference's own, older, constants)
+_HARTREE_TO_EV = 27.2113834279111
+_POT_CONV = 1.0 / (_BOHR ** 3 * _HARTREE_TO_EV)
+
+
+def read_recpot(path):
+    """ion_utils.py:62-75 : (k grid [1/bohr], v(k) [Ha bohr^3], ion charge) of a CASTEP .recpot file."""
+    vals = []
+    with open(path, 'r') as fh:
+        for line in fh:
+            if 'END COMMENT' in line:
+                break
+        fh.readline()
+        k_max = float(fh.readline()) * _BOHR
+        for line in fh:
+            cols = line.split()
+            if len(cols) == 3:
+                vals += cols
+    pot = np.asarray(vals, dtype=np.float64) * _POT_CONV
+    ks, dk = np.linspace(0, k_max, pot.size, retstep=True)
+    z = round((pot[1] - pot[0]) * dk * dk / (-4 * PI))
+    return ks, pot, z
+
+
+def interpolate_recpot(path, kabs):
+    """ion_utils.py:49-81 : Coulomb tail added back, cubic Hermite on min(k, k_max), tail removed for k != 0."""
+    ks, pot, z = read_recpot(path)
+    pot = pot.copy()
+    pot[1:] += 4 * PI * z / (ks[1:] * ks[1:])
+    x, y = torch.as_tensor(ks, dtype=DT), torch.as_tensor(pot, dtype=DT)
+    val = interpolate(x, y, torch.minimum(kabs, x[-1]))
+    nz = kabs != 0
+    out = val.clone()
+    out[nz] = val[nz] - 4 * PI * z / kabs[nz].pow(2)
+    return out
+
+
+def ionic_potential(box, shape, species):
+    """system.py:183-205 + ion_utils.py:88-137 (exact structure factor).  ``species`` = [(recpot path,
+    (n, 3) CARTESIAN coordinates), ...].  Differentiable w.r.t. the coordinates and the box."""
+    g = Grid(box, shape)
+    k = g.kabs                                                   # system.py:185-186 (masked sqrt: k = 0 stays 0)
+    v = torch.zeros(g.shape, dtype=DT)
+    for path, cart in species:
+        phase = (g.kvec[0].unsqueeze(-1) * cart[:, 0] + g.kvec[1].unsqueeze(-1) * cart[:, 1]
+                 + g.kvec[2].unsqueeze(-1) * cart[:, 2])
+        S = torch.complex(torch.cos(phase), -torch.sin(phase)).sum(-1)
+        v = v + torch.fft.irfftn(S * interpolate_recpot(path, k), g.shape, norm='forward') / g.vol
+    return v
+
+
+def ion_electron_forces(box, den, species):
+    """IonElectron part of system.py:913-925 : -d/dR of mean(den * v_ext[R]) * vol, by autograd."""
+    carts = [c.detach().clone().requires_grad_(True) for _, c in species]
+    v = ionic_potential(box, den.shape, [(p, c) for (p, _), c in zip(species, carts)])
+    U = IonElectron(box, den, v)
+    grads = torch.autograd.grad(U, carts)
+    return -torch.cat(grads)
+
+
+def stress(box, den, functional):
+    """functional_tools.py:73-100 : (1/vol) dF/dh h^T by autograd, with the density rescaled so that the
+    electron number is conserved under the strain."""
+    b = box.detach().clone().requires_grad_(True)
+    vol = torch.abs(torch.linalg.det(b))
+    d = den * vol.detach() / vol
+    (g,) = torch.autograd.grad(functional(b, d).reshape(()), b)
+    return (g.T @ b.detach()) / vol.detach()
+
+
+def ion_electron_stress(box, den, species_frac):
+    """IonElectron part of system.py:927-935 : ions at fixed FRACTIONAL coordinates follow the strain."""
+    b = box.detach().clone().requires_grad_(True)
+    vol = torch.abs(torch.linalg.det(b))
+    d = den * vol.detach() / vol
+    v = ionic_potential(b, den.shape, [(p, f @ b) for p, f in species_frac])
+    (g,) = torch.autograd.grad(IonElectron(b, d, v), b)
+    st = (g.T @ b.detach()) / vol.detach()
+    return 0.5 * (st + st.T)
+
+
+# ----------------------------------------------------------------------------------------------
 #  deterministic synthetic inputs (SURVEY.md section 8(d), BASELINE.md section 4)
 # ----------------------------------------------------------------------------------------------
 def synth_smooth(n, side):

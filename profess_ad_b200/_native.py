@@ -52,6 +52,9 @@ SIGNATURES = {
     'pad_laplacian': (_int, [_vp, _vp, _vp, _vp]),
     # struct pointers (pad_terms*, pad_denopt_params*, pad_denopt_result*) are passed with ctypes.byref
     'pad_eval_total': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    # pad_species* is passed as a ctypes array of _density_opt-style Structures
+    'pad_ionic_potential': (_int, [_vp, _vp, _int, _vp, _vp]),
+    'pad_ion_forces': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'pad_chi_to_density': (_int, [_vp, _vp, _dbl, _vp, _vp]),
     'pad_chi_project': (_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
     'pad_denopt_create': (_int, [ctypes.POINTER(_vp), _vp, _vp, _vp]),

@@ -214,6 +214,11 @@ struct pad_plan {
     cudaStream_t xy_stream;
     cufftDoubleComplex* zbuf[4];
     size_t bytes_allocated;
+    // ionic potential / forces (ions.cu): per-ion 1-D phase tables + table slopes, force partial sums
+    void* ion_scratch;
+    size_t ion_scratch_bytes;
+    double* ion_partial;
+    size_t ion_partial_bytes;
     // slab decomposition over `world` ranks (plan.cu, "slab plans"): real space is split along axis 0
     // (n0_loc planes per rank), reciprocal space along axis 1 (n1_loc rows per rank, all of axis 0).
     // N and Nk above are then the LOCAL point counts; dV, vol, geom.inv_n stay global.
@@ -257,3 +262,7 @@ struct FinalizeArgs {
     double* E_out;        // may be null
 };
 void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s);
+// slab plans (no-ops otherwise): combine `n` device values over the ranks, in place and ordered with `s`.
+// max: non-negative doubles held as their bit patterns (the atomicMax convention of the reduction kernels).
+int pad_allreduce_max_bits(pad_plan* p, unsigned long long* bits, int n, cudaStream_t s);
+int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s);

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "table.cuh"
 
 #define HC_MAX_NODES 512
 
@@ -30,42 +31,7 @@ constexpr double k3Pi2 = 29.608813203268074;
 constexpr double kCHC = 680.1106493955546;          // 0.3 (3 pi^2)^{2/3} * 8 * 3 pi^2
 constexpr double kCS = 0.026121172985233605;        // (1/4)(3 pi^2)^{-2/3}
 
-struct HcTable {
-    const double* eta;     // n points, uniform
-    const double* w;
-    const double* m;       // Hermite slopes (functional_tools.py:309-310)
-    int n;
-    double eta_max, inv_d;
-};
-
-__global__ void k_table_slopes(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ m, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    auto sec = [&](int j) { return (y[j + 1] - y[j]) / (x[j + 1] - x[j]); };
-    double v;
-    if (i == 0) v = sec(0);
-    else if (i == n - 1) v = sec(n - 2);
-    else v = 0.5 * (sec(i) + sec(i - 1));
-    m[i] = v;
-}
-
-__device__ __forceinline__ void hermite(double t, double& h00, double& h10, double& h01, double& h11) {
-    const double t2 = t * t, t3 = t2 * t;
-    h00 = 1.0 - 3.0 * t2 + 2.0 * t3; h10 = t - 2.0 * t2 + t3; h01 = 3.0 * t2 - 2.0 * t3; h11 = t3 - t2;
-}
-
-// omega(eta) by cubic Hermite on the uniform table; interval = searchsorted(x[1:], eta) (left)
-__device__ __forceinline__ double table_lookup(const HcTable& T, double eta) {
-    eta = fmin(eta, T.eta_max);
-    int i = (int)ceil(eta * T.inv_d) - 1;
-    i = max(0, min(i, T.n - 2));
-    while (i < T.n - 2 && T.eta[i + 1] < eta) ++i;
-    while (i > 0 && T.eta[i] >= eta) --i;
-    const double x0 = T.eta[i], dx = T.eta[i + 1] - x0;
-    double h00, h10, h01, h11;
-    hermite((eta - x0) / dx, h00, h10, h01, h11);
-    return h00 * T.w[i] + h10 * T.m[i] * dx + h01 * T.w[i + 1] + h11 * T.m[i + 1] * dx;
-}
+typedef UniformTable HcTable;
 
 __device__ __forceinline__ double kabs3(double kx, double ky, double kz) {
     const double k2 = kx * kx + ky * ky + kz * kz;
@@ -167,12 +133,33 @@ __device__ __forceinline__ NodeWeights node_weights(const double* __restrict__ x
     return r;
 }
 
+// slab plans: mm[0] holds ~bits(min xi) and mm[1] bits(max xi); both order like non-negative doubles only after the
+// complement is undone, so the exchange goes through (-min, max) as doubles
+__global__ void k_mm_pack(unsigned long long* mm, double* scratch, int to_scratch) {
+    if (to_scratch) {
+        scratch[0] = -__longlong_as_double((long long)(~mm[0]));
+        scratch[1] = __longlong_as_double((long long)mm[1]);
+    } else {
+        mm[0] = ~(unsigned long long)__double_as_longlong(-scratch[0]);
+        mm[1] = (unsigned long long)__double_as_longlong(scratch[1]);
+    }
+}
+
+int pad_allreduce_max_bits_raw(pad_plan* p, unsigned long long* mm, cudaStream_t s) {
+    if (!p->dist) return PAD_OK;
+    k_mm_pack<<<1, 1, 0, s>>>(mm, p->comm_scratch, 1);
+    PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_REDUCE_MAX, 2, s));
+    k_mm_pack<<<1, 1, 0, s>>>(mm, p->comm_scratch, 0);
+    g_pad_launches += 2;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
 }  // namespace
 
 extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa,
                            int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out,
                            int accumulate, int* n_nodes_out, void* stream) {
-    if (p && p->dist) { pad_set_error("pad_eval_hc: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !den || !table_dev) { pad_set_error("pad_eval_hc: null argument"); return PAD_ERR_ARG; }
     if (variant != 0 && variant != 1) { pad_set_error("pad_eval_hc: variant must be 0 (HC) or 1 (revHC)"); return PAD_ERR_ARG; }
     if (n_eta < 3) { pad_set_error("pad_eval_hc: kernel table too short"); return PAD_ERR_ARG; }
@@ -213,6 +200,8 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
     ++g_pad_launches;
     unsigned long long mm_h[2];
     double eta_ends[2];
+    // slab plans: the node list must be the same on every rank -> global min / max (both are maxima of bit patterns)
+    PAD_TRY(pad_allreduce_max_bits_raw(p, mm, s));
     PAD_CUDA(cudaMemcpyAsync(mm_h, mm, sizeof(mm_h), cudaMemcpyDeviceToHost, s));
     PAD_CUDA(cudaMemcpyAsync(&eta_ends[0], table_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
     PAD_CUDA(cudaMemcpyAsync(&eta_ends[1], table_dev + n_eta - 1, sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,324 @@
+// Ionic (local pseudopotential) potential and the ion-electron forces, straight from the ion positions.
+//
+// Replaces System.__potential_from_ions (system.py:183-205) -> interpolate_recpot (ion_utils.py:49-81) ->
+// lattice_sum (ion_utils.py:88-118) -> structure_factor (ion_utils.py:121-137):
+//     v_ext(r) = irfftn( sum_s v_s(|k|) S_s(k) ) / vol,      S_s(k) = sum_{I in s} exp(-i k.R_I)
+// and the IonElectron part of System.__compute_forces (system.py:913-925), which the reference obtains by autograd
+// through the same expression:
+//     F_I = -dE/dR_I = -(dV / vol) sum_k w_k v_s(|k|) k Im[ exp(-i k.R_I) conj(rho_hat(k)) ]
+// (w_k = 1 on the self-conjugate planes of the half spectrum, 2 elsewhere).
+//
+// The reference materialises an N_k x N_ion phase tensor (34.6 GB for 256 atoms on 256^3).  Here
+// exp(-i k.R) = e0[j0] e1[j1] e2[j2] with k.R = 2 pi sum_a f_a u_a (u = fractional coordinates, f = integer
+// frequencies), so each ion needs three 1-D phase tables (n0 + n1 + n2/2 + 1 complex numbers, sincospi of an exactly
+// reduced argument) and a k-point costs one complex multiply-add per ion instead of a sincos.  A CTA owns one
+// (j0, j1) row of the half spectrum: e0 e1 of 128 ions is staged in shared memory, the threads run along j2 where
+// the e2 loads coalesce.  On the self-conjugate planes the "Nyquist made positive" spectrum is not Hermitian and the
+// reference's irfftn keeps only its Hermitian part; the kernel forms that part explicitly
+// from the partner wave vector, so any c2r transform reproduces the reference.
+#include "common.cuh"
+#include "table.cuh"
+
+namespace {
+
+constexpr int ION_T = 128;       // threads per CTA (and ions staged per shared-memory chunk)
+constexpr int ION_MAXJ = 9;      // half-spectrum points per thread along z: n2/2 + 1 <= 1152
+constexpr int ION_IPC = 8;       // ions per CTA in the force kernel
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// E_a[ion][j] = exp(-2 pi i f_a(j) u_a[ion]); the product f u is reduced modulo 1 exactly (fma remainder) first
+__global__ void __launch_bounds__(PAD_THREADS) k_ion_phases(const double* __restrict__ frac, int n_ions, int n0, int n1, int nzh,
+                                                          double2* __restrict__ E0, double2* __restrict__ E1,
+                                                          double2* __restrict__ E2) {
+    const int per = n0 + n1 + nzh;
+    const size_t total = (size_t)n_ions * per;
+    for (size_t e = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * PAD_THREADS) {
+        const int ion = (int)(e / per);
+        int j = (int)(e - (size_t)ion * per);
+        int axis;
+        double f;
+        double2* dst;
+        if (j < n0) { axis = 0; f = (double)(j <= n0 / 2 ? j : j - n0); dst = E0 + (size_t)ion * n0 + j; }
+        else if (j < n0 + n1) { j -= n0; axis = 1; f = (double)(j <= n1 / 2 ? j : j - n1); dst = E1 + (size_t)ion * n1 + j; }
+        else { j -= n0 + n1; axis = 2; f = (double)j; dst = E2 + (size_t)ion * nzh + j; }
+        const double u = frac[3 * ion + axis];
+        const double t = f * u, lo = fma(f, u, -t);
+        const double fr = (t - rint(t)) + lo;
+        double sn, cs;
+        sincospi(-2.0 * fr, &sn, &cs);
+        *dst = make_double2(cs, sn);
+    }
+}
+
+// v_s(|k|): Hermite interpolation of the tail-free table, Coulomb tail removed again (ion_utils.py:71-80)
+__device__ __forceinline__ double recpot_value(const UniformTable& T, double z, double kx, double ky, double kz) {
+    const double k2 = kx * kx + ky * ky + kz * kz;
+    if (k2 == 0.0) return table_lookup(T, 0.0);
+    return table_lookup(T, sqrt(k2)) - 4.0 * kPi * z / k2;
+}
+
+__global__ void __launch_bounds__(ION_T) k_ion_spectrum(KGeom g, int nrows, UniformTable T, double z, int n_ions,
+                                                      const double2* __restrict__ E0, const double2* __restrict__ E1,
+                                                      const double2* __restrict__ E2, double inv_vol, int accumulate,
+                                                      double2* __restrict__ out) {
+    __shared__ double2 s01[ION_T], s01b[ION_T];
+    const int nzh = g.nzh;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int j0 = row / g.n1_loc, j1 = row - j0 * g.n1_loc + g.j1_off;
+        const bool nyq0 = g.e0 && j0 == g.n0 / 2, nyq1 = g.e1 && j1 == g.n1 / 2;
+        double2 acc[ION_MAXJ], accb[ION_MAXJ];
+        bool sp[ION_MAXJ];
+#pragma unroll
+        for (int m = 0; m < ION_MAXJ; ++m) {
+            const int j2 = threadIdx.x + m * ION_T;
+            acc[m] = make_double2(0.0, 0.0);
+            accb[m] = make_double2(0.0, 0.0);
+            sp[m] = j2 < nzh && ((j2 == 0 && (nyq0 || nyq1)) || (g.e2 && j2 == g.n2 / 2));
+        }
+        for (int base = 0; base < n_ions; base += ION_T) {
+            const int ion = base + threadIdx.x;
+            if (ion < n_ions) {
+                double2 a = E0[(size_t)ion * g.n0 + j0], b = E1[(size_t)ion * g.n1 + j1];
+                s01[threadIdx.x] = cmul(a, b);
+                if (!nyq0) a.y = -a.y;          // partner wave vector: frequency -f unless f is the (positive) Nyquist one
+                if (!nyq1) b.y = -b.y;
+                s01b[threadIdx.x] = cmul(a, b);
+            }
+            __syncthreads();
+            const int cnt = min(ION_T, n_ions - base);
+            for (int i = 0; i < cnt; ++i) {
+                const double2 e = s01[i];
+                const double2* __restrict__ e2 = E2 + (size_t)(base + i) * nzh;
+#pragma unroll
+                for (int m = 0; m < ION_MAXJ; ++m) {
+                    const int j2 = threadIdx.x + m * ION_T;
+                    if (j2 < nzh) {
+                        const double2 ph = e2[j2];
+                        acc[m].x = fma(e.x, ph.x, fma(-e.y, ph.y, acc[m].x));
+                        acc[m].y = fma(e.x, ph.y, fma(e.y, ph.x, acc[m].y));
+                        if (sp[m]) {
+                            const double2 eb = s01b[i];
+                            accb[m].x = fma(eb.x, ph.x, fma(-eb.y, ph.y, accb[m].x));
+                            accb[m].y = fma(eb.x, ph.y, fma(eb.y, ph.x, accb[m].y));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int m = 0; m < ION_MAXJ; ++m) {
+            const int j2 = threadIdx.x + m * ION_T;
+            if (j2 < nzh) {
+                const KPoint p = make_kpoint_at(g, j0, j1, j2);
+                const double f = recpot_value(T, z, p.kx, p.ky, p.kz);
+                double2 G = make_double2(f * acc[m].x, f * acc[m].y);
+                if (p.special) {
+                    const double fb = recpot_value(T, z, p.px, p.py, p.pz);
+                    G.x = 0.5 * (G.x + fb * accb[m].x);
+                    G.y = 0.5 * (G.y - fb * accb[m].y);
+                }
+                const size_t idx = (size_t)row * nzh + j2;
+                double2 o = accumulate ? out[idx] : make_double2(0.0, 0.0);
+                o.x += G.x * inv_vol;
+                o.y += G.y * inv_vol;
+                out[idx] = o;
+            }
+        }
+    }
+}
+
+// partial force sums of ION_IPC ions over one chunk of half-spectrum rows
+__global__ void __launch_bounds__(ION_T) k_ion_force_partial(KGeom g, int nrows, int rows_per_chunk, int n_ions,
+                                                           const double2* __restrict__ E0, const double2* __restrict__ E1,
+                                                           const double2* __restrict__ E2, const double2* __restrict__ B,
+                                                           double* __restrict__ partial /* [ion][chunk][3] */) {
+    __shared__ double2 s01[ION_IPC];
+    __shared__ double red[3 * ION_IPC][ION_T / 32];
+    const int nzh = g.nzh;
+    const int chunk = blockIdx.x, nchunks = gridDim.x, ion0 = blockIdx.y * ION_IPC;
+    const int r_lo = chunk * rows_per_chunk, r_hi = min(nrows, r_lo + rows_per_chunk);
+    double acc[ION_IPC][3];
+#pragma unroll
+    for (int q = 0; q < ION_IPC; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.0;
+    for (int row = r_lo; row < r_hi; ++row) {
+        const int j0 = row / g.n1_loc, j1 = row - j0 * g.n1_loc + g.j1_off;
+        if (threadIdx.x < ION_IPC) {
+            const int ion = ion0 + threadIdx.x;
+            s01[threadIdx.x] = ion < n_ions ? cmul(E0[(size_t)ion * g.n0 + j0], E1[(size_t)ion * g.n1 + j1]) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int j2 = threadIdx.x; j2 < nzh; j2 += ION_T) {
+            const KPoint p = make_kpoint_at(g, j0, j1, j2);
+            const double2 b = B[(size_t)row * nzh + j2];
+#pragma unroll
+            for (int q = 0; q < ION_IPC; ++q) {
+                const int ion = ion0 + q;
+                if (ion < n_ions) {
+                    const double2 e = cmul(s01[q], E2[(size_t)ion * nzh + j2]);
+                    const double im = fma(e.x, b.y, e.y * b.x);
+                    acc[q][0] = fma(p.kx, im, acc[q][0]);
+                    acc[q][1] = fma(p.ky, im, acc[q][1]);
+                    acc[q][2] = fma(p.kz, im, acc[q][2]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < ION_IPC; ++q)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double v = warp_sum(acc[q][a]);
+            if (lane == 0) red[3 * q + a][warp] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 3 * ION_IPC) {
+        const int q = threadIdx.x / 3, a = threadIdx.x - 3 * q;
+        if (ion0 + q < n_ions) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < ION_T / 32; ++w) v += red[threadIdx.x][w];
+            partial[((size_t)(ion0 + q) * nchunks + chunk) * 3 + a] = v;
+        }
+    }
+}
+
+__global__ void k_ion_force_finish(const double* __restrict__ partial, int n_ions, int nchunks, double* __restrict__ forces) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * n_ions) return;
+    const int ion = e / 3, a = e - 3 * ion;
+    double v = 0.0;
+    for (int c = 0; c < nchunks; ++c) v += partial[((size_t)ion * nchunks + c) * 3 + a];
+    forces[e] = -v;
+}
+
+struct IonScratch {
+    double2 *E0, *E1, *E2;
+    double* slopes;
+};
+
+int check_species(const pad_plan* p, const pad_species* sp, int n_species, const char* who) {
+    if (!p || !sp || n_species < 1) { pad_set_error("%s: null argument / no species", who); return PAD_ERR_ARG; }
+    if (p->nzh > ION_T * ION_MAXJ) { pad_set_error("%s: n2 = %d too large (n2/2 + 1 <= %d)", who, p->n2, ION_T * ION_MAXJ); return PAD_ERR_ARG; }
+    for (int s = 0; s < n_species; ++s) {
+        if (!sp[s].table_dev || sp[s].n_table < 3 || !(sp[s].k_max > 0.0) || sp[s].n_ions < 0 || (sp[s].n_ions > 0 && !sp[s].frac_dev)) {
+            pad_set_error("%s: bad species %d (table %p, n_table %d, k_max %g, n_ions %d)", who, s, (const void*)sp[s].table_dev,
+                          sp[s].n_table, sp[s].k_max, sp[s].n_ions);
+            return PAD_ERR_ARG;
+        }
+    }
+    return PAD_OK;
+}
+
+// phase tables and table slopes of one species in the plan's (grown on demand) ion scratch
+int prepare_species(pad_plan* p, const pad_species& sp, cudaStream_t s, IonScratch& W, UniformTable& T) {
+    const size_t per = (size_t)p->n0 + p->n1 + p->nzh;
+    const size_t need = sizeof(double2) * per * (size_t)(sp.n_ions > 0 ? sp.n_ions : 1) + sizeof(double) * (size_t)sp.n_table;
+    if (p->ion_scratch_bytes < need) {
+        if (p->ion_scratch) { PAD_CUDA(cudaStreamSynchronize(s)); cudaFree(p->ion_scratch); p->bytes_allocated -= p->ion_scratch_bytes; }
+        PAD_CUDA(cudaMalloc(&p->ion_scratch, need));
+        p->ion_scratch_bytes = need;
+        p->bytes_allocated += need;
+    }
+    W.E0 = reinterpret_cast<double2*>(p->ion_scratch);
+    W.E1 = W.E0 + (size_t)sp.n_ions * p->n0;
+    W.E2 = W.E1 + (size_t)sp.n_ions * p->n1;
+    W.slopes = reinterpret_cast<double*>(W.E2 + (size_t)sp.n_ions * p->nzh);
+    k_table_slopes<<<(sp.n_table + 255) / 256, 256, 0, s>>>(sp.table_dev, sp.table_dev + sp.n_table, W.slopes, sp.n_table);
+    ++g_pad_launches;
+    if (sp.n_ions > 0) {
+        k_ion_phases<<<pad_grid_for(per * sp.n_ions), PAD_THREADS, 0, s>>>(sp.frac_dev, sp.n_ions, p->n0, p->n1, p->nzh, W.E0, W.E1, W.E2);
+        ++g_pad_launches;
+    }
+    T.eta = sp.table_dev; T.w = sp.table_dev + sp.n_table; T.m = W.slopes; T.n = sp.n_table;
+    T.eta_max = sp.k_max;
+    T.inv_d = (double)(sp.n_table - 1) / sp.k_max;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+}  // namespace
+
+extern "C" int pad_ionic_potential(pad_plan* p, const pad_species* species, int n_species, double* v_ext_out, void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ionic_potential"));
+    if (!v_ext_out) { pad_set_error("pad_ionic_potential: null output"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cufftDoubleComplex* G;
+    PAD_TRY(pad_get_cbuf(p, 0, &G));
+    const int nrows = p->n0 * p->geom.n1_loc;
+    const int grid = nrows < 148 * 8 ? nrows : 148 * 8;
+    for (int sI = 0; sI < n_species; ++sI) {
+        IonScratch W;
+        UniformTable T;
+        PAD_TRY(prepare_species(p, species[sI], s, W, T));
+        k_ion_spectrum<<<grid, ION_T, 0, s>>>(p->geom, nrows, T, species[sI].z, species[sI].n_ions, W.E0, W.E1, W.E2, 1.0 / p->vol,
+                                            sI > 0, reinterpret_cast<double2*>(G));
+        ++g_pad_launches;
+        PAD_CUDA(cudaGetLastError());
+    }
+    // unnormalised c2r = irfftn(..., norm='forward') (ion_utils.py:118)
+    PAD_TRY(pad_fft_inverse(p, G, v_ext_out, s));
+    return PAD_OK;
+}
+
+extern "C" int pad_ion_forces(pad_plan* p, const pad_species* species, int n_species, const double* den, double* forces_out,
+                              void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ion_forces"));
+    if (!den || !forces_out) { pad_set_error("pad_ion_forces: null argument"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cufftDoubleComplex *R, *Bs;
+    PAD_TRY(pad_get_cbuf(p, 0, &R));
+    PAD_TRY(pad_get_cbuf(p, 1, &Bs));
+    PAD_TRY(pad_fft_forward(p, den, R, s));      // out-of-place r2c: the input is left untouched
+    const int nrows = p->n0 * p->geom.n1_loc;
+    const KGeom geom = p->geom;
+    const double scale = p->dV / p->vol;
+    const int gridk = pad_grid_for(p->Nk);
+    int ion_off = 0;
+    for (int sI = 0; sI < n_species; ++sI) {
+        const pad_species& sp = species[sI];
+        if (sp.n_ions == 0) continue;
+        IonScratch W;
+        UniformTable T;
+        PAD_TRY(prepare_species(p, sp, s, W, T));
+        {
+            const cufftDoubleComplex* Rc = R;
+            cufftDoubleComplex* Bc = Bs;
+            const double z = sp.z;
+            auto f = [=] __device__(uint32_t idx, const KPoint& k) {
+                const bool edge = k.j2 == 0 || (geom.e2 && k.j2 == geom.n2 / 2);
+                const double w = scale * (edge ? 1.0 : 2.0) * recpot_value(T, z, k.kx, k.ky, k.kz);
+                const cufftDoubleComplex r = Rc[idx];
+                Bc[idx] = make_cuDoubleComplex(w * r.x, -w * r.y);
+            };
+            ks_kernel<decltype(f)><<<gridk, PAD_THREADS, 0, s>>>(geom, (uint32_t)p->Nk, f);
+            ++g_pad_launches;
+        }
+        const int groups = (sp.n_ions + ION_IPC - 1) / ION_IPC;
+        int nchunks = (148 * 6 + groups - 1) / groups;
+        if (nchunks > nrows) nchunks = nrows;
+        if (nchunks < 1) nchunks = 1;
+        const int rows_per_chunk = (nrows + nchunks - 1) / nchunks;
+        nchunks = (nrows + rows_per_chunk - 1) / rows_per_chunk;
+        const size_t pbytes = sizeof(double) * 3 * (size_t)sp.n_ions * nchunks;
+        if (p->ion_partial_bytes < pbytes) {
+            if (p->ion_partial) { PAD_CUDA(cudaStreamSynchronize(s)); cudaFree(p->ion_partial); }
+            PAD_CUDA(cudaMalloc(&p->ion_partial, pbytes));
+            p->ion_partial_bytes = pbytes;
+        }
+        k_ion_force_partial<<<dim3(nchunks, groups), ION_T, 0, s>>>(geom, nrows, rows_per_chunk, sp.n_ions, W.E0, W.E1, W.E2,
+                                                                    reinterpret_cast<const double2*>(Bs), p->ion_partial);
+        k_ion_force_finish<<<(3 * sp.n_ions + 127) / 128, 128, 0, s>>>(p->ion_partial, sp.n_ions, nchunks, forces_out + 3 * (size_t)ion_off);
+        g_pad_launches += 2;
+        PAD_CUDA(cudaGetLastError());
+        ion_off += sp.n_ions;
+    }
+    return PAD_OK;
+}

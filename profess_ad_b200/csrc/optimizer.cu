@@ -80,6 +80,25 @@ __device__ void reduce_partials(const double* __restrict__ partials, int nblocks
     }
 }
 
+// the sums a transition kernel needs: reduced here from the per-block partials (single GPU), or already reduced
+// and all-reduced over the ranks in `totals` (slab plans, see slab_reduce below)
+__device__ void gather_sums(const double* __restrict__ partials, int nblocks, int nterms, const double* __restrict__ totals,
+                            double* out /*shared, nterms*/) {
+    if (totals) {
+        if ((int)threadIdx.x < nterms) out[threadIdx.x] = totals[threadIdx.x];
+        __syncthreads();
+    } else {
+        reduce_partials(partials, nblocks, nterms, PAD_MAX_BLOCKS, out);
+    }
+}
+
+__global__ void __launch_bounds__(PAD_THREADS) k_reduce_to(const double* __restrict__ partials, int nblocks, int nterms,
+                                                         double* __restrict__ out) {
+    __shared__ double sums[OPT_NACC];
+    reduce_partials(partials, nblocks, nterms, PAD_MAX_BLOCKS, sums);
+    if ((int)threadIdx.x < nterms) out[threadIdx.x] = sums[threadIdx.x];
+}
+
 // stop rule of System.optimize_density (system.py:869-901), run at the end of every optimiser step
 __device__ void end_step(OptState& st, const OptParams& P, double* trace) {
     st.outer_iter++;
@@ -100,9 +119,9 @@ __device__ void end_step(OptState& st, const OptParams& P, double* trace) {
 
 // after the closure: finish the gradient reductions, then the L-BFGS / TPGD state machine
 __global__ void __launch_bounds__(PAD_THREADS) k_after_closure(OptState* stp, OptParams P, const double* __restrict__ partials,
-                                                             int nblocks, double* trace) {
+                                                             int nblocks, const double* __restrict__ totals, double* trace) {
     __shared__ double sums[2];
-    reduce_partials(partials, nblocks, 2, PAD_MAX_BLOCKS, sums);
+    gather_sums(partials, nblocks, 2, totals, sums);
     if (threadIdx.x != 0) return;
     OptState& st = *stp;
     if (st.done) { st.do_move = 0; st.do_pass1 = 0; return; }
@@ -211,11 +230,11 @@ __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_pass1(size_t n, const Opt
 
 // scalar part: curvature test, history update, two-loop recursion in coefficient space
 __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_direction(OptState* stp, OptParams P, const double* __restrict__ partials,
-                                                               int nblocks) {
+                                                               int nblocks, const double* __restrict__ totals) {
     __shared__ double sums[OPT_NACC];
     OptState& st = *stp;
     if (!st.do_move) return;
-    if (st.do_pass1) reduce_partials(partials, nblocks, OPT_NACC, PAD_MAX_BLOCKS, sums);
+    if (st.do_pass1) gather_sums(partials, nblocks, OPT_NACC, totals, sums);
     if (threadIdx.x != 0) return;
     if (st.n_iter_total == 1) {
         st.k = 0;
@@ -320,10 +339,10 @@ __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_pass2(size_t n, const Opt
 }
 
 __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_after_move(OptState* stp, OptParams P, const double* __restrict__ partials,
-                                                                int nblocks, double* trace) {
+                                                                int nblocks, const double* __restrict__ totals, double* trace) {
     __shared__ double sums[1];
     if (!stp->do_move) return;
-    reduce_partials(partials, nblocks, 1, PAD_MAX_BLOCKS, sums);
+    gather_sums(partials, nblocks, 1, totals, sums);
     if (threadIdx.x != 0) return;
     OptState& st = *stp;
     st.d_l1 = sums[0];
@@ -357,10 +376,10 @@ __global__ void __launch_bounds__(PAD_THREADS) k_tpgd_dots(size_t n, const OptSt
 }
 
 __global__ void __launch_bounds__(PAD_THREADS) k_tpgd_alpha(OptState* stp, OptParams P, const double* __restrict__ partials,
-                                                          int nblocks, double* trace) {
+                                                          int nblocks, const double* __restrict__ totals, double* trace) {
     __shared__ double sums[2];
     if (!stp->do_move) return;
-    reduce_partials(partials, nblocks, 2, PAD_MAX_BLOCKS, sums);
+    gather_sums(partials, nblocks, 2, totals, sums);
     if (threadIdx.x != 0) return;
     OptState& st = *stp;
     double alpha = P.lr;
@@ -436,7 +455,6 @@ static void finalize_sums(pad_plan* p, cudaStream_t s, int nterms, double* sums_
 }
 
 extern "C" int pad_chi_to_density(pad_plan* p, const double* chi, double n_elec, double* den_out, void* stream) {
-    if (p && p->dist) { pad_set_error("pad_chi_to_density: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !chi || !den_out) { pad_set_error("pad_chi_to_density: null argument"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -509,7 +527,6 @@ __global__ void k_pack_stats(const double* partials_sums, const unsigned long lo
 
 extern "C" int pad_chi_project(pad_plan* p, const double* chi, const double* den, const double* v, double n_elec,
                                double* grad_out, double* stats_out, void* stream) {
-    if (p && p->dist) { pad_set_error("pad_chi_project: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!p || !chi || !den || !v || !grad_out) { pad_set_error("pad_chi_project: null argument"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -520,6 +537,7 @@ extern "C" int pad_chi_project(pad_plan* p, const double* chi, const double* den
     PAD_CUDA(cudaMemsetAsync(bits, 0, 2 * sizeof(unsigned long long), s));
     PAD_TRY(chi_project_impl(p, s, chi, den, v, n_elec, scal + S_TMP0 + 4, scal + S_TMP0 + 5, grad_out, bits, nullptr));
     if (stats_out) {
+        PAD_TRY(pad_allreduce_max_bits(p, bits, 2, s));
         finalize_sums(p, s, 2, scal + S_E_PARTS);
         k_pack_stats<<<1, 1, 0, s>>>(scal + S_E_PARTS, bits, stats_out);
         ++g_pad_launches;
@@ -546,7 +564,6 @@ struct pad_denopt {
 };
 
 extern "C" int pad_denopt_create(pad_denopt** out, pad_plan* plan, const pad_terms* terms, const pad_denopt_params* prm) {
-    if (plan && plan->dist) { pad_set_error("pad_denopt_create: not available on slab plans yet"); return PAD_ERR_ARG; }
     if (!out || !plan || !terms || !prm) { pad_set_error("pad_denopt_create: null argument"); return PAD_ERR_ARG; }
     if (prm->method != 0 && prm->method != 1) { pad_set_error("pad_denopt_create: method must be 0 (LBFGS) or 1 (TPGD)"); return PAD_ERR_ARG; }
     if (prm->history < 1 || prm->history > OPT_M) { pad_set_error("pad_denopt_create: history must be in 1..%d", OPT_M); return PAD_ERR_ARG; }
@@ -594,6 +611,20 @@ extern "C" int pad_denopt_destroy(pad_denopt* o) {
     return PAD_OK;
 }
 
+// slab plans: per-block partials -> `nterms` totals in the plan's communication scratch -> ONE all-reduce over the
+// ranks; returns the pointer the following transition kernel reads its sums from (nullptr on single-GPU plans, where
+// that kernel reduces the partials itself).  The all-reduce is enqueued unconditionally -- every rank takes the same
+// branches because every scalar the state machine sees has been all-reduced.
+static int slab_reduce(pad_plan* p, const double* partials, int nterms, cudaStream_t s, const double** totals) {
+    *totals = nullptr;
+    if (!p->dist) return PAD_OK;
+    k_reduce_to<<<1, PAD_THREADS, 0, s>>>(partials, pad_grid_for(p->N), nterms, p->comm_scratch);
+    ++g_pad_launches;
+    PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_REDUCE, nterms, s));
+    *totals = p->comm_scratch;
+    return PAD_OK;
+}
+
 // one closure: chi -> n -> E, v -> projected gradient (+ its reductions, left in o->partials rows 0,1)
 static int enqueue_closure(pad_denopt* o, const double* v_ext, cudaStream_t s) {
     pad_plan* p = o->plan;
@@ -612,6 +643,7 @@ static int enqueue_closure(pad_denopt* o, const double* v_ext, cudaStream_t s) {
     k_reset_max<<<1, 1, 0, s>>>(st);
     ++g_pad_launches;
     PAD_TRY(chi_project_impl(p, s, chi, den, o->v, n_elec, &st->sum_chi2, &st->sum_vrho, o->g, &st->max_dEdchi_bits, &st->done));
+    PAD_TRY(pad_allreduce_max_bits(p, &st->max_dEdchi_bits, 2, s));       // max_dEdchi_bits, max_euler_bits are adjacent
     return PAD_OK;
 }
 
@@ -643,17 +675,22 @@ extern "C" int pad_denopt_run(pad_denopt* o, double* den_inout, const double* v_
             PAD_CUDA(cudaEventSynchronize(o->ev[j % OPT_RING]));
             if (o->host_ring[j % OPT_RING].done) { done = true; break; }
         }
+        const double* tot = nullptr;
         PAD_TRY(enqueue_closure(o, v_ext, s));
-        k_after_closure<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, o->trace);
+        PAD_TRY(slab_reduce(p, p->partials, 2, s, &tot));
+        k_after_closure<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, tot, o->trace);
         if (P.method == 0) {
             k_lbfgs_pass1<<<grid, PAD_THREADS, 0, s>>>(N, st, o->g, o->prev_g, o->d, o->Sh, o->Yh, o->partials);
-            k_lbfgs_direction<<<1, PAD_THREADS, 0, s>>>(st, P, o->partials, grid);
+            PAD_TRY(slab_reduce(p, o->partials, OPT_NACC, s, &tot));       // all 5k+5 inner products in one all-reduce
+            k_lbfgs_direction<<<1, PAD_THREADS, 0, s>>>(st, P, o->partials, grid, tot);
             k_lbfgs_pass2<<<grid, PAD_THREADS, 0, s>>>(N, st, o->g, o->prev_g, o->d, o->chi, o->Sh, o->Yh, p->partials);
-            k_lbfgs_after_move<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, o->trace);
+            PAD_TRY(slab_reduce(p, p->partials, 1, s, &tot));
+            k_lbfgs_after_move<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, tot, o->trace);
             g_pad_launches += 5;
         } else {
             k_tpgd_dots<<<grid, PAD_THREADS, 0, s>>>(N, st, o->chi, o->g, o->x_prev, o->prev_g, p->partials);
-            k_tpgd_alpha<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, o->trace);
+            PAD_TRY(slab_reduce(p, p->partials, 2, s, &tot));
+            k_tpgd_alpha<<<1, PAD_THREADS, 0, s>>>(st, P, p->partials, grid, tot, o->trace);
             k_tpgd_update<<<grid, PAD_THREADS, 0, s>>>(N, st, o->chi, o->g);
             g_pad_launches += 4;
         }

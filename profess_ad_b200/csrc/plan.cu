@@ -238,6 +238,8 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     if (p->hc_scratch) cudaFree(p->hc_scratch);
     if (p->hc_slopes) cudaFree(p->hc_slopes);
     if (p->hc_conv) cudaFree(p->hc_conv);
+    if (p->ion_scratch) cudaFree(p->ion_scratch);
+    if (p->ion_partial) cudaFree(p->ion_partial);
     if (p->xy_ready) cufftDestroy(p->xy);
     if (p->xy_work) cudaFree(p->xy_work);
     for (int i = 0; i < 4; ++i) if (p->zbuf[i]) cudaFree(p->zbuf[i]);
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(PAD_THREADS) slab_permute_kernel(const double2
     }
 }
 
-static int slab_comm(pad_plan* p, int op, long long count, cudaStream_t s) {
+int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s) {
     const int rc = p->comm_fn(p->comm_user, op, count, (void*)s);
     if (rc != 0) {
         pad_set_error("slab plan: the communication callback failed (op %d, rc %d)", op, rc);
@@ -364,7 +366,7 @@ static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* o
     slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(out),
         reinterpret_cast<double2*>(p->send_buf), p->n0_loc, p->n1, p->n1_loc, p->nzh, 1);
     PAD_CUDA(cudaGetLastError());
-    PAD_TRY(slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (n0, n1_loc, nzh)
+    PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (n0, n1_loc, nzh)
     PAD_CUFFT(cufftExecZ2Z(p->z2z_x, reinterpret_cast<cufftDoubleComplex*>(p->recv_buf), out, CUFFT_FORWARD));
     g_pad_fft_execs += 2;
     ++g_pad_launches;
@@ -375,7 +377,7 @@ static int fft_inverse_slab(pad_plan* p, cufftDoubleComplex* in, double* out, cu
     PAD_TRY(ensure_fft_slab(p, s));
     // x inverse into the send buffer: (n0, n1_loc, nzh) is already blocked by x range
     PAD_CUFFT(cufftExecZ2Z(p->z2z_x, in, reinterpret_cast<cufftDoubleComplex*>(p->send_buf), CUFFT_INVERSE));
-    PAD_TRY(slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (world, n0_loc, n1_loc, nzh)
+    PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (world, n0_loc, n1_loc, nzh)
     slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(p->recv_buf),
         reinterpret_cast<double2*>(in), p->n0_loc, p->n1, p->n1_loc, p->nzh, 0);
     PAD_CUDA(cudaGetLastError());
@@ -441,6 +443,24 @@ __global__ void finalize_apply_kernel(const double* __restrict__ totals, Finaliz
     if (a.E_out) a.E_out[0] = (a.accumulate ? a.E_out[0] : 0.0) + e;
 }
 
+__global__ void k_bits_to_scratch(const unsigned long long* bits, double* scratch, int n, int to_scratch) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    if (to_scratch) scratch[i] = __longlong_as_double((long long)bits[i]);
+    else const_cast<unsigned long long*>(bits)[i] = (unsigned long long)__double_as_longlong(scratch[i]);
+}
+
+int pad_allreduce_max_bits(pad_plan* p, unsigned long long* bits, int n, cudaStream_t s) {
+    if (!p->dist) return PAD_OK;
+    if (n > PAD_COMM_SCRATCH) { pad_set_error("pad_allreduce_max_bits: %d values", n); return PAD_ERR_ARG; }
+    k_bits_to_scratch<<<1, 64, 0, s>>>(bits, p->comm_scratch, n, 1);
+    PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_REDUCE_MAX, n, s));
+    k_bits_to_scratch<<<1, 64, 0, s>>>(bits, p->comm_scratch, n, 0);
+    g_pad_launches += 2;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
 void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s) {
     if (!p->dist) {
         finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, a);
@@ -451,7 +471,7 @@ void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s) {
     raw.sums_out = p->comm_scratch;
     raw.E_out = nullptr;
     finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->partials, raw);
-    if (slab_comm(p, PAD_COMM_ALL_REDUCE, a.nterms, s) != PAD_OK) return;      // error text is set; the caller's next CUDA check reports
+    if (pad_slab_comm(p, PAD_COMM_ALL_REDUCE, a.nterms, s) != PAD_OK) return;      // error text is set; the caller's next CUDA check reports
     finalize_apply_kernel<<<1, 1, 0, s>>>(p->comm_scratch, a);
     g_pad_launches += 2;
 }

@@ -5,6 +5,8 @@ These run once per geometry, not per optimiser iteration (r
 written with device-resident torch ops (no Python loop over ions, no O(N_k N_ion) temporaries); they
 produce the constant ``v_ext`` the CUDA hot path consumes.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -58,6 +60,78 @@ def interpolate_recpot(path, ks_interp):
     nz = ks_interp != 0
     safe = torch.where(nz, ks_interp, torch.ones_like(ks_interp))
     return torch.where(nz, val - 4 * np.pi * z / safe.pow(2), val)
+
+
+class PadSpecies(ctypes.Structure):
+    """pad_species of include/professad_b200.h"""
+    _fields_ = [('table_dev', ctypes.c_void_p), ('n_table', ctypes.c_int), ('k_max', ctypes.c_double),
+                ('z', ctypes.c_double), ('frac_dev', ctypes.c_void_p), ('n_ions', ctypes.c_int)]
+
+
+_table_cache = {}
+
+
+def _species_table(path, device):
+    """[k | v(k) + 4 pi z / k^2] on the device: the smooth table the reference interpolates (ion_utils.py:62-66)."""
+    key = (path, str(device))
+    hit = _table_cache.get(key)
+    if hit is None:
+        ks, pot, z = _read_recpot(path)
+        smooth = pot.copy()
+        smooth[1:] += 4 * np.pi * z / (ks[1:] * ks[1:])
+        tab = torch.as_tensor(np.concatenate([ks, smooth]), dtype=torch.double, device=device).contiguous()
+        hit = (tab, int(ks.size), float(ks[-1]), float(z))
+        _table_cache[key] = hit
+    return hit
+
+
+def _pad_species_array(species, device):
+    """ctypes array of pad_species for [(recpot path, (n, 3) fractional coordinates), ...]; also returns the
+    tensors that must stay alive for the duration of the call."""
+    arr = (PadSpecies * len(species))()
+    keep = []
+    for i, (path, frac) in enumerate(species):
+        tab, n_tab, k_max, z = _species_table(path, device)
+        fr = frac.detach().to(device=device, dtype=torch.double).contiguous()
+        keep += [tab, fr]
+        arr[i] = PadSpecies(tab.data_ptr(), n_tab, k_max, z, fr.data_ptr(), int(fr.shape[0]))
+    return arr, keep
+
+
+def ionic_potential(box_vecs, shape, species):
+    """v_ext on the grid from the ion positions, one C-ABI call (pad_ionic_potential): exact structure factor x
+    interpolated local pseudopotential -> c2r.  ``species`` = [(recpot path, (n, 3) fractional coordinates), ...].
+    Inside ``parallel.slab(...)`` ``shape`` is the LOCAL slab shape and the local slab of v_ext is returned.
+    Replaces System.__potential_from_ions (system.py:183-205)."""
+    from . import _native
+    dev = box_vecs.device
+    v_ext = torch.empty(tuple(int(s) for s in shape), dtype=torch.double, device=dev)
+    _native.require_cuda(v_ext, 'box_vecs')
+    plan = _native.get_plan(box_vecs, v_ext)
+    arr, keep = _pad_species_array(species, dev)
+    _native.check(plan.lib.pad_ionic_potential(plan.handle, arr, len(species), _native.ptr(v_ext), _native.stream_ptr(dev)))
+    del keep
+    return v_ext
+
+
+def ion_electron_forces(box_vecs, den, species):
+    """-d IonElectron / d R_I at fixed density, (N_ion, 3) Cartesian in Ha/bohr (pad_ion_forces); the IonElectron
+    part of System.__compute_forces (system.py:913-925).  Inside ``parallel.slab(...)`` the partial sums of the
+    ranks are added here."""
+    from . import _native, parallel
+    _native.require_cuda(den)
+    den = den.detach().contiguous()
+    plan = _native.get_plan(box_vecs, den)
+    arr, keep = _pad_species_array(species, den.device)
+    n_ions = sum(int(f.shape[0]) for _, f in species)
+    forces = torch.zeros((n_ions, 3), dtype=torch.double, device=den.device)
+    _native.check(plan.lib.pad_ion_forces(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(forces),
+                                          _native.stream_ptr(den.device)))
+    del keep
+    ctx = parallel.current()
+    if ctx is not None:
+        ctx.comm.all_reduce(forces.view(-1))
+    return forces
 
 
 def hermitian_symmetrize(G, n2):

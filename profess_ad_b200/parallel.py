@@ -17,8 +17,9 @@ Usage (one process per GPU, ``torch.distributed`` initialised, the same script o
         E = WangGovindCarter99().forward(box_vecs, den_local)  # the GLOBAL energy, identical on every rank
         (g,) = torch.autograd.grad(E, den_local)               # this rank's slab of dE/dn * dV
 
-Inside the context the ordinary functional callables take LOCAL slabs.  Not available on slabs yet:
-HuangCarter, the device-resident optimiser (System.optimize_density) -- they raise.
+Inside the context the ordinary functional callables (HuangCarter included) take LOCAL slabs, and
+``parallel.optimize_density`` runs the device-resident L-BFGS / TPGD loop with every rank holding its slab of
+chi, the gradient and the history; the inner products of an iteration travel in one batched all-reduce.
 
 There is no analogue in the reference (single process).
 """
@@ -31,7 +32,7 @@ import torch
 from . import _native
 
 _COMM_FN = _native.COMM_FN
-COMM_SCRATCH = 16
+COMM_SCRATCH = 64
 _state = threading.local()
 
 
@@ -51,6 +52,9 @@ class TorchDistComm:
     def all_reduce(self, t):
         self.dist.all_reduce(t, group=self.group)
 
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+
 
 class SingleComm:
     """world = 1: the exchange is a copy (exercises the slab code path on one GPU)."""
@@ -60,6 +64,9 @@ class SingleComm:
         recv.copy_(send)
 
     def all_reduce(self, t):
+        pass
+
+    def all_reduce_max(self, t):
         pass
 
 
@@ -91,16 +98,20 @@ class ThreadComm:
         torch.cuda.current_stream(send.device).synchronize()
         sh.barrier.wait()
 
-    def all_reduce(self, t):
+    def all_reduce(self, t, op=torch.add):
         sh = self.shared
         torch.cuda.current_stream(t.device).synchronize()
         sh.vals[self.rank] = t.clone()
         sh.barrier.wait()
         total = sh.vals[0].clone()
-        for r in range(1, self.world):      # fixed order: every rank gets bit-identical sums
-            total += sh.vals[r]
+        for r in range(1, self.world):      # fixed order: every rank gets bit-identical results
+            total = op(total, sh.vals[r])
+        torch.cuda.current_stream(t.device).synchronize()
         sh.barrier.wait()
         t.copy_(total)
+
+    def all_reduce_max(self, t):
+        self.all_reduce(t, op=torch.maximum)
 
 
 class SlabPlan(_native.Plan):
@@ -126,8 +137,12 @@ class SlabPlan(_native.Plan):
             try:
                 if op == 0:
                     self.comm.all_to_all(self.recv, self.send)
-                else:
+                elif op == 1:
                     self.comm.all_reduce(self.scratch[:count])
+                elif op == 2:
+                    self.comm.all_reduce_max(self.scratch[:count])
+                else:
+                    raise ValueError(f'unknown communication op {op}')
                 return 0
             except BaseException as e:      # noqa: BLE001 -- must not propagate through the C frame
                 self.error = e
@@ -219,3 +234,19 @@ def local_slab(field_global, comm=None):
         raise RuntimeError('local_slab needs an active parallel.slab(...) context or an explicit comm')
     lo, hi = slab_bounds(field_global.shape[0], comm.rank, comm.world)
     return field_global[lo:hi].contiguous()
+
+
+def optimize_density(box_vecs, den_local, v_ext_local, terms, n_elec, ntol=1e-7, n_conv_cond_count=3, n_method='LBFGS',
+                     n_step_size=0.1, n_maxiter=1000, conv_target='dE'):
+    """``System.optimize_density`` (system.py:774-908) for one grid spread over the ranks: call inside
+    ``with parallel.slab(global_shape):`` with this rank's slabs of the starting density and of the ionic
+    potential.  ``den_local`` is overwritten with the optimised density; returns (result dict, trace) --
+    identical on every rank.  ``terms`` is the reference-style list of native functionals."""
+    from . import _density_opt
+    if current() is None:
+        raise RuntimeError('parallel.optimize_density must be called inside a parallel.slab(...) context')
+    T = _density_opt.describe_terms(terms)
+    if T is None:
+        raise NotImplementedError('parallel.optimize_density needs every term to be a native functional')
+    return _density_opt.run(box_vecs, den_local, v_ext_local, T, n_elec, ntol, n_conv_cond_count, n_method,
+                            n_step_size, n_maxiter, conv_target)

@@ -18,7 +18,8 @@ rows f2/f4) and raise ``NotImplementedError``.
 import numpy as np
 import torch
 
-from .ion_utils import get_ion_charge, interpolate_recpot, lattice_sum, ion_interaction_sum
+from .ion_utils import (get_ion_charge, interpolate_recpot, lattice_sum, ion_interaction_sum, ionic_potential,
+                        ion_electron_forces)
 from .functional_tools import wavevecs
 from ._optimizers.lbfgs.lbfgsnew import LBFGSNew
 from ._optimizers.tpgd.two_point_gradient_descent import TPGD
@@ -128,7 +129,18 @@ class System():
             self.__den = self.__den * (old_vol / self.__vol())
             self.__ene = self.__compute_energy()
 
+    def __species(self):
+        out, first = [], 0
+        for _, path, count, _ in self.__ions:
+            out.append((path, self.__frac_ion_coords[first:first + count]))
+            first += count
+        return out
+
     def __potential_from_ions(self, cart_ion_coords):
+        """system.py:183-205.  Exact structure factor (pme_order None, the reference's default): one native call
+        that never materialises the N_k x N_ion phases; particle-mesh Ewald orders use the torch spline path."""
+        if self.__pme_order is None and self.__N_ions > 0:
+            return ionic_potential(self.__box_vecs, self.__shape, self.__species())
         kx, ky, kz, k2 = wavevecs(self.__box_vecs, self.__shape)
         k = torch.sqrt(k2)
         v_ext = torch.zeros(self.__shape, dtype=torch.double, device=self.__device)
@@ -277,7 +289,20 @@ class System():
         self.__second_order('bulk_modulus')
 
     def forces(self, units='Ha/b'):
-        self.__second_order('forces')
+        """F = -dE/dR at fixed density (system.py:623-643, 913-925): the IonElectron part is one native
+        reciprocal-space reduction per ion (pad_ion_forces), the IonIon part autograd through the real-space pair
+        sum.  Like the reference, exact structure factors are differentiated even if v_ext came from PME."""
+        if units not in ('Ha/b', 'eV/a'):
+            raise ValueError('Parameter \'units\' can only be \'Ha/b\' or \'eV/a\'')
+        names = [_term_name(f) for f in self.__terms]
+        forces = torch.zeros((self.__N_ions, 3), dtype=torch.double, device=self.__device)
+        if 'IonElectron' in names:
+            forces = forces + ion_electron_forces(self.__box_vecs, self.__den, self.__species())
+        if 'IonIon' in names:
+            cart = torch.matmul(self.__frac_ion_coords, self.__box_vecs).detach().requires_grad_(True)
+            U = self.__ion_ion_interaction(cart)
+            forces = forces - torch.autograd.grad(U, cart)[0]
+        return forces if units == 'Ha/b' else forces * self.eV_per_Ha / self.A_per_b
 
     def stress(self, units='Ha/b3'):
         self.__second_order('stress')

@@ -1,0 +1,109 @@
+"""Native ionic potential and ion-electron forces (csrc/ions.cu) against the unmodified reference's vectors
+(tests/golden/ions_*.npz), the CPU oracle and the product's own torch lattice sum."""
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from test_oracle_ions import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_native_vext_and_forces_match_reference(case, golden_dir, potentials_dir):
+    from profess_ad_b200 import ion_utils as IU
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    b = box.to(DEV)
+    sp = [(p, f.to(DEV)) for p, f in species]
+    v = IU.ionic_potential(b, den.shape, sp).cpu().numpy()
+    assert np.abs(v - g['v_ext']).max() <= 1e-11 * np.abs(g['v_ext']).max()
+    F = IU.ion_electron_forces(b, den.to(DEV), sp).cpu().numpy()
+    assert np.abs(F - g['forces_IonElectron']).max() <= 1e-10 * np.abs(g['forces_IonElectron']).max()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_system_forces_match_reference(case, golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    ions = [[os.path.basename(p)[:2].capitalize(), p, f] for p, f in species]
+    s = System(box, tuple(den.shape), ions, [F.IonIon, F.IonElectron, F.Hartree, F.ThomasFermi], units='b',
+               coord_type='fractional')
+    assert np.abs(s.ionic_potential().cpu().numpy() - g['v_ext']).max() <= 1e-11 * np.abs(g['v_ext']).max()
+    s.set_density(torch.from_numpy(g['den']))
+    forces = s.forces('Ha/b').cpu().numpy()
+    assert np.abs(forces - g['forces_Ha_b']).max() <= 1e-9 * np.abs(g['forces_Ha_b']).max()
+    ev_a = s.forces('eV/a').cpu().numpy()
+    assert np.allclose(ev_a, forces * System.eV_per_Ha / System.A_per_b, rtol=1e-14)
+    with pytest.raises(ValueError):
+        s.forces('N')
+
+
+def test_many_ions_vs_torch_lattice_sum_and_oracle(potentials_dir):
+    """More ions than one shared-memory chunk (128), all-even grid on a skewed cell: the native kernel against
+    the O(N_k N_ion) torch path of the product and the autograd forces of the CPU oracle."""
+    from oracle import ofdft_oracle as orc
+    from profess_ad_b200 import ion_utils as IU
+    from profess_ad_b200.functional_tools import wavevecs
+    shape = (20, 16, 18)
+    box, den = orc.synth_rough(shape, seed=9, L=14.0)
+    gen = torch.Generator().manual_seed(4)
+    f_al = torch.rand(150, 3, dtype=torch.double, generator=gen)
+    f_li = torch.rand(3, 3, dtype=torch.double, generator=gen)
+    pa, pl = os.path.join(potentials_dir, 'al.gga.recpot'), os.path.join(potentials_dir, 'li.gga.recpot')
+    b = box.to(DEV)
+    v = IU.ionic_potential(b, shape, [(pa, f_al.to(DEV)), (pl, f_li.to(DEV))])
+    k = torch.sqrt(wavevecs(b, shape)[3])
+    v_t = (IU.lattice_sum(b, shape, (f_al @ box).to(DEV), IU.interpolate_recpot(pa, k))
+           + IU.lattice_sum(b, shape, (f_li @ box).to(DEV), IU.interpolate_recpot(pl, k)))
+    assert ((v - v_t).abs().max() / v_t.abs().max()).item() < 1e-11
+    v_o = orc.ionic_potential(box, shape, [(pa, f_al @ box), (pl, f_li @ box)])
+    assert ((v.cpu() - v_o).abs().max() / v_o.abs().max()).item() < 1e-11
+    F_o = orc.ion_electron_forces(box, den, [(pa, f_al @ box), (pl, f_li @ box)])
+    F = IU.ion_electron_forces(b, den.to(DEV), [(pa, f_al.to(DEV)), (pl, f_li.to(DEV))]).cpu()
+    assert ((F - F_o).abs().max() / F_o.abs().max()).item() < 1e-10
+
+
+def _slab_rank(comm, shape, box, den, species, out, idx, errors):
+    from profess_ad_b200 import parallel, ion_utils as IU
+    try:
+        dev = torch.device(DEV)
+        with torch.cuda.stream(torch.cuda.Stream(dev)):
+            with parallel.slab(shape, comm=comm) as ctx:
+                sp = [(p, f.to(dev)) for p, f in species]
+                v = IU.ionic_potential(box.to(dev), ctx.local_shape, sp)
+                d = parallel.local_slab(den.to(dev))
+                F = IU.ion_electron_forces(box.to(dev), d, sp)
+                torch.cuda.current_stream(dev).synchronize()
+                out[idx] = (v.cpu(), F.cpu())
+    except BaseException as e:      # noqa: BLE001
+        errors.append(e)
+        try:
+            comm.shared.barrier.abort()
+        except Exception:
+            pass
+
+
+def test_slab_vext_and_forces(golden_dir, potentials_dir):
+    from profess_ad_b200 import parallel
+    world = 2
+    g, box, den, species = load_case('li2_even', golden_dir, potentials_dir)      # (12, 14, 12): n0, n1 multiples of 2
+    shape = tuple(den.shape)
+    out, errors = [None] * world, []
+    shared = parallel.ThreadComm.Shared(world)
+    threads = [threading.Thread(target=_slab_rank, args=(parallel.ThreadComm(shared, r), shape, box, den, species, out, r, errors))
+               for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    if errors:
+        raise errors[0]
+    v = torch.cat([o[0] for o in out], dim=0).numpy()
+    assert np.abs(v - g['v_ext']).max() <= 1e-11 * np.abs(g['v_ext']).max()
+    for o in out:
+        assert np.abs(o[1].numpy() - g['forces_IonElectron']).max() <= 1e-10 * np.abs(g['forces_IonElectron']).max()
