@@ -37,6 +37,9 @@ UNIT = 'evals/s'
 GRID = int(os.environ.get('PAD_BENCH_GRID', '256'))
 SIDE = 4
 N_FFT = 14
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this pipeline
+# (profiles/r01_ncu_full_wgc99_256_fused_final.md, 256^3): the dominant stage and the 11 kernels of one evaluation
+NCU_TRAFFIC_256 = {'x-fwd * kernel-mix * x-inv (3 fields)': 1.0733e9, 'evaluation': 9.091e9}
 
 
 def algorithmic_bytes(n):
@@ -332,7 +335,9 @@ def run_gpu(args):
             'gpu_launches': launches + fft_execs,
             'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': NCU_TRAFFIC_256['evaluation'] if GRID == 256 else None,
+                         'traffic_source': 'profiles/r01_ncu_full_wgc99_256_fused_final.md (ncu --set full, 11 kernels of one evaluation)',
+                         'peak_source': peak_src,
                          'kernel': 'whole WGC99 E+V evaluation (14 FFTs + fused elementwise passes)',
                          'algorithmic_bytes_per_eval': balg,
                          'kernels': stages},
@@ -342,6 +347,8 @@ def run_gpu(args):
             line['roofline']['dominant_kernel'] = {
                 'stage': dom['stage'], 'ms_per_eval': dom['ms_per_eval'], 'achieved': dom['GBps'],
                 'frac': (dom['GBps'] / peak) if dom['GBps'] else None,
+                'traffic_per_launch': NCU_TRAFFIC_256.get(dom['stage']) if GRID == 256 else None,
+                'launches_per_eval': dom['launches_per_eval'],
                 'note': 'CUDA events on the launch stream around this stage, mean of 5 evaluations'}
         if world == 1 and not args.no_denopt:
             line['density_optimization'] = density_optimization_leg(dev)

@@ -176,13 +176,8 @@ def perdew_zunger(box, den):
     return g.integ(ex + eps * den), vx + vc
 
 
-def pbe(box, den):
-    """8-FFT PBE: rfft(n); 3 c2r for grad n; local GGA kernel; 3 r2c of w_i = 2 f_sigma g_i; 1 c2r of i k . w."""
-    g = KGrid(box, den.shape)
-    ik = [g.sym(lambda kx, ky, kz, c=c: 1j * (kx, ky, kz)[c]) for c in range(3)]
-    R = g.fwd(den)
-    gr = [g.inv(m * R) for m in ik]
-    sig = gr[0] ** 2 + gr[1] ** 2 + gr[2] ** 2
+def pbe_local(den, sig):
+    """f, df/dn, df/dsigma of the PBE exchange-correlation energy density (sigma = |grad n|^2)."""
     # exchange
     cx = -0.75 * (3 / PI) ** (1.0 / 3.0)
     cs = 0.25 * (3 * PI * PI) ** (-2.0 / 3.0)
@@ -226,6 +221,17 @@ def pbe(box, den):
     f = f + den * (eps + H)
     f_rho = f_rho + eps + H + den * (deps + dH_rho)
     f_sig = f_sig + den * dH_sig
+    return f, f_rho, f_sig
+
+
+def pbe(box, den):
+    """8-FFT PBE: rfft(n); 3 c2r for grad n; local GGA kernel; 3 r2c of w_i = 2 f_sigma g_i; 1 c2r of i k . w."""
+    g = KGrid(box, den.shape)
+    ik = [g.sym(lambda kx, ky, kz, c=c: 1j * (kx, ky, kz)[c]) for c in range(3)]
+    R = g.fwd(den)
+    gr = [g.inv(m * R) for m in ik]
+    sig = gr[0] ** 2 + gr[1] ** 2 + gr[2] ** 2
+    f, f_rho, f_sig = pbe_local(den, sig)
     div = sum(m * g.fwd(2 * f_sig * gi) for m, gi in zip(ik, gr))
     return g.integ(f), f_rho - g.inv(div)
 
@@ -238,3 +244,125 @@ def chi_projection(box, chi, n_elec, v):
     den = scale * chi * chi
     mu = float((v * den).sum()) * dV / n_elec
     return scale * 2 * chi * (v - mu) * dV
+
+
+# ----------------------------------------------------------------------------------------------
+#  analytic stresses  sigma_ij = (1/vol) dE/d eps_ij  at fixed electron number (the density scales as 1/vol)
+#  -- what functional_tools.py:73-100 obtains by autograd through box_vecs.  For even multipliers the
+#  Hermitian symmetrisation drops out of the energy (the self-conjugate planes contain p and pbar), so the
+#  reciprocal-space sums run over the plain "Nyquist made positive" k with half-spectrum weights w.
+# ----------------------------------------------------------------------------------------------
+def _weights(g):
+    return torch.where(g.selfconj, torch.ones((), dtype=torch.double), 2.0 * torch.ones((), dtype=torch.double))
+
+
+def _tensor_sum(g, scalar):
+    """sum_k scalar(k) k_i k_j  as a symmetric 3 x 3 tensor."""
+    out = torch.zeros(3, 3, dtype=torch.double)
+    for i in range(3):
+        for j in range(i, 3):
+            out[i, j] = out[j, i] = float((scalar * g.k[i] * g.k[j]).sum())
+    return out
+
+
+def stress_local(box, den, E, v):
+    """TF, LDA exchange, PZ correlation: delta_ij (E - int v n) / vol."""
+    g = KGrid(box, den.shape)
+    return (E - g.integ(v * den)) / g.vol * torch.eye(3, dtype=torch.double)
+
+
+def stress_hartree(box, den):
+    g = KGrid(box, den.shape)
+    c = g.fwd(den) / g.N
+    k2 = g.k[0] ** 2 + g.k[1] ** 2 + g.k[2] ** 2
+    safe = torch.where(k2 != 0, k2, torch.ones_like(k2))
+    aux = torch.where(k2 != 0, _weights(g) * 4 * PI * (c.real ** 2 + c.imag ** 2) / (safe * safe), torch.zeros_like(k2))
+    E = hartree(box, den)[0]
+    return _tensor_sum(g, aux) - E / g.vol * torch.eye(3, dtype=torch.double)
+
+
+def stress_weizsaecker(box, den):
+    g = KGrid(box, den.shape)
+    c = g.fwd(torch.sqrt(den)) / g.N
+    return -_tensor_sum(g, _weights(g) * (c.real ** 2 + c.imag ** 2))
+
+
+def stress_wt_nonlocal(box, den, alpha, beta):
+    """tests/tools_for_tests.py:258-307 (non_local_KEF_stress without its TF and vW parts)."""
+    g = KGrid(box, den.shape)
+    n0 = float(den.mean())
+    kF = (3 * PI * PI * n0) ** (1.0 / 3.0)
+    E = wt_nonlocal(box, den, alpha, beta)[0]
+    pref = 0.5 * PI * PI / alpha / beta / n0 ** (alpha + beta - 2) / kF
+    a, b = g.fwd(den.pow(alpha)) / g.N, g.fwd(den.pow(beta)) / g.N
+    ab = (a * b.conj()).real * _weights(g)                          # filter * aux1 = (w / 2) * 2 Re(a conj b)
+    k2 = g.k[0] ** 2 + g.k[1] ** 2 + g.k[2] ** 2
+    nz = k2 != 0
+    safe = torch.where(nz, k2, torch.ones_like(k2))
+    eta = torch.sqrt(safe) / (2 * kF)
+    lg = torch.log(torch.abs((1 + eta) / (1 - eta)))
+    lind = 0.5 + (1 - eta * eta) / (4 * eta) * lg
+    aux3 = eta / lind ** 2 * (0.5 / eta - 0.25 * (1 + 1 / (eta * eta)) * lg) + 6 * eta * eta
+    s = torch.where(nz, ab * aux3 / safe, torch.zeros_like(k2))
+    iso = float(torch.where(nz, ab * aux3, torch.zeros_like(k2)).sum()) / 3.0
+    eye = torch.eye(3, dtype=torch.double)
+    return pref * (_tensor_sum(g, s) - iso * eye) - 2.0 * E / 3.0 / g.vol * eye
+
+
+def stress_pbe(box, den):
+    """tests/tools_for_tests.py:367-472: delta_ij mean(f - n f_n - 2 sigma f_sigma) - 2 mean(f_sigma g_i g_j)."""
+    g = KGrid(box, den.shape)
+    ik = [g.sym(lambda kx, ky, kz, c=c: 1j * (kx, ky, kz)[c]) for c in range(3)]
+    R = g.fwd(den)
+    gr = [g.inv(m * R) for m in ik]
+    f, f_rho, f_sig = pbe_local(den, gr[0] ** 2 + gr[1] ** 2 + gr[2] ** 2)
+    out = float((f - den * f_rho - 2 * (gr[0] ** 2 + gr[1] ** 2 + gr[2] ** 2) * f_sig).mean()) * torch.eye(3, dtype=torch.double)
+    for i in range(3):
+        for j in range(3):
+            out[i, j] -= 2 * float((f_sig * gr[i] * gr[j]).mean())
+    return out
+
+
+def recpot_value_and_slope(ks, smooth, z, k):
+    """v(k) = H(min(k, k_max)) - 4 pi z / k^2 and dv/dk for the Hermite interpolant H of the tail-free table."""
+    x, y = torch.as_tensor(ks), torch.as_tensor(smooth)
+    sec = (y[1:] - y[:-1]) / (x[1:] - x[:-1])
+    m = torch.cat([sec[:1], 0.5 * (sec[1:] + sec[:-1]), sec[-1:]])
+    kc = torch.minimum(k, x[-1])
+    idx = torch.searchsorted(x[1:], kc)
+    dx = x[idx + 1] - x[idx]
+    t = (kc - x[idx]) / dx
+    t2, t3 = t * t, t * t * t
+    val = (1 - 3 * t2 + 2 * t3) * y[idx] + (t - 2 * t2 + t3) * m[idx] * dx + (3 * t2 - 2 * t3) * y[idx + 1] + (t3 - t2) * m[idx + 1] * dx
+    slope = ((-6 * t + 6 * t2) * y[idx] + (1 - 4 * t + 3 * t2) * m[idx] * dx + (6 * t - 6 * t2) * y[idx + 1] + (3 * t2 - 2 * t) * m[idx + 1] * dx) / dx
+    slope = torch.where(k > x[-1], torch.zeros_like(slope), slope)
+    nz = k != 0
+    ksafe = torch.where(nz, k, torch.ones_like(k))
+    val = torch.where(nz, val - 4 * PI * z / ksafe ** 2, val)
+    slope = torch.where(nz, slope + 8 * PI * z / ksafe ** 3, torch.zeros_like(slope))
+    return val, slope
+
+
+def stress_ion_electron(box, den, species):
+    """species = [(ks, smooth table, z, (n, 3) fractional coordinates)].  At fixed fractional coordinates S(k) does not
+    depend on the cell:  sigma_ij = -delta_ij E / vol - (1/vol) sum_k w v'(k) k_i k_j / k Re(S conj c)."""
+    g = KGrid(box, den.shape)
+    n0, n1, n2 = g.shape
+    c = g.fwd(den) / g.N
+    kabs = torch.sqrt(g.k[0] ** 2 + g.k[1] ** 2 + g.k[2] ** 2)
+    f0 = np.fft.fftfreq(n0) * n0
+    f0[n0 // 2] = abs(f0[n0 // 2])
+    f1 = np.fft.fftfreq(n1) * n1
+    f1[n1 // 2] = abs(f1[n1 // 2])
+    f2 = np.fft.rfftfreq(n2) * n2
+    A, B, C = (torch.from_numpy(a) for a in np.meshgrid(f0, f1, f2, indexing='ij'))
+    E, scal = 0.0, torch.zeros_like(kabs)
+    w = _weights(g)
+    for ks, smooth, z, frac in species:
+        ph = -2 * PI * (A.unsqueeze(-1) * frac[:, 0] + B.unsqueeze(-1) * frac[:, 1] + C.unsqueeze(-1) * frac[:, 2])
+        S = torch.complex(torch.cos(ph), torch.sin(ph)).sum(-1)
+        val, slope = recpot_value_and_slope(ks, smooth, z, kabs)
+        re = w * (S * c.conj()).real
+        E += float((val * re).sum())
+        scal = scal + torch.where(kabs != 0, slope * re / torch.where(kabs != 0, kabs, torch.ones_like(kabs)), torch.zeros_like(kabs))
+    return -E / g.vol * torch.eye(3, dtype=torch.double) - _tensor_sum(g, scal) / g.vol

@@ -100,13 +100,14 @@ def test_slab_huang_carter_matches_oracle(world, shape, golden_dir):
     import numpy as np
     import profess_ad_b200.functionals as F
     from oracle import ofdft_oracle as orc
-    tab = np.load(os.path.join(golden_dir, 'hc_table.npz'))
+    with np.load(os.path.join(golden_dir, 'hc_table.npz')) as tab:      # NpzFile is not thread-safe: read it up front
+        t_hc, t_rev = torch.from_numpy(tab['hc']), torch.from_numpy(tab['revhc'])
     box, den = orc.synth_rough(shape, seed=31 + world, L=8.5)
     dV = abs(torch.linalg.det(box).item()) / den.numel()
-    cases = [('revHC', lambda: F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15), kernel=torch.from_numpy(tab['revhc'])).forward,
-              orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=torch.from_numpy(tab['revhc']))),
-             ('HC', lambda: F.HuangCarter((0.01177, 0.7143, 1.2), kernel=torch.from_numpy(tab['hc'])).forward,
-              orc.HuangCarter(0.01177, 0.7143, 1.2, kernel=torch.from_numpy(tab['hc'])))]
+    cases = [('revHC', lambda: F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15), kernel=t_rev.clone()).forward,
+              orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=t_rev)),
+             ('HC', lambda: F.HuangCarter((0.01177, 0.7143, 1.2), kernel=t_hc.clone()).forward,
+              orc.HuangCarter(0.01177, 0.7143, 1.2, kernel=t_hc))]
     for name, make_f, oracle_f in cases:
         E_ref, V_ref = orc.energy_and_potential(box, den, oracle_f)
         energies, g = _evaluate_slabs(world, shape, box, den, make_f)
