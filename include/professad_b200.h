@@ -171,6 +171,11 @@ int pad_ionic_potential(pad_plan* plan, const pad_species* species, int n_specie
 int pad_ion_forces(pad_plan* plan, const pad_species* species, int n_species, const double* den, double* forces_out,
                    void* stream);
 
+/* IonElectron part of the stress (system.py:927-935) at fixed fractional coordinates and electron number;
+ * stress_out: DEVICE, 9 doubles (row-major symmetric 3 x 3, Ha/bohr^3), overwritten unless accumulate != 0 */
+int pad_ion_stress(pad_plan* plan, const pad_species* species, int n_species, const double* den, double* stress_out,
+                   int accumulate, void* stream);
+
 /* ---- fused evaluation of a whole term list: replaces System.__compute_energy + autograd
  *      (system.py:759-772, 830-838).  E_out = sum of terms, v_out = total dE/dn. ---------------- */
 typedef struct pad_terms {
@@ -183,6 +188,12 @@ typedef struct pad_terms {
 } pad_terms;
 int pad_eval_total(pad_plan* plan, const pad_terms* terms, const double* den, const double* v_ext,
                    double* E_out, double* v_out, void* stream);
+
+/* Analytic stress sigma_ij = (1/vol) dE/d eps_ij of the terms of a pad_terms descriptor (everything except
+ * IonElectron, see pad_ion_stress): replaces get_stress / System.__compute_stress (functional_tools.py:73-100,
+ * system.py:927-935; formulas tests/tools_for_tests.py:212-472).  stress_out: DEVICE, 9 doubles, overwritten.
+ * Not available for kinetic == 2 (WangGovindCarter99). */
+int pad_stress_terms(pad_plan* plan, const pad_terms* terms, const double* den, double* stress_out, void* stream);
 
 /* ---- chi-parametrisation (system.py:830-854): n = N chi^2 / int chi^2 and the projected gradient
  *      dE/dchi_ijk = dV (N/Ntilde) 2 chi (v - mu), mu = int v n / N.  grad_out = N doubles. -------- */

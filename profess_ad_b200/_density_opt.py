@@ -93,6 +93,19 @@ def eval_total(box_vecs, den, v_ext, T, want_potential=True):
     return E, v
 
 
+def stress_terms(box_vecs, den, T):
+    """Analytic stress (3, 3) in Ha/bohr^3 of a described term list without its IonElectron part (pad_stress_terms)."""
+    _native.require_cuda(den)
+    if T.kinetic == 2:
+        raise NotImplementedError('stress of WangGovindCarter99: the reference\'s autograd result depends on the state of its '
+                                  'kernel cache (functionals.py:961-966), there is no well-defined value to reproduce')
+    den = den.detach().contiguous()
+    plan = _native.get_plan(box_vecs, den)
+    out = torch.empty(9, dtype=torch.double, device=den.device)
+    check(plan.lib.pad_stress_terms(plan.handle, ctypes.byref(T), ptr(den), ptr(out), stream_ptr(den.device)))
+    return out.reshape(3, 3)
+
+
 def chi_to_density(box_vecs, chi, n_elec):
     chi = chi.detach().contiguous()
     plan = _native.get_plan(box_vecs, chi)

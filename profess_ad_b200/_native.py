@@ -55,6 +55,8 @@ SIGNATURES = {
     # pad_species* is passed as a ctypes array of _density_opt-style Structures
     'pad_ionic_potential': (_int, [_vp, _vp, _int, _vp, _vp]),
     'pad_ion_forces': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    'pad_ion_stress': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
+    'pad_stress_terms': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'pad_chi_to_density': (_int, [_vp, _vp, _dbl, _vp, _vp]),
     'pad_chi_project': (_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
     'pad_denopt_create': (_int, [ctypes.POINTER(_vp), _vp, _vp, _vp]),

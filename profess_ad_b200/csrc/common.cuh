@@ -266,3 +266,7 @@ void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s);
 // max: non-negative doubles held as their bit patterns (the atomicMax convention of the reduction kernels).
 int pad_allreduce_max_bits(pad_plan* p, unsigned long long* bits, int n, cudaStream_t s);
 int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s);
+// stress.cu: the 7 block-reduced sums [iso, xx, yy, zz, xy, xz, yz] left in p->partials by a kernel with `nblocks`
+// CTAs are finished (all-reduced on slab plans) and added to the row-major 3 x 3 device tensor `sig`:
+// sig_ij += c_t T_ij + c_iso iso delta_ij
+int pad_stress_accumulate(pad_plan* p, cudaStream_t s, int nblocks, double c_iso, double c_t, double* sig);

@@ -63,6 +63,7 @@ __device__ __forceinline__ double recpot_value(const UniformTable& T, double z, 
 __global__ void __launch_bounds__(ION_T) k_ion_spectrum(KGeom g, int nrows, UniformTable T, double z, int n_ions,
                                                       const double2* __restrict__ E0, const double2* __restrict__ E1,
                                                       const double2* __restrict__ E2, double inv_vol, int accumulate,
+                                                      int raw /* 1: plain S(k), no potential factor, no symmetrisation */,
                                                       double2* __restrict__ out) {
     __shared__ double2 s01[ION_T], s01b[ION_T];
     const int nzh = g.nzh;
@@ -114,9 +115,9 @@ __global__ void __launch_bounds__(ION_T) k_ion_spectrum(KGeom g, int nrows, Unif
             const int j2 = threadIdx.x + m * ION_T;
             if (j2 < nzh) {
                 const KPoint p = make_kpoint_at(g, j0, j1, j2);
-                const double f = recpot_value(T, z, p.kx, p.ky, p.kz);
+                const double f = raw ? 1.0 : recpot_value(T, z, p.kx, p.ky, p.kz);
                 double2 G = make_double2(f * acc[m].x, f * acc[m].y);
-                if (p.special) {
+                if (p.special && !raw) {
                     const double fb = recpot_value(T, z, p.px, p.py, p.pz);
                     G.x = 0.5 * (G.x + fb * accb[m].x);
                     G.y = 0.5 * (G.y - fb * accb[m].y);
@@ -258,7 +259,7 @@ extern "C" int pad_ionic_potential(pad_plan* p, const pad_species* species, int 
         UniformTable T;
         PAD_TRY(prepare_species(p, species[sI], s, W, T));
         k_ion_spectrum<<<grid, ION_T, 0, s>>>(p->geom, nrows, T, species[sI].z, species[sI].n_ions, W.E0, W.E1, W.E2, 1.0 / p->vol,
-                                            sI > 0, reinterpret_cast<double2*>(G));
+                                            sI > 0, 0, reinterpret_cast<double2*>(G));
         ++g_pad_launches;
         PAD_CUDA(cudaGetLastError());
     }
@@ -320,5 +321,62 @@ extern "C" int pad_ion_forces(pad_plan* p, const pad_species* species, int n_spe
         PAD_CUDA(cudaGetLastError());
         ion_off += sp.n_ions;
     }
+    return PAD_OK;
+}
+
+// IonElectron part of System.__compute_stress (system.py:927-935): ions at fixed fractional coordinates, so S(k) does
+// not depend on the cell and only v_s(|k|) / vol does:
+//   sigma_ij = -delta_ij E / vol - (1/vol) sum_k w v_s'(|k|) k_i k_j / |k| Re(S_s(k) conj c_k),   E = sum_k w v_s Re(S_s conj c_k)
+extern "C" int pad_ion_stress(pad_plan* p, const pad_species* species, int n_species, const double* den, double* stress_out,
+                              int accumulate, void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ion_stress"));
+    if (!den || !stress_out) { pad_set_error("pad_ion_stress: null argument"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate) PAD_CUDA(cudaMemsetAsync(stress_out, 0, sizeof(double) * 9, s));
+    cufftDoubleComplex *R, *Sk;
+    PAD_TRY(pad_get_cbuf(p, 0, &R));
+    PAD_TRY(pad_get_cbuf(p, 1, &Sk));
+    PAD_TRY(pad_fft_forward(p, den, R, s));
+    const int nrows = p->n0 * p->geom.n1_loc;
+    const int grid = nrows < 148 * 8 ? nrows : 148 * 8;
+    const KGeom geom = p->geom;
+    const double inv_n = geom.inv_n;
+    for (int sI = 0; sI < n_species; ++sI) {
+        const pad_species& sp = species[sI];
+        if (sp.n_ions == 0) continue;
+        IonScratch W;
+        UniformTable T;
+        PAD_TRY(prepare_species(p, sp, s, W, T));
+        k_ion_spectrum<<<grid, ION_T, 0, s>>>(geom, nrows, T, sp.z, sp.n_ions, W.E0, W.E1, W.E2, 1.0, 0, 1, reinterpret_cast<double2*>(Sk));
+        ++g_pad_launches;
+        const cufftDoubleComplex *Rc = R, *Sc = Sk;
+        const double z = sp.z;
+        auto f = [=] __device__(size_t i, double(&acc)[7]) {
+            const KPoint k = make_kpoint(geom, (uint32_t)i);
+            const cufftDoubleComplex r = Rc[i], sk = Sc[i];
+            const bool edge = k.j2 == 0 || (geom.e2 && k.j2 == geom.n2 / 2);
+            const double re = (edge ? 1.0 : 2.0) * (sk.x * r.x + sk.y * r.y) * inv_n;
+            const double k2 = k.kx * k.kx + k.ky * k.ky + k.kz * k.kz;
+            double val, slope;
+            if (k2 == 0.0) {
+                table_lookup_slope(T, 0.0, val, slope);
+                acc[0] -= val * re;
+                return;
+            }
+            const double ka = sqrt(k2);
+            table_lookup_slope(T, ka, val, slope);
+            val -= 4.0 * kPi * z / k2;
+            slope += 8.0 * kPi * z / (k2 * ka);
+            acc[0] -= val * re;
+            const double t = -slope / ka * re;
+            acc[1] += t * k.kx * k.kx; acc[2] += t * k.ky * k.ky; acc[3] += t * k.kz * k.kz;
+            acc[4] += t * k.kx * k.ky; acc[5] += t * k.kx * k.kz; acc[6] += t * k.ky * k.kz;
+        };
+        ew_kernel<7, decltype(f)><<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->Nk, f, p->partials);
+        ++g_pad_launches;
+        PAD_TRY(pad_stress_accumulate(p, s, pad_grid_for(p->Nk), 1.0 / p->vol, 1.0 / p->vol, stress_out));
+    }
+    PAD_CUDA(cudaGetLastError());
     return PAD_OK;
 }

@@ -41,3 +41,21 @@ __device__ __forceinline__ double table_lookup(const UniformTable& T, double eta
     hermite((eta - x0) / dx, h00, h10, h01, h11);
     return h00 * T.w[i] + h10 * T.m[i] * dx + h01 * T.w[i + 1] + h11 * T.m[i + 1] * dx;
 }
+
+// value and d/d eta of the interpolant; the clamp makes the slope zero beyond the table end (torch.minimum)
+__device__ __forceinline__ void table_lookup_slope(const UniformTable& T, double eta, double& val, double& slope) {
+    const bool beyond = eta > T.eta_max;
+    eta = fmin(eta, T.eta_max);
+    int i = (int)ceil(eta * T.inv_d) - 1;
+    i = max(0, min(i, T.n - 2));
+    while (i < T.n - 2 && T.eta[i + 1] < eta) ++i;
+    while (i > 0 && T.eta[i] >= eta) --i;
+    const double x0 = T.eta[i], dx = T.eta[i + 1] - x0;
+    const double t = (eta - x0) / dx, t2 = t * t;
+    double h00, h10, h01, h11;
+    hermite(t, h00, h10, h01, h11);
+    const double y0 = T.w[i], y1 = T.w[i + 1], m0 = T.m[i] * dx, m1 = T.m[i + 1] * dx;
+    val = h00 * y0 + h10 * m0 + h01 * y1 + h11 * m1;
+    slope = beyond ? 0.0
+                   : ((-6.0 * t + 6.0 * t2) * y0 + (1.0 - 4.0 * t + 3.0 * t2) * m0 + (6.0 * t - 6.0 * t2) * y1 + (3.0 * t2 - 2.0 * t) * m1) / dx;
+}

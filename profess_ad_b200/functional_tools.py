@@ -30,6 +30,25 @@ def get_functional_derivative(box_vecs, den, functional, requires_grad=False):
     return grad / (torch.abs(torch.linalg.det(box_vecs)) / den.numel())
 
 
+def get_stress(box_vecs, den, functional, requires_grad=False):
+    """Functional contribution to the stress, (1/vol) dF/d eps at fixed electron number (functional_tools.py:73-100).
+    The reference differentiates through ``box_vecs``; for the native functionals this is one C-ABI call evaluating
+    the analytic expressions (csrc/stress.cu).  User-defined Python functionals are outside this path."""
+    if requires_grad:
+        raise NotImplementedError('second derivatives (requires_grad=True) are outside the B200 hot path')
+    from . import _density_opt
+    name = getattr(functional, '__qualname__', '') or getattr(functional, '__name__', '')
+    T = _density_opt.describe_terms([functional]) if name not in ('IonElectron', 'IonIon') else None
+    if T is None:
+        raise NotImplementedError('get_stress: only native functionals of (box_vecs, den) have an analytic stress here')
+    return _density_opt.stress_terms(box_vecs, den, T)
+
+
+def get_pressure(box_vecs, den, functional, requires_grad=False):
+    """-dF/dvol at fixed electron number (functional_tools.py:103-127) = -trace(stress) / 3."""
+    return -torch.trace(get_stress(box_vecs, den, functional, requires_grad)) / 3
+
+
 def wavevecs(box_vecs, shape):
     """k_x, k_y, k_z, k^2 on the half-spectrum grid (functional_tools.py:135-162), Nyquist index
     positive on axes 0 and 1."""

@@ -134,6 +134,21 @@ def ion_electron_forces(box_vecs, den, species):
     return forces
 
 
+def ion_electron_stress(box_vecs, den, species):
+    """IonElectron part of the stress, (3, 3) in Ha/bohr^3 (pad_ion_stress; system.py:927-935): ions at fixed
+    fractional coordinates, electron number conserved."""
+    from . import _native
+    _native.require_cuda(den)
+    den = den.detach().contiguous()
+    plan = _native.get_plan(box_vecs, den)
+    arr, keep = _pad_species_array(species, den.device)
+    out = torch.empty(9, dtype=torch.double, device=den.device)
+    _native.check(plan.lib.pad_ion_stress(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(out), 0,
+                                          _native.stream_ptr(den.device)))
+    del keep
+    return out.reshape(3, 3)
+
+
 def hermitian_symmetrize(G, n2):
     """Make a half-spectrum Hermitian-consistent on its self-conjugate planes (j2 = 0 and, for even
     n2, j2 = n2/2): G <- (G(p) + conj G(pbar)) / 2.  This is what the reference's CPU irfftn

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .ion_utils import (get_ion_charge, interpolate_recpot, lattice_sum, ion_interaction_sum, ionic_potential,
-                        ion_electron_forces)
+                        ion_electron_forces, ion_electron_stress)
 from .functional_tools import wavevecs
 from ._optimizers.lbfgs.lbfgsnew import LBFGSNew
 from ._optimizers.tpgd.two_point_gradient_descent import TPGD
@@ -279,11 +279,31 @@ class System():
         raise NotImplementedError(f'System.{what}: implicit differentiation / second derivatives are outside the '
                                   'B200 hot path (SURVEY.md section 8: out of scope)')
 
+    def __pressure_units(self, units):
+        if units == 'Ha/b3':
+            return 1.0
+        if units == 'eV/a3':
+            return self.eV_per_Ha / self.A_per_b**3
+        if units == 'GPa':
+            return self.GPa_per_atomic
+        raise ValueError('Parameter \'units\' can only be \'Ha/b3\', \'eV/a3\' or \'GPa\'')
+
     def pressure(self, units='Ha/b3', requires_grad=False):
-        self.__second_order('pressure')
+        """P = -dE/dvol at fixed electron number and fractional ionic coordinates (system.py:494-522)
+        = -trace(stress) / 3."""
+        if requires_grad:
+            self.__second_order('pressure(requires_grad=True)')
+        factor = self.__pressure_units(units)
+        return -torch.trace(self.__compute_stress()).item() / 3 * factor
 
     def enthalpy(self, units='Ha'):
-        self.__second_order('enthalpy')
+        """H = E + P vol (system.py:524-540)."""
+        H = self.energy('Ha') + self.pressure('Ha/b3') * self.volume('b3')
+        if units == 'Ha':
+            return H
+        if units == 'eV':
+            return H * self.eV_per_Ha
+        raise ValueError('Parameter \'units\' can only be \'Ha\' or \'eV\'')
 
     def bulk_modulus(self, units='Ha/b3', requires_grad=False):
         self.__second_order('bulk_modulus')
@@ -304,8 +324,35 @@ class System():
             forces = forces - torch.autograd.grad(U, cart)[0]
         return forces if units == 'Ha/b' else forces * self.eV_per_Ha / self.A_per_b
 
+    def __compute_stress(self):
+        """system.py:927-935: (1/vol) dE/d eps with the density rescaled to conserve N and the ions at fixed
+        fractional coordinates, symmetrised.  Native terms: analytic kernels (pad_stress_terms, pad_ion_stress);
+        IonIon: autograd through the real-space pair sum."""
+        plain = [f for f in self.__terms if _term_name(f) not in ('IonElectron', 'IonIon')]
+        names = [_term_name(f) for f in self.__terms]
+        sig = torch.zeros((3, 3), dtype=torch.double, device=self.__device)
+        if plain:
+            T = _density_opt.describe_terms(plain)
+            if T is None:
+                raise NotImplementedError('System.stress: analytic stresses exist for the native functionals only '
+                                          '(user-defined Python terms need autograd through box_vecs)')
+            sig = sig + _density_opt.stress_terms(self.__box_vecs, self.__den, T)
+        if 'IonElectron' in names:
+            sig = sig + ion_electron_stress(self.__box_vecs, self.__den, self.__species())
+        if 'IonIon' in names:
+            box = self.__box_vecs.detach().clone().requires_grad_(True)
+            saved, self.__box_vecs = self.__box_vecs, box
+            try:
+                U = self.__ion_ion_interaction(torch.matmul(self.__frac_ion_coords, box))
+            finally:
+                self.__box_vecs = saved
+            dEdcell = torch.autograd.grad(U, box)[0].T
+            sig = sig + torch.matmul(dEdcell, self.__box_vecs) / self.__vol()
+        return 0.5 * (sig + sig.T)
+
     def stress(self, units='Ha/b3'):
-        self.__second_order('stress')
+        """Stress tensor (system.py:645-668)."""
+        return self.__compute_stress() * self.__pressure_units(units)
 
     def elastic_constants(self, units='Ha/b3'):
         self.__second_order('elastic_constants')

@@ -45,3 +45,31 @@ def test_chi_projection_equals_autograd():
     assert ((g_auto - g_proj).abs().max() / g_auto.abs().max()).item() < 1e-12
     g_orc = orc.chi_gradient_from_potential(box, chi, n_elec, v)
     assert ((g_auto - g_orc).abs().max() / g_auto.abs().max()).item() < 1e-12
+
+
+@pytest.mark.parametrize('shape,seed', [((8, 10, 12), 1), ((9, 7, 11), 2), ((8, 9, 10), 3)])
+def test_analytic_stresses_equal_autograd(shape, seed):
+    """The stress formulas csrc/stress.cu and csrc/ions.cu implement, against autograd through box_vecs
+    (functional_tools.py:73-100) on even, odd and mixed skewed grids."""
+    import numpy as np
+    import os
+    box, den = orc.synth_rough(shape, seed=seed)
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max())
+    E, v = am.thomas_fermi(box, den)
+    assert rel(am.stress_local(box, den, E, v), orc.stress(box, den, orc.ThomasFermi)) < 1e-12
+    E, v = am.perdew_zunger(box, den)
+    assert rel(am.stress_local(box, den, E, v), orc.stress(box, den, orc.PerdewZunger)) < 1e-12
+    assert rel(am.stress_hartree(box, den), orc.stress(box, den, orc.Hartree)) < 1e-12
+    assert rel(am.stress_weizsaecker(box, den), orc.stress(box, den, orc.Weizsaecker)) < 1e-12
+    for a, b in ((5 / 6, 5 / 6), ((5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6)):
+        ref = orc.stress(box, den, lambda bx, d: orc.nonlocal_wt_term(bx, d, a, b))
+        assert rel(am.stress_wt_nonlocal(box, den, a, b), ref) < 1e-12
+    assert rel(am.stress_pbe(box, den), orc.stress(box, den, orc.PerdewBurkeErnzerhof)) < 1e-12
+    frac = torch.rand(3, 3, dtype=torch.double, generator=torch.Generator().manual_seed(seed))
+    path = os.path.join(os.path.dirname(__file__), 'potentials', 'al.gga.recpot')
+    ks, pot, z = orc.read_recpot(path)
+    smooth = pot.copy()
+    smooth[1:] += 4 * np.pi * z / ks[1:] ** 2
+    assert rel(am.stress_ion_electron(box, den, [(ks, smooth, z, frac)]), orc.ion_electron_stress(box, den, [(path, frac)])) < 1e-11

@@ -107,3 +107,111 @@ def test_slab_vext_and_forces(golden_dir, potentials_dir):
     assert np.abs(v - g['v_ext']).max() <= 1e-11 * np.abs(g['v_ext']).max()
     for o in out:
         assert np.abs(o[1].numpy() - g['forces_IonElectron']).max() <= 1e-10 * np.abs(g['forces_IonElectron']).max()
+
+
+# ------------------------------------------------------------------------------------------------
+#  stress: native analytic kernels vs the reference's autograd vectors
+# ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_functional_stresses_match_reference(case, golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import ion_utils as IU
+    from profess_ad_b200.functional_tools import get_stress, get_pressure
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    b, d = box.to(DEV), den.to(DEV)
+    n = 0
+    for key in g.files:
+        if key.startswith('stress_') and key[7:] not in ('Ha_b3', 'IonElectron', 'IonIon'):
+            f = getattr(F, key[7:])
+            st = get_stress(b, d, f).cpu().numpy()
+            assert _rel(st, g[key]) < 1e-10, (key, _rel(st, g[key]))
+            assert abs(get_pressure(b, d, f).item() + np.trace(g[key]) / 3) <= 1e-10 * np.abs(g[key]).max()
+            n += 1
+    assert n >= 3
+    st = IU.ion_electron_stress(b, d, [(p, f.to(DEV)) for p, f in species]).cpu().numpy()
+    assert _rel(st, g['stress_IonElectron']) < 1e-10
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_system_stress_and_pressure_match_reference(case, golden_dir, potentials_dir):
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    ions = [[os.path.basename(p)[:2].capitalize(), p, f] for p, f in species]
+    if case == 'alli_mixed':
+        terms = [F.IonIon, F.IonElectron, F.Hartree, F.ThomasFermi, F.Weizsaecker, F.PerdewZunger]
+    else:
+        terms = [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+    s = System(box, tuple(den.shape), ions, terms, units='b', coord_type='fractional')
+    s.set_density(torch.from_numpy(g['den']))
+    assert abs(s.energy('Ha') - float(g['energy_Ha'])) < 1e-10
+    st = s.stress('Ha/b3').cpu().numpy()
+    assert np.abs(st - g['stress_Ha_b3']).max() <= 1e-9 * np.abs(g['stress_Ha_b3']).max(), np.abs(st - g['stress_Ha_b3']).max()
+    assert abs(s.pressure('Ha/b3') - float(g['pressure_Ha_b3'])) <= 1e-9 * np.abs(g['stress_Ha_b3']).max()
+    assert np.allclose(s.stress('GPa').cpu().numpy(), st * System.GPa_per_atomic, rtol=1e-14)
+    assert abs(s.enthalpy('Ha') - (s.energy('Ha') + s.pressure() * s.volume('b3'))) < 1e-14
+    with pytest.raises(ValueError):
+        s.stress('bar')
+
+
+def test_stress_vs_oracle_rough_grids_and_unsupported():
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.functional_tools import get_stress
+    pairs = [(F.ThomasFermi, orc.ThomasFermi), (F.Weizsaecker, orc.Weizsaecker), (F.Hartree, orc.Hartree),
+             (F.WangTeter, orc.WangTeter), (F.WangGovindCarter98, orc.WangGovindCarter98), (F.SmargiassiMadden, orc.SmargiassiMadden),
+             (F.PerdewZunger, orc.PerdewZunger), (F.PerdewBurkeErnzerhof, orc.PerdewBurkeErnzerhof),
+             (F.pbe_exchange, orc.pbe_exchange), (F.lda_exchange, orc.lda_exchange)]
+    for shape, seed in (((16, 18, 20), 3), ((15, 17, 13), 4), ((12, 15, 16), 5)):
+        box, den = orc.synth_rough(shape, seed=seed)
+        for f, fo in pairs:
+            ref = orc.stress(box, den, fo).numpy()
+            st = get_stress(box.to(DEV), den.to(DEV), f).cpu().numpy()
+            assert _rel(st, ref) < 1e-10, (shape, f.__name__, _rel(st, ref))
+    with pytest.raises(NotImplementedError):
+        get_stress(box.to(DEV), den.to(DEV), F.WangGovindCarter99().forward)
+    with pytest.raises(NotImplementedError):
+        get_stress(box.to(DEV), den.to(DEV), lambda b, n: F.ThomasFermi(b, n))
+
+
+def test_slab_stress(golden_dir, potentials_dir):
+    """Stress on slab plans: the 7 sums of every piece are all-reduced (world 2, ranks as threads)."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import parallel, ion_utils as IU
+    from profess_ad_b200.functional_tools import get_stress
+    g, box, den, species = load_case('li2_even', golden_dir, potentials_dir)
+    shape, world = tuple(den.shape), 2
+    out, errors = [None] * world, []
+
+    def rank(comm, idx):
+        try:
+            dev = torch.device(DEV)
+            with torch.cuda.stream(torch.cuda.Stream(dev)):
+                with parallel.slab(shape, comm=comm):
+                    d = parallel.local_slab(den.to(dev))
+                    b = box.to(dev)
+                    st = get_stress(b, d, F.WangTeter) + get_stress(b, d, F.PerdewBurkeErnzerhof) + get_stress(b, d, F.Hartree)
+                    st = st + IU.ion_electron_stress(b, d, [(p, f.to(dev)) for p, f in species])
+                    torch.cuda.current_stream(dev).synchronize()
+                    out[idx] = st.cpu().numpy()
+        except BaseException as e:      # noqa: BLE001
+            errors.append(e)
+            try:
+                comm.shared.barrier.abort()
+            except Exception:
+                pass
+    shared = parallel.ThreadComm.Shared(world)
+    threads = [threading.Thread(target=rank, args=(parallel.ThreadComm(shared, r), r)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    if errors:
+        raise errors[0]
+    ref = g['stress_WangTeter'] + g['stress_PerdewBurkeErnzerhof'] + g['stress_Hartree'] + g['stress_IonElectron']
+    for st in out:
+        assert _rel(st, ref) < 1e-10
