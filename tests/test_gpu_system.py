@@ -113,7 +113,8 @@ def test_setters_and_errors(golden_dir, potentials_dir):
     with pytest.raises(ValueError):
         s.optimize_density(n_method='nope')
     with pytest.raises(NotImplementedError):
-        s.stress()
+        s.elastic_constants()
+    assert s.stress().shape == (3, 3)
     with pytest.raises(AssertionError):
         s.set_density(torch.ones(3, 3, 3, dtype=torch.double))
 
