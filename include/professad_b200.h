@@ -181,10 +181,17 @@ int pad_ion_stress(pad_plan* plan, const pad_species* species, int n_species, co
 typedef struct pad_terms {
     int local_mask;      /* PAD_LOCAL_* bits (IonElectron needs v_ext)                       */
     int hartree;         /* 0/1                                                              */
-    int kinetic;         /* 0 none, 1 Wang-Teter family (alpha, beta, kinetic_parts), 2 WGC99 */
+    int kinetic;         /* 0 none, 1 Wang-Teter family (alpha, beta, kinetic_parts), 2 WGC99,
+                            3 Huang-Carter family (hc_* below; beta, kappa from the shared fields)      */
     int kinetic_parts;   /* PAD_PART_* mask for kinetic == 1 (e.g. PAD_PART_VW alone = Weizsaecker) */
     int pbe;             /* 0 none, 1 exchange, 2 correlation, 3 both                        */
     double alpha, beta, gamma, kappa;
+    /* kinetic == 3: arguments of pad_eval_hc */
+    int hc_variant;              /* 0 HuangCarter (hc_p0 = lambda), 1 RevisedHuangCarter (hc_p0 = a, hc_p1 = b) */
+    int hc_geometric;
+    int hc_n_eta;
+    double hc_p0, hc_p1;
+    const double* hc_table_dev;  /* DEVICE, 2 * hc_n_eta doubles [eta | omega(eta)]                             */
 } pad_terms;
 int pad_eval_total(pad_plan* plan, const pad_terms* terms, const double* den, const double* v_ext,
                    double* E_out, double* v_out, void* stream);

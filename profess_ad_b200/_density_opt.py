@@ -17,7 +17,9 @@ class PadTerms(ctypes.Structure):
     _fields_ = [('local_mask', ctypes.c_int), ('hartree', ctypes.c_int), ('kinetic', ctypes.c_int),
                 ('kinetic_parts', ctypes.c_int), ('pbe', ctypes.c_int),
                 ('alpha', ctypes.c_double), ('beta', ctypes.c_double), ('gamma', ctypes.c_double),
-                ('kappa', ctypes.c_double)]
+                ('kappa', ctypes.c_double),
+                ('hc_variant', ctypes.c_int), ('hc_geometric', ctypes.c_int), ('hc_n_eta', ctypes.c_int),
+                ('hc_p0', ctypes.c_double), ('hc_p1', ctypes.c_double), ('hc_table_dev', ctypes.c_void_p)]
 
 
 class PadDenoptParams(ctypes.Structure):
@@ -73,6 +75,14 @@ def describe_terms(terms):
                 return None
             T.kinetic = 2
             T.alpha, T.beta, T.gamma, T.kappa = spec[1:5]
+        elif kind == 'hc':
+            if T.kinetic:
+                return None
+            T.kinetic = 3
+            _, T.hc_variant, T.hc_p0, T.hc_p1, T.beta, T.kappa, T.hc_geometric, table = spec
+            T.hc_n_eta = int(table.shape[1])
+            T.hc_table_dev = table.data_ptr()
+            T._keep = table             # the descriptor holds a raw device pointer: keep the tensor alive with it
         else:
             return None
     if not (T.local_mask or T.hartree or T.kinetic or T.pbe):
@@ -96,6 +106,8 @@ def eval_total(box_vecs, den, v_ext, T, want_potential=True):
 def stress_terms(box_vecs, den, T):
     """Analytic stress (3, 3) in Ha/bohr^3 of a described term list without its IonElectron part (pad_stress_terms)."""
     _native.require_cuda(den)
+    if T.kinetic == 3:
+        raise NotImplementedError('stress of the Huang-Carter family is not available')
     if T.kinetic == 2:
         raise NotImplementedError('stress of WangGovindCarter99: the reference\'s autograd result depends on the state of its '
                                   'kernel cache (functionals.py:961-966), there is no well-defined value to reproduce')

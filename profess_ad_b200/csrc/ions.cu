@@ -21,8 +21,9 @@
 
 namespace {
 
-constexpr int ION_T = 128;       // threads per CTA (and ions staged per shared-memory chunk)
-constexpr int ION_MAXJ = 9;      // half-spectrum points per thread along z: n2/2 + 1 <= 1152
+constexpr int ION_T = 128;       // threads per CTA of the force kernel
+constexpr int ION_RB = 8;        // half-spectrum rows per CTA sweep in the structure-factor kernel
+constexpr int ION_CH = 128;      // ions staged per shared-memory chunk
 constexpr int ION_IPC = 8;       // ions per CTA in the force kernel
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -60,73 +61,88 @@ __device__ __forceinline__ double recpot_value(const UniformTable& T, double z, 
     return table_lookup(T, sqrt(k2)) - 4.0 * kPi * z / k2;
 }
 
-__global__ void __launch_bounds__(ION_T) k_ion_spectrum(KGeom g, int nrows, UniformTable T, double z, int n_ions,
-                                                      const double2* __restrict__ E0, const double2* __restrict__ E1,
-                                                      const double2* __restrict__ E2, double inv_vol, int accumulate,
-                                                      int raw /* 1: plain S(k), no potential factor, no symmetrisation */,
-                                                      double2* __restrict__ out) {
-    __shared__ double2 s01[ION_T], s01b[ION_T];
+// One CTA owns ION_RB consecutive (j0, j1) rows at a time; its threads run along j2.  Per ion the e2 phase of a column
+// is loaded once and used for all ION_RB rows (the e0 e1 products of ION_CH ions x ION_RB rows are staged in shared
+// memory), so the traffic from L2 is 1 / ION_RB of a row-at-a-time sweep and the loop is FMA-bound.
+__global__ void __launch_bounds__(256) k_ion_spectrum(KGeom g, int nrows, UniformTable T, double z, int n_ions,
+                                                    const double2* __restrict__ E0, const double2* __restrict__ E1,
+                                                    const double2* __restrict__ E2, double inv_vol, int accumulate,
+                                                    int raw /* 1: plain S(k), no potential factor, no symmetrisation */,
+                                                    double2* __restrict__ out) {
+    __shared__ double2 s01[ION_RB][ION_CH], s01b[ION_RB][ION_CH];
     const int nzh = g.nzh;
-    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int j0 = row / g.n1_loc, j1 = row - j0 * g.n1_loc + g.j1_off;
-        const bool nyq0 = g.e0 && j0 == g.n0 / 2, nyq1 = g.e1 && j1 == g.n1 / 2;
-        double2 acc[ION_MAXJ], accb[ION_MAXJ];
-        bool sp[ION_MAXJ];
+    const bool nyq2_any = g.e2;
+    for (int row0 = blockIdx.x * ION_RB; row0 < nrows; row0 += gridDim.x * ION_RB) {
+        int j0r[ION_RB], j1r[ION_RB];
 #pragma unroll
-        for (int m = 0; m < ION_MAXJ; ++m) {
-            const int j2 = threadIdx.x + m * ION_T;
-            acc[m] = make_double2(0.0, 0.0);
-            accb[m] = make_double2(0.0, 0.0);
-            sp[m] = j2 < nzh && ((j2 == 0 && (nyq0 || nyq1)) || (g.e2 && j2 == g.n2 / 2));
+        for (int r = 0; r < ION_RB; ++r) {
+            const int row = min(row0 + r, nrows - 1);
+            j0r[r] = row / g.n1_loc;
+            j1r[r] = row - j0r[r] * g.n1_loc + g.j1_off;
         }
-        for (int base = 0; base < n_ions; base += ION_T) {
-            const int ion = base + threadIdx.x;
-            if (ion < n_ions) {
-                double2 a = E0[(size_t)ion * g.n0 + j0], b = E1[(size_t)ion * g.n1 + j1];
-                s01[threadIdx.x] = cmul(a, b);
-                if (!nyq0) a.y = -a.y;          // partner wave vector: frequency -f unless f is the (positive) Nyquist one
-                if (!nyq1) b.y = -b.y;
-                s01b[threadIdx.x] = cmul(a, b);
-            }
-            __syncthreads();
-            const int cnt = min(ION_T, n_ions - base);
-            for (int i = 0; i < cnt; ++i) {
-                const double2 e = s01[i];
-                const double2* __restrict__ e2 = E2 + (size_t)(base + i) * nzh;
+        for (int jbase = 0; jbase < nzh; jbase += blockDim.x) {
+            const int j2 = jbase + threadIdx.x;
+            const bool live = j2 < nzh;
+            const bool zedge0 = live && j2 == 0, zedgeN = live && nyq2_any && j2 == g.n2 / 2;
+            const bool maybe_sp = !raw && (zedge0 || zedgeN);
+            double2 acc[ION_RB], accb[ION_RB];
 #pragma unroll
-                for (int m = 0; m < ION_MAXJ; ++m) {
-                    const int j2 = threadIdx.x + m * ION_T;
-                    if (j2 < nzh) {
-                        const double2 ph = e2[j2];
-                        acc[m].x = fma(e.x, ph.x, fma(-e.y, ph.y, acc[m].x));
-                        acc[m].y = fma(e.x, ph.y, fma(e.y, ph.x, acc[m].y));
-                        if (sp[m]) {
-                            const double2 eb = s01b[i];
-                            accb[m].x = fma(eb.x, ph.x, fma(-eb.y, ph.y, accb[m].x));
-                            accb[m].y = fma(eb.x, ph.y, fma(eb.y, ph.x, accb[m].y));
+            for (int r = 0; r < ION_RB; ++r) { acc[r] = make_double2(0.0, 0.0); accb[r] = make_double2(0.0, 0.0); }
+            for (int base = 0; base < n_ions; base += ION_CH) {
+                __syncthreads();
+                for (int e = threadIdx.x; e < ION_CH * ION_RB; e += blockDim.x) {
+                    const int r = e / ION_CH, i = e - r * ION_CH, ion = base + i;
+                    if (ion < n_ions) {
+                        const int rr = min(row0 + r, nrows - 1);
+                        const int jj0 = rr / g.n1_loc, jj1 = rr - jj0 * g.n1_loc + g.j1_off;
+                        double2 a = E0[(size_t)ion * g.n0 + jj0], b = E1[(size_t)ion * g.n1 + jj1];
+                        s01[r][i] = cmul(a, b);
+                        if (!(g.e0 && jj0 == g.n0 / 2)) a.y = -a.y;   // partner wave vector: -f unless f is the (positive) Nyquist frequency
+                        if (!(g.e1 && jj1 == g.n1 / 2)) b.y = -b.y;
+                        s01b[r][i] = cmul(a, b);
+                    }
+                }
+                __syncthreads();
+                const int cnt = min(ION_CH, n_ions - base);
+                if (live) {
+                    const double2* __restrict__ e2 = E2 + (size_t)base * nzh + j2;
+                    for (int i = 0; i < cnt; ++i) {
+                        const double2 ph = e2[(size_t)i * nzh];
+#pragma unroll
+                        for (int r = 0; r < ION_RB; ++r) {
+                            const double2 e = s01[r][i];
+                            acc[r].x = fma(e.x, ph.x, fma(-e.y, ph.y, acc[r].x));
+                            acc[r].y = fma(e.x, ph.y, fma(e.y, ph.x, acc[r].y));
+                        }
+                        if (maybe_sp) {
+#pragma unroll
+                            for (int r = 0; r < ION_RB; ++r) {
+                                const double2 eb = s01b[r][i];
+                                accb[r].x = fma(eb.x, ph.x, fma(-eb.y, ph.y, accb[r].x));
+                                accb[r].y = fma(eb.x, ph.y, fma(eb.y, ph.x, accb[r].y));
+                            }
                         }
                     }
                 }
             }
-            __syncthreads();
-        }
+            if (live) {
 #pragma unroll
-        for (int m = 0; m < ION_MAXJ; ++m) {
-            const int j2 = threadIdx.x + m * ION_T;
-            if (j2 < nzh) {
-                const KPoint p = make_kpoint_at(g, j0, j1, j2);
-                const double f = raw ? 1.0 : recpot_value(T, z, p.kx, p.ky, p.kz);
-                double2 G = make_double2(f * acc[m].x, f * acc[m].y);
-                if (p.special && !raw) {
-                    const double fb = recpot_value(T, z, p.px, p.py, p.pz);
-                    G.x = 0.5 * (G.x + fb * accb[m].x);
-                    G.y = 0.5 * (G.y - fb * accb[m].y);
+                for (int r = 0; r < ION_RB; ++r) {
+                    if (row0 + r >= nrows) continue;
+                    const KPoint p = make_kpoint_at(g, j0r[r], j1r[r], j2);
+                    const double f = raw ? 1.0 : recpot_value(T, z, p.kx, p.ky, p.kz);
+                    double2 G = make_double2(f * acc[r].x, f * acc[r].y);
+                    if (p.special && !raw) {
+                        const double fb = recpot_value(T, z, p.px, p.py, p.pz);
+                        G.x = 0.5 * (G.x + fb * accb[r].x);
+                        G.y = 0.5 * (G.y - fb * accb[r].y);
+                    }
+                    const size_t idx = (size_t)(row0 + r) * nzh + j2;
+                    double2 o = accumulate ? out[idx] : make_double2(0.0, 0.0);
+                    o.x += G.x * inv_vol;
+                    o.y += G.y * inv_vol;
+                    out[idx] = o;
                 }
-                const size_t idx = (size_t)row * nzh + j2;
-                double2 o = accumulate ? out[idx] : make_double2(0.0, 0.0);
-                o.x += G.x * inv_vol;
-                o.y += G.y * inv_vol;
-                out[idx] = o;
             }
         }
     }
@@ -198,6 +214,20 @@ __global__ void k_ion_force_finish(const double* __restrict__ partial, int n_ion
     forces[e] = -v;
 }
 
+// block size (multiple of 32, <= 256) that wastes the fewest lanes on the n2/2 + 1 columns of a row
+int spectrum_threads(int nzh) {
+    int best = 256, best_waste = 1 << 30;
+    for (int t = 96; t <= 256; t += 32) {
+        const int waste = (nzh + t - 1) / t * t - nzh;
+        if (waste < best_waste || (waste == best_waste && t > best)) { best = t; best_waste = waste; }
+    }
+    return best;
+}
+int spectrum_grid(int nrows) {
+    const int blocks = (nrows + ION_RB - 1) / ION_RB;
+    return blocks < 148 * 4 ? blocks : 148 * 4;
+}
+
 struct IonScratch {
     double2 *E0, *E1, *E2;
     double* slopes;
@@ -205,7 +235,6 @@ struct IonScratch {
 
 int check_species(const pad_plan* p, const pad_species* sp, int n_species, const char* who) {
     if (!p || !sp || n_species < 1) { pad_set_error("%s: null argument / no species", who); return PAD_ERR_ARG; }
-    if (p->nzh > ION_T * ION_MAXJ) { pad_set_error("%s: n2 = %d too large (n2/2 + 1 <= %d)", who, p->n2, ION_T * ION_MAXJ); return PAD_ERR_ARG; }
     for (int s = 0; s < n_species; ++s) {
         if (!sp[s].table_dev || sp[s].n_table < 3 || !(sp[s].k_max > 0.0) || sp[s].n_ions < 0 || (sp[s].n_ions > 0 && !sp[s].frac_dev)) {
             pad_set_error("%s: bad species %d (table %p, n_table %d, k_max %g, n_ions %d)", who, s, (const void*)sp[s].table_dev,
@@ -253,12 +282,13 @@ extern "C" int pad_ionic_potential(pad_plan* p, const pad_species* species, int 
     cufftDoubleComplex* G;
     PAD_TRY(pad_get_cbuf(p, 0, &G));
     const int nrows = p->n0 * p->geom.n1_loc;
-    const int grid = nrows < 148 * 8 ? nrows : 148 * 8;
+    const int threads = spectrum_threads(p->nzh);
+    const int grid = spectrum_grid(nrows);
     for (int sI = 0; sI < n_species; ++sI) {
         IonScratch W;
         UniformTable T;
         PAD_TRY(prepare_species(p, species[sI], s, W, T));
-        k_ion_spectrum<<<grid, ION_T, 0, s>>>(p->geom, nrows, T, species[sI].z, species[sI].n_ions, W.E0, W.E1, W.E2, 1.0 / p->vol,
+        k_ion_spectrum<<<grid, threads, 0, s>>>(p->geom, nrows, T, species[sI].z, species[sI].n_ions, W.E0, W.E1, W.E2, 1.0 / p->vol,
                                             sI > 0, 0, reinterpret_cast<double2*>(G));
         ++g_pad_launches;
         PAD_CUDA(cudaGetLastError());
@@ -339,7 +369,8 @@ extern "C" int pad_ion_stress(pad_plan* p, const pad_species* species, int n_spe
     PAD_TRY(pad_get_cbuf(p, 1, &Sk));
     PAD_TRY(pad_fft_forward(p, den, R, s));
     const int nrows = p->n0 * p->geom.n1_loc;
-    const int grid = nrows < 148 * 8 ? nrows : 148 * 8;
+    const int threads = spectrum_threads(p->nzh);
+    const int grid = spectrum_grid(nrows);
     const KGeom geom = p->geom;
     const double inv_n = geom.inv_n;
     for (int sI = 0; sI < n_species; ++sI) {
@@ -348,7 +379,7 @@ extern "C" int pad_ion_stress(pad_plan* p, const pad_species* species, int n_spe
         IonScratch W;
         UniformTable T;
         PAD_TRY(prepare_species(p, sp, s, W, T));
-        k_ion_spectrum<<<grid, ION_T, 0, s>>>(geom, nrows, T, sp.z, sp.n_ions, W.E0, W.E1, W.E2, 1.0, 0, 1, reinterpret_cast<double2*>(Sk));
+        k_ion_spectrum<<<grid, threads, 0, s>>>(geom, nrows, T, sp.z, sp.n_ions, W.E0, W.E1, W.E2, 1.0, 0, 1, reinterpret_cast<double2*>(Sk));
         ++g_pad_launches;
         const cufftDoubleComplex *Rc = R, *Sc = Sk;
         const double z = sp.z;

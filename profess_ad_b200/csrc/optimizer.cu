@@ -193,22 +193,27 @@ __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_pass1(size_t n, const Opt
     double* __restrict__ y_new = Yh + (size_t)fs * n;
     const size_t stride = (size_t)gridDim.x * PAD_THREADS;
     for (size_t i = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; i < n; i += stride) {
-        const double gi = g[i];
-        const double y = gi - prev_g[i];
-        const double s = t * d[i];
+        // every load of the iteration is issued before the first use (predicated loads, no branches): with up to
+        // 2 k + 3 vectors to stream the pass is bound by the bytes a thread keeps in flight
+        const double gi = g[i], pg = prev_g[i], di = d[i];
+        double sa[OPT_SLOTS], ya[OPT_SLOTS];
+#pragma unroll
+        for (int a = 0; a < OPT_SLOTS; ++a) {
+            sa[a] = used[a] ? Sh[(size_t)a * n + i] : 0.0;
+            ya[a] = used[a] ? Yh[(size_t)a * n + i] : 0.0;
+        }
+        const double y = gi - pg;
+        const double s = t * di;
         s_new[i] = s;
         y_new[i] = y;
         acc[0] += s * y; acc[1] += y * y; acc[2] += s * s; acc[3] += s * gi; acc[4] += y * gi;
 #pragma unroll
         for (int a = 0; a < OPT_SLOTS; ++a) {
-            if (used[a]) {
-                const double sa = Sh[(size_t)a * n + i], ya = Yh[(size_t)a * n + i];
-                acc[5 + 5 * a + 0] += sa * y;     // s_a . y_new
-                acc[5 + 5 * a + 1] += s * ya;     // s_new . y_a
-                acc[5 + 5 * a + 2] += ya * y;     // y_a . y_new
-                acc[5 + 5 * a + 3] += sa * gi;    // s_a . g
-                acc[5 + 5 * a + 4] += ya * gi;    // y_a . g
-            }
+            acc[5 + 5 * a + 0] += sa[a] * y;      // s_a . y_new
+            acc[5 + 5 * a + 1] += s * ya[a];      // s_new . y_a
+            acc[5 + 5 * a + 2] += ya[a] * y;      // y_a . y_new
+            acc[5 + 5 * a + 3] += sa[a] * gi;     // s_a . g
+            acc[5 + 5 * a + 4] += ya[a] * gi;     // y_a . g
         }
     }
     // block reduction of OPT_NACC sums
@@ -325,14 +330,20 @@ __global__ void __launch_bounds__(PAD_THREADS) k_lbfgs_pass2(size_t n, const Opt
     double acc[1] = {0.0};
     const size_t stride = (size_t)gridDim.x * PAD_THREADS;
     for (size_t i = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; i < n; i += stride) {
-        const double gi = g[i];
+        const double gi = g[i], xi = chi[i];
+        double sa[OPT_SLOTS], ya[OPT_SLOTS];
+#pragma unroll
+        for (int a = 0; a < OPT_SLOTS; ++a) {      // all loads first (see pass 1)
+            sa[a] = used[a] ? Sh[(size_t)a * n + i] : 0.0;
+            ya[a] = used[a] ? Yh[(size_t)a * n + i] : 0.0;
+        }
         double di = cg * gi;
 #pragma unroll
         for (int a = 0; a < OPT_SLOTS; ++a)
-            if (used[a]) di += cS[a] * Sh[(size_t)a * n + i] + cY[a] * Yh[(size_t)a * n + i];
+            if (used[a]) di += cS[a] * sa[a] + cY[a] * ya[a];
         d[i] = di;
         prev_g[i] = gi;
-        chi[i] += t * di;
+        chi[i] = xi + t * di;
         acc[0] += fabs(di);
     }
     block_reduce_store<1>(acc, partials);
@@ -424,6 +435,13 @@ extern "C" int pad_eval_total(pad_plan* p, const pad_terms* T, const double* den
         acc = 1;
     } else if (T->kinetic == 2) {
         PAD_TRY(pad_eval_wgc99(p, den, T->alpha, T->beta, T->gamma, T->kappa, E_out, v_out, acc, stream));
+        acc = 1;
+    } else if (T->kinetic == 3) {
+        // pad_eval_hc adds into v_out, so the potential must exist before it is called
+        if (!acc && v_out) PAD_CUDA(cudaMemsetAsync(v_out, 0, sizeof(double) * p->N, (cudaStream_t)stream));
+        if (!acc && E_out) PAD_CUDA(cudaMemsetAsync(E_out, 0, sizeof(double), (cudaStream_t)stream));
+        PAD_TRY(pad_eval_hc(p, den, T->hc_variant, T->hc_p0, T->hc_p1, T->beta, T->kappa, T->hc_geometric, T->hc_table_dev,
+                            T->hc_n_eta, E_out, v_out, 1, nullptr, stream));
         acc = 1;
     }
     if (T->pbe) {

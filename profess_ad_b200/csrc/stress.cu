@@ -72,6 +72,7 @@ extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* d
         pad_set_error("pad_stress_terms: no stress for WangGovindCarter99 (the reference's autograd result depends on its kernel-cache state)");
         return PAD_ERR_ARG;
     }
+    if (T->kinetic == 3) { pad_set_error("pad_stress_terms: no stress for the Huang-Carter family"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     const KGeom geom = p->geom;

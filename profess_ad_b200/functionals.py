@@ -363,6 +363,20 @@ class _HuangCarterFamily(KineticFunctional):
     mode = 'geometric'
     _variant = 0
 
+    def _pad_term_of(self):
+        """Descriptor for the fused evaluator / device-resident optimiser (_density_opt.describe_terms)."""
+        if self.mode not in ('geometric', 'arithmetic'):
+            return None
+        table = self.kernel
+        if table.device.type != 'cuda' or table.dtype != torch.double or not table.is_contiguous():
+            if not torch.cuda.is_available():
+                return None
+            table = table.to(device=torch.device('cuda', torch.cuda.current_device()), dtype=torch.double).contiguous()
+            self.kernel = table
+        p0, p1 = self._params()
+        return ('hc', self._variant, p0, p1, float(self.beta.item()), float(self.kappa),
+                1 if self.mode == 'geometric' else 0, table)
+
     def generate_kernel(self, eta_max=50, N_eta=10000):
         self.kernel = huang_carter_kernel_table(float(self.beta.item()), eta_max, N_eta)
 

@@ -157,3 +157,32 @@ def test_fused_evaluator_and_projection_match_oracle():
             assert abs(stats[2].item() - (g_ref / dV).abs().max().item()) <= 1e-9 * (g_ref / dV).abs().max().item()
     assert D.describe_terms([F.Hartree, lambda b, n: F.ThomasFermi(b, n)]) is None      # user term -> generic path
     assert D.describe_terms([F.ThomasFermi, F.ThomasFermi]) is None
+
+
+def test_huang_carter_density_optimisation_native_vs_oracle(golden_dir, potentials_dir):
+    """Huang-Carter family in the fused evaluator and the device-resident optimiser (pad_terms.kinetic == 3):
+    same optimised energy as the CPU oracle's restatement of the reference loop, with the same omega(eta) table
+    injected on both sides."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    from profess_ad_b200 import _density_opt as D
+    from oracle import ofdft_oracle as orc
+    g = np.load(os.path.join(golden_dir, 'denopt_al_fcc4_config1.npz'))
+    with np.load(os.path.join(golden_dir, 'hc_table.npz')) as tab:
+        t_rev = torch.from_numpy(tab['revhc'])
+    box = torch.from_numpy(g['box_bohr'])
+    shape = (12, 12, 12)
+    frac = torch.from_numpy(g['frac'])
+    pot = os.path.join(potentials_dir, 'al.gga.recpot')
+    hc = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15), kernel=t_rev.clone())
+    terms = [F.IonElectron, F.Hartree, hc.forward, F.PerdewZunger]
+    assert D.describe_terms(terms) is not None and D.describe_terms(terms).kinetic == 3
+    s = System(box, shape, [['Al', pot, frac]], terms, units='b', coord_type='fractional')
+    s.optimize_density(ntol=1e-7, from_uniform=True)
+    assert s.last_optimization.get('native') and s.last_optimization['converged']
+    v_ext = s.ionic_potential().cpu()
+    n_elec = s.electron_count()
+    den0 = torch.full(shape, n_elec / s.volume(), dtype=torch.double)
+    ohc = orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=t_rev)
+    ref = orc.optimize_density(box, den0, n_elec, [orc.IonElectron, orc.Hartree, ohc, orc.PerdewZunger], v_ext=v_ext, ntol=1e-7)
+    assert abs(s.energy('Ha') - ref['energy']) * EV / frac.shape[0] < 1e-6, (s.energy('Ha'), ref['energy'])
