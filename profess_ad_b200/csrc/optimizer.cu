@@ -15,6 +15,8 @@
 //    the history instead of ~4 m sequential dot/axpy launches with a host sync each;
 //  * the host enqueues "ticks" (closure + transition + move) and polls a pinned copy of the status
 //    a few ticks behind the GPU: no host synchronisation inside an outer iteration.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define OPT_M 8                 // max history
@@ -684,6 +686,7 @@ extern "C" int pad_denopt_run(pad_denopt* o, double* den_inout, const double* v_
     launch_ew_opt<0>(p, s, [=] __device__(size_t i, double(&)[1]) { chi[i] = sqrt(den_inout[i]); });
     PAD_CUDA(cudaGetLastError());
 
+    const bool debug = getenv("PAD_DENOPT_DEBUG") != nullptr;       // per-tick state dump on stderr
     const long long max_ticks = (long long)P.n_maxiter * (P.method == 0 ? P.max_iter : 1) + OPT_LOOKAHEAD + 2;
     long long tick = 0;
     bool done = false;
@@ -691,6 +694,11 @@ extern "C" int pad_denopt_run(pad_denopt* o, double* den_inout, const double* v_
         if (tick >= OPT_LOOKAHEAD) {
             const long long j = tick - OPT_LOOKAHEAD;
             PAD_CUDA(cudaEventSynchronize(o->ev[j % OPT_RING]));
+            if (debug) {
+                const OptState& h = o->host_ring[j % OPT_RING];
+                fprintf(stderr, "[denopt] tick %lld closures %d outer %d it %d phase %d E %.12f |g|1 %.6e gg %.6e k %d H %.6e t %.3e gtd %.6e |d|1 %.6e\n",
+                        j, h.closures, h.outer_iter, h.it, h.phase, h.E, h.g_l1, h.gg, h.k, h.H, h.t, h.gtd, h.d_l1);
+            }
             if (o->host_ring[j % OPT_RING].done) { done = true; break; }
         }
         const double* tot = nullptr;
