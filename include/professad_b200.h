@@ -90,11 +90,17 @@ int pad_plan_destroy(pad_plan* plan);
 #define PAD_COMM_ALL_TO_ALL 0
 #define PAD_COMM_ALL_REDUCE 1
 #define PAD_COMM_ALL_REDUCE_MAX 2
+#define PAD_COMM_ALL_TO_ALL_2 3          /* as PAD_COMM_ALL_TO_ALL, on the second buffer pair (pad_plan_set_overlap_buffers) */
 #define PAD_COMM_SCRATCH 64
 typedef int (*pad_comm_fn)(void* user, int op, long long count, void* stream);
 int pad_plan_create_slab(pad_plan** plan, const double* box_host, const int* global_shape_host, int device,
                          int rank, int world, void* send_buf, void* recv_buf, double* comm_scratch,
                          pad_comm_fn fn, void* user);
+/* Optional second exchange buffer pair (Nk complex each, caller-owned).  With it, batches of transforms inside one
+ * evaluation are software-pipelined: the all-to-all of one field is issued on a communication stream of the plan's own
+ * (`fn` is then called with THAT stream and op PAD_COMM_ALL_TO_ALL / PAD_COMM_ALL_TO_ALL_2) while the local FFTs of the
+ * neighbouring fields run on the caller's stream. */
+int pad_plan_set_overlap_buffers(pad_plan* plan, void* send_buf2, void* recv_buf2);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
 size_t pad_plan_workspace_bytes(const pad_plan* plan);
 

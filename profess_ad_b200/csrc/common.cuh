@@ -226,6 +226,12 @@ struct pad_plan {
     int rank, world, n0_loc, n1_loc;
     cufftHandle d2z_yz, z2d_yz, z2z_x;
     void *send_buf, *recv_buf;   // Nk complex each, owned by the caller
+    // second exchange buffer pair + a communication stream: batches of transforms are software-pipelined so that the
+    // all-to-all of one field runs while the local FFTs of its neighbours do (pad_fft_forward_many / _inverse_many)
+    void *send_buf2, *recv_buf2;
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_ready[2], ev_a2a[2], ev_free[2];
+    bool comm_ready;
     double* comm_scratch;        // PAD_COMM_SCRATCH doubles, owned by the caller
     pad_comm_fn comm_fn;
     void* comm_user;
@@ -245,6 +251,10 @@ int pad_get_rbuf(pad_plan* p, int i, double** out);
 int pad_get_cbuf(pad_plan* p, int i, cufftDoubleComplex** out);
 int pad_fft_forward(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s);
 int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s);
+// n independent transforms; on slab plans with a second exchange buffer pair the all-to-all of field f overlaps the
+// local transforms of fields f - 1 and f + 1 (otherwise a plain loop)
+int pad_fft_forward_many(pad_plan* p, const double* const* in, cufftDoubleComplex* const* out, int n, cudaStream_t s);
+int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* const* out, int n, cudaStream_t s);
 extern int g_pad_own_xy;
 extern int g_pad_profile;          // 1: record CUDA events between pipeline stages (pad_profile_begin/end)
 void pad_stage_begin(cudaStream_t s);

@@ -181,9 +181,9 @@ extern "C" int pad_gradient(pad_plan* p, const double* f, double* gx, double* gy
     PAD_TRY(pad_get_cbuf(p, 2, &C2)); PAD_TRY(pad_get_cbuf(p, 3, &C3));
     PAD_TRY(pad_fft_forward(p, f, C0, s));
     PAD_TRY(spectral_gradient(p, s, C0, C1, C2, C3));
-    PAD_TRY(pad_fft_inverse(p, C1, gx, s));
-    PAD_TRY(pad_fft_inverse(p, C2, gy, s));
-    PAD_TRY(pad_fft_inverse(p, C3, gz, s));
+    cufftDoubleComplex* Cs[3] = {C1, C2, C3};
+    double* Gs[3] = {gx, gy, gz};
+    PAD_TRY(pad_fft_inverse_many(p, Cs, Gs, 3, s));
     return PAD_OK;
 }
 
@@ -554,7 +554,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     });
     PAD_CHECK_LAUNCH();
     pad_stage_mark("gen a,a.th,a.th2,chi", s);
-    for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    PAD_TRY(pad_fft_forward_many(p, R, C, 4, s));
     pad_stage_mark("cuFFT D2Z x4", s);
     cufftDoubleComplex *CA = C[0], *CB = C[1], *CC = C[2], *CX = C[3];
     launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {
@@ -570,7 +570,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     });
     PAD_CHECK_LAUNCH();
     pad_stage_mark("kernel mix + (-k^2)", s);
-    for (int i = 0; i < 4; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // u1, u2, u3, lap(chi)
+    PAD_TRY(pad_fft_inverse_many(p, C, R, 4, s));                            // u1, u2, u3, lap(chi)
     pad_stage_mark("cuFFT Z2D x4", s);
 
     // --- energy densities, first half of the potential, fields for the adjoint convolutions -------
@@ -605,7 +605,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     if (!want_v) return PAD_OK;
 
     // --- adjoint convolutions --------------------------------------------------------------------
-    for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_forward(p, R[i], C[i], s));
+    PAD_TRY(pad_fft_forward_many(p, R, C, 3, s));
     pad_stage_mark("cuFFT D2Z x3", s);
     launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint&) {
         const double w0 = W0[idx], k1 = K1[idx], k2 = K2[idx], k3 = K3[idx];
@@ -616,7 +616,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     });
     PAD_CHECK_LAUNCH();
     pad_stage_mark("kernel mix", s);
-    for (int i = 0; i < 3; ++i) PAD_TRY(pad_fft_inverse(p, C[i], R[i], s));   // g1, g2, g3
+    PAD_TRY(pad_fft_inverse_many(p, C, R, 3, s));                            // g1, g2, g3
     pad_stage_mark("cuFFT Z2D x3", s);
     launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
         const double n = den[i];
@@ -644,7 +644,7 @@ extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E
     for (int i = 0; i < 4; ++i) { PAD_TRY(pad_get_rbuf(p, i, &R[i])); PAD_TRY(pad_get_cbuf(p, i, &C[i])); }
     PAD_TRY(pad_fft_forward(p, den, C[0], s));
     PAD_TRY(spectral_gradient(p, s, C[0], C[1], C[2], C[3]));
-    for (int c = 0; c < 3; ++c) PAD_TRY(pad_fft_inverse(p, C[c + 1], R[c], s));
+    PAD_TRY(pad_fft_inverse_many(p, C + 1, R, 3, s));
     double *Gx = R[0], *Gy = R[1], *Gz = R[2], *Fr = R[3];
     const bool do_x = which & 1, do_c = which & 2, want_v = v_out != nullptr;
     launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
@@ -666,7 +666,7 @@ extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E
     if (E_out) finalize(p, s, 1, coef, E_out, accumulate);
     PAD_CHECK_LAUNCH();
     if (!want_v) return PAD_OK;
-    for (int c = 0; c < 3; ++c) PAD_TRY(pad_fft_forward(p, R[c], C[c], s));
+    PAD_TRY(pad_fft_forward_many(p, R, C, 3, s));
     cufftDoubleComplex *C0 = C[0], *C1 = C[1], *C2 = C[2];
     const double inv_n = p->geom.inv_n;
     launch_ks(p, s, [=] __device__(uint32_t idx, const KPoint& k) {

@@ -353,7 +353,7 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
         ew_kernel<0, decltype(f)><<<grid, PAD_THREADS, 0, s>>>(N, f, p->partials);
         ++g_pad_launches;
     }
-    for (int c = 0; c < 3; ++c) PAD_TRY(pad_fft_forward(p, R[c], C[c], s));
+    PAD_TRY(pad_fft_forward_many(p, R, C, 3, s));
     {
         cufftDoubleComplex *C0 = C[0], *C1 = C[1], *C2 = C[2];
         auto fk = [=] __device__(uint32_t idx, const KPoint& k) {

@@ -230,6 +230,10 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     cudaSetDevice(p->device);
     if (p->fft_ready && !p->dist) { cufftDestroy(p->d2z); cufftDestroy(p->z2d); }
     if (p->fft_ready && p->dist) { cufftDestroy(p->d2z_yz); cufftDestroy(p->z2d_yz); cufftDestroy(p->z2z_x); }
+    if (p->comm_ready) {
+        cudaStreamDestroy(p->comm_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(p->ev_ready[i]); cudaEventDestroy(p->ev_a2a[i]); cudaEventDestroy(p->ev_free[i]); }
+    }
     if (p->fft_work) cudaFree(p->fft_work);
     for (int i = 0; i < PAD_N_RBUF; ++i) if (p->rbuf[i]) cudaFree(p->rbuf[i]);
     for (int i = 0; i < PAD_N_CBUF; ++i) if (p->cbuf[i]) cudaFree(p->cbuf[i]);
@@ -384,6 +388,111 @@ static int fft_inverse_slab(pad_plan* p, cufftDoubleComplex* in, double* out, cu
     PAD_CUFFT(cufftExecZ2D(p->z2d_yz, in, out));
     g_pad_fft_execs += 2;
     ++g_pad_launches;
+    return PAD_OK;
+}
+
+// ---- pipelined batches ---------------------------------------------------------------------------------------
+extern "C" int pad_plan_set_overlap_buffers(pad_plan* p, void* send_buf2, void* recv_buf2) {
+    if (!p || !p->dist) { pad_set_error("pad_plan_set_overlap_buffers: needs a slab plan"); return PAD_ERR_ARG; }
+    p->send_buf2 = send_buf2;
+    p->recv_buf2 = recv_buf2;
+    return PAD_OK;
+}
+
+static int ensure_comm_stream(pad_plan* p) {
+    if (p->comm_ready) return PAD_OK;
+    PAD_CUDA(cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PAD_CUDA(cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming));
+        PAD_CUDA(cudaEventCreateWithFlags(&p->ev_a2a[i], cudaEventDisableTiming));
+        PAD_CUDA(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
+    }
+    p->comm_ready = true;
+    return PAD_OK;
+}
+
+static bool can_overlap(const pad_plan* p, int n) { return p->dist && p->world > 1 && p->send_buf2 && p->recv_buf2 && n >= 2; }
+
+// exchange of buffer pair b on the communication stream: after the producer on `s` (ev_ready[b]) and, from the third
+// field on, after the consumer of the pair's previous contents (ev_free[b])
+static int exchange_async(pad_plan* p, int b, bool wait_free, cudaStream_t s) {
+    PAD_CUDA(cudaEventRecord(p->ev_ready[b], s));
+    PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_ready[b], 0));
+    if (wait_free) PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_free[b], 0));
+    PAD_TRY(pad_slab_comm(p, b ? PAD_COMM_ALL_TO_ALL_2 : PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, p->comm_stream));
+    PAD_CUDA(cudaEventRecord(p->ev_a2a[b], p->comm_stream));
+    return PAD_OK;
+}
+
+int pad_fft_forward_many(pad_plan* p, const double* const* in, cufftDoubleComplex* const* out, int n, cudaStream_t s) {
+    if (!can_overlap(p, n)) {
+        for (int f = 0; f < n; ++f) PAD_TRY(pad_fft_forward(p, in[f], out[f], s));
+        return PAD_OK;
+    }
+    PAD_TRY(ensure_fft_slab(p, s));
+    PAD_TRY(ensure_comm_stream(p));
+    void* sb[2] = {p->send_buf, p->send_buf2};
+    void* rb[2] = {p->recv_buf, p->recv_buf2};
+    auto local_then_exchange = [&](int f) -> int {
+        const int b = f & 1;
+        if (f >= 2) PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));          // exchange f - 2 has left the send buffer
+        PAD_CUFFT(cufftExecD2Z(p->d2z_yz, const_cast<double*>(in[f]), out[f]));
+        slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(out[f]),
+            reinterpret_cast<double2*>(sb[b]), p->n0_loc, p->n1, p->n1_loc, p->nzh, 1);
+        PAD_CUDA(cudaGetLastError());
+        return exchange_async(p, b, f >= 2, s);
+    };
+    auto finish = [&](int f) -> int {
+        const int b = f & 1;
+        PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));
+        PAD_CUFFT(cufftExecZ2Z(p->z2z_x, reinterpret_cast<cufftDoubleComplex*>(rb[b]), out[f], CUFFT_FORWARD));
+        PAD_CUDA(cudaEventRecord(p->ev_free[b], s));
+        return PAD_OK;
+    };
+    PAD_TRY(local_then_exchange(0));
+    for (int f = 1; f < n; ++f) {
+        PAD_TRY(local_then_exchange(f));
+        PAD_TRY(finish(f - 1));
+    }
+    PAD_TRY(finish(n - 1));
+    g_pad_fft_execs += 2 * n;
+    g_pad_launches += n;
+    return PAD_OK;
+}
+
+int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* const* out, int n, cudaStream_t s) {
+    if (!can_overlap(p, n)) {
+        for (int f = 0; f < n; ++f) PAD_TRY(pad_fft_inverse(p, in[f], out[f], s));
+        return PAD_OK;
+    }
+    PAD_TRY(ensure_fft_slab(p, s));
+    PAD_TRY(ensure_comm_stream(p));
+    void* sb[2] = {p->send_buf, p->send_buf2};
+    void* rb[2] = {p->recv_buf, p->recv_buf2};
+    auto local_then_exchange = [&](int f) -> int {
+        const int b = f & 1;
+        if (f >= 2) PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));
+        PAD_CUFFT(cufftExecZ2Z(p->z2z_x, in[f], reinterpret_cast<cufftDoubleComplex*>(sb[b]), CUFFT_INVERSE));
+        return exchange_async(p, b, f >= 2, s);
+    };
+    auto finish = [&](int f) -> int {
+        const int b = f & 1;
+        PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));
+        slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(rb[b]),
+            reinterpret_cast<double2*>(in[f]), p->n0_loc, p->n1, p->n1_loc, p->nzh, 0);
+        PAD_CUDA(cudaGetLastError());
+        PAD_CUDA(cudaEventRecord(p->ev_free[b], s));
+        PAD_CUFFT(cufftExecZ2D(p->z2d_yz, in[f], out[f]));
+        return PAD_OK;
+    };
+    PAD_TRY(local_then_exchange(0));
+    for (int f = 1; f < n; ++f) {
+        PAD_TRY(local_then_exchange(f));
+        PAD_TRY(finish(f - 1));
+    }
+    PAD_TRY(finish(n - 1));
+    g_pad_fft_execs += 2 * n;
+    g_pad_launches += n;
     return PAD_OK;
 }
 

@@ -25,6 +25,7 @@ There is no analogue in the reference (single process).
 """
 import contextlib
 import ctypes
+import os
 import threading
 
 import torch
@@ -117,7 +118,7 @@ class ThreadComm:
 class SlabPlan(_native.Plan):
     """``pad_plan`` for this rank's slab of a global grid."""
 
-    def __init__(self, box_host, global_shape, device_index, comm):
+    def __init__(self, box_host, global_shape, device_index, comm, overlap=True):
         self.lib = _native.load_library()
         self.comm = comm
         self.global_shape = tuple(int(s) for s in global_shape)
@@ -132,17 +133,32 @@ class SlabPlan(_native.Plan):
         self.recv = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
         self.scratch = torch.zeros(COMM_SCRATCH, dtype=torch.double, device=dev)
         self.error = None
+        # second exchange pair: lets the library overlap the all-to-all of one field with the FFTs of the next
+        self.overlap = overlap and comm.world > 1
+        if self.overlap:
+            self.send2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+            self.recv2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+        streams = {}
 
-        def callback(_user, op, count, _stream):
+        def callback(_user, op, count, stream):
+            # the library names the stream the collective has to be ordered with (its own communication stream for
+            # the pipelined exchanges, the caller's stream otherwise)
             try:
-                if op == 0:
-                    self.comm.all_to_all(self.recv, self.send)
-                elif op == 1:
-                    self.comm.all_reduce(self.scratch[:count])
-                elif op == 2:
-                    self.comm.all_reduce_max(self.scratch[:count])
-                else:
-                    raise ValueError(f'unknown communication op {op}')
+                key = int(stream or 0)
+                ext = streams.get(key)
+                if ext is None:
+                    ext = streams[key] = torch.cuda.ExternalStream(key, device=dev)
+                with torch.cuda.stream(ext):
+                    if op == 0:
+                        self.comm.all_to_all(self.recv, self.send)
+                    elif op == 3:
+                        self.comm.all_to_all(self.recv2, self.send2)
+                    elif op == 1:
+                        self.comm.all_reduce(self.scratch[:count])
+                    elif op == 2:
+                        self.comm.all_reduce_max(self.scratch[:count])
+                    else:
+                        raise ValueError(f'unknown communication op {op}')
                 return 0
             except BaseException as e:      # noqa: BLE001 -- must not propagate through the C frame
                 self.error = e
@@ -156,6 +172,8 @@ class SlabPlan(_native.Plan):
         _native.check(self.lib.pad_plan_create_slab(ctypes.byref(self.handle), box_arr, shp, device_index, comm.rank,
                                                     comm.world, _native.ptr(self.send), _native.ptr(self.recv),
                                                     _native.ptr(self.scratch), self._callback, None))
+        if self.overlap:
+            _native.check(self.lib.pad_plan_set_overlap_buffers(self.handle, _native.ptr(self.send2), _native.ptr(self.recv2)))
         self.box = tuple(box_host)
         self._set_geometry()
 
@@ -167,9 +185,10 @@ class SlabPlan(_native.Plan):
 
 
 class _SlabContext:
-    def __init__(self, global_shape, comm):
+    def __init__(self, global_shape, comm, overlap=True):
         self.global_shape = tuple(int(s) for s in global_shape)
         self.comm = comm
+        self.overlap = overlap
         self.plans = {}
 
     @property
@@ -185,7 +204,7 @@ class _SlabContext:
         host = _native.box_to_host(box_vecs)
         plan = self.plans.get(dev)
         if plan is None:
-            plan = SlabPlan(host, self.global_shape, dev, self.comm)
+            plan = SlabPlan(host, self.global_shape, dev, self.comm, self.overlap)
             self.plans[dev] = plan
         else:
             plan.set_box(host)
@@ -203,12 +222,16 @@ def current():
 
 
 @contextlib.contextmanager
-def slab(global_shape, comm=None, group=None):
-    """Evaluate native functionals on this rank's slab of a ``global_shape`` grid (see the module docstring)."""
+def slab(global_shape, comm=None, group=None, overlap=None):
+    """Evaluate native functionals on this rank's slab of a ``global_shape`` grid (see the module docstring).
+    ``overlap``: allocate a second exchange buffer pair so that batches of transforms are software-pipelined
+    (all-to-all of one field on a communication stream while the neighbouring fields' FFTs run)."""
     if comm is None:
         import torch.distributed as dist
         comm = TorchDistComm(group) if dist.is_available() and dist.is_initialized() else SingleComm()
-    ctx = _SlabContext(global_shape, comm)
+    if overlap is None:
+        overlap = os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'
+    ctx = _SlabContext(global_shape, comm, overlap)
     prev = current()
     _state.ctx = ctx
     try:
