@@ -407,7 +407,10 @@ def run_slab(args):
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29533')
     if not dist.is_initialized():
-        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+        # high-priority NCCL stream: the exchange of one field is meant to run WHILE the FFT kernels of the next one
+        # fill the SMs (pipelined batches in csrc/plan.cu); its CTAs must not queue behind them
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev, pg_options=opts)
     import profess_ad_b200.functionals as F
     from profess_ad_b200 import parallel
     from profess_ad_b200.synthetic import smooth_supercell
@@ -452,7 +455,8 @@ def run_slab(args):
             'data': 'synthetic',
             'config': {'workload': f'Al {4 * side ** 3}-atom supercell, WangGovindCarter99 E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
                        'grid': [n] * 3, 'energy_Ha': e_val,
-                       'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform'},
+                       'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
+                       'exchange_overlap': os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'},
             'roofline': {'bound': 'hbm', 'achieved': balg / (ms * 1e-3) / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
                          'frac': balg / (ms * 1e-3) / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
                          'algorithmic_bytes_per_eval': balg, 'per': 'GPU',
@@ -460,6 +464,27 @@ def run_slab(args):
                          'nvlink_GBps_each_way': a2a_bytes / (ms * 1e-3) / 1e9},
         }), flush=True)
     dist.destroy_process_group()
+
+
+class CleanStdout:
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner from
+    inside ncclCommInit whatever NCCL_DEBUG says): while the benchmark runs, file descriptor 1 points at stderr, and
+    print() of the result line goes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        self.prev = sys.stdout
+        sys.stdout = os.fdopen(self.real, 'w', buffering=1, closefd=False)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        sys.stdout = self.prev
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
 
 
 def main():
@@ -473,12 +498,13 @@ def main():
     ap.add_argument('--slab-grid', type=int, default=0,
                     help='strong-scaling mode: ONE n^3 grid slab-decomposed over the --gpus ranks (e.g. 512)')
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference(args)
-    elif args.slab_grid:
-        run_slab(args)
-    else:
-        run_gpu(args)
+    with CleanStdout():
+        if args.impl == 'reference':
+            run_reference(args)
+        elif args.slab_grid:
+            run_slab(args)
+        else:
+            run_gpu(args)
 
 
 if __name__ == '__main__':

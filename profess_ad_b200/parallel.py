@@ -145,9 +145,15 @@ class SlabPlan(_native.Plan):
             # the pipelined exchanges, the caller's stream otherwise)
             try:
                 key = int(stream or 0)
-                ext = streams.get(key)
-                if ext is None:
-                    ext = streams[key] = torch.cuda.ExternalStream(key, device=dev)
+                cur = torch.cuda.current_stream(dev)
+                if key == cur.cuda_stream:
+                    ext = cur                   # (wrapping the caller's own stream as an ExternalStream breaks the ordering
+                elif key == 0:                  #  of torch's NCCL collectives when the handle is the NULL stream)
+                    ext = torch.cuda.default_stream(dev)
+                else:
+                    ext = streams.get(key)
+                    if ext is None:
+                        ext = streams[key] = torch.cuda.ExternalStream(key, device=dev)
                 with torch.cuda.stream(ext):
                     if op == 0:
                         self.comm.all_to_all(self.recv, self.send)
