@@ -4,8 +4,10 @@
 
 Written from the algorithm, not from the reference file: the (y, s) history lives in two
 preallocated (m, N) ring buffers, the two-loop recursion works on rows of them, and the
-curvature products are computed once per update.  ``line_search_fn=True`` / ``batch_mode=True``
-(geometry optimisation and stochastic training) are outside the hot path and raise.
+curvature products are computed once per update.  ``line_search_fn=True`` (geometry optimisation,
+system.py:937-1198) selects the strong-Wolfe line search of lbfgsnew.py:208-509 (Fletcher's bracketing +
+zoom with finite-difference slopes), restated in ``_WolfeSearch`` below; ``batch_mode=True`` (stochastic
+training) is outside this path and raises.
 
 Semantics kept exactly:
   * first-ever step length t = min(1, 1/|g|_1) * lr, afterwards t = lr;
@@ -25,13 +27,120 @@ import torch
 from torch.optim import Optimizer
 
 
+class _WolfeSearch:
+    """Strong-Wolfe line search along ``d`` from the current point (lbfgsnew.py:208-509, after Fletcher, Practical
+    Methods of Optimization): bracketing phase with at most three trial steps starting at 10 lr, then a zoom phase
+    of at most four cubic-interpolation refinements; directional derivatives by central differences of the closure
+    with half-width ``h``.  The variable is restored to its starting value before ``run`` returns."""
+    SIGMA, RHO, T1, T2, T3 = 0.1, 0.01, 9.0, 0.1, 0.5
+
+    def __init__(self, x, d, closure, lr):
+        self.x, self.d, self.closure, self.lr = x, d, closure, lr
+        self.x0 = x.data.clone()
+        self.evals = 0
+
+    def phi(self, alpha):
+        self.x.data.copy_(self.x0)
+        self.x.data.add_(self.d.view_as(self.x.data), alpha=alpha)
+        self.evals += 1
+        v = self.closure()
+        return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
+
+    def slope(self, alpha, h):
+        return (self.phi(alpha + h) - self.phi(alpha - h)) / (2.0 * h)
+
+    def restore(self):
+        self.x.data.copy_(self.x0)
+
+    def interpolate(self, a, b, h):
+        """Minimiser of the cubic through (a, phi, phi') and (b, phi, phi'), clipped to the better end point
+        (lbfgsnew.py:334-424); a > b is allowed."""
+        f0, f0d = self.phi(a), self.slope(a, h)
+        f1, f1d = self.phi(b), self.slope(b, h)
+        aa = 3.0 * (f0 - f1) / (b - a) + f1d - f0d
+        disc = aa * aa - f0d * f1d
+        if disc <= 0.0:
+            return a if f0 < f1 else b
+        cc = math.sqrt(disc)
+        if f1d - f0d + 2.0 * cc == 0.0:
+            return 0.5 * (a + b)
+        z0 = b - (f1d + cc - aa) * (b - a) / (f1d - f0d + 2.0 * cc)
+        if z0 > max(a, b) or z0 < min(a, b):
+            fz0 = f0 + f1
+        else:
+            fz0 = self.phi(a + z0 * (b - a))          # sic: the reference samples a + z0 (b - a), lbfgsnew.py:398
+        if f0 < f1 and f0 < fz0:
+            return a
+        if f1 < fz0:
+            return b
+        return z0
+
+    def zoom(self, a, b, phi0, g0, h):
+        """lbfgsnew.py:429-509"""
+        aj, bj, alphaj = a, b, a
+        for _ in range(4):
+            alphaj = self.interpolate(aj + self.T2 * (bj - aj), bj - self.T3 * (bj - aj), h)
+            phi_j = self.phi(alphaj)
+            phi_aj = self.phi(aj)
+            if phi_j > phi0 + self.RHO * alphaj * g0 or phi_j >= phi_aj:
+                bj = alphaj
+                continue
+            gj = self.slope(alphaj, h)
+            if (aj - alphaj) * gj <= h:               # round-off termination (Fletcher p. 38)
+                return alphaj
+            if abs(gj) <= -self.SIGMA * g0:
+                return alphaj
+            if gj * (bj - aj) >= 0.0:
+                bj = aj
+            aj = alphaj
+        return alphaj
+
+    def run(self, h):
+        """lbfgsnew.py:208-331; returns the step length."""
+        try:
+            alphak = self.lr
+            phi0 = self.phi(0.0)
+            tol = min(phi0 * 0.01, 1e-6)
+            g0 = self.slope(0.0, h)
+            if abs(g0) < 1e-12:
+                return 1.0
+            mu = (tol - phi0) / (self.RHO * g0)
+            if math.isnan(mu):
+                return 1.0
+            alphai, alphai1, phi_prev = 10.0 * self.lr, 0.0, phi0
+            ci = 1
+            while ci < 4:
+                phi_i = self.phi(alphai)
+                if phi_i < tol:
+                    return alphai
+                if phi_i > phi0 + alphai * g0 or (ci > 1 and phi_i >= phi_prev):
+                    return self.zoom(alphai1, alphai, phi0, g0, h)
+                gi = self.slope(alphai, h)
+                if abs(gi) <= -self.SIGMA * g0:
+                    return alphai
+                if gi >= 0.0:
+                    return self.zoom(alphai, alphai1, phi0, g0, h)
+                if mu <= 2.0 * alphai - alphai1:
+                    alphai1, alphai = alphai, mu
+                else:
+                    # (the previous trial step is deliberately NOT advanced on this branch: lbfgsnew.py:312-318)
+                    lo, hi = 2.0 * alphai - alphai1, min(mu, alphai + self.T1 * (alphai - alphai1))
+                    alphai = self.interpolate(lo, hi, h)
+                phi_prev = phi_i
+                ci += 1
+            return alphak
+        finally:
+            self.restore()
+
+
 class LBFGSNew(Optimizer):
 
     def __init__(self, params, lr=1, max_iter=10, max_eval=None, tolerance_grad=1e-5, tolerance_change=1e-9,
                  history_size=7, line_search_fn=False, batch_mode=False):
-        if line_search_fn or batch_mode:
-            raise NotImplementedError('LBFGSNew: line searches / batch mode are not part of the density-optimisation '
-                                      'hot path (geometry optimisation and stochastic training are out of scope)')
+        if batch_mode:
+            raise NotImplementedError('LBFGSNew: batch mode (stochastic training) is outside the density / geometry '
+                                      'optimisation path')
+        self._line_search = bool(line_search_fn)
         if max_eval is None:
             max_eval = max_iter * 5 // 4
         defaults = dict(lr=lr, max_iter=max_iter, max_eval=max_eval, tolerance_grad=tolerance_grad,
@@ -131,6 +240,14 @@ class LBFGSNew(Optimizer):
             gtd = float(torch.dot(g, d))
             if math.isnan(gtd):
                 print('Warning grad norm infinite')
+            if self._line_search:
+                # lbfgsnew.py:691-707: phi(alpha) = E(x + alpha d) sampled through the closure, step 1e-6 for the slopes
+                search = _WolfeSearch(self._x, d.clone(), closure, lr)
+                t = search.run(1e-6)
+                self.func_evals += search.evals
+                if math.isnan(t):
+                    print('Warning: stepsize nan')
+                    t = lr
             self._x.data.add_(d.view_as(self._x.data), alpha=t)
             if it != max_iter:
                 loss = closure()

@@ -360,11 +360,127 @@ class System():
     def force_constants(self, primitive_ion_indices, units='eV/a2'):
         self.__second_order('force_constants')
 
-    def optimize_geometry(self, *args, **kwargs):
-        self.__second_order('optimize_geometry')
+    # -------------------------------------------------------------------------- geometry optimisation
+    def optimize_geometry(self, ftol=0.02, stol=0.002, g_conv_cond_count=3, g_method='LBFGSlinesearch',
+                          g_step_size=0.1, g_maxiter=1000, g_verbose=False, **den_opt_kwargs):
+        """Minimise the energy over the fractional ionic coordinates (``ftol`` in eV/A, None = ions fixed) and / or
+        the lattice vectors (``stol`` in eV/A^3, None = cell fixed); system.py:937-1068.  Same optimisers, closure
+        and stop rule; the gradients come from the analytic forces and stress instead of autograd."""
+        if (ftol is None) and (stol is None):
+            raise ValueError('At least one of \'stol\' or \'ftol\' cannot be \'None\'')
+        n_f = 3 * self.__N_ions if ftol is not None else 0
+        frac0, box0 = self.__frac_ion_coords.detach().clone(), self.__box_vecs.detach().clone()
+        pieces = ([frac0.reshape(-1)] if ftol is not None else []) + ([box0.reshape(-1)] if stol is not None else [])
+        params = torch.cat(pieces).clone()
 
-    def optimize_parameterized_geometry(self, *args, **kwargs):
-        self.__second_order('optimize_parameterized_geometry')
+        def geometry(p):
+            frac = p[:n_f].reshape(-1, 3) if ftol is not None else frac0
+            box = p[n_f:].reshape(3, 3) if stol is not None else box0
+            return box, frac
+        return self.optimize_parameterized_geometry(params, geometry, ftol, stol, g_conv_cond_count, g_method,
+                                                    g_step_size, g_maxiter, g_verbose, None, **den_opt_kwargs)
+
+    def optimize_parameterized_geometry(self, params, parameterized_geometry, ftol=0.02, stol=0.002,
+                                        g_conv_cond_count=3, g_method='LBFGSlinesearch', g_step_size=0.1,
+                                        g_maxiter=1000, g_verbose=False, param_string=None, **den_opt_kwargs):
+        """system.py:1070-1198: ``parameterized_geometry(params) -> (box_vecs [bohr], frac_ion_coords)``.
+        Closure (system.py:1124-1137): at fixed chi = sqrt(n) the ions and the cell move, v_ext is rebuilt, the
+        density is renormalised to N electrons, E is the total energy.  dE/dparams is assembled from the analytic
+        pieces -- dE/dfrac = -F box^T, dE/dbox = vol box^-T sigma -- and pulled back through the user's
+        parametrisation by autograd."""
+        den_opt_inputs = {'ntol': 1e-10, 'n_conv_cond_count': 3, 'n_method': 'LBFGS', 'n_step_size': 0.1,
+                          'n_maxiter': 1000, 'conv_target': 'dE', 'n_verbose': False, 'from_uniform': False}
+        den_opt_inputs.update(den_opt_kwargs)
+        if (ftol is None) and (stol is None):
+            raise ValueError('At least one of \'stol\' or \'ftol\' cannot be \'None\'')
+        params = params.detach().to(device=self.__device, dtype=torch.double).clone().requires_grad_(True)
+        if g_method == 'RPROP':
+            optimizer = torch.optim.Rprop([params], lr=g_step_size)
+        elif g_method == 'TPGD':
+            optimizer = TPGD([params], lr=g_step_size)
+        elif g_method == 'LBFGSlinesearch':
+            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6, line_search_fn=True)
+        elif g_method == 'LBFGS':
+            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6)
+        else:
+            raise ValueError('Only \'LBFGSlinesearch\', \'LBFGS\', \'RPROP\' or \'TPGD\' recognized for \'g_method\'')
+        state = {'chi': None}
+
+        def closure():
+            if torch.is_grad_enabled():
+                optimizer.zero_grad()
+            with torch.enable_grad():
+                box, frac = parameterized_geometry(params)
+            self.__box_vecs = box.detach().to(self.__device).double()
+            self.__frac_ion_coords = frac.detach().to(self.__device).double()
+            self.__update_ionic_potential()
+            chi = state['chi']
+            N_tilde = torch.mean(chi.pow(2)) * self.__vol()
+            self.__den = (self.__N_elec / N_tilde) * chi.pow(2)
+            E = self.__compute_energy()
+            outs, grads = [], []
+            if frac.requires_grad:
+                outs.append(frac)
+                grads.append(-torch.matmul(self.forces('Ha/b'), self.__box_vecs.T).to(frac.dtype))
+            if box.requires_grad:
+                outs.append(box)
+                grads.append(self.__vol() * torch.matmul(torch.linalg.inv(self.__box_vecs).T, self.__compute_stress()))
+            params.grad = torch.autograd.grad(outs, params, grads)[0] if outs else torch.zeros_like(params)
+            return E.detach()
+
+        def max_abs(fn, *a):
+            try:
+                return torch.max(torch.abs(fn(*a))).item()
+            except NotImplementedError:
+                return float('nan')
+
+        self.optimize_density(**den_opt_inputs)
+        E_prev = self.energy('eV') / self.ion_count()
+        head = '{:^7} {:^20} {:^20} {:^20} {:^20}'.format('Iter', 'E [eV per atom]', 'dE [eV per atom]', 'Max Force [eV/Å]',
+                                                          'Max Stress [eV/Å³]')
+        row = '{:^7} {:^20.6f} {:^20.6g} {:^20.6g} {:^20.6g}'
+        if g_verbose:
+            print(head + ('Params' if param_string is not None else ''), flush=True)
+            print(row.format(0, E_prev, 0, max_abs(self.forces, 'eV/a'), max_abs(self.stress, 'eV/a3'))
+                  + (param_string(params) if param_string is not None else ''), flush=True)
+        conv_counter, success_iter = 0, None
+        self.last_geometry_optimization = {'iterations': 0, 'converged': False}
+        for it in range(1, round(g_maxiter) + 1):
+            state['chi'] = torch.sqrt(self.__den)
+            optimizer.step(closure)
+            # The optimiser's last move is not followed by a closure: bring the System to the final parameters.  (The
+            # reference's System sees the moved tensors too, but re-optimises the density in the ionic potential of the
+            # last closure, system.py:1024-1027; here v_ext is rebuilt so that E, forces and stress of an iteration
+            # all belong to the same geometry.)
+            with torch.no_grad():
+                box, frac = parameterized_geometry(params.detach())
+            self.__box_vecs = box.detach().to(self.__device).double().clone()
+            self.__frac_ion_coords = frac.detach().to(self.__device).double().clone()
+            self.__update_ionic_potential()
+            self.detach()
+            self.optimize_density(**den_opt_inputs)
+            E_new = self.energy('eV') / self.ion_count()
+            max_force = max_abs(self.forces, 'eV/a')
+            max_stress = max_abs(self.stress, 'eV/a3') if (stol is not None or g_verbose) else float('nan')
+            if g_verbose:
+                print(row.format(it, E_new, E_new - E_prev, max_force, max_stress)
+                      + (param_string(params) if param_string is not None else ''), flush=True)
+            E_prev = E_new
+            if it > 3:      # convergence is only checked after the 3rd iteration
+                ok = (ftol is None or max_force < ftol) and (stol is None or max_stress < stol)
+                conv_counter = conv_counter + 1 if ok else 0
+            self.last_geometry_optimization = {'iterations': it, 'converged': False, 'max_force_eV_A': max_force,
+                                               'max_stress_eV_A3': max_stress, 'energy_eV_per_atom': E_new}
+            if conv_counter == g_conv_cond_count:
+                success_iter = it
+                self.last_geometry_optimization['converged'] = True
+                break
+        if g_verbose:
+            if success_iter is not None:
+                print('Geometry optimization successfully converged in {} step(s) \n'.format(success_iter), flush=True)
+            else:
+                print('Geometry optimization failed to converge in {} step(s) \n'.format(g_maxiter), flush=True)
+        return success_iter is not None
 
     # ------------------------------------------------------------------------------- ion-ion
     def set_Rc(self, Rc=None):

@@ -1,0 +1,65 @@
+"""System.optimize_geometry (analytic forces / stress + the reference's optimisers and stop rule) against geometry
+optimisations recorded from the unmodified reference (tests/golden/make_golden_geometry.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(g, potentials_dir):
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    terms = [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+    ions = [['Li', os.path.join(potentials_dir, 'li.gga.recpot'), torch.from_numpy(g['frac0'])]]
+    return System(torch.from_numpy(g['box0_A']), tuple(int(n) for n in g['shape']), ions, terms, units='a',
+                  coord_type='fractional')
+
+
+@pytest.mark.parametrize('case,kw', [('li2_ions', dict(ftol=0.02, stol=None)), ('li2_full', dict(ftol=0.02, stol=0.002))])
+def test_optimize_geometry_matches_reference(case, kw, golden_dir, potentials_dir):
+    g = np.load(os.path.join(golden_dir, f'geometry_{case}.npz'))
+    s = _system(g, potentials_dir)
+    ok = s.optimize_geometry(g_maxiter=60, ntol=1e-9, **kw)
+    assert ok and bool(g['converged'])
+    # both runs stop as soon as forces / stresses are below the tolerances, i.e. at slightly different points of
+    # the same valley: compare the things the tolerances control
+    assert abs(s.energy('eV') - float(g['energy_eV'])) < 2e-3, (s.energy('eV'), float(g['energy_eV']))
+    assert s.forces('eV/a').abs().max().item() < 0.02
+    if kw['stol'] is not None:
+        assert s.stress('eV/a3').abs().max().item() < 0.002
+        assert abs(s.volume('a3') - float(g['volume_A3'])) < 0.02 * float(g['volume_A3'])
+    else:
+        assert abs(s.volume('a3') - float(g['volume_A3'])) < 1e-9
+    d = (s.fractional_ionic_coordinates()[1] - s.fractional_ionic_coordinates()[0]).cpu().numpy()
+    d_ref = g['frac'][1] - g['frac'][0]
+    delta = (d - d_ref + 0.5) % 1.0 - 0.5
+    assert np.abs(delta).max() < 0.02, (d, d_ref)
+
+
+def test_geometry_methods_and_errors(golden_dir, potentials_dir):
+    g = np.load(os.path.join(golden_dir, 'geometry_li2_ions.npz'))
+    s = _system(g, potentials_dir)
+    with pytest.raises(ValueError):
+        s.optimize_geometry(ftol=None, stol=None)
+    with pytest.raises(ValueError):
+        s.optimize_geometry(g_method='nope')
+    s.optimize_density(ntol=1e-9)
+    e0 = s.energy('eV')
+    f0 = s.forces('eV/a').abs().max().item()
+    for method in ('TPGD', 'LBFGS'):
+        s2 = _system(g, potentials_dir)
+        s2.optimize_geometry(ftol=0.02, stol=None, g_method=method, g_maxiter=5, ntol=1e-9)
+        assert s2.energy('eV') < e0 and s2.forces('eV/a').abs().max().item() < f0
+
+    # parameterised: only the cell volume varies (isotropic scaling)
+    s3 = _system(g, potentials_dir)
+    box0 = s3.lattice_vectors('b').clone()
+    frac0 = s3.fractional_ionic_coordinates().clone()
+    ok = s3.optimize_parameterized_geometry(torch.ones(1, dtype=torch.double), lambda p: (p[0] * box0, frac0), ftol=None,
+                                            stol=0.002, g_maxiter=30, ntol=1e-9)
+    assert ok and abs(s3.pressure('eV/a3')) < 0.002
+    ratio = s3.lattice_vectors('b') / box0
+    assert torch.allclose(ratio, ratio[0, 0].expand(3, 3), rtol=1e-12)

@@ -88,7 +88,7 @@ def test_lbfgs_rejects_out_of_scope_modes():
     from profess_ad_b200._optimizers.lbfgs.lbfgsnew import LBFGSNew
     x = torch.zeros(3, dtype=torch.double, requires_grad=True)
     with pytest.raises(NotImplementedError):
-        LBFGSNew([x], line_search_fn=True)
+        LBFGSNew([x], batch_mode=True)
 
 
 def test_ion_utils_reproduce_reference_vext_and_ion_energy(golden_dir, potentials_dir):
@@ -168,3 +168,21 @@ def test_fit_eos_recovers_parameters():
     e = birch_murnaghan(v, 0.48, 4.2, -57.2, 16.7)
     params, err = fit_eos(v, e)
     assert np.allclose(params, [0.48, 4.2, -57.2, 16.7], rtol=1e-6)
+
+
+@pytest.mark.parametrize('case', ['rosen', 'quart'])
+@pytest.mark.parametrize('mode', ['linesearch', 'fixed'])
+def test_lbfgs_follows_reference_trajectories(case, mode, golden_dir):
+    """LBFGSNew (fixed step and the strong-Wolfe line search used by optimize_geometry) against iterates recorded
+    from the unmodified reference optimiser (tests/golden/make_golden_lbfgs.py)."""
+    import importlib.util
+    import numpy as np
+    from profess_ad_b200._optimizers.lbfgs.lbfgsnew import LBFGSNew
+    spec = importlib.util.spec_from_file_location('make_golden_lbfgs', os.path.join(golden_dir, 'make_golden_lbfgs.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fn, x0 = gen.CASES[case]
+    ref = np.load(os.path.join(golden_dir, 'lbfgs_trajectories.npz'))[f'{case}_{mode}']
+    got = gen.trajectory(LBFGSNew, fn, x0, line_search_fn=(mode == 'linesearch'))
+    assert np.abs(got - ref).max() < (1e-5 if mode == 'linesearch' else 1e-9), np.abs(got - ref).max(axis=1)
+    assert np.abs(got[:4] - ref[:4]).max() < 1e-9
