@@ -418,11 +418,18 @@ def run_slab(args):
     side = max(1, n // 64)
     lo, hi = parallel.slab_bounds(n, rank, world)
     box, den = smooth_supercell(n, side, device=dev, x_range=(lo, hi))
-    wgc = F.WangGovindCarter99()
+    n_fft = N_FFT
+    if args.slab_functional == 'wgc99':
+        fun, label = F.WangGovindCarter99().forward, 'WangGovindCarter99'
+    elif args.slab_functional == 'pbe':
+        fun, label, n_fft = F.PerdewBurkeErnzerhof, 'PerdewBurkeErnzerhof', 8
+    else:       # BASELINE.json configs[2]: Huang-Carter field-dependent spline kernel
+        hc = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15)) if args.slab_functional == 'revhc' else F.HuangCarter((0.01177, 0.7143, 1.2))
+        fun, label = hc.forward, type(hc).__name__
     with parallel.slab((n, n, n)):
         def step():
             d = den.requires_grad_(True)
-            E = wgc.forward(box, d)
+            E = fun(box, d)
             (g,) = torch.autograd.grad(E, d)
             den.requires_grad_(False)
             return E, g
@@ -444,16 +451,19 @@ def run_slab(args):
         e_val = E.item()
     if rank == 0:
         npts = n ** 3
-        balg = 16 * npts * N_FFT + 16 * npts
+        if args.slab_functional in ('hc', 'revhc'):
+            n_fft = 12 + 2 * int(getattr(hc, 'last_n_nodes', 0))
+        balg = 16 * npts * n_fft + 16 * npts
         peak, peak_src = measured_peak()
         nk = n * n * (n // 2 + 1)
-        a2a_bytes = 14 * (world - 1) / world ** 2 * nk * 16          # per GPU and direction, per evaluation
+        a2a_bytes = n_fft * (world - 1) / world ** 2 * nk * 16       # per GPU and direction, per evaluation
         print(json.dumps({
-            'metric': f'WGC99 energy+potential evaluations per second at {n}^3, one grid slab-decomposed over the GPUs',
+            'metric': f'{"WGC99" if args.slab_functional == "wgc99" else label} energy+potential evaluations per second at {n}^3, one grid slab-decomposed over the GPUs',
             'value': 1e3 / ms, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': f'Al {4 * side ** 3}-atom supercell, WangGovindCarter99 E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
+            'config': {'workload': f'Al {4 * side ** 3}-atom supercell, {label} E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
+                       'n_fft': n_fft,
                        'grid': [n] * 3, 'energy_Ha': e_val,
                        'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
                        'exchange_overlap': os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'},
@@ -495,6 +505,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-denopt', action='store_true', help='skip the density-optimisation timing leg')
+    ap.add_argument('--slab-functional', default='wgc99', choices=['wgc99', 'hc', 'revhc', 'pbe'],
+                    help='functional evaluated in --slab-grid mode')
     ap.add_argument('--slab-grid', type=int, default=0,
                     help='strong-scaling mode: ONE n^3 grid slab-decomposed over the --gpus ranks (e.g. 512)')
     args = ap.parse_args()

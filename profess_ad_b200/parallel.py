@@ -279,3 +279,41 @@ def optimize_density(box_vecs, den_local, v_ext_local, terms, n_elec, ntol=1e-7,
         raise NotImplementedError('parallel.optimize_density needs every term to be a native functional')
     return _density_opt.run(box_vecs, den_local, v_ext_local, T, n_elec, ntol, n_conv_cond_count, n_method,
                             n_step_size, n_maxiter, conv_target)
+
+
+def eos_fit(make_system, f=0.05, N=9, eos='bm', group=None, **den_opt_kwargs):
+    """Energy-volume scan + equation-of-state fit (``System.eos_fit``, system.py:568-621) with the N volumes spread
+    over the ranks, one independent System per GPU -- the "independent systems" mode of SURVEY.md section 8e (no
+    collective in the loop, one gather of N (volume, energy) pairs at the end).
+
+    ``make_system()`` builds the System at its reference volume on this rank's device.  The reference carries the
+    density from one volume to the next as a warm start; here every rank starts its first volume from the
+    reference-volume density (rescaled by ``set_lattice``) and warm-starts along its own sub-sequence.  Returns
+    (params, err) in the reference's order -- K0 [GPa], K0', E0 [eV], V0 [A^3] -- on every rank."""
+    import numpy as np
+    import torch.distributed as dist
+    from .elastic_tools import fit_eos
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    opts = {'ntol': 1e-10, 'n_conv_cond_count': 3, 'n_method': 'LBFGS', 'n_step_size': 0.1, 'n_maxiter': 1000,
+            'conv_target': 'dE', 'n_verbose': False, 'from_uniform': False}
+    opts.update(den_opt_kwargs)
+    s = make_system()
+    v0 = s.volume('a3')
+    shape_vecs = s.lattice_vectors('a') / v0 ** (1 / 3)
+    volumes = v0 * np.linspace(1 - f, 1 + f, N)
+    mine = []
+    for i in range(rank, N, world):
+        s.set_lattice(volumes[i] ** (1 / 3) * shape_vecs, units='a')
+        s.optimize_density(**opts)
+        mine.append((i, s.volume('a3') / s.ion_count(), s.energy('eV') / s.ion_count()))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        mine = [row for part in gathered for row in part]
+    mine.sort()
+    vols, enes = [r[1] for r in mine], [r[2] for r in mine]
+    params, err = fit_eos(vols, enes, eos, False)
+    to_gpa = s.GPa_per_atomic / (s.eV_per_Ha / s.A_per_b ** 3)
+    params[0] *= to_gpa
+    err[0] *= to_gpa
+    return params, err

@@ -189,3 +189,24 @@ def test_huang_carter_density_optimisation_native_vs_oracle(golden_dir, potentia
     ohc = orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=t_rev)
     ref = orc.optimize_density(box, den0, n_elec, [orc.IonElectron, orc.Hartree, ohc, orc.PerdewZunger], v_ext=v_ext, ntol=1e-7)
     assert abs(s.energy('Ha') - ref['energy']) * EV / frac.shape[0] < 1e-6, (s.energy('Ha'), ref['energy'])
+
+
+def test_eos_scan_reproduces_published_table(potentials_dir):
+    """docs/source/example_elastic.rst:81-86 (fcc Al, WT + PBE, 2000 eV): V0 = 16.76389 A^3, E0 = -57.18370 eV,
+    K0 = 78.80961 GPa -- through parallel.eos_fit (independent systems per GPU; world 1 here)."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import parallel
+    from profess_ad_b200.crystal_tools import get_cell
+    from profess_ad_b200.system import System
+    pot = os.path.join(potentials_dir, 'al.gga.recpot')
+
+    def make_system():
+        box, frac = get_cell('fcc', vol_per_atom=16.9, coord_type='fractional')
+        terms = [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+        s = System(box, System.ecut2shape(2000, box), [['Al', pot, frac]], terms, units='a', coord_type='fractional')
+        s.optimize_density(ntol=1e-10)
+        return s
+    params, err = parallel.eos_fit(make_system, f=0.05, N=9, eos='bm')
+    assert abs(params[3] - 16.76389) < 2e-4
+    assert abs(params[2] - (-57.18370)) < 2e-5
+    assert abs(params[0] - 78.80961) < 0.02
