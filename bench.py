@@ -396,7 +396,77 @@ def density_optimization_leg(dev):
 # --------------------------------------------------------------------------------------------------
 #  one large grid over N GPUs (slab-decomposed FFT, all-to-all over NVLink): strong scaling
 # --------------------------------------------------------------------------------------------------
-def run_slab(args):
+def slab_measure(n, functional, steps, warmup, overlap=None):
+    """One strong-scaling measurement (torch.distributed must be initialised): dict for the JSON line."""
+    import torch
+    import torch.distributed as dist
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import parallel
+    from profess_ad_b200.synthetic import smooth_supercell
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    side = max(1, n // 64)
+    lo, hi = parallel.slab_bounds(n, rank, world)
+    box, den = smooth_supercell(n, side, device=dev, x_range=(lo, hi))
+    n_fft = N_FFT
+    hc = None
+    if functional == 'wgc99':
+        fun, label = F.WangGovindCarter99().forward, 'WangGovindCarter99'
+    elif functional == 'pbe':
+        fun, label, n_fft = F.PerdewBurkeErnzerhof, 'PerdewBurkeErnzerhof', 8
+    else:       # BASELINE.json configs[2]: Huang-Carter field-dependent spline kernel
+        hc = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15)) if functional == 'revhc' else F.HuangCarter((0.01177, 0.7143, 1.2))
+        fun, label = hc.forward, type(hc).__name__
+    if overlap is None:
+        overlap = os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'
+    with parallel.slab((n, n, n), overlap=overlap):
+        def step():
+            d = den.requires_grad_(True)
+            E = fun(box, d)
+            (g,) = torch.autograd.grad(E, d)
+            den.requires_grad_(False)
+            return E, g
+        for _ in range(max(3, warmup)):
+            E, g = step()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            E, g = step()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.double, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item() / steps
+        e_val = E.item()
+    npts = n ** 3
+    if hc is not None:
+        n_fft = 12 + 2 * int(getattr(hc, 'last_n_nodes', 0))
+    balg = 16 * npts * n_fft + 16 * npts
+    peak, peak_src = measured_peak()
+    nk = n * n * (n // 2 + 1)
+    a2a_bytes = n_fft * (world - 1) / world ** 2 * nk * 16       # per GPU and direction, per evaluation
+    return {
+        'metric': f'{"WGC99" if functional == "wgc99" else label} energy+potential evaluations per second at {n}^3, one grid slab-decomposed over the GPUs',
+        'value': 1e3 / ms, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': max(3, warmup),
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': f'Al {4 * side ** 3}-atom supercell, {label} E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
+                   'n_fft': n_fft, 'grid': [n] * 3, 'energy_Ha': e_val,
+                   'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
+                   'exchange_overlap': bool(overlap)},
+        'roofline': {'bound': 'hbm', 'achieved': balg / (ms * 1e-3) / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
+                     'frac': balg / (ms * 1e-3) / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_eval': balg, 'per': 'GPU',
+                     'nvlink_bytes_per_gpu_per_eval_each_way': a2a_bytes,
+                     'nvlink_GBps_each_way': a2a_bytes / (ms * 1e-3) / 1e9},
+    }
+
+
+def slab_init():
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
@@ -411,68 +481,15 @@ def run_slab(args):
         # fill the SMs (pipelined batches in csrc/plan.cu); its CTAs must not queue behind them
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev, pg_options=opts)
-    import profess_ad_b200.functionals as F
-    from profess_ad_b200 import parallel
-    from profess_ad_b200.synthetic import smooth_supercell
-    n = args.slab_grid
-    side = max(1, n // 64)
-    lo, hi = parallel.slab_bounds(n, rank, world)
-    box, den = smooth_supercell(n, side, device=dev, x_range=(lo, hi))
-    n_fft = N_FFT
-    if args.slab_functional == 'wgc99':
-        fun, label = F.WangGovindCarter99().forward, 'WangGovindCarter99'
-    elif args.slab_functional == 'pbe':
-        fun, label, n_fft = F.PerdewBurkeErnzerhof, 'PerdewBurkeErnzerhof', 8
-    else:       # BASELINE.json configs[2]: Huang-Carter field-dependent spline kernel
-        hc = F.RevisedHuangCarter((0.45, 0.10, 2.0 / 3.0, 1.15)) if args.slab_functional == 'revhc' else F.HuangCarter((0.01177, 0.7143, 1.2))
-        fun, label = hc.forward, type(hc).__name__
-    with parallel.slab((n, n, n)):
-        def step():
-            d = den.requires_grad_(True)
-            E = fun(box, d)
-            (g,) = torch.autograd.grad(E, d)
-            den.requires_grad_(False)
-            return E, g
-        for _ in range(max(3, args.warmup)):
-            E, g = step()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        torch.cuda.synchronize(dev)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            E, g = step()
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.double, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item() / args.steps
-        e_val = E.item()
+    return rank, world
+
+
+def run_slab(args):
+    import torch.distributed as dist
+    rank, world = slab_init()
+    line = slab_measure(args.slab_grid, args.slab_functional, args.steps, args.warmup)
     if rank == 0:
-        npts = n ** 3
-        if args.slab_functional in ('hc', 'revhc'):
-            n_fft = 12 + 2 * int(getattr(hc, 'last_n_nodes', 0))
-        balg = 16 * npts * n_fft + 16 * npts
-        peak, peak_src = measured_peak()
-        nk = n * n * (n // 2 + 1)
-        a2a_bytes = n_fft * (world - 1) / world ** 2 * nk * 16       # per GPU and direction, per evaluation
-        print(json.dumps({
-            'metric': f'{"WGC99" if args.slab_functional == "wgc99" else label} energy+potential evaluations per second at {n}^3, one grid slab-decomposed over the GPUs',
-            'value': 1e3 / ms, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
-            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {'workload': f'Al {4 * side ** 3}-atom supercell, {label} E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
-                       'n_fft': n_fft,
-                       'grid': [n] * 3, 'energy_Ha': e_val,
-                       'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
-                       'exchange_overlap': os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'},
-            'roofline': {'bound': 'hbm', 'achieved': balg / (ms * 1e-3) / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
-                         'frac': balg / (ms * 1e-3) / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_eval': balg, 'per': 'GPU',
-                         'nvlink_bytes_per_gpu_per_eval_each_way': a2a_bytes,
-                         'nvlink_GBps_each_way': a2a_bytes / (ms * 1e-3) / 1e9},
-        }), flush=True)
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
 

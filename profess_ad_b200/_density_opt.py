@@ -108,9 +108,6 @@ def stress_terms(box_vecs, den, T):
     _native.require_cuda(den)
     if T.kinetic == 3:
         raise NotImplementedError('stress of the Huang-Carter family is not available')
-    if T.kinetic == 2:
-        raise NotImplementedError('stress of WangGovindCarter99: the reference\'s autograd result depends on the state of its '
-                                  'kernel cache (functionals.py:961-966), there is no well-defined value to reproduce')
     den = den.detach().contiguous()
     plan = _native.get_plan(box_vecs, den)
     out = torch.empty(9, dtype=torch.double, device=den.device)

@@ -280,3 +280,6 @@ int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s);
 // CTAs are finished (all-reduced on slab plans) and added to the row-major 3 x 3 device tensor `sig`:
 // sig_ij += c_t T_ij + c_iso iso delta_ij
 int pad_stress_accumulate(pad_plan* p, cudaStream_t s, int nblocks, double c_iso, double c_t, double* sig);
+// functionals.cu (needs the WGC99 series constants of that translation unit): non-local WGC99 stress, added to sig[9]
+int pad_stress_wgc99_nl(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* sig,
+                        cudaStream_t s);

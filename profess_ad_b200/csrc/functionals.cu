@@ -333,15 +333,17 @@ struct WgcSeries {
 };
 __constant__ WgcSeries c_wgc;
 
-// w(eta), w'(eta), w''(eta) (unscaled), functionals.py:845-939
-__device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double& w2) {
+// w(eta), w'(eta), w''(eta) (unscaled), functionals.py:845-939; WANT3: also w'''(eta) (the stress needs dK/d eta)
+template <bool WANT3>
+__device__ __forceinline__ void wgc_w_t(double eta, double& w0, double& w1, double& w2, double& w3) {
     const WgcSeries& S = c_wgc;
+    w3 = 0.0;
     if (eta == 0.0) { w0 = w1 = w2 = 0.0; return; }
     const bool inside = eta <= 1.0;
     double C1, C2;
     if (S.u >= 0.0) { C1 = inside ? S.c1 : 0.0; C2 = inside ? S.c2 : 0.0; }
     else { C1 = inside ? 0.0 : S.c1; C2 = inside ? 0.0 : S.c2; }
-    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
     if (C1 != 0.0 || C2 != 0.0) {
         const double le = log(eta), u = S.u;
         if (S.vcase > 0) {
@@ -350,11 +352,16 @@ __device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double
             h0 = C1 * ex + C2 * ey;
             h1 = (C1 * x * ex + C2 * y * ey) / eta;
             h2 = (C1 * x * (x - 1.0) * ex + C2 * y * (y - 1.0) * ey) / (eta * eta);
+            if (WANT3) h3 = (C1 * x * (x - 1.0) * (x - 2.0) * ex + C2 * y * (y - 1.0) * (y - 2.0) * ey) / (eta * eta * eta);
         } else if (S.vcase == 0) {
             const double eu = exp(u * le);
             h0 = eu * (C2 * le + C1);
             h1 = (C2 * eu * (1.0 + u * le) + C1 * u * eu) / eta;
             h2 = (C2 * ((u - 1.0) * eu * (1.0 + u * le) + eu) + C1 * u * (u - 1.0) * eu) / (eta * eta);
+            if (WANT3) {       // (f g)''' with f = eta^u, g = C2 ln eta + C1
+                const double f1 = u, f2 = u * (u - 1.0), f3 = u * (u - 1.0) * (u - 2.0);
+                h3 = eu / (eta * eta * eta) * (f3 * (C2 * le + C1) + 3.0 * f2 * C2 - 3.0 * f1 * C2 + 2.0 * C2);
+            }
         } else {
             const double sv = sqrt(-S.v), eu = exp(u * le);
             double ts, tc;
@@ -363,28 +370,42 @@ __device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double
             h0 = eu * (C1 * tc + C2 * ts);
             h1 = eu / eta * (C1 * p1 + C2 * p2);
             h2 = eu / (eta * eta) * ((u - 1.0) * (C1 * p1 + C2 * p2) + sv * (C2 * p1 - C1 * p2));
+            if (WANT3) {       // Re[(C1 - i C2) z (z - 1) (z - 2) eta^(z - 3)], z = u + i sv
+                const double ar = u * (u - 1.0) - sv * sv, ai = sv * (2.0 * u - 1.0);          // z (z - 1)
+                const double br = ar * (u - 2.0) - ai * sv, bi = ar * sv + ai * (u - 2.0);     // z (z - 1) (z - 2)
+                const double cr = C1 * br + C2 * bi, ci = C1 * bi - C2 * br;                   // (C1 - i C2) * b
+                h3 = eu / (eta * eta * eta) * (cr * tc - ci * ts);
+            }
         }
     }
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (inside) {
         const double x = eta * eta;
         double pw = 1.0;
         for (int i = 0; i < WGC_TERMS; ++i) {
             const double t = S.cB[i] * pw, two_i = 2.0 * i;
             s0 += t; s1 += t * two_i; s2 += t * two_i * (two_i - 1.0);
+            if (WANT3) s3 += t * two_i * (two_i - 1.0) * (two_i - 2.0);
             pw *= x;
         }
         w0 = h0 + s0; w1 = h1 + s1 / eta; w2 = h2 + s2 / x;
+        if (WANT3) w3 = h3 + s3 / (x * eta);
     } else {
         const double y = 1.0 / (eta * eta);
         double pw = 1.0;
         for (int i = 0; i < WGC_TERMS; ++i) {
             const double t = S.cA[i] * pw, two_i = 2.0 * i;
             s0 += t; s1 -= t * two_i; s2 += t * two_i * (two_i + 1.0);
+            if (WANT3) s3 -= t * two_i * (two_i + 1.0) * (two_i + 2.0);
             pw *= y;
         }
         w0 = h0 + s0; w1 = h1 + s1 / eta; w2 = h2 + s2 * y;
+        if (WANT3) w3 = h3 + s3 * y / eta;
     }
+}
+__device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double& w2) {
+    double w3;
+    wgc_w_t<false>(eta, w0, w1, w2, w3);
 }
 
 __global__ void wgc_scalars_kernel(double* scal, double alpha, double beta, double kappa, double dV, double vol) {
@@ -480,6 +501,102 @@ static void wgc_host_series(double alpha, double beta, double gamma, WgcSeries* 
     S->u = u; S->v = v; S->gamma = gamma;
 }
 
+// the series coefficients live in one constant bank per device, shared by all plans
+static int wgc_ensure_series(pad_plan* p, double alpha, double beta, double gamma, cudaStream_t s) {
+    static double bank_key[64][3];
+    static bool bank_valid[64];
+    const int dv = p->device & 63;
+    if (!bank_valid[dv] || bank_key[dv][0] != alpha || bank_key[dv][1] != beta || bank_key[dv][2] != gamma) {
+        WgcSeries S;
+        wgc_host_series(alpha, beta, gamma, &S);
+        // stream-ordered: in-flight kernels of earlier calls on this stream finish first
+        PAD_CUDA(cudaMemcpyToSymbolAsync(c_wgc, &S, sizeof(S), 0, cudaMemcpyHostToDevice, s));
+        bank_key[dv][0] = alpha; bank_key[dv][1] = beta; bank_key[dv][2] = gamma;
+        bank_valid[dv] = true;
+    }
+    return PAD_OK;
+}
+
+// Non-local part of the WGC99 stress, added to the device tensor sig[9] (the TF and vW parts are handled with the
+// other terms in stress.cu).  All six terms of the energy scale as vol^(-2/3) under isotropic strain with eta
+// invariant (n, n_ref, theta ~ 1/vol; T ~ n_ref^(5/3 - alpha - beta)), and d eta / d eps_ij = -eta (k_i k_j / k^2 - delta_ij / 3):
+//   sigma_ij = -(2/3) delta_ij E_NL / vol - C_TF sum_k w (k_i k_j / k^2 - delta_ij / 3) eta Re[ conj(P)(W0' A + K1' B + K2' C)
+//                                                     + conj(P th)(K1' A + K3' B) + conj(P th2) K2' A ]
+// with ' = d/d eta at fixed n_ref: W0' = T w', K1' = -T (w' + eta w'') / (6 n_ref),
+// K2', K3' = T (2 eta w'' + eta^2 w''' + (7 - gamma | 1 + gamma)(w' + eta w'')) / (36 n_ref^2).
+// This is the derivative with the kernel regenerated for the strained cell -- what the reference's autograd gives with
+// a fresh kernel (checked to 4e-16 on CPU); with a kernel cached from an earlier call at the same cell the reference
+// silently drops the kernel's own eta-dependence (functionals.py:961-966).
+int pad_stress_wgc99_nl(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* sig,
+                        cudaStream_t s) {
+    double* R[3];
+    cufftDoubleComplex* C[4];
+    for (int i = 0; i < 3; ++i) PAD_TRY(pad_get_rbuf(p, i, &R[i]));
+    for (int i = 0; i < 4; ++i) PAD_TRY(pad_get_cbuf(p, i, &C[i]));
+    double* scal = p->scal;
+    const KGeom geom = p->geom;
+    const double inv_n = geom.inv_n;
+    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
+    const double one[1] = {1.0};
+    finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
+    wgc_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, kappa, p->dV, p->vol);
+    ++g_pad_launches;
+    PAD_TRY(wgc_ensure_series(p, alpha, beta, gamma, s));
+    double *Ra = R[0], *Rb = R[1], *Rc = R[2];
+    launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+        const double n = den[i], th = n - scal[S_NREF], a = pow_pos(n, beta);
+        Ra[i] = a; Rb[i] = a * th; Rc[i] = 0.5 * a * th * th;
+    });
+    PAD_TRY(pad_fft_forward_many(p, R, C, 3, s));
+    const cufftDoubleComplex *CA = C[0], *CB = C[1], *CC = C[2], *CP = C[3];
+    for (int term = 0; term < 3; ++term) {
+        launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
+            const double n = den[i], th = n - scal[S_NREF], P = pow_pos(n, alpha);
+            Ra[i] = term == 0 ? P : (term == 1 ? P * th : 0.5 * P * th * th);
+        });
+        PAD_TRY(pad_fft_forward(p, Ra, C[3], s));
+        auto f = [=] __device__(size_t i, double(&acc)[7]) {
+            const KPoint k = make_kpoint(geom, (uint32_t)i);
+            const double k2 = k.kx * k.kx + k.ky * k.ky + k.kz * k.kz;
+            if (k2 == 0.0) return;
+            const double n_ref = scal[S_NREF], T = scal[S_TMP0 + 1], gam = c_wgc.gamma;
+            const double eta = sqrt(k2) * scal[S_TMP0 + 0];
+            double w0, w1, w2, w3;
+            wgc_w_t<true>(eta, w0, w1, w2, w3);
+            const double d1 = w1 + eta * w2, d2 = 2.0 * eta * w2 + eta * eta * w3;
+            const double c36 = T / (36.0 * n_ref * n_ref), c6 = -T / (6.0 * n_ref);
+            const double W0 = T * w0, K1 = c6 * eta * w1, K2 = c36 * (eta * eta * w2 + (7.0 - gam) * eta * w1),
+                         K3 = c36 * (eta * eta * w2 + (1.0 + gam) * eta * w1);
+            const double W0p = T * w1, K1p = c6 * d1, K2p = c36 * (d2 + (7.0 - gam) * d1), K3p = c36 * (d2 + (1.0 + gam) * d1);
+            const cufftDoubleComplex A = CA[i], B = CB[i], Cc = CC[i], P = CP[i];
+            double yr, yi, xr, xi;      // Y = unprimed combination (energy), X = primed one
+            if (term == 0) {
+                yr = W0 * A.x + K1 * B.x + K2 * Cc.x; yi = W0 * A.y + K1 * B.y + K2 * Cc.y;
+                xr = W0p * A.x + K1p * B.x + K2p * Cc.x; xi = W0p * A.y + K1p * B.y + K2p * Cc.y;
+            } else if (term == 1) {
+                yr = K1 * A.x + K3 * B.x; yi = K1 * A.y + K3 * B.y;
+                xr = K1p * A.x + K3p * B.x; xi = K1p * A.y + K3p * B.y;
+            } else {
+                yr = K2 * A.x; yi = K2 * A.y;
+                xr = K2p * A.x; xi = K2p * A.y;
+            }
+            const bool edge = k.j2 == 0 || (geom.e2 && k.j2 == geom.n2 / 2);
+            const double w = (edge ? 1.0 : 2.0) * inv_n * inv_n * kCTF;
+            const double e = w * (P.x * yr + P.y * yi);              // C_TF w Re[conj(P) Y]
+            const double x = w * eta * (P.x * xr + P.y * xi);        // C_TF w eta Re[conj(P) X]
+            acc[0] += -(2.0 / 3.0) * e + x / 3.0;
+            const double t = -x / k2;
+            acc[1] += t * k.kx * k.kx; acc[2] += t * k.ky * k.ky; acc[3] += t * k.kz * k.kz;
+            acc[4] += t * k.kx * k.ky; acc[5] += t * k.kx * k.kz; acc[6] += t * k.ky * k.kz;
+        };
+        ew_kernel<7, decltype(f)><<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->Nk, f, p->partials);
+        ++g_pad_launches;
+        PAD_CHECK_LAUNCH();
+        PAD_TRY(pad_stress_accumulate(p, s, pad_grid_for(p->Nk), 1.0, 1.0, sig));
+    }
+    return PAD_OK;
+}
+
 extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa,
                               double* E_out, double* v_out, int accumulate, void* stream) {
     PAD_TRY(check_common(p, den, "pad_eval_wgc99"));
@@ -514,18 +631,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     }
     const bool same = p->wgc_key[5] == 1.0 && p->wgc_key[0] == alpha && p->wgc_key[1] == beta &&
                       p->wgc_key[2] == gamma && p->wgc_key[3] == kappa && p->wgc_key[4] == (double)p->box_generation;
-    // the series coefficients live in one constant bank per device, shared by all plans
-    static double bank_key[64][3];
-    static bool bank_valid[64];
-    const int dv = p->device & 63;
-    if (!bank_valid[dv] || bank_key[dv][0] != alpha || bank_key[dv][1] != beta || bank_key[dv][2] != gamma) {
-        WgcSeries S;
-        wgc_host_series(alpha, beta, gamma, &S);
-        // stream-ordered: in-flight kernels of earlier calls on this stream finish first
-        PAD_CUDA(cudaMemcpyToSymbolAsync(c_wgc, &S, sizeof(S), 0, cudaMemcpyHostToDevice, s));
-        bank_key[dv][0] = alpha; bank_key[dv][1] = beta; bank_key[dv][2] = gamma;
-        bank_valid[dv] = true;
-    }
+    PAD_TRY(wgc_ensure_series(p, alpha, beta, gamma, s));
     if (!same) {
         p->wgc_key[0] = alpha; p->wgc_key[1] = beta; p->wgc_key[2] = gamma; p->wgc_key[3] = kappa;
         p->wgc_key[4] = (double)p->box_generation; p->wgc_key[5] = 1.0;

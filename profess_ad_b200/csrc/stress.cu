@@ -12,9 +12,11 @@
 //   Wang-Teter family NL    : pref sum_k w Re(a_k conj b_k) aux3(eta) (k_i k_j / k^2 - delta_ij / 3) - (2/3) delta_ij T_NL / vol
 //   PBE                     : delta_ij mean(f - n f_n - 2 sigma f_sigma) - 2 mean(f_sigma g_i g_j)
 // (c_k, chi_k, a_k, b_k: Fourier coefficients, norm = 'forward', of n, sqrt n, n^alpha, n^beta.)
-// WangGovindCarter99 and the Huang-Carter family are not covered: the reference's own autograd stress for WGC99 depends
-// on whether its kernel cache was filled with or without a graph (functionals.py:961-966), so there is no well-defined
-// number to reproduce.
+//   WangGovindCarter99 NL   : pad_stress_wgc99_nl (functionals.cu): same structure with the eta-derivatives of the four kernels;
+//                             the derivative with the kernel regenerated for the strained cell (the reference's autograd
+//                             with a fresh kernel; with a kernel cached at the same cell the reference silently drops the
+//                             kernel's own eta-dependence, functionals.py:961-966)
+// The Huang-Carter family is not covered.
 #include "common.cuh"
 #include "xc.cuh"
 
@@ -68,10 +70,6 @@ int pad_stress_accumulate(pad_plan* p, cudaStream_t s, int nblocks, double c_iso
 
 extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* den, double* stress_out, void* stream) {
     if (!p || !T || !den || !stress_out) { pad_set_error("pad_stress_terms: null argument"); return PAD_ERR_ARG; }
-    if (T->kinetic == 2) {
-        pad_set_error("pad_stress_terms: no stress for WangGovindCarter99 (the reference's autograd result depends on its kernel-cache state)");
-        return PAD_ERR_ARG;
-    }
     if (T->kinetic == 3) { pad_set_error("pad_stress_terms: no stress for the Huang-Carter family"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -84,7 +82,8 @@ extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* d
     for (int i = 0; i < 3; ++i) PAD_TRY(pad_get_cbuf(p, i, &C[i]));
 
     // ---- local terms (IonElectron is handled by pad_ion_stress) ------------------------------------------
-    int parts = T->kinetic == 1 ? T->kinetic_parts : 0;
+    // WangGovindCarter99 = TF + vW + its own non-local term (functionals.py:983-985)
+    int parts = T->kinetic == 1 ? T->kinetic_parts : (T->kinetic == 2 ? (PAD_PART_TF | PAD_PART_VW) : 0);
     // ThomasFermi can appear as a term of its own and inside a Wang-Teter style functional: count both
     const double tfc = ((T->local_mask & PAD_LOCAL_TF) ? 1.0 : 0.0) + ((parts & PAD_PART_TF) ? 1.0 : 0.0);
     const bool tf = tfc != 0.0;
@@ -136,6 +135,7 @@ extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* d
     }
 
     // ---- non-local term of the Wang-Teter family ---------------------------------------------------------------
+    if (T->kinetic == 2) PAD_TRY(pad_stress_wgc99_nl(p, den, T->alpha, T->beta, T->gamma, T->kappa, stress_out, s));
     if (parts & PAD_PART_NL) {
         const double alpha = T->alpha, beta = T->beta;
         PAD_TRY(pad_get_rbuf(p, 0, &R[0]));

@@ -72,6 +72,13 @@ def main():
             if f.__name__ in ('IonIon', 'IonElectron'):
                 continue
             out['stress_' + f.__name__] = T.get_stress(box, den, f).detach().numpy()
+        # WangGovindCarter99 with a FRESH functional object per call: the kernel is then generated inside the autograd
+        # graph and the stress contains the kernel's own dependence on the cell (a kernel cached by an earlier call at the
+        # same cell would be reused without its graph, functionals.py:961-966)
+        A98, B98 = (5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6
+        out['stressfresh_WGC99'] = T.get_stress(box, den, F.WangGovindCarter99().forward).detach().numpy()
+        out['stressfresh_WGC99_gamma05'] = T.get_stress(box, den, F.WangGovindCarter99((A98, B98, 0.5, 1.0)).forward).detach().numpy()
+        out['stressfresh_WGC99_kappa12'] = T.get_stress(box, den, F.WangGovindCarter99((A98, B98, 2.7, 1.2)).forward).detach().numpy()
         np.savez_compressed(os.path.join(HERE, f'ions_{name}.npz'), **out)
         print(name, tuple(den.shape), 'E', out['energy_Ha'], 'max|F|', np.abs(out['forces_Ha_b']).max(),
               'stress diag', np.diag(out['stress_Ha_b3']))

@@ -158,6 +158,21 @@ def test_system_stress_and_pressure_match_reference(case, golden_dir, potentials
         s.stress('bar')
 
 
+@pytest.mark.parametrize('case', CASES)
+def test_wgc99_stress_matches_reference_fresh_kernel(case, golden_dir, potentials_dir):
+    """WGC99 stress = the reference's autograd with a freshly generated kernel (all three branches of the kernel's
+    homogeneous solution: default gamma -> complex exponents, gamma = 0.5 -> real exponents; kappa != 1)."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.functional_tools import get_stress
+    g, box, den, _ = load_case(case, golden_dir, potentials_dir)
+    b, d = box.to(DEV), den.to(DEV)
+    A98, B98 = (5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6
+    for key, f in (('stressfresh_WGC99', F.WangGovindCarter99()), ('stressfresh_WGC99_gamma05', F.WangGovindCarter99((A98, B98, 0.5, 1.0))),
+                   ('stressfresh_WGC99_kappa12', F.WangGovindCarter99((A98, B98, 2.7, 1.2)))):
+        st = get_stress(b, d, f.forward).cpu().numpy()
+        assert _rel(st, g[key]) < 1e-9, (key, _rel(st, g[key]))
+
+
 def test_stress_vs_oracle_rough_grids_and_unsupported():
     from oracle import ofdft_oracle as orc
     import profess_ad_b200.functionals as F
@@ -172,8 +187,6 @@ def test_stress_vs_oracle_rough_grids_and_unsupported():
             ref = orc.stress(box, den, fo).numpy()
             st = get_stress(box.to(DEV), den.to(DEV), f).cpu().numpy()
             assert _rel(st, ref) < 1e-10, (shape, f.__name__, _rel(st, ref))
-    with pytest.raises(NotImplementedError):
-        get_stress(box.to(DEV), den.to(DEV), F.WangGovindCarter99().forward)
     with pytest.raises(NotImplementedError):
         get_stress(box.to(DEV), den.to(DEV), lambda b, n: F.ThomasFermi(b, n))
 
