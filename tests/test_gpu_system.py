@@ -210,3 +210,27 @@ def test_eos_scan_reproduces_published_table(potentials_dir):
     assert abs(params[3] - 16.76389) < 2e-4
     assert abs(params[2] - (-57.18370)) < 2e-5
     assert abs(params[0] - 78.80961) < 0.02
+
+
+def test_exact_single_orbital_limits(potentials_dir):
+    """The reference's own known answers (tests/test_den_opt.py:13-41): with Weizsaecker as the only kinetic term a
+    one-electron system is exact -- hydrogen atom in a 20 bohr box: -0.5 Ha (2 places); harmonic oscillator with
+    k = 10: 3/2 sqrt(k) Ha (5 places; docs/source/example_density_optimization.rst:175-221 quotes 4.74341650)."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.system import System
+    L = 20.0
+    box = L * torch.eye(3, dtype=torch.double)
+    shape = System.ecut2shape(250, box)
+    ions = [['H', os.path.join(potentials_dir, 'H.coulomb-kcut-15.recpot'), torch.tensor([[0.5, 0.5, 0.5]]).double()]]
+    s = System(box, shape, ions, [F.IonElectron, F.Weizsaecker], units='b', coord_type='fractional')
+    s.set_electron_number(1)
+    s.optimize_density(ntol=1e-4)
+    assert abs(s.energy('Ha') - (-0.5)) < 5e-3
+    k = 10
+    f = [torch.arange(n, dtype=torch.double) / n for n in shape]
+    x, y, z = torch.meshgrid(*[L * fi for fi in f], indexing='ij')
+    qho = 0.5 * k * ((x - L / 2).pow(2) + (y - L / 2).pow(2) + (z - L / 2).pow(2))
+    s.set_potential(qho)
+    s.initialize_density()
+    s.optimize_density(ntol=1e-4)
+    assert abs(s.energy('Ha') - 1.5 * np.sqrt(k)) < 5e-6

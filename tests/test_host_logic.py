@@ -186,3 +186,28 @@ def test_lbfgs_follows_reference_trajectories(case, mode, golden_dir):
     got = gen.trajectory(LBFGSNew, fn, x0, line_search_fn=(mode == 'linesearch'))
     assert np.abs(got - ref).max() < (1e-5 if mode == 'linesearch' else 1e-9), np.abs(got - ref).max(axis=1)
     assert np.abs(got[:4] - ref[:4]).max() < 1e-9
+
+
+def test_field_dependent_convolution_spline_vs_naive():
+    """tests/test_field_dependent_convolution_spline.py:10-42 (Yukawa kernel, xi = cos^2 r + 1, atol 1e-10), on a
+    smaller grid: the generic spline helper kept for user kernels against the point-by-point convolution."""
+    from profess_ad_b200.functional_tools import field_dependent_convolution, wavevecs
+    shape = (10, 9, 8)
+    box = 2 * torch.eye(3, dtype=torch.double)
+    f = [torch.arange(n, dtype=torch.double) / n for n in shape]
+    x, y, z = torch.meshgrid(*[2 * fi for fi in f], indexing='ij')
+    r = torch.sqrt(x * x + y * y + z * z)
+    _, _, _, k2 = wavevecs(box, shape)
+
+    def K_tilde(k2, xi_sparse):
+        return 4 * np.pi / (k2.unsqueeze(3).expand((-1, -1, -1, len(xi_sparse))) + xi_sparse.pow(2))
+    xis = torch.cos(r).pow(2) + 1
+    g = xis.pow(1 / 3)
+    u = field_dependent_convolution(k2, K_tilde, g, xis, kappa=0.01)
+    G = torch.fft.rfftn(g)
+    naive = torch.empty(shape, dtype=torch.double)
+    for i in range(shape[0]):
+        for j in range(shape[1]):
+            for k in range(shape[2]):
+                naive[i, j, k] = torch.fft.irfftn(G * 4 * np.pi / (k2 + xis[i, j, k].pow(2)), shape)[i, j, k]
+    assert torch.allclose(u, naive, atol=1e-10)
