@@ -124,6 +124,20 @@ class ClockSampler:
                 'power_w_max': max(self.power) if self.power else None, 'samples': len(sm)}
 
 
+def host_cores():
+    """Physical cores this process may run on (what torch picks by default when OMP_NUM_THREADS is not set)."""
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = os.cpu_count() or 1
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or allowed
+    except Exception:      # noqa: BLE001
+        physical = allowed
+    return max(1, min(allowed, physical))
+
+
 def dist_env():
     os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     rank = int(os.environ.get('RANK', '0'))
@@ -141,6 +155,8 @@ def cpu_reference_run(steps, warmup, sample_grid=None):
     threads) after one warm-up that also builds and caches the kernel (~10-20 s, not timed, as on the GPU)."""
     import torch
     from oracle import ofdft_oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can
+    torch.set_num_threads(host_cores())
     cores = torch.get_num_threads()
     n = sample_grid or GRID
     n_timed = max(1, min(steps, 5))
@@ -350,6 +366,8 @@ def run_gpu(args):
                 'traffic_per_launch': NCU_TRAFFIC_256.get(dom['stage']) if GRID == 256 else None,
                 'launches_per_eval': dom['launches_per_eval'],
                 'note': 'CUDA events on the launch stream around this stage, mean of 5 evaluations'}
+        if world == 1:
+            line['also'] = also_reported(dev, box, den)
         if world == 1 and not args.no_denopt:
             line['density_optimization'] = density_optimization_leg(dev)
         if world == 1 and not args.no_cpu_baseline:
@@ -358,6 +376,49 @@ def run_gpu(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def also_reported(dev, box, den):
+    """SURVEY.md section 8(d), "also reported": E+V evaluations per second of the other non-local kinetic functionals and
+    of the full term stack at 256^3, and of WGC99 at 128^3 (device-resident inputs, CUDA events, 20 evaluations each)."""
+    import torch
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _density_opt as D
+    from profess_ad_b200.synthetic import smooth_supercell
+
+    def rate(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return n / (e0.elapsed_time(e1) * 1e-3)
+
+    def ev(f, b, d):
+        def go():
+            x = d.requires_grad_(True)
+            E = f(b, x)
+            torch.autograd.grad(E, x)
+            d.requires_grad_(False)
+        return go
+    out = {}
+    try:
+        out['WangTeter E+V, 256^3'] = rate(ev(F.WangTeter, box, den))
+        out['WangGovindCarter98 E+V, 256^3'] = rate(ev(F.WangGovindCarter98, box, den))
+        out['PerdewBurkeErnzerhof E+V, 256^3'] = rate(ev(F.PerdewBurkeErnzerhof, box, den))
+        terms = [F.IonElectron, F.Hartree, F.WangGovindCarter99().forward, F.PerdewZunger]
+        T = D.describe_terms(terms)
+        v_ext = -0.1 * den / den.mean()
+        out['IonElectron + Hartree + WGC99 + PerdewZunger E+V (fused term list), 256^3'] = rate(lambda: D.eval_total(box, den, v_ext, T))
+        b128, d128 = smooth_supercell(128, 2, device=dev)
+        out['WangGovindCarter99 E+V, 128^3'] = rate(ev(F.WangGovindCarter99().forward, b128, d128), 50)
+    except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
+        out['error'] = repr(e)
+    return {'unit': UNIT, 'values': out}
 
 
 def density_optimization_leg(dev):

@@ -637,7 +637,10 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
         p->wgc_key[4] = (double)p->box_generation; p->wgc_key[5] = 1.0;
     }
     double* kern = p->wgc_kern;
-    wgc_build_kernel<<<pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, p->wgc_kern4, scal, same ? 0 : 1);
+    // when parameters and lattice are unchanged the kernel only has to compare n_ref with the cached key on the device
+    // (it changes when the electron number does): a one-wave grid is enough for the check, and still rebuilds the
+    // kernel (grid-stride, slower) in the rare case that the key differs
+    wgc_build_kernel<<<same ? 148 : pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, p->wgc_kern4, scal, same ? 0 : 1);
     PAD_CHECK_LAUNCH();
     wgc_key_kernel<<<1, 1, 0, s>>>(scal);
     g_pad_launches += 2;
