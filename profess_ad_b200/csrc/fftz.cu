@@ -878,6 +878,164 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     return PAD_OK;
 }
 
+// =================================================================================================
+//  Wang-Teter family (TF + vW + non-local term with the Lindhard kernel, functionals.py:644-725) on the fused
+//  pipeline: ONE round trip -- [gen n^beta - n0^beta (, n^alpha - n0^alpha), chi + z r2c] -> y -> [x . (K | -k^2) . x^-1]
+//  -> y^-1 -> [z c2r + energies + potential].  Called by pad_eval_wt after n0 and the kernel prefactor are in the
+//  scalar block (S_TMP0 + 0..3: 1/(2 kF), 5 / (9 alpha beta n0^(alpha+beta-5/3)), n0^alpha, n0^beta).
+// =================================================================================================
+template <bool TWO>
+struct GenWt {
+    static constexpr int NST = 3, NIN = 1;      // staged: n, n^beta, n^alpha
+    const double* scal;
+    double alpha, beta;
+    __device__ void stage(const double2* in, double* a, double* b) const {
+        a[0] = in[0].x; a[1] = pow_pos_ool(in[0].x, beta); a[2] = TWO ? pow_pos_ool(in[0].x, alpha) : a[1];
+        b[0] = in[0].y; b[1] = pow_pos_ool(in[0].y, beta); b[2] = TWO ? pow_pos_ool(in[0].y, alpha) : b[1];
+    }
+    template <int F>
+    __device__ double field(const double* s) const {
+        if constexpr (F == 0) return s[1] - scal[S_TMP0 + 3];
+        else if constexpr (TWO && F == 1) return s[2] - scal[S_TMP0 + 2];
+        else {
+            if (fm_ok(s[0])) return fm_sqrt_from_rsqrt(s[0], fm_rsqrt(s[0]));
+            return s[0] != 0.0 ? sqrt(s[0]) : 0.0;
+        }
+    }
+};
+
+// 1 / G^-1(eta) - 3 eta^2 - 1 with the Lindhard function of functionals.py:617-628
+__device__ __forceinline__ double lindhard_minus_z(double eta) {
+    double ginv;
+    if (eta == 0.0) ginv = 1.0;
+    else if (eta == 1.0) ginv = 0.5;
+    else ginv = 0.5 + ((1.0 - eta * eta) / (4.0 * eta)) * log(fabs((1.0 + eta) / (1.0 - eta)));
+    return 1.0 / ginv - 3.0 * eta * eta - 1.0;
+}
+
+template <bool TWO>
+struct MixWt {                         // fields 0 (, 1): Lindhard kernel / N;  last field: -k^2 / N
+    const double* scal;
+    double inv_n;
+    struct Coef { double nl, lap; };
+    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+        Coef c{0.0, 0.0};
+        if (!live) return c;
+        const KPoint k = make_kpoint_at(g, kx, ky, z);
+        const double inv2kF = scal[S_TMP0 + 0];
+        c.lap = -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
+        c.nl = inv_n * scal[S_TMP0 + 1] * sym_even(k, [=](double x, double y, double w) {
+                   const double k2 = x * x + y * y + w * w;
+                   return lindhard_minus_z((k2 != 0.0 ? sqrt(k2) : 0.0) * inv2kF);
+               });
+        return c;
+    }
+    __device__ __forceinline__ void apply(const Coef& c, cd* q) const {
+        q[0] = cd{q[0].x * c.nl, q[0].y * c.nl};
+        if (TWO) q[1] = cd{q[1].x * c.nl, q[1].y * c.nl};
+        constexpr int L = TWO ? 2 : 1;
+        q[L] = cd{q[L].x * c.lap, q[L].y * c.lap};
+    }
+};
+
+struct WtOut {
+    double v, e_tf, e_vw, e_nl;
+};
+__device__ __noinline__ WtOut wt_point(double n, double alpha, double beta, bool two, double n0a, double conv_b, double conv_a,
+                                      double lap) {
+    WtOut o;
+    if (fm_ok(n)) {
+        const double l = fm_log(n);
+        const double pb = fm_exp(beta * l);
+        const double pa = two ? fm_exp(alpha * l) : pb;
+        const double c2 = fm_exp((2.0 / 3.0) * l);
+        const double y = fm_rsqrt(n);
+        const double chi = fm_sqrt_from_rsqrt(n, y);
+        o.e_tf = kCTF * n * c2;
+        o.e_vw = chi * lap;
+        o.e_nl = (pa - n0a) * conv_b;
+        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * pa * conv_b + beta * pb * conv_a) * (y * y);
+        return o;
+    }
+    const double ln = log(n);
+    const double pb = exp(beta * ln);
+    const double pa = two ? exp(alpha * ln) : pb;
+    const double c = cbrt(n);
+    const double chi = n != 0.0 ? sqrt(n) : 0.0;
+    o.e_tf = kCTF * n * c * c;
+    o.e_vw = chi * lap;
+    o.e_nl = (pa - n0a) * conv_b;
+    double v = (5.0 / 3.0) * kCTF * c * c;
+    if (n != 0.0) v += -0.5 * lap / chi;
+    v += kCTF * (alpha * pa * conv_b + beta * pb * conv_a) / n;
+    o.v = v;
+    return o;
+}
+
+template <bool TWO>
+struct PostWt {
+    static constexpr bool kDen = true, kVin = false;
+    const double* scal;
+    double* v_out;
+    double alpha, beta;
+    int accumulate, want_v;
+    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc) const {
+        constexpr int L = TWO ? 2 : 1;
+        const double n0a = scal[S_TMP0 + 2];
+        const WtOut a = wt_point(n.x, alpha, beta, TWO, n0a, u0[0], TWO ? u0[1] : u0[0], u0[L]);
+        const WtOut b = wt_point(n.y, alpha, beta, TWO, n0a, u1[0], TWO ? u1[1] : u1[0], u1[L]);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
+        if (want_v) {
+            double2 vo = make_double2(0.0, 0.0);
+            if (accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+        }
+    }
+};
+
+template <bool TWO>
+static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double beta, double* E_out, double* v_out,
+                        int accumulate, cudaStream_t s) {
+    constexpr int NF = TWO ? 3 : 2;
+    PAD_TRY(ensure_twiddles(p->device));
+    cd* B[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NF; ++i) PAD_TRY(get_zbuf(p, i, &B[i]));
+    const double* scal = p->scal;
+    pad_stage_begin(s);
+    GenWt<TWO> gen{scal, alpha, beta};
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, NF>(p, s, gen, den, nullptr, B[0], B[1], B[2], nullptr))));
+    pad_stage_mark("WT: gen fields + z-r2c", s);
+    PAD_TRY(launch_spass(p, s, 1, -1, B, NF));
+    pad_stage_mark("WT: y-fwd", s);
+    PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->geom.inv_n})));
+    pad_stage_mark("WT: x-fwd * (Lindhard | -k^2) * x-inv", s);
+    PAD_TRY(launch_spass(p, s, 1, +1, B, NF));
+    pad_stage_mark("WT: y-inv", s);
+    int grid = 1;
+    PostWt<TWO> post{scal, v_out, alpha, beta, accumulate, v_out ? 1 : 0};
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, NF, 3>(p, s, post, B[0], B[1], B[2], nullptr, den, nullptr, &grid))));
+    pad_stage_mark("WT: z-c2r + energies + potential", s);
+    if (E_out) {
+        FinalizeArgs a;
+        a.nblocks = grid; a.nterms = 3; a.accumulate = accumulate;
+        for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
+        a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
+        a.sums_out = nullptr;
+        a.E_out = E_out;
+        pad_launch_finalize(p, a, s);
+    }
+    return PAD_OK;
+}
+
+int pad_wt_fast_supported(const pad_plan* p) { return fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
+
+int pad_wt_fast(pad_plan* p, const double* den, double alpha, double beta, double* E_out, double* v_out, int accumulate,
+                cudaStream_t s) {
+    return alpha != beta ? wt_fast_impl<true>(p, den, alpha, beta, E_out, v_out, accumulate, s)
+                         : wt_fast_impl<false>(p, den, alpha, beta, E_out, v_out, accumulate, s);
+}
+
 // fastmath.cuh against the library functions: out[0..n) = fm_exp(e * fm_log(x)), out[n..2n) = sqrt via fm_rsqrt,
 // out[2n..3n) = fm_rsqrt(x)^2 (used as 1/x); ref[...] the same from exp/log, sqrt and division
 __global__ void fastmath_probe_kernel(const double* x, size_t n, double e, double* out, double* ref) {

@@ -223,10 +223,6 @@ extern "C" int pad_eval_wt(pad_plan* p, const double* den, double alpha, double 
     double* scal = p->scal;
     const double inv_n = p->geom.inv_n;
 
-    if (vw) { PAD_TRY(pad_get_rbuf(p, 0, &R0)); PAD_TRY(pad_get_cbuf(p, 0, &C0)); }
-    if (nl) { PAD_TRY(pad_get_rbuf(p, 1, &R1)); PAD_TRY(pad_get_cbuf(p, 1, &C1)); }
-    if (two) { PAD_TRY(pad_get_rbuf(p, 2, &R2)); PAD_TRY(pad_get_cbuf(p, 2, &C2)); }
-
     if (nl) {
         launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
         PAD_CHECK_LAUNCH();
@@ -236,6 +232,12 @@ extern "C" int pad_eval_wt(pad_plan* p, const double* den, double alpha, double 
         ++g_pad_launches;
         PAD_CHECK_LAUNCH();
     }
+    // the whole functional (TF + vW + NL) on the hand-written fused FFT pipeline where the grid allows it
+    if (tf && vw && nl && g_pad_fast_fft && pad_wt_fast_supported(p)) return pad_wt_fast(p, den, alpha, beta, E_out, v_out, accumulate, s);
+
+    if (vw) { PAD_TRY(pad_get_rbuf(p, 0, &R0)); PAD_TRY(pad_get_cbuf(p, 0, &C0)); }
+    if (nl) { PAD_TRY(pad_get_rbuf(p, 1, &R1)); PAD_TRY(pad_get_cbuf(p, 1, &C1)); }
+    if (two) { PAD_TRY(pad_get_rbuf(p, 2, &R2)); PAD_TRY(pad_get_cbuf(p, 2, &C2)); }
     if (vw || nl) {
         launch_ew<0>(p, s, [=] __device__(size_t i, double(&)[1]) {
             const double n = den[i];

@@ -128,3 +128,46 @@ def test_fast_math_accuracy(expo):
     assert err[0] < 4e-16, (err, err_lib)
     assert err[1] < 2.5e-16, (err, err_lib)        # sqrt: correctly rounded or 1 ulp
     assert err[2] < 7e-16, (err, err_lib)          # 1/x as rsqrt^2
+
+
+@pytest.mark.parametrize('shape,seed', [((64, 64, 128), 41), ((64, 128, 256), 42), ((128, 64, 128), 43)])
+def test_wt_family_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
+    """Wang-Teter family (alpha == beta: WT, Perrot, SM; alpha != beta: WGC98) on the fused FFT pipeline (one round trip,
+    Lindhard kernel evaluated inside the x pass) against the oracle and against the cuFFT path."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native
+    lib = _native.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=seed, L=9.0)
+    b, d = box.to(dev), den.to(dev)
+    v0 = torch.rand(*shape, dtype=torch.double, generator=torch.Generator().manual_seed(seed)).to(dev)
+    for name, f, fo in (('WT', F.WangTeter, orc.WangTeter), ('SM', F.SmargiassiMadden, orc.SmargiassiMadden),
+                        ('WGC98', F.WangGovindCarter98, orc.WangGovindCarter98)):
+        E_ref, V_ref = orc.energy_and_potential(box, den, fo)
+        res = {}
+        for fast in (1, 0):
+            old = lib.pad_set_fast_fft(fast)
+            try:
+                E, V = F.energy_and_potential(b, d, f)
+                e_only = f(b, d).item()
+            finally:
+                lib.pad_set_fast_fft(old)
+            res[fast] = E.item()
+            assert abs(E.item() - E_ref.item()) <= 1e-10 * abs(E_ref.item()), (name, fast, E.item(), E_ref.item())
+            assert ((V.cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9, (name, fast)
+            assert abs(e_only - E.item()) <= 1e-13 * abs(E.item())
+        assert abs(res[1] - res[0]) <= 1e-12 * abs(res[0])
+    # accumulate path (fused term list): E += , v +=
+    from profess_ad_b200 import _density_opt as D
+    T = D.describe_terms([F.Hartree, F.WangGovindCarter98, F.PerdewZunger])
+    out = {}
+    for fast in (1, 0):
+        old = lib.pad_set_fast_fft(fast)
+        try:
+            E, v = D.eval_total(b, d, None, T)
+        finally:
+            lib.pad_set_fast_fft(old)
+        out[fast] = (E.item(), v.clone())
+    assert abs(out[1][0] - out[0][0]) <= 1e-12 * abs(out[0][0])
+    assert ((out[1][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11
