@@ -200,6 +200,9 @@ struct pad_plan {
     double* wgc_kern4;           // same kernels, interleaved (W0,K1,K2,K3) per k-point over the PADDED half-spectrum layout
     double wgc_key[6];           // alpha, beta, gamma, kappa, + box generation, valid flag
     uint64_t box_generation;
+    // fused Wang-Teter pipeline: 1/G^-1(eta) - 3 eta^2 - 1 per k-point over the padded half-spectrum layout
+    double* wt_kern;
+    uint64_t wt_kern_generation;
     // Huang-Carter scratch: xi-node list (+ min/max words), table slopes, n_xi convolution fields
     double* hc_scratch;
     double* hc_slopes;
@@ -243,6 +246,7 @@ enum {
     S_N0 = 1,           // mean density
     S_NREF = 2,         // WGC99 reference density kappa * round(N_elec) / vol
     S_NREF_KEY = 3,     // n_ref the cached WGC99 kernel was built for
+    S_WT_KEY = 4,       // n0 the cached Lindhard kernel table of the fused Wang-Teter pipeline was built for
     S_TMP0 = 8,         // 8 slots of per-call temporaries
     S_E_PARTS = 16      // component energies
 };

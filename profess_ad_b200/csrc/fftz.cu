@@ -913,26 +913,42 @@ __device__ __forceinline__ double lindhard_minus_z(double eta) {
     return 1.0 / ginv - 3.0 * eta * eta - 1.0;
 }
 
+// Lindhard table of the fused Wang-Teter pipeline: depends on the lattice and on kF(n0) only; rebuilt when the lattice
+// changes (host key) or n0 does (device key, as for the WGC99 kernel)
+__global__ void __launch_bounds__(PAD_THREADS) wt_build_kernel(KGeom g, uint32_t nk, int nzp, double* __restrict__ table,
+                                                              double* scal, int force) {
+    if (!force && scal[S_N0] == scal[S_WT_KEY]) return;
+    const double inv2kF = scal[S_TMP0 + 0];
+    const uint32_t stride = gridDim.x * PAD_THREADS;
+    for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
+        const KPoint k = make_kpoint(g, idx);
+        const uint32_t row = idx / (uint32_t)g.nzh;
+        table[(size_t)row * nzp + (uint32_t)k.j2] = sym_even(k, [=](double x, double y, double w) {
+            const double k2 = x * x + y * y + w * w;
+            return lindhard_minus_z((k2 != 0.0 ? sqrt(k2) : 0.0) * inv2kF);
+        });
+    }
+}
+__global__ void wt_key_kernel(double* scal) { scal[S_WT_KEY] = scal[S_N0]; }
+
 template <bool TWO>
 struct MixWt {                         // fields 0 (, 1): Lindhard kernel / N;  last field: -k^2 / N
     const double* scal;
+    const double* table;               // [(kx n1 + ky) nzp + z]
     double inv_n;
     struct Coef { double nl, lap; };
-    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t pidx, bool live) const {
         Coef c{0.0, 0.0};
         if (!live) return c;
+        c.nl = __ldcs(table + pidx);
         const KPoint k = make_kpoint_at(g, kx, ky, z);
-        const double inv2kF = scal[S_TMP0 + 0];
         c.lap = -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
-        c.nl = inv_n * scal[S_TMP0 + 1] * sym_even(k, [=](double x, double y, double w) {
-                   const double k2 = x * x + y * y + w * w;
-                   return lindhard_minus_z((k2 != 0.0 ? sqrt(k2) : 0.0) * inv2kF);
-               });
         return c;
     }
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const {
-        q[0] = cd{q[0].x * c.nl, q[0].y * c.nl};
-        if (TWO) q[1] = cd{q[1].x * c.nl, q[1].y * c.nl};
+        const double m = c.nl * inv_n * scal[S_TMP0 + 1];
+        q[0] = cd{q[0].x * m, q[0].y * m};
+        if (TWO) q[1] = cd{q[1].x * m, q[1].y * m};
         constexpr int L = TWO ? 2 : 1;
         q[L] = cd{q[L].x * c.lap, q[L].y * c.lap};
     }
@@ -1003,12 +1019,29 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     for (int i = 0; i < NF; ++i) PAD_TRY(get_zbuf(p, i, &B[i]));
     const double* scal = p->scal;
     pad_stage_begin(s);
+    {   // Lindhard table (padded layout), cached per lattice and n0
+        bool fresh = false;
+        if (!p->wt_kern) {
+            const size_t bytes = sizeof(double) * (size_t)p->n0 * p->n1 * p->nzp;
+            PAD_CUDA(cudaMalloc(&p->wt_kern, bytes));
+            PAD_CUDA(cudaMemsetAsync(p->wt_kern, 0, bytes, s));
+            p->bytes_allocated += bytes;
+            fresh = true;
+        }
+        const bool same = !fresh && p->wt_kern_generation == p->box_generation;
+        p->wt_kern_generation = p->box_generation;
+        wt_build_kernel<<<same ? 148 : pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, p->nzp, p->wt_kern, p->scal, same ? 0 : 1);
+        wt_key_kernel<<<1, 1, 0, s>>>(p->scal);
+        g_pad_launches += 2;
+        PAD_CUDA(cudaGetLastError());
+    }
+    pad_stage_mark("WT: Lindhard table check", s);
     GenWt<TWO> gen{scal, alpha, beta};
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, NF>(p, s, gen, den, nullptr, B[0], B[1], B[2], nullptr))));
     pad_stage_mark("WT: gen fields + z-r2c", s);
     PAD_TRY(launch_spass(p, s, 1, -1, B, NF));
     pad_stage_mark("WT: y-fwd", s);
-    PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->geom.inv_n})));
+    PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n})));
     pad_stage_mark("WT: x-fwd * (Lindhard | -k^2) * x-inv", s);
     PAD_TRY(launch_spass(p, s, 1, +1, B, NF));
     pad_stage_mark("WT: y-inv", s);

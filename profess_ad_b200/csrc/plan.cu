@@ -239,6 +239,7 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     for (int i = 0; i < PAD_N_CBUF; ++i) if (p->cbuf[i]) cudaFree(p->cbuf[i]);
     if (p->wgc_kern) cudaFree(p->wgc_kern);
     if (p->wgc_kern4) cudaFree(p->wgc_kern4);
+    if (p->wt_kern) cudaFree(p->wt_kern);
     if (p->hc_scratch) cudaFree(p->hc_scratch);
     if (p->hc_slopes) cudaFree(p->hc_slopes);
     if (p->hc_conv) cudaFree(p->hc_conv);
