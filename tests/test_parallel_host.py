@@ -76,3 +76,63 @@ def test_slab_bounds_and_errors():
         parallel.slab_bounds(10, 0, 4)
     with pytest.raises(RuntimeError):
         parallel.local_slab(torch.zeros(4, 2, 2))
+
+
+class _FakeSystem:
+    """Duck-typed stand-in for System (the real one needs a GPU): E(V) is a Birch-Murnaghan curve."""
+    GPa_per_atomic, eV_per_Ha, A_per_b = 29421.02648438959, 27.211386245988, 0.529177210903
+
+    def __init__(self):
+        self.box = 16.9 ** (1 / 3) * torch.eye(3, dtype=torch.double)
+        self.optimised = 0
+
+    def volume(self, units):
+        return abs(torch.linalg.det(self.box).item())
+
+    def lattice_vectors(self, units):
+        return self.box
+
+    def set_lattice(self, box, units='a'):
+        self.box = box.clone()
+
+    def optimize_density(self, **kw):
+        self.optimised += 1
+
+    def ion_count(self):
+        return 1
+
+    def energy(self, units):
+        from profess_ad_b200.elastic_tools import birch_murnaghan
+        import numpy as np
+        return float(birch_murnaghan(np.array([self.volume('a3')]), 0.49, 4.3, -57.2, 16.76)[0])
+
+
+def _eos_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from profess_ad_b200 import parallel
+        made = []
+
+        def make():
+            made.append(_FakeSystem())
+            return made[-1]
+        params, err = parallel.eos_fit(make, f=0.05, N=9, eos='bm')
+        # 9 volumes over 2 ranks: 5 + 4 density optimisations, the same fit on every rank
+        assert made[0].optimised == (5 if rank == 0 else 4)
+        s = made[0]
+        k0 = 0.49 * s.GPa_per_atomic / (s.eV_per_Ha / s.A_per_b ** 3)
+        assert abs(params[0] - k0) < 1e-6 * k0 and abs(params[2] + 57.2) < 1e-8 and abs(params[3] - 16.76) < 1e-7
+        out[rank] = [float(p) for p in params]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_eos_fit_world2_gloo():
+    """parallel.eos_fit: the volumes of the scan are dealt round-robin to the ranks (independent systems, no
+    collective in the loop), gathered once, and every rank returns the same fit."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_eos_worker, args=(2, 29655, out), nprocs=2, join=True)
+    assert out[0] == out[1]
