@@ -171,3 +171,36 @@ def test_wt_family_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
         out[fast] = (E.item(), v.clone())
     assert abs(out[1][0] - out[0][0]) <= 1e-12 * abs(out[0][0])
     assert ((out[1][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11
+
+
+def test_full_size_properties_256():
+    """BASELINE.json's headline size (256^3), where the CPU oracle takes tens of seconds per evaluation: properties
+    that do not depend on the size.  (1) supercell consistency: tiling a 128^3 cell twice per axis multiplies every
+    energy by 8 and tiles the potential; (2) translation by whole grid points leaves E unchanged and translates v;
+    (3) the potential is the derivative of the energy along a random direction (central difference)."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.synthetic import smooth_supercell
+    dev = torch.device('cuda:0')
+    box1, den1 = smooth_supercell(128, 2, device=dev)
+    gen = torch.Generator().manual_seed(3)
+    den1 = den1 * (1 + 0.05 * torch.rand(128, 128, 128, dtype=torch.double, generator=gen).to(dev))   # no symmetry left
+    box2, den2 = 2 * box1, den1.repeat(2, 2, 2).contiguous()
+    dV = abs(torch.linalg.det(box2).item()) / den2.numel()
+    for name, f in (('WGC99', F.WangGovindCarter99().forward), ('WT', F.WangTeter), ('WGC98', F.WangGovindCarter98),
+                    ('Hartree', F.Hartree), ('PBE', F.PerdewBurkeErnzerhof)):
+        E1, V1 = F.energy_and_potential(box1, den1, f)
+        E2, V2 = F.energy_and_potential(box2, den2, f)
+        assert abs(E2.item() - 8 * E1.item()) <= 2e-12 * abs(E2.item()), (name, E2.item(), 8 * E1.item())
+        assert ((V2 - V1.repeat(2, 2, 2)).abs().max() / V1.abs().max()).item() < 1e-10, name
+        shift = (37, 101, 6)
+        E3, V3 = F.energy_and_potential(box2, torch.roll(den2, shift, (0, 1, 2)).contiguous(), f)
+        assert abs(E3.item() - E2.item()) <= 2e-12 * abs(E2.item()), name
+        assert ((V3 - torch.roll(V2, shift, (0, 1, 2))).abs().max() / V2.abs().max()).item() < 1e-10, name
+        if name in ('WGC99', 'WT', 'PBE'):
+            delta = den2 * 0.01 * (torch.rand(den2.shape, dtype=torch.double, generator=gen).to(dev) - 0.5)
+            eps = 1e-3
+            Ep = f(box2, (den2 + eps * delta).contiguous()).item()
+            Em = f(box2, (den2 - eps * delta).contiguous()).item()
+            lhs = (Ep - Em) / (2 * eps)
+            rhs = (V2 * delta).sum().item() * dV
+            assert abs(lhs - rhs) <= 1e-7 * abs(rhs) + 1e-12, (name, lhs, rhs)
