@@ -47,3 +47,32 @@ def get_cell(crystal, vol_per_atom, c_over_a=np.sqrt(8 / 3), coord_type='fractio
     if coord_type == 'cartesian':
         return lattice_vectors, frac @ lattice_vectors
     raise ValueError('Only \'fractional\' or \'cartesian\' allowed for argument \'coord_type\'.')
+
+
+# the reference's per-lattice constructors (crystal_tools.py:62-136), same signatures
+def _cell_type(prim, conv, cell_type, vol_per_atom, c_over_a=None):
+    if cell_type == 'primitive':
+        return _cell(prim, vol_per_atom, c_over_a)
+    if cell_type == 'conventional':
+        return _cell(conv, vol_per_atom, c_over_a)
+    raise ValueError('Only \'primitive\' or \'conventional\' allowed for argument \'cell_type\'.')
+
+
+def simple_cubic(vol_per_atom):
+    return _cell('sc', vol_per_atom, None)
+
+
+def body_centered_cubic(vol_per_atom, cell_type='conventional'):
+    return _cell_type('bcc', 'bcc-c', cell_type, vol_per_atom)
+
+
+def face_centered_cubic(vol_per_atom, cell_type='primitive'):
+    return _cell_type('fcc', 'fcc-c', cell_type, vol_per_atom)
+
+
+def diamond_cubic(vol_per_atom, cell_type='conventional'):
+    return _cell_type('dc', 'dc-c', cell_type, vol_per_atom)
+
+
+def hexagonal_close_packed(vol_per_atom, c_over_a=1.633):
+    return _cell('hcp', vol_per_atom, c_over_a)

@@ -249,3 +249,41 @@ def test_bench_helpers():
     assert 3000 < peak < 9000
     ns = 256 * 256 * 129
     assert bench.stage_bytes('y-fwd (4 fields)', 256 ** 3, ns) == 2 * 4 * 16 * ns
+
+
+def test_elastic_averages_and_crystal_constructors():
+    """elastic_tools.py:80-176 on the published Al XWM constants (docs/source/example_elastic.rst:161-178:
+    C11/C12/C44 = 107.08 / 61.215 / 37.861 GPa) and the identities an isotropic medium must satisfy;
+    crystal_tools.py:62-136 constructors against get_cell."""
+    from profess_ad_b200 import elastic_tools as E, crystal_tools as X
+    c11, c12, c44 = 107.08, 61.215, 37.861
+    C = torch.zeros(6, 6, dtype=torch.double)
+    C[:3, :3] = c12
+    C[0, 0] = C[1, 1] = C[2, 2] = c11
+    C[3, 3] = C[4, 4] = C[5, 5] = c44
+    kv, gv = E.voigt_moduli(C)
+    kr, gr = E.reuss_moduli(C)
+    assert abs(kv - (c11 + 2 * c12) / 3) < 1e-12 and abs(kr - kv) < 1e-10          # cubic: K_V = K_R
+    assert abs(gv - ((c11 - c12) + 3 * c44) / 5) < 1e-12
+    assert abs(gr - 5 * (c11 - c12) * c44 / (4 * c44 + 3 * (c11 - c12))) < 1e-10
+    assert gr <= E.shear_average(C, 'geometric') <= E.shear_average(C) <= gv
+    iso = torch.zeros(6, 6, dtype=torch.double)                                     # isotropic: lambda = 2, mu = 1
+    iso[:3, :3] = 2.0
+    iso += torch.diag(torch.tensor([2.0, 2.0, 2.0, 1.0, 1.0, 1.0], dtype=torch.double))
+    k, g = E.voigt_moduli(iso)
+    assert abs(k - (2 + 2 / 3)) < 1e-12 and abs(g - 1) < 1e-12
+    assert all(abs(a - b) < 1e-12 for a, b in zip(E.reuss_moduli(iso), (k, g)))
+    nu, y = E.poissons_ratio(k, g), E.youngs_modulus(k, g)
+    assert abs(nu - 2 / (2 * (2 + 1))) < 1e-12 and abs(y - 2 * g * (1 + nu)) < 1e-12
+    with pytest.raises(ValueError):
+        E.shear_average(C, 'harmonic')
+    for fn, args, name in ((X.simple_cubic, (), 'sc'), (X.body_centered_cubic, ('primitive',), 'bcc'),
+                           (X.body_centered_cubic, (), 'bcc-c'), (X.face_centered_cubic, (), 'fcc'),
+                           (X.face_centered_cubic, ('conventional',), 'fcc-c'), (X.diamond_cubic, ('primitive',), 'dc'),
+                           (X.diamond_cubic, (), 'dc-c')):
+        a, b = fn(16.8, *args), X.get_cell(name, 16.8)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    lat, frac = X.hexagonal_close_packed(16.8)
+    assert frac.shape == (2, 3) and abs(torch.linalg.det(lat).abs().item() / 2 - 16.8) < 1e-10
+    with pytest.raises(ValueError):
+        X.face_centered_cubic(16.8, 'nope')
