@@ -124,7 +124,7 @@ def _eos_worker(rank, world, port, out):
         s = made[0]
         k0 = 0.49 * s.GPa_per_atomic / (s.eV_per_Ha / s.A_per_b ** 3)
         assert abs(params[0] - k0) < 1e-6 * k0 and abs(params[2] + 57.2) < 1e-8 and abs(params[3] - 16.76) < 1e-7
-        out[rank] = [float(p) for p in params]
+        out.put((rank, [float(p) for p in params]))
     finally:
         dist.destroy_process_group()
 
@@ -132,7 +132,7 @@ def _eos_worker(rank, world, port, out):
 def test_distributed_eos_fit_world2_gloo():
     """parallel.eos_fit: the volumes of the scan are dealt round-robin to the ranks (independent systems, no
     collective in the loop), gathered once, and every rank returns the same fit."""
-    mgr = mp.Manager()
-    out = mgr.dict()
+    out = mp.get_context('spawn').SimpleQueue()
     mp.spawn(_eos_worker, args=(2, 29655, out), nprocs=2, join=True)
-    assert out[0] == out[1]
+    got = dict(out.get() for _ in range(2))
+    assert got[0] == got[1]
