@@ -11,9 +11,11 @@ user scripts switch by changing the import.  What differs is underneath:
 * user-defined Python terms (lambdas, ``nn.Module.forward``) still work through the generic
   autograd closure, exactly as in the reference (system.py:830-854).
 
-Cell derivatives (stress, pressure, elastic constants) and ionic forces need autograd through
-``box_vecs`` / ion positions and second derivatives; they are outside this path (SURVEY.md section 8,
-rows f2/f4) and raise ``NotImplementedError``.
+First derivatives are analytic as well: the ionic potential, the
+ion-electron forces and the stress are native reductions (``csrc/ions.cu``, ``csrc/stress.cu``), and
+``optimize_geometry`` drives the reference's optimisers with them.  Second derivatives (bulk modulus,
+elastic constants, force constants: implicit differentiation through the density optimisation) are outside
+this path and raise ``NotImplementedError``.
 """
 import numpy as np
 import torch
