@@ -366,3 +366,56 @@ def stress_ion_electron(box, den, species):
         E += float((val * re).sum())
         scal = scal + torch.where(kabs != 0, slope * re / torch.where(kabs != 0, kabs, torch.ones_like(kabs)), torch.zeros_like(kabs))
     return -E / g.vol * torch.eye(3, dtype=torch.double) - _tensor_sum(g, scal) / g.vol
+
+
+def stress_huang_carter_nonlocal(box, den, f):
+    """Analytic stress of the non-local Huang-Carter term for an oracle functional object ``f`` (HuangCarter or
+    RevisedHuangCarter of oracle/ofdft_oracle.py) -- the formula a CUDA implementation has to evaluate; the xi-node
+    list is a constant, as in the reference (functional_tools.py:408-416 reads min / max on the host):
+
+      sigma_ab = (1/vol) [ delta_ab (E_NL - int v_NL n)                       volume element + density scaling (n ~ 1/vol)
+                           - sum_r (dE/dg_a)(r) g_b(r)                        strain of the spectral gradient, g -> (1 - eps) g
+                           - sum_j sum_k w (omega'(|k| / xi_j) / xi_j) (k_a k_b / |k|) Re[conj(W_j^) g^] / N ]
+    with g = grad n, dE/dg_a = 2 E_xi xi_sigma g_a dV, W_j = dE/dconv_j (the node weights of the adjoint convolution)
+    and g^ = rfftn(n^beta).  The partial derivatives are taken by autograd here; the kernels hold them explicitly
+    (csrc/hc.cu: Ex, xi_s, W_j)."""
+    from oracle import ofdft_oracle as orc
+    g = KGrid(box, den.shape)
+    og = orc.Grid(box, den.shape)
+    eta_1d, w_1d = f.kernel
+    n = den.clone().requires_grad_(True)
+    gr = [x.detach().clone().requires_grad_(True) for x in og.grad(den)]
+    sig_field = gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]
+    if hasattr(f, 'lamb'):
+        xis = 2 * (3 * PI * PI * n).pow(1 / 3) * (1 + f.lamb * sig_field / (n.pow(8 / 3) + 1e-30))
+    else:
+        s2 = 0.25 * (3 * PI * PI) ** (-2 / 3) * sig_field / n.pow(8 / 3)
+        xis = 2 * (3 * PI * PI * n).pow(1 / 3) * (1 + f.a * s2 / (1 + f.b * s2))
+    nodes = orc.xi_nodes(xis.min().item(), xis.max().item(), f.kappa, 'geometric')
+    eta = og.kabs.unsqueeze(3) / nodes
+    G = torch.fft.rfftn(den.pow(f.beta)).unsqueeze(3)
+    omega = orc.interpolate(eta_1d, w_1d, torch.minimum(eta, eta_1d[-1]))
+    conv = torch.fft.irfftn(omega * G, s=den.shape, dim=(0, 1, 2)).detach().clone().requires_grad_(True)
+    K = orc.interpolate_kernel(nodes, conv, xis)
+    E_nl = C_TF * 8 * (3 * PI * PI) * torch.mean(n.pow(8 / 3 - f.beta) * K / xis.pow(3)) * g.vol
+    dE_dg = torch.autograd.grad(E_nl, gr, retain_graph=True)
+    (W,) = torch.autograd.grad(E_nl, conv)
+    _, v_nl = orc.energy_and_potential(box, den, lambda b, d: f.forward(b, d) - orc.ThomasFermi(b, d) - orc.Weizsaecker(b, d))
+    out = (float(E_nl) - g.integ(v_nl * den)) / g.vol * torch.eye(3, dtype=torch.double)
+    for a in range(3):
+        for b in range(3):
+            out[a, b] -= float((dE_dg[a] * gr[b].detach()).sum()) / g.vol
+    # d omega / d eta of the Hermite table (zero beyond its end: the argument is clamped)
+    sec = (w_1d[1:] - w_1d[:-1]) / (eta_1d[1:] - eta_1d[:-1])
+    m = torch.cat([sec[:1], 0.5 * (sec[1:] + sec[:-1]), sec[-1:]])
+    ec = torch.minimum(eta, eta_1d[-1])
+    idx = torch.searchsorted(eta_1d[1:], ec)
+    dx = eta_1d[idx + 1] - eta_1d[idx]
+    t = (ec - eta_1d[idx]) / dx
+    slope = ((-6 * t + 6 * t * t) * w_1d[idx] + (1 - 4 * t + 3 * t * t) * m[idx] * dx + (6 * t - 6 * t * t) * w_1d[idx + 1]
+             + (3 * t * t - 2 * t) * m[idx + 1] * dx) / dx
+    slope = torch.where(eta > eta_1d[-1], torch.zeros_like(slope), slope)
+    re = (torch.fft.rfftn(W, dim=(0, 1, 2)).conj() * G).real / g.N * _weights(g).unsqueeze(3)
+    kk = og.kabs.unsqueeze(3)
+    scal = torch.where(kk != 0, slope / nodes * re / torch.where(kk != 0, kk, torch.ones_like(kk)), torch.zeros_like(re)).sum(3)
+    return out - _tensor_sum(g, scal) / g.vol

@@ -73,3 +73,20 @@ def test_analytic_stresses_equal_autograd(shape, seed):
     smooth = pot.copy()
     smooth[1:] += 4 * np.pi * z / ks[1:] ** 2
     assert rel(am.stress_ion_electron(box, den, [(ks, smooth, z, frac)]), orc.ion_electron_stress(box, den, [(path, frac)])) < 1e-11
+
+
+@pytest.mark.parametrize('shape,seed', [((8, 10, 12), 1), ((9, 7, 11), 2)])
+def test_huang_carter_stress_formula_equals_autograd(shape, seed, golden_dir):
+    """The analytic Huang-Carter stress (volume / density-scaling term from the potential, strained spectral gradient,
+    eta-derivative of the kernel table through the node weights) against autograd through box_vecs -- the formula for
+    the kernels that do not exist yet (pad_stress_terms raises for kinetic == 3)."""
+    import os
+    import numpy as np
+    tab = np.load(os.path.join(golden_dir, 'hc_table.npz'))
+    box, den = orc.synth_rough(shape, seed=seed)
+    for f in (orc.RevisedHuangCarter(0.45, 0.10, 2 / 3, 1.15, kernel=torch.from_numpy(tab['revhc'])),
+              orc.HuangCarter(0.01177, 0.7143, 1.2, kernel=torch.from_numpy(tab['hc']))):
+        ref = orc.stress(box, den, f)
+        E, v = am.thomas_fermi(box, den)
+        got = am.stress_huang_carter_nonlocal(box, den, f) + am.stress_local(box, den, E, v) + am.stress_weizsaecker(box, den)
+        assert float((got - ref).abs().max() / ref.abs().max()) < 1e-12
