@@ -149,14 +149,14 @@ def dist_env():
 # --------------------------------------------------------------------------------------------------
 #  CPU reference arm / cpu_baseline
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_grid=None):
+def cpu_reference_run(steps, warmup, sample_grid=None, threads=None):
     """Oracle port of WangGovindCarter99 E+V (the reference algorithm: torch CPU fp64, autograd potential, all host
     threads) on the SAME 256^3 workload.  Bounded sample: at most 5 timed evaluations (about 1 s each on 16
     threads) after one warm-up that also builds and caches the kernel (~10-20 s, not timed, as on the GPU)."""
     import torch
     from oracle import ofdft_oracle as orc
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can
-    torch.set_num_threads(host_cores())
+    torch.set_num_threads(threads or host_cores())
     cores = torch.get_num_threads()
     n = sample_grid or GRID
     n_timed = max(1, min(steps, 5))
@@ -378,6 +378,11 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = cpu_reference_run(3, 1)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+            try:        # also at one thread (bounded: 2 evaluations at 128^3, scaled N log N)
+                v1, _, _, sample1 = cpu_reference_run(2, 1, sample_grid=min(GRID, 128), threads=1)
+                line['cpu_baseline']['one_thread'] = {'value': v1, 'unit': UNIT, 'cores': 1, 'sample': sample1}
+            except Exception as e:      # noqa: BLE001
+                line['cpu_baseline']['one_thread'] = {'error': repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
