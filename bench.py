@@ -13,11 +13,13 @@ BASELINE.md section 4 (`synth(256, side=4)`), i.e. BASELINE.json configs[1].
               evaluation, D2H of the energy and the potential, all inside the timed region
   roofline  : algorithmic bytes per evaluation (16 N n_fft + 16 N, n_fft = 14)
               / measured time per evaluation, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the oracle port (oracle/ofdft_oracle.py = the reference algorithm, torch CPU fp64,
-              all host threads) on a bounded sample, N=1 rank 0 only
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref, built by oracle/make_ref.py; kind "reference") -- or, if that
+              directory is absent, the oracle port (oracle/ofdft_oracle.py, kind "port") -- torch CPU fp64 on all host
+              threads, bounded sample, N=1 rank 0 only; its E and dE/dn at 256^3 are compared with the GPU's (`parity`)
 
-Multi-GPU (torchrun): independent systems, one per GPU (BASELINE.json configs[3] style weak scaling);
-no data-path collective, only the timing barrier / max-reduce.
+Multi-GPU (torchrun): the headline line is independent systems, one per GPU (BASELINE.json configs[3] style weak
+scaling, no data-path collective).  For N > 1 the same line carries a `slab` block: ONE grid slab-decomposed over the N
+GPUs (all-to-all over NVLink inside every 3-D transform, strong scaling) for BASELINE.json configs[2] and [4].
 """
 import argparse
 import json
@@ -37,9 +39,17 @@ UNIT = 'evals/s'
 GRID = int(os.environ.get('PAD_BENCH_GRID', '256'))
 SIDE = 4
 N_FFT = 14
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this pipeline
-# (profiles/r01_ncu_full_wgc99_256_fused_final.md, 256^3): the dominant stage and the 11 kernels of one evaluation
+# dram__bytes_read.sum + dram__bytes_write.sum from an ncu capture of this pipeline at 256^3 -- NOT measured in the bench
+# run (a run under ncu is never a bench value): per launch of the dominant stage, and summed over one evaluation
 NCU_TRAFFIC_256 = {'x-fwd * kernel-mix * x-inv (3 fields)': 1.0733e9, 'evaluation': 9.091e9}
+NCU_TRAFFIC_SOURCE = 'profiles/r01_ncu_full_wgc99_256_fused_final.md (ncu --set full of one evaluation; not measured in this run)'
+
+
+def workload_config():
+    """`config` of the JSON line: identical in the B200 arm and in the reference arm."""
+    return {'workload': f'Al 256-atom supercell, WangGovindCarter99 E+V, {GRID}^3 grid (BASELINE.json configs[1])',
+            'grid': [GRID] * 3, 'functional': 'WangGovindCarter99 (TF + vW + non-local, kernel cached)',
+            'density': f'synthetic smooth_supercell({GRID}, side={SIDE})'}
 
 
 def algorithmic_bytes(n):
@@ -139,7 +149,6 @@ def host_cores():
 
 
 def dist_env():
-    os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -149,43 +158,72 @@ def dist_env():
 # --------------------------------------------------------------------------------------------------
 #  CPU reference arm / cpu_baseline
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_grid=None, threads=None):
-    """Oracle port of WangGovindCarter99 E+V (the reference algorithm: torch CPU fp64, autograd potential, all host
-    threads) on the SAME 256^3 workload.  Bounded sample: at most 5 timed evaluations (about 1 s each on 16
-    threads) after one warm-up that also builds and caches the kernel (~10-20 s, not timed, as on the GPU)."""
+def reference_functional():
+    """(callable (box, den) -> (E, dE/dn), kind, label): the unmodified reference from oracle/_ref when it is there
+    (WangGovindCarter99.forward differentiated by torch.autograd, functional_tools.get_functional_derivative), else the
+    oracle port."""
+    import torch
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    if ref is not None:
+        wgc = ref.functionals.WangGovindCarter99()
+
+        def run(box, den):
+            d = den.clone().requires_grad_(True)
+            E = wgc.forward(box, d)
+            (g,) = torch.autograd.grad(E, d)
+            dV = torch.abs(torch.linalg.det(box)) / den.numel()
+            return E.detach().reshape(()), g / dV
+        return run, 'reference', 'unmodified reference (oracle/_ref: professad.functionals.WangGovindCarter99 + autograd)'
+    from oracle import ofdft_oracle as orc
+    wgc = orc.WangGovindCarter99()
+    return (lambda box, den: orc.energy_and_potential(box, den, wgc)), 'port', 'oracle port (oracle/ofdft_oracle.py)'
+
+
+def cpu_reference_run(steps, warmup, sample_grid=None, threads=None, max_timed=3, keep=False):
+    """The reference's own CPU implementation of the path (torch CPU fp64, all host threads) on the SAME workload.
+    Bounded sample: at most `max_timed` timed evaluations after one warm-up that also builds and caches the kernel
+    (not timed, as on the GPU).  Returns a dict; with keep=True it also holds the last E and dE/dn."""
     import torch
     from oracle import ofdft_oracle as orc
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can
     torch.set_num_threads(threads or host_cores())
     cores = torch.get_num_threads()
     n = sample_grid or GRID
-    n_timed = max(1, min(steps, 5))
+    n_timed = max(1, min(steps, max_timed))
     box, den = orc.synth_smooth(n, SIDE)
-    wgc = orc.WangGovindCarter99()
-    orc.energy_and_potential(box, den, wgc)
+    run, kind, label = reference_functional()
+    t0 = time.perf_counter()
+    run(box, den)
+    t_first = time.perf_counter() - t0
     t0 = time.perf_counter()
     for _ in range(n_timed):
-        orc.energy_and_potential(box, den, wgc)
+        E, V = run(box, den)
     dt = (time.perf_counter() - t0) / n_timed
     scale = (GRID ** 3 * math.log2(GRID ** 3)) / (n ** 3 * math.log2(n ** 3))
     sec_per_eval = dt * scale
-    sample = (f'{n_timed} evals (+1 warm-up, kernel cached) of the oracle port at {n}^3 on {cores} threads'
+    sample = (f'{n_timed} evals (+1 warm-up of {t_first:.1f} s that builds the kernel) of the {label} at {n}^3 on {cores} threads'
               + ('' if n == GRID else f', scaled x{scale:.2f} (N log N) to {GRID}^3'))
-    return 1.0 / sec_per_eval, sec_per_eval * 1e3, cores, sample
+    out = {'value': 1.0 / sec_per_eval, 'ms': sec_per_eval * 1e3, 'cores': cores, 'sample': sample, 'kind': kind,
+           'n_timed': n_timed}
+    if keep:
+        out['E'], out['V'] = float(E), V
+    return out
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    value, ms, cores, sample = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': r['n_timed'], 'warmup': 1, 'steps_requested': args.steps, 'warmup_requested': args.warmup,
+        'ms_per_step': r['ms'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'Al 256-atom supercell, WangGovindCarter99 E+V, {GRID}^3 grid (BASELINE.json configs[1])'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': workload_config(),
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
@@ -204,7 +242,10 @@ def run_gpu(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        # high-priority NCCL stream: in the slab block the exchange of one field runs while the FFT kernels of the next one
+        # fill the SMs; its CTAs must not queue behind them
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group('nccl', device_id=dev, pg_options=opts)
 
     import profess_ad_b200.functionals as F
     from profess_ad_b200.synthetic import smooth_supercell
@@ -296,7 +337,7 @@ def run_gpu(args):
     outs = [v_pins[i % 2] for i in range(n_e2e)]
     pipe.run(ins[:4], outs[:4], e_pin[:4])
     barrier()
-    # the host link is shared with whatever else runs on the box: three repetitions, the fastest one is reported
+    # the host link is shared with whatever else runs on the box: three repetitions, the MEDIAN is reported
     # (all three are kept in e2e.repeats)
     e2e_repeats = []
     for _ in range(3):
@@ -308,7 +349,7 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_repeats.append(world * n_e2e / (t.item() * 1e-3))
-    e2e_value = max(e2e_repeats)
+    e2e_value = sorted(e2e_repeats)[len(e2e_repeats) // 2]
     e_check = float(e_pin[-1])
 
     den_in = torch.empty_like(den)
@@ -337,6 +378,15 @@ def run_gpu(args):
     e2e_serial = world * 6 / (t.item() * 1e-3)
     dV = abs(torch.linalg.det(box_h).item()) / npts
 
+    slab = None
+    if world > 1 and not args.no_slab:
+        # free the per-GPU 256^3 working set first: the slab plans of a 512^3 / 1024^3 grid want the memory
+        del pipe, den_in
+        from profess_ad_b200 import _native as _nat
+        _nat.release_plans()
+        torch.cuda.empty_cache()
+        slab = slab_block(world, args.steps, args.warmup)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         balg = algorithmic_bytes(GRID)
@@ -345,10 +395,10 @@ def run_gpu(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'Al 256-atom supercell, WangGovindCarter99 E+V, {GRID}^3 grid (BASELINE.json configs[1])',
-                       'grid': [GRID] * 3, 'per_gpu': 'one independent system per GPU',
-                       'l2': 'working set per evaluation (>= 2 GB of fields) exceeds the 126 MB L2',
-                       'energy_Ha': e_check},
+            'config': workload_config(),
+            'config_detail': {'per_gpu': 'one independent system per GPU',
+                              'l2': 'working set per evaluation (>= 2 GB of fields) exceeds the 126 MB L2',
+                              'energy_Ha': e_check, 'pipelined_zy_kernels': bool(int(os.environ.get('PAD_PIPE', '1')))},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': npts * 8, 'd2h_bytes_per_step': npts * 8 + 8,
                     'how': 'profess_ad_b200.streaming.HostPipeline: H2D / evaluate / D2H of consecutive steps on 3 streams, 2 device buffers',
@@ -357,7 +407,7 @@ def run_gpu(args):
             'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': NCU_TRAFFIC_256['evaluation'] if GRID == 256 else None,
-                         'traffic_source': 'profiles/r01_ncu_full_wgc99_256_fused_final.md (ncu --set full, 11 kernels of one evaluation)',
+                         'traffic_source': NCU_TRAFFIC_SOURCE,
                          'peak_source': peak_src,
                          'kernel': 'whole WGC99 E+V evaluation (14 FFTs + fused elementwise passes)',
                          'algorithmic_bytes_per_eval': balg,
@@ -371,16 +421,30 @@ def run_gpu(args):
                 'traffic_per_launch': NCU_TRAFFIC_256.get(dom['stage']) if GRID == 256 else None,
                 'launches_per_eval': dom['launches_per_eval'],
                 'note': 'CUDA events on the launch stream around this stage, mean of 5 evaluations'}
+        if slab is not None:
+            line['slab'] = slab
         if world == 1:
             line['also'] = also_reported(dev, box, den)
         if world == 1 and not args.no_denopt:
-            line['density_optimization'] = density_optimization_leg(dev)
+            line['density_optimization'] = density_optimization_leg(dev, with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores, sample = cpu_reference_run(3, 1)
-            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+            r = cpu_reference_run(2, 1, max_timed=2, keep=True)
+            line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
+            # parity at the headline size: E and dE/dn of the CPU leg just timed against the GPU's (north_star tolerances:
+            # 1e-8 Ha/atom, 1e-9 relative max-abs)
+            try:
+                E_g, V_g = step_device()
+                V_g = (V_g / dV).cpu()
+                line['parity'] = {'against': r['kind'], 'grid': [GRID] * 3,
+                                  'dE_Ha_per_atom': abs(E_g.item() - r['E']) / (4 * SIDE ** 3),
+                                  'dV_rel': ((V_g - r['V']).abs().max() / r['V'].abs().max()).item(),
+                                  'E_gpu_Ha': E_g.item(), 'E_cpu_Ha': r['E'],
+                                  'tolerance': {'dE_Ha_per_atom': 1e-8, 'dV_rel': 1e-9}}
+            except Exception as e:      # noqa: BLE001
+                line['parity'] = {'error': repr(e)}
             try:        # also at one thread (bounded: 2 evaluations at 128^3, scaled N log N)
-                v1, _, _, sample1 = cpu_reference_run(2, 1, sample_grid=min(GRID, 128), threads=1)
-                line['cpu_baseline']['one_thread'] = {'value': v1, 'unit': UNIT, 'cores': 1, 'sample': sample1}
+                r1 = cpu_reference_run(2, 1, sample_grid=min(GRID, 128), threads=1, max_timed=2)
+                line['cpu_baseline']['one_thread'] = {'value': r1['value'], 'unit': UNIT, 'cores': 1, 'sample': r1['sample']}
             except Exception as e:      # noqa: BLE001
                 line['cpu_baseline']['one_thread'] = {'error': repr(e)}
         print(json.dumps(line), flush=True)
@@ -431,21 +495,51 @@ def also_reported(dev, box, den):
     return {'unit': UNIT, 'values': out}
 
 
-def density_optimization_leg(dev):
-    """BASELINE.json metric 2, "s per density optimisation": System.optimize_density(ntol=1e-7, LBFGS, from uniform)
-    for a 256-atom fcc Al supercell with [IonElectron, Hartree, WangGovindCarter99, PerdewZunger] and the
-    tests/potentials/al.gga.recpot local pseudopotential; wall clock around the public call, second of two runs."""
+def _denopt_workloads():
+    """(name, box_bohr, shape, frac, terms-as-names): BASELINE.json metric 2 workloads.  The first two are small enough for the
+    reference's CPU path to run next to the GPU in the default bench; the 256^3 one is GPU only."""
+    import torch
+    from profess_ad_b200.synthetic import fcc_supercell
+    a0 = 0.529177210903
+    box1 = (4 * 16.8) ** (1.0 / 3.0) / a0 * torch.eye(3, dtype=torch.double)          # crystal_tools.get_cell('fcc-c', 16.8 A^3/atom)
+    frac1 = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.5, 0.5], [0.5, 0.0, 0.5], [0.5, 0.5, 0.0]], dtype=torch.double)
+    box4, frac4 = fcc_supercell(4)
+    cfg1 = ['IonElectron', 'Hartree', 'ThomasFermi', 'Weizsaecker', 'PerdewZunger']
+    wgc = ['IonElectron', 'Hartree', 'WangGovindCarter99', 'PerdewZunger']
+    return [
+        ('BASELINE.json configs[0]: fcc Al 4-atom cell, ecut2shape(1600 eV), TF + vW + Hartree + PZ + IonElectron', box1, None, frac1, cfg1, True),
+        ('Al 256-atom fcc supercell, 64^3 grid, IonElectron + Hartree + WGC99 + PZ', box4, (64,) * 3, frac4, wgc, True),
+        ('Al 256-atom fcc supercell, 128^3 grid, IonElectron + Hartree + WGC99 + PZ', box4, (128,) * 3, frac4, wgc, False),
+        ('Al 256-atom fcc supercell, 256^3 grid, IonElectron + Hartree + WGC99 + PZ', box4, (256,) * 3, frac4, wgc, False),
+    ]
+
+
+def _terms(F, names):
+    return [F.WangGovindCarter99().forward if n == 'WangGovindCarter99' else getattr(F, n) for n in names]
+
+
+def density_optimization_leg(dev, with_cpu=True):
+    """BASELINE.json metric 2, "s per density optimisation": System.optimize_density(ntol=1e-7, LBFGS, from uniform) with the
+    tests/potentials/al.gga.recpot local pseudopotential; wall clock around the public call, second of two runs on the GPU.
+    For the two small workloads the UNMODIFIED reference's System (oracle/_ref) runs the same call on the host cores."""
     import torch
     import profess_ad_b200.functionals as F
-    from profess_ad_b200.synthetic import fcc_supercell
     from profess_ad_b200.system import System
     pot = os.path.join(ROOT, 'tests', 'potentials', 'al.gga.recpot')
-    out = []
-    for grid in (128, 256):
+    ref = None
+    if with_cpu:
         try:
-            box, frac = fcc_supercell(4)
-            terms = [F.IonElectron, F.Hartree, F.WangGovindCarter99().forward, F.PerdewZunger]
-            s = System(box, (grid,) * 3, [['Al', pot, frac]], terms, units='b', coord_type='fractional', device=dev)
+            from oracle import ref_loader
+            ref = ref_loader.load_reference()
+        except Exception:      # noqa: BLE001
+            ref = None
+    out = []
+    for name, box, shape, frac, term_names, cpu_ok in _denopt_workloads():
+        row = {'workload': name}
+        try:
+            shp = tuple(shape) if shape is not None else tuple(int(x) for x in System.ecut2shape(1600, box * 0.529177210903))
+            row['grid'] = list(shp)
+            s = System(box, shp, [['Al', pot, frac]], _terms(F, term_names), units='b', coord_type='fractional', device=dev)
             dt = None
             for _ in range(2):
                 torch.cuda.synchronize(dev)
@@ -454,13 +548,28 @@ def density_optimization_leg(dev):
                 torch.cuda.synchronize(dev)
                 dt = time.perf_counter() - t0
             info = s.last_optimization
-            out.append({'workload': f'Al 256-atom fcc supercell, {grid}^3 grid, IonElectron + Hartree + WGC99 + PZ',
-                        'seconds': dt, 'iterations': info.get('iterations'), 'closures': info.get('closures'),
-                        'converged': bool(info.get('converged')), 'energy_eV_per_atom': s.energy('eV') / 256,
+            n_at = frac.shape[0]
+            row.update({'seconds': dt, 'iterations': info.get('iterations'), 'closures': info.get('closures'),
+                        'converged': bool(info.get('converged')), 'energy_eV_per_atom': s.energy('eV') / n_at,
                         'optimizer': 'device-resident L-BFGS' if info.get('native') else 'host-driven L-BFGS'})
             del s
+            if cpu_ok and ref is not None:
+                torch.set_num_threads(host_cores())
+                RF = ref.functionals
+                rs = ref.system.System(box.clone(), shp, [['Al', pot, frac.clone()]], _terms(RF, term_names), units='b',
+                                       coord_type='fractional')
+                t0 = time.perf_counter()
+                rs.optimize_density(ntol=1e-7, n_method='LBFGS', from_uniform=True)
+                cpu_dt = time.perf_counter() - t0
+                e_ref = rs.energy('eV') / n_at
+                row['cpu_reference'] = {'seconds': cpu_dt, 'cores': torch.get_num_threads(), 'kind': 'reference',
+                                        'energy_eV_per_atom': e_ref, 'sample': 'one full System.optimize_density of the unmodified reference (oracle/_ref), all host threads'}
+                row['dE_eV_per_atom_vs_reference'] = abs(row['energy_eV_per_atom'] - e_ref)
+                row['speedup_vs_cpu_reference'] = cpu_dt / dt
+                del rs
         except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
-            out.append({'workload': f'{grid}^3', 'error': repr(e)})
+            row['error'] = repr(e)
+        out.append(row)
     return out
 
 
@@ -537,6 +646,97 @@ def slab_measure(n, functional, steps, warmup, overlap=None):
     }
 
 
+def slab_geometry_step(n, steps=2):
+    """BASELINE.json configs[4]: one geometry-optimisation step's worth of derivatives on ONE n^3 grid over the ranks for a bcc Li
+    supercell: PerdewBurkeErnzerhof E + dE/dn, its stress, the ion-electron forces of every atom and the ion-electron stress
+    (everything that scales with the grid; v_ext is built once per geometry and timed separately)."""
+    import torch
+    import torch.distributed as dist
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import parallel, ion_utils as IU
+    from profess_ad_b200.functional_tools import get_stress
+    from profess_ad_b200.synthetic import smooth_supercell
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    side = max(1, n // 64)
+    lo, hi = parallel.slab_bounds(n, rank, world)
+    box, den = smooth_supercell(n, side, device=dev, x_range=(lo, hi))           # smooth density on the same cubic cell
+    den = den * (2.0 / 12.0)                                                     # 2 atoms x 1 e- per cell instead of 4 x 3
+    r = torch.arange(side, dtype=torch.double)
+    cells = torch.stack(torch.meshgrid(r, r, r, indexing='ij'), dim=-1).reshape(-1, 1, 3)
+    basis = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]], dtype=torch.double)
+    frac = ((cells + basis[None]) / side).reshape(-1, 3).to(dev)
+    pot = os.path.join(ROOT, 'tests', 'potentials', 'li.gga.recpot')
+    species = [(pot, frac)]
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.double, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+    with parallel.slab((n, n, n)) as ctx:
+        def ev():
+            d = den.requires_grad_(True)
+            E = F.PerdewBurkeErnzerhof(box, d)
+            (g,) = torch.autograd.grad(E, d)
+            den.requires_grad_(False)
+            return E
+        ms_vext, _ = timed(lambda: IU.ionic_potential(box, ctx.local_shape, species), 1)
+        ms_ev, E = timed(ev, max(steps, 3))
+        ms_st, _ = timed(lambda: get_stress(box, den, F.PerdewBurkeErnzerhof), steps)
+        ms_f, _ = timed(lambda: IU.ion_electron_forces(box, den, species), 1)
+        ms_is, _ = timed(lambda: IU.ion_electron_stress(box, den, species), 1)
+        e_val = E.item()
+    npts = n ** 3
+    peak, _ = measured_peak()
+    balg = 16 * npts * 8 + 16 * npts
+    nk = n * n * (n // 2 + 1)
+    a2a = 8 * (world - 1) / world ** 2 * nk * 16
+    return {'workload': f'bcc Li {frac.shape[0]}-atom supercell, {n}^3 grid: PBE E+V, PBE stress, ion-electron forces + stress (BASELINE.json configs[4])',
+            'n_gpus': world, 'grid': [n] * 3, 'atoms': int(frac.shape[0]),
+            'ms': {'PBE E+V': ms_ev, 'PBE stress': ms_st, 'ion-electron forces': ms_f, 'ion-electron stress': ms_is,
+                   'v_ext build (once per geometry)': ms_vext},
+            'ms_per_step': ms_ev + ms_st + ms_f + ms_is, 'energy_Ha': e_val,
+            'PBE_E+V_hbm_frac_per_gpu': balg / (ms_ev * 1e-3) / 1e9 / world / peak,
+            'PBE_E+V_nvlink_GBps_each_way': a2a / (ms_ev * 1e-3) / 1e9}
+
+
+def slab_block(world, steps, warmup):
+    """`slab` entries of the N > 1 line: one grid over the N GPUs (strong scaling).  512^3 WangGovindCarter99 and
+    RevisedHuangCarter (BASELINE.json configs[2]) at every N; the 1024^3 PBE geometry step (configs[4]) where it fits."""
+    import torch
+    out = []
+    plan = [('wgc99', 512, min(steps, 10)), ('revhc', 512, min(steps, 5))]
+    for fun, n, k in plan:
+        try:
+            m = slab_measure(n, fun, max(2, k), min(warmup, 3))
+            out.append({'workload': m['config']['workload'], 'metric': m['metric'], 'n_gpus': world, 'grid': [n] * 3,
+                        'ms_per_eval': m['ms_per_step'], 'evals_per_s': m['value'], 'n_fft': m['config']['n_fft'],
+                        'energy_Ha': m['config']['energy_Ha'],
+                        'hbm_frac_per_gpu': m['roofline']['frac'], 'hbm_GBps_per_gpu': m['roofline']['achieved'],
+                        'nvlink_GBps_each_way': m['roofline']['nvlink_GBps_each_way'],
+                        'nvlink_frac_of_900': m['roofline']['nvlink_GBps_each_way'] / 900.0,
+                        'transforms': m['config']['transforms'], 'exchange_overlap': m['config']['exchange_overlap']})
+        except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
+            out.append({'workload': f'{fun} {n}^3', 'error': repr(e)})
+        torch.cuda.empty_cache()
+    if world >= 8:
+        try:
+            out.append(slab_geometry_step(1024))
+        except Exception as e:      # noqa: BLE001
+            out.append({'workload': 'PBE geometry step 1024^3', 'error': repr(e)})
+        torch.cuda.empty_cache()
+    return out
+
+
 def slab_init():
     import torch
     import torch.distributed as dist
@@ -593,6 +793,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-denopt', action='store_true', help='skip the density-optimisation timing leg')
+    ap.add_argument('--no-slab', action='store_true', help='N > 1: skip the one-grid-over-N-GPUs (slab) block')
     ap.add_argument('--slab-functional', default='wgc99', choices=['wgc99', 'hc', 'revhc', 'pbe'],
                     help='functional evaluated in --slab-grid mode')
     ap.add_argument('--slab-grid', type=int, default=0,

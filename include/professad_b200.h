@@ -60,7 +60,9 @@ unsigned long long pad_fft_exec_count(void);
  * 0: plain cuFFT 3-D transforms + separate elementwise kernels.  Returns the previous setting. */
 int pad_set_fast_fft(int on);
 /* tuning switches (process-wide): "fast_fft" (as above), "own_xy" (1: hand-written strided x/y passes with the
- * reciprocal-space multiply fused into the x pass; 0: batched 2-D cuFFT).  Returns the previous value, -1 on error. */
+ * reciprocal-space multiply fused into the x pass; 0: batched 2-D cuFFT), "pipe" (1: the z and y passes of an x-plane run
+ * as items of ONE persistent kernel and hand the plane over through the L2, csrc/zy_pipe.cuh; 0: one kernel per pass),
+ * "pipe_lpi" / "pipe_tpi" (lines per z item / tiles per y item, 0: default).  Returns the previous value, -1 on error. */
 int pad_set_option(const char* name, int value);
 /* Live per-stage device timing (CUDA events on the launch stream between the kernels of the fused WGC99
  * pipeline).  pad_profile_begin() switches it on and clears the sums; pad_profile_end() switches it off and
@@ -151,6 +153,11 @@ int pad_irfft3_fast(pad_plan* plan, double* in_cplx_padded /* destroyed */, doub
 /* one strided pass on its own: in-place complex FFT of a padded half-spectrum along axis 0 or 1 (length 64/128/256),
  * dir = -1 forward, +1 inverse, unnormalised (torch.fft.fft / ifft * n along that axis) */
 int pad_fft_axis_fast(pad_plan* plan, double* cplx_padded, int axis, int dir, void* stream);
+/* 1 if the software-pipelined (z, y) kernels serve this plan's shape (and the "pipe" option is on), else 0 */
+int pad_pipe_supported(const pad_plan* plan);
+/* synchronises `stream` and returns the watchdog word of the pipelined kernels' control block: 0 = every launch on this
+ * plan ran to completion, 1 = a CTA gave up waiting for work (the results are then invalid); -1: no pipelined launch yet */
+int pad_pipe_status(pad_plan* plan, void* stream);
 /* test hook: the table-driven pow / sqrt / reciprocal of csrc/fastmath.cuh next to the CUDA library results */
 int pad_dbg_fastmath(const double* x, size_t n, double e, double* out3n, double* ref3n, void* stream);
 

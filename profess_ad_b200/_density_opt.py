@@ -38,9 +38,10 @@ class PadDenoptResult(ctypes.Structure):
 _vp = ctypes.c_void_p
 
 
-def describe_terms(terms):
+def describe_terms(terms, device=None):
     """pad_terms for a list of native functionals (IonIon is skipped, as in the density optimisation),
-    or None if a term is not native or the combination is not representable."""
+    or None if a term is not native or the combination is not representable.  ``device``: the CUDA device the
+    described terms will be evaluated on (tables that travel as raw pointers are moved there); default: current."""
     T = PadTerms()
     for f in terms:
         name = getattr(f, '__qualname__', '') or getattr(f, '__name__', '')
@@ -50,7 +51,7 @@ def describe_terms(terms):
         owner = getattr(f, '__self__', None)
         if spec is None and owner is not None:
             maker = getattr(owner, '_pad_term_of', None)
-            spec = maker() if maker is not None else None
+            spec = maker(device) if maker is not None else None
         if spec is None:
             return None
         kind = spec[0]

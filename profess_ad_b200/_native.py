@@ -47,6 +47,8 @@ SIGNATURES = {
     'pad_profile_end': (_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     'pad_fft_axis_fast': (_int, [_vp, _vp, _int, _int, _vp]),
     'pad_fast_fft_supported': (_int, [_vp]),
+    'pad_pipe_supported': (_int, [_vp]),
+    'pad_pipe_status': (_int, [_vp, _vp]),
     'pad_rfft3_fast': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'pad_irfft3_fast': (_int, [_vp, _vp, _vp, _vp]),
     'pad_gradient': (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -88,7 +90,8 @@ def load_library():
             fn = getattr(lib, name)       # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy')):
+        for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy'), ('PAD_PIPE', b'pipe'),
+                         ('PAD_PIPE_LPI', b'pipe_lpi'), ('PAD_PIPE_TPI', b'pipe_tpi')):
             if os.environ.get(env, '').lstrip('-').isdigit():
                 lib.pad_set_option(opt, int(os.environ[env]))
         _lib = lib

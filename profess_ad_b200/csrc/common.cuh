@@ -217,6 +217,10 @@ struct pad_plan {
     cudaStream_t xy_stream;
     cufftDoubleComplex* zbuf[4];
     size_t bytes_allocated;
+    // software-pipelined (z, y) kernels (zy_pipe.cuh): control block, per-item partial sums
+    void* pipe_ctl;
+    double* pipe_part;
+    size_t pipe_part_n;
     // ionic potential / forces (ions.cu): per-ion 1-D phase tables + table slopes, force partial sums
     void* ion_scratch;
     size_t ion_scratch_bytes;
@@ -260,6 +264,9 @@ int pad_fft_inverse(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream
 int pad_fft_forward_many(pad_plan* p, const double* const* in, cufftDoubleComplex* const* out, int n, cudaStream_t s);
 int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* const* out, int n, cudaStream_t s);
 extern int g_pad_own_xy;
+extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
+extern int g_pad_pipe_lpi;         // lines per z item (0: default)
+extern int g_pad_pipe_tpi;         // tiles per y item (0: default)
 extern int g_pad_profile;          // 1: record CUDA events between pipeline stages (pad_profile_begin/end)
 void pad_stage_begin(cudaStream_t s);
 void pad_stage_mark(const char* name, cudaStream_t s);

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "fft_strided.cuh"
+#include "zy_pipe.cuh"
 #include "fastmath.cuh"
 
 namespace {
@@ -218,7 +219,8 @@ struct ZSpec {
 };
 
 //   Post::kDen / Post::kVin          the post-op reads the density / the previous potential at its points
-//   post.apply(g, n, vold, u0[NF], u1[NF], acc)    for the points g and g + 1 (n, vold: double2)
+//   post.apply(g, n, vold, u0[NF], u1[NF], acc, sta[NST], stb[NST])   for the points g and g + 1 (n, vold: double2);
+//   Post::NST staged values per point go on to a forward transform in the pipelined kernels (zinv_item), else unused
 template <int M, int TPL, int NF, int NRED, class Post>
 __global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, ZSpec in, const double* __restrict__ den,
                                                      const double* __restrict__ vin, int nlines, int nzp,
@@ -302,8 +304,9 @@ __global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, ZSpec in, const
                 double u0[NF], u1[NF];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) { u0[f] = res[f][r].x; u1[f] = res[f][r].y; }
+                double sta[Post::NST > 0 ? Post::NST : 1], stb[Post::NST > 0 ? Post::NST : 1];
                 post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), Post::kDen ? nn[r] : make_double2(0.0, 0.0),
-                           Post::kVin ? vv[r] : make_double2(0.0, 0.0), u0, u1, acc);
+                           Post::kVin ? vv[r] : make_double2(0.0, 0.0), u0, u1, acc, sta, stb);
             }
         }
     }
@@ -373,6 +376,398 @@ int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* 
     if (grid_out) *grid_out = grid;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  software-pipelined (z, y) kernels (zy_pipe.cuh): the z passes above as ITEMS over a group of lines of one
+//  x-plane, next to the y items of that plane
+// ------------------------------------------------------------------------------------------------
+// forward z item: lines [line_begin, line_end) (global line index = x n1 + y)
+template <int M, int TPL, int NF, class Gen>
+__device__ __forceinline__ void zfwd_item(const Gen& gen, const ZIn& in, const SPassFields& out, int line_begin, int line_end, int nzp,
+                                          unsigned char* zarea, const cd* tw1, const cd* tw2) {
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST, NIN = Gen::NIN;
+    constexpr int kLineBytes = L::fwd_line_bytes(NIN);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sub = lane / TPL, t = lane % TPL;
+    unsigned char* slot = zarea + (size_t)(warp * LPW + sub) * kLineBytes;
+    cd* S = reinterpret_cast<cd*>(slot);
+    double2* land = reinterpret_cast<double2*>(slot + (L::kScratch > M + 1 ? L::kScratch : M + 2) * 16);   // [NIN][M] pairs
+    const int stride = wpb * LPW;
+    auto issue = [&](int line) {
+        if (line < line_end) {
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) {
+                const double2* src = reinterpret_cast<const double2*>(in.f[q] + (size_t)line * (2 * M)) + t;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cp_async16(land + q * M + t + TPL * j, src + TPL * j);
+            }
+        }
+        cp_async_commit();
+    };
+    int line0 = line_begin + warp * LPW;
+    issue(line0 + sub);
+    for (; line0 < line_end; line0 += stride) {
+        const int line = line0 + sub;
+        const bool live = line < line_end;
+        cp_async_wait<0>();
+        double sa[NST][8], sb[NST][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double2 pin[NIN];
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) pin[q] = live ? land[q * M + t + TPL * j] : make_double2(1.0, 1.0);
+            double a[NST], b[NST];
+            gen.stage(pin, a, b);
+#pragma unroll
+            for (int s = 0; s < NST; ++s) { sa[s][j] = a[s]; sb[s][j] = b[s]; }
+        }
+        issue(line + stride);
+        const size_t orow = (size_t)(live ? line : line_begin) * nzp;
+        zfwd_field<M, TPL, 0>(gen, sa, sb, S, tw1, tw2, t, out.f[0] + orow, live);
+        if constexpr (NF > 1) zfwd_field<M, TPL, 1>(gen, sa, sb, S, tw1, tw2, t, out.f[1] + orow, live);
+        if constexpr (NF > 2) zfwd_field<M, TPL, 2>(gen, sa, sb, S, tw1, tw2, t, out.f[2] + orow, live);
+        if constexpr (NF > 3) zfwd_field<M, TPL, 3>(gen, sa, sb, S, tw1, tw2, t, out.f[3] + orow, live);
+    }
+    cp_async_wait<0>();
+}
+
+// inverse z item: NF half-spectrum lines -> NF real lines in registers -> post-op; if NFW > 0 the post-op hands
+// Post::NST staged values per point to GenF and NFW fields generated from them are transformed forward again and
+// written over the lines of spec.f[0..NFW-1] (the inputs of the line are in shared memory by then).
+//   post.apply(g, n, vold, u0[NF], u1[NF], acc, sta[NST], stb[NST])
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
+__device__ __forceinline__ void zinv_item(const Post& post, const GenF& genf, const SPassFields& spec, const double* __restrict__ den,
+                                          const double* __restrict__ vin, int line_begin, int line_end, int nzp, unsigned char* zarea,
+                                          const cd* tw1, const cd* tw2, double* acc) {
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp;
+    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
+    constexpr int G = NF + NREAL;
+    constexpr int kLineBytes = L::inv_line_bytes(NF, NREAL);
+    constexpr int NST = Post::NST > 0 ? Post::NST : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sub = lane / TPL, t = lane % TPL;
+    unsigned char* slot = zarea + (size_t)(warp * LPW + sub) * kLineBytes;
+    cd* S = reinterpret_cast<cd*>(slot);
+    cd* sp = S + L::kScratch;                                  // [NF][kSpecLine]
+    double2* rland = reinterpret_cast<double2*>(sp + NF * L::kSpecLine);   // [NREAL][M] pairs
+    const int stride = wpb * LPW;
+
+    auto issue_spec = [&](int f, int line) {
+        if (line < line_end) {
+            const cd* src = spec.f[f] + (size_t)line * nzp + t;
+            cd* dst = sp + f * L::kSpecLine + t;
+#pragma unroll
+            for (int i = 0; i < (M + TPL) / TPL; ++i)
+                if (t + TPL * i <= M) cp_async16(dst + TPL * i, src + TPL * i);
+        }
+        cp_async_commit();
+    };
+    auto issue_real = [&](int q, const double* base, int line) {
+        if (line < line_end) {
+            const double2* src = reinterpret_cast<const double2*>(base + (size_t)line * (2 * M)) + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async16(rland + q * M + t + TPL * j, src + TPL * j);
+        }
+        cp_async_commit();
+    };
+    int line0 = line_begin + warp * LPW;
+    {
+        const int line = line0 + sub;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) issue_spec(f, line);
+        if constexpr (Post::kDen) issue_real(0, den, line);
+        if constexpr (Post::kVin) issue_real(Post::kDen ? 1 : 0, vin, line);
+    }
+    for (; line0 < line_end; line0 += stride) {
+        const int line = line0 + sub;
+        const bool live = line < line_end;
+        const int next = line + stride;
+        const size_t base = (size_t)line * (2 * M);
+        cd res[NF][8];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            cp_async_wait<G - 1>();
+            __syncwarp();
+            zinv_field<M, TPL>(sp + f * L::kSpecLine, res[f], S, tw1, tw2, t);
+            issue_spec(f, next);
+        }
+        double2 nn[8], vv[8];
+        if constexpr (Post::kDen) {
+            cp_async_wait<G - 1>();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) nn[r] = rland[t + TPL * fft_nat<8>(r)];
+            issue_real(0, den, next);
+        }
+        if constexpr (Post::kVin) {
+            cp_async_wait<G - 1>();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) vv[r] = rland[(Post::kDen ? M : 0) + t + TPL * fft_nat<8>(r)];
+            issue_real(Post::kDen ? 1 : 0, vin, next);
+        }
+        double sa[NST][8], sb[NST][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double u0[NF], u1[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) { u0[f] = res[f][r].x; u1[f] = res[f][r].y; }
+            double a[NST], b[NST];
+#pragma unroll
+            for (int s = 0; s < NST; ++s) { a[s] = 1.0; b[s] = 1.0; }
+            if (live)
+                post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), Post::kDen ? nn[r] : make_double2(0.0, 0.0),
+                           Post::kVin ? vv[r] : make_double2(0.0, 0.0), u0, u1, acc, a, b);
+#pragma unroll
+            for (int s = 0; s < NST; ++s) { sa[s][fft_nat<8>(r)] = a[s]; sb[s][fft_nat<8>(r)] = b[s]; }
+        }
+        if constexpr (NFW > 0) {
+            __syncwarp();
+            const size_t orow = (size_t)(live ? line : line_begin) * nzp;
+            zfwd_field<M, TPL, 0>(genf, sa, sb, S, tw1, tw2, t, spec.f[0] + orow, live);
+            if constexpr (NFW > 1) zfwd_field<M, TPL, 1>(genf, sa, sb, S, tw1, tw2, t, spec.f[1] + orow, live);
+            if constexpr (NFW > 2) zfwd_field<M, TPL, 2>(genf, sa, sb, S, tw1, tw2, t, spec.f[2] + orow, live);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+struct GenNone {                       // placeholder GenF of inverse kernels without a forward part
+    static constexpr int NST = 1, NIN = 1;
+    __device__ void stage(const double2*, double*, double*) const {}
+    template <int F>
+    __device__ double field(const double* s) const { return s[0]; }
+};
+
+template <int M, int LY>
+__device__ __forceinline__ cd* pipe_tables(unsigned char* smem_raw, cd*& tw1, cd*& tw2, cd*& twy) {
+    tw1 = reinterpret_cast<cd*>(smem_raw);
+    tw2 = tw1 + M;
+    twy = tw2 + M;
+    load_twiddles<M>(tw1, tw2);
+    spass_load_twiddles<LY>(twy);
+    return twy + LY;
+}
+
+// forward: stage 0 = [gen + z r2c] of a line group, stage 1 = in-place y FFT of a group of tiles
+template <int M, int TPL, int NF, class Gen, int LY>
+__global__ void __launch_bounds__(128, 4) zy_fwd_kernel(Gen gen, ZIn in, SPassFields out, PipeCtl* ctl, PipeShape sh, ZYGeom g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sm_item[4];
+    cd *tw1, *tw2, *twy;
+    cd* work = pipe_tables<M, LY>(smem_raw, tw1, tw2, twy);
+    const int ntiles = NF * g.chunks + 1;
+    PipeSched ps;
+    pipe_begin<2>(ctl, ps);
+    for (;;) {
+        const PipeItem it = pipe_next<2>(ctl, sh, sm_item, ps);
+        if (it.stage < 0) break;
+        if (it.stage == 0) {
+            const int l0 = it.plane * g.n1 + it.sub * g.lpi;
+            zfwd_item<M, TPL, NF>(gen, in, out, l0, l0 + g.lpi, g.nzp, reinterpret_cast<unsigned char*>(work), tw1, tw2);
+        } else {
+            const int w0 = it.sub * g.tpi;
+            ytile_item_direct<LY, -1, true>(out, NF, g, it.plane, w0, min(w0 + g.tpi, ntiles), ntiles, work, twy);
+        }
+        pipe_done(ctl, sh, it);
+    }
+    pipe_exit(ctl, sh, sm_item);
+}
+
+// inverse: stage 0 = in-place inverse y FFT of a group of tiles (NF fields), stage 1 = [z c2r + post-op (+ gen + z r2c of
+// NFW fields)] of a line group, stage 2 (NFW > 0) = in-place forward y FFT of the NFW new fields.
+// part: per-item partial sums [NRED][nplanes * items[1]] (deterministic whatever CTA ran the item)
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF, int LY>
+__global__ void __launch_bounds__(128, 2) yz_inv_kernel(Post post, GenF genf, SPassFields spec, const double* __restrict__ den,
+                                                       const double* __restrict__ vin, PipeCtl* ctl, PipeShape sh, ZYGeom g,
+                                                       double* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sm_item[4];
+    __shared__ double red[NRED > 0 ? NRED : 1][4];
+    cd *tw1, *tw2, *twy;
+    cd* work = pipe_tables<M, LY>(smem_raw, tw1, tw2, twy);
+    const int nt_in = NF * g.chunks + 1, nt_out = NFW * g.chunks + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NSTAGE = NFW > 0 ? 3 : 2;
+    PipeSched ps;
+    pipe_begin<NSTAGE>(ctl, ps);
+    for (;;) {
+        const PipeItem it = pipe_next<NSTAGE>(ctl, sh, sm_item, ps);
+        if (it.stage < 0) break;
+        if (it.stage == 0) {
+            const int w0 = it.sub * g.tpi;
+            ytile_item_async<LY, +1, false>(spec, NF, g, it.plane, w0, min(w0 + g.tpi, nt_in), nt_in, work, twy);
+        } else if (it.stage == 1) {
+            double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+            for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
+            const int l0 = it.plane * g.n1 + it.sub * g.lpi;
+            zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, l0, l0 + g.lpi, g.nzp,
+                                                         reinterpret_cast<unsigned char*>(work), tw1, tw2, acc);
+            if constexpr (NRED > 0) {
+#pragma unroll
+                for (int r = 0; r < NRED; ++r) {
+                    const double w = warp_sum(acc[r]);
+                    if (lane == 0) red[r][warp] = w;
+                }
+                __syncthreads();
+                if (threadIdx.x < NRED) {
+                    const double s = (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]);
+                    part[(size_t)threadIdx.x * ((size_t)sh.nplanes * sh.items[1]) + (size_t)it.plane * sh.items[1] + it.sub] = s;
+                }
+            }
+        } else {
+            const int w0 = it.sub * g.tpi;
+            ytile_item_async<LY, -1, true>(spec, NFW, g, it.plane, w0, min(w0 + g.tpi, nt_out), nt_out, work, twy);
+        }
+        pipe_done(ctl, sh, it);
+    }
+    pipe_exit(ctl, sh, sm_item);
+}
+
+// sum of the per-item partials in a fixed order
+__global__ void __launch_bounds__(PAD_THREADS) pipe_finalize_kernel(const double* __restrict__ part, int nitems, FinalizeArgs a) {
+    __shared__ double sm[PAD_THREADS / 32];
+    __shared__ double total[PAD_MAX_RED];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = 0; t < a.nterms; ++t) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < nitems; b += PAD_THREADS) v += part[(size_t)t * nitems + b];
+        v = warp_sum(v);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double w = lane < PAD_THREADS / 32 ? sm[lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) total[t] = w;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int t = 0; t < a.nterms; ++t) {
+            if (a.sums_out) a.sums_out[t] = total[t];
+            e += a.coef[t] * total[t];
+        }
+        if (a.E_out) a.E_out[0] = (a.accumulate ? a.E_out[0] : 0.0) + e;
+    }
+}
+
+inline bool pipe_len_ok(int n) { return n == 128 || n == 256; }
+bool pipe_shape(const pad_plan* p) {
+    return g_pad_pipe && g_pad_own_xy && !p->dist && (p->n2 == 128 || p->n2 == 256) && pipe_len_ok(p->n1) &&
+           (p->n0 == 64 || p->n0 == 128 || p->n0 == 256) && p->n0 <= PIPE_MAX_PLANES;
+}
+
+int pipe_prepare(pad_plan* p, int lines_per_iter, ZYGeom* g) {
+    if (!p->pipe_ctl) {
+        PAD_CUDA(cudaMalloc(&p->pipe_ctl, sizeof(PipeCtl)));
+        PAD_CUDA(cudaMemset(p->pipe_ctl, 0, sizeof(PipeCtl)));
+        p->bytes_allocated += sizeof(PipeCtl);
+    }
+    g->n1 = p->n1; g->nzp = p->nzp; g->nzh = p->nzh; g->chunks = p->nzh / 8;
+    g->plane = (long long)p->n1 * p->nzp;
+    int lpi = g_pad_pipe_lpi > 0 ? g_pad_pipe_lpi : 2 * lines_per_iter;
+    lpi = (lpi / lines_per_iter) * lines_per_iter;
+    if (lpi < lines_per_iter) lpi = lines_per_iter;
+    while (lpi > lines_per_iter && p->n1 % lpi) lpi -= lines_per_iter;
+    if (p->n1 % lpi) { pad_set_error("pipelined (z, y) pass: n1 = %d is not a multiple of %d lines", p->n1, lpi); return PAD_ERR_ARG; }
+    g->lpi = lpi;
+    g->tpi = g_pad_pipe_tpi > 0 ? g_pad_pipe_tpi : 4;
+    return PAD_OK;
+}
+
+template <int M, int TPL, int NF, class Gen, int LY>
+int launch_zy_fwd_L(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* const* out) {
+    using L = ZLayout<M, TPL>;
+    using P = SPass<LY>;
+    constexpr int warps = 4;
+    constexpr int zbytes = warps * L::kLinesPerWarp * L::fwd_line_bytes(Gen::NIN);
+    constexpr int ybytes = P::TPC * P::TILE_CD * 16;
+    constexpr int smem = (2 * M + LY) * 16 + (zbytes > ybytes ? zbytes : ybytes);
+    auto kern = zy_fwd_kernel<M, TPL, NF, Gen, LY>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    ZYGeom g;
+    PAD_TRY(pipe_prepare(p, warps * L::kLinesPerWarp, &g));
+    PipeShape sh;
+    sh.nstage = 2; sh.nplanes = p->n0;
+    sh.items[0] = p->n1 / g.lpi;
+    sh.items[1] = (NF * g.chunks + 1 + g.tpi - 1) / g.tpi;
+    sh.items[2] = 0;
+    constexpr int by_smem = (227 * 1024) / (smem + 1024);
+    const int grid = 148 * (by_smem < 4 ? by_smem : 4);
+    ZIn in{{in0, in1}};
+    SPassFields o;
+    for (int i = 0; i < 4; ++i) o.f[i] = i < NF ? out[i] : nullptr;
+    kern<<<grid, warps * 32, smem, s>>>(gen, in, o, reinterpret_cast<PipeCtl*>(p->pipe_ctl), sh, g);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+template <int M, int TPL, int NF, class Gen>
+int launch_zy_fwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* const* out) {
+    if (p->n1 == 256) return launch_zy_fwd_L<M, TPL, NF, Gen, 256>(p, s, gen, in0, in1, out);
+    return launch_zy_fwd_L<M, TPL, NF, Gen, 128>(p, s, gen, in0, in1, out);
+}
+
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF, int LY>
+int launch_yz_inv_L(pad_plan* p, cudaStream_t s, Post post, GenF genf, cd* const* spec, const double* den, const double* vin,
+                    const FinalizeArgs* fin) {
+    using L = ZLayout<M, TPL>;
+    using P = SPass<LY>;
+    constexpr int warps = 4;
+    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
+    constexpr int zbytes = warps * L::kLinesPerWarp * L::inv_line_bytes(NF, NREAL);
+    constexpr int ybytes = 2 * P::TPC * P::TILE_CD * 16;
+    constexpr int smem = (2 * M + LY) * 16 + (zbytes > ybytes ? zbytes : ybytes);
+    auto kern = yz_inv_kernel<M, TPL, NF, NRED, Post, NFW, GenF, LY>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    ZYGeom g;
+    PAD_TRY(pipe_prepare(p, warps * L::kLinesPerWarp, &g));
+    PipeShape sh;
+    sh.nstage = NFW > 0 ? 3 : 2; sh.nplanes = p->n0;
+    sh.items[0] = (NF * g.chunks + 1 + g.tpi - 1) / g.tpi;
+    sh.items[1] = p->n1 / g.lpi;
+    sh.items[2] = NFW > 0 ? (NFW * g.chunks + 1 + g.tpi - 1) / g.tpi : 0;
+    const size_t nitems = (size_t)sh.nplanes * sh.items[1];
+    if (NRED > 0 && p->pipe_part_n < nitems * NRED) {
+        if (p->pipe_part) PAD_CUDA(cudaFree(p->pipe_part));
+        p->pipe_part = nullptr;
+        PAD_CUDA(cudaMalloc(&p->pipe_part, sizeof(double) * nitems * NRED));
+        p->pipe_part_n = nitems * NRED;
+        p->bytes_allocated += sizeof(double) * nitems * NRED;
+    }
+    constexpr int by_smem = (227 * 1024) / (smem + 1024);
+    static_assert(by_smem >= 1, "pipelined inverse pass: line slots do not fit in shared memory");
+    const int grid = 148 * (by_smem < 2 ? by_smem : 2);
+    SPassFields f;
+    for (int i = 0; i < 4; ++i) f.f[i] = i < NF ? spec[i] : nullptr;
+    kern<<<grid, warps * 32, smem, s>>>(post, genf, f, den, vin, reinterpret_cast<PipeCtl*>(p->pipe_ctl), sh, g, p->pipe_part);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    if (NRED > 0 && fin) {
+        pipe_finalize_kernel<<<1, PAD_THREADS, 0, s>>>(p->pipe_part, (int)nitems, *fin);
+        ++g_pad_launches;
+        PAD_CUDA(cudaGetLastError());
+    }
+    return PAD_OK;
+}
+
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
+int launch_yz_inv(pad_plan* p, cudaStream_t s, Post post, GenF genf, cd* const* spec, const double* den, const double* vin,
+                  const FinalizeArgs* fin) {
+    if (p->n1 == 256) return launch_yz_inv_L<M, TPL, NF, NRED, Post, NFW, GenF, 256>(p, s, post, genf, spec, den, vin, fin);
+    return launch_yz_inv_L<M, TPL, NF, NRED, Post, NFW, GenF, 128>(p, s, post, genf, spec, den, vin, fin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,8 +963,9 @@ struct GenCopy {                       // plain r2c of one real field
 
 struct PostStore {                     // plain c2r of one real field
     static constexpr bool kDen = false, kVin = false;
+    static constexpr int NST = 0;
     double* out;
-    __device__ void apply(size_t g, double2, double2, const double* u0, const double* u1, double*) const {
+    __device__ void apply(size_t g, double2, double2, const double* u0, const double* u1, double*, double*, double*) const {
         *reinterpret_cast<double2*>(out + g) = make_double2(u0[0], u1[0]);
     }
 };
@@ -657,12 +1053,13 @@ __device__ __noinline__ MidOut wgc_mid_point(double n, double n_ref, double alph
 
 struct PostWgcMid {
     static constexpr bool kDen = true, kVin = false;
+    static constexpr int NST = 2;              // staged for the second forward batch (GenWgcP): n, P = n^alpha
     const double* scal;
     double* v_out;
-    double* P_out;
+    double* P_out;                             // null: P stays on chip (pipelined kernel with the forward part fused)
     double alpha;
     int accumulate, want_v;
-    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc) const {
+    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc, double* sta, double* stb) const {
         double2 vo = make_double2(0.0, 0.0);
         if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
         const double n_ref = scal[S_NREF];
@@ -670,9 +1067,11 @@ struct PostWgcMid {
         const MidOut b = wgc_mid_point(n.y, n_ref, alpha, u1[0], u1[1], u1[2], u1[3]);
         acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
         acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
+        sta[0] = n.x; sta[1] = a.P;
+        stb[0] = n.y; stb[1] = b.P;
         if (want_v) {
             *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
-            *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
+            if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
         }
     }
 };
@@ -694,10 +1093,11 @@ __device__ __noinline__ double wgc_fin_point(double n, double n_ref, double beta
 
 struct PostWgcFin {
     static constexpr bool kDen = true, kVin = true;
+    static constexpr int NST = 0;
     const double* scal;
     double* v_out;
     double beta;
-    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double*) const {
+    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double*, double*, double*) const {
         const double n_ref = scal[S_NREF];
         v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]);
         v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]);
@@ -770,6 +1170,16 @@ int xy_convolve_own(pad_plan* p, cudaStream_t s, cd* const* B, cd* lap, Mix mix)
 //  public: custom 3-D r2c / c2r (used by tests and by pad_gradient-like helpers)
 // =================================================================================================
 extern "C" int pad_fast_fft_supported(const pad_plan* p) { return p && fast_shape(p) ? 1 : 0; }
+extern "C" int pad_pipe_supported(const pad_plan* p) { return p && fast_shape(p) && pipe_shape(p) ? 1 : 0; }
+extern "C" int pad_pipe_status(pad_plan* p, void* stream) {
+    if (!p) { pad_set_error("pad_pipe_status: null plan"); return PAD_ERR_ARG; }
+    if (!p->pipe_ctl) return -1;
+    PAD_CUDA(cudaSetDevice(p->device));
+    PAD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned err = 0;
+    PAD_CUDA(cudaMemcpy(&err, &reinterpret_cast<PipeCtl*>(p->pipe_ctl)->error, sizeof(err), cudaMemcpyDeviceToHost));
+    return err ? 1 : 0;
+}
 
 // out: padded half-spectrum (n0, n1, nzp) complex; returns nzp through *nzp_out
 extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_padded, int* nzp_out, void* stream) {
@@ -781,8 +1191,12 @@ extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_pa
     if (nzp_out) *nzp_out = p->nzp;
     cd* o = reinterpret_cast<cd*>(out_cplx_padded);
     GenCopy gen{};
-    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, gen, in, nullptr, o, nullptr, nullptr, nullptr))));
     cd* one[1] = {o};
+    if (pipe_shape(p)) {
+        ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, 1>(p, s, gen, in, nullptr, one))));
+        return launch_spass(p, s, 0, -1, one, 1);
+    }
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, gen, in, nullptr, o, nullptr, nullptr, nullptr))));
     PAD_TRY(xy_transform(p, s, one, 1, -1));
     return PAD_OK;
 }
@@ -796,8 +1210,13 @@ extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out,
     PAD_TRY(ensure_twiddles(p->device));
     cd* i = reinterpret_cast<cd*>(in_cplx_padded);
     cd* one[1] = {i};
-    PAD_TRY(xy_transform(p, s, one, 1, +1));
     PostStore post{out};
+    if (pipe_shape(p)) {
+        PAD_TRY(launch_spass(p, s, 0, +1, one, 1));
+        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 1, 0, PostStore, 0>(p, s, post, GenNone{}, one, nullptr, nullptr, nullptr))));
+        return PAD_OK;
+    }
+    PAD_TRY(xy_transform(p, s, one, 1, +1));
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, post, i, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))));
     return PAD_OK;
 }
@@ -821,10 +1240,38 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     const bool want_v = v_out != nullptr;
 
     GenWgcA genA{scal, beta};
-    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, den, nullptr, B[0], B[1], B[2], B[3]))));
-    pad_stage_mark("gen a,a.th,a.th2,chi + z-r2c (4 fields)", s);
     const bool own = g_pad_own_xy && own_xy_shape(p);
     const MixWgc mixw{reinterpret_cast<const double2*>(kern)};
+    if (pipe_shape(p) && want_v) {
+        // five launches: [gen + z + y] -> x.mix.x^-1 (+ the Laplacian field) -> [y^-1 + z^-1 + mid + gen + z + y] -> x.mix.x^-1 -> [y^-1 + z^-1 + fin]
+        ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, 4>(p, s, genA, den, nullptr, B))));
+        pad_stage_mark("[gen a,a.th,a.th2,chi + z-r2c + y-fwd] (4 fields)", s);
+        PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
+        pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
+        {
+            cd* one[1] = {B[3]};
+            PAD_TRY((launch_xmix<1>(p, s, one, MixLaplace{p->geom.inv_n})));
+            pad_stage_mark("x-fwd * (-k^2) * x-inv (1 field)", s);
+        }
+        FinalizeArgs a;
+        a.nblocks = 0; a.nterms = 3; a.accumulate = accumulate;
+        for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
+        a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
+        a.sums_out = nullptr;
+        a.E_out = E_out;
+        PostWgcMid mid{scal, v_out, nullptr, alpha, accumulate, 1};
+        GenWgcP genP{scal};
+        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 3, PostWgcMid, 3>(p, s, mid, genP, B, den, nullptr, E_out ? &a : nullptr))));
+        pad_stage_mark("[y-inv (4) + z-c2r + energy/v1 + gen P.. + z-r2c + y-fwd (3)]", s);
+        PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
+        pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
+        PostWgcFin fin{scal, v_out, beta};
+        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 3, 0, PostWgcFin, 0>(p, s, fin, GenNone{}, B, den, v_out, nullptr))));
+        pad_stage_mark("[y-inv (3) + z-c2r + v2]", s);
+        return PAD_OK;
+    }
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, den, nullptr, B[0], B[1], B[2], B[3]))));
+    pad_stage_mark("gen a,a.th,a.th2,chi + z-r2c (4 fields)", s);
     if (own) {
         PAD_TRY((xy_convolve_own<3>(p, s, B, B[3], mixw)));
     } else {
@@ -991,11 +1438,12 @@ __device__ __noinline__ WtOut wt_point(double n, double alpha, double beta, bool
 template <bool TWO>
 struct PostWt {
     static constexpr bool kDen = true, kVin = false;
+    static constexpr int NST = 0;
     const double* scal;
     double* v_out;
     double alpha, beta;
     int accumulate, want_v;
-    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc) const {
+    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc, double*, double*) const {
         constexpr int L = TWO ? 2 : 1;
         const double n0a = scal[S_TMP0 + 2];
         const WtOut a = wt_point(n.x, alpha, beta, TWO, n0a, u0[0], TWO ? u0[1] : u0[0], u0[L]);
@@ -1037,6 +1485,22 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     }
     pad_stage_mark("WT: Lindhard table check", s);
     GenWt<TWO> gen{scal, alpha, beta};
+    if (pipe_shape(p)) {
+        ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, NF>(p, s, gen, den, nullptr, B))));
+        pad_stage_mark("WT: [gen fields + z-r2c + y-fwd]", s);
+        PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n})));
+        pad_stage_mark("WT: x-fwd * (Lindhard | -k^2) * x-inv", s);
+        FinalizeArgs a;
+        a.nblocks = 0; a.nterms = 3; a.accumulate = accumulate;
+        for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
+        a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
+        a.sums_out = nullptr;
+        a.E_out = E_out;
+        PostWt<TWO> post{scal, v_out, alpha, beta, accumulate, v_out ? 1 : 0};
+        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, NF, 3, PostWt<TWO>, 0>(p, s, post, GenNone{}, B, den, nullptr, E_out ? &a : nullptr))));
+        pad_stage_mark("WT: [y-inv + z-c2r + energies + potential]", s);
+        return PAD_OK;
+    }
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, NF>(p, s, gen, den, nullptr, B[0], B[1], B[2], nullptr))));
     pad_stage_mark("WT: gen fields + z-r2c", s);
     PAD_TRY(launch_spass(p, s, 1, -1, B, NF));

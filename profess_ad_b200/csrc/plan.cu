@@ -14,11 +14,16 @@ extern "C" unsigned long long pad_fft_exec_count(void) { return g_pad_fft_execs;
 int g_pad_fast_fft = 1;      // hand-written fused FFT pipeline where the grid allows it (0: plain cuFFT 3-D + separate elementwise kernels)
 extern "C" int pad_set_fast_fft(int on) { const int old = g_pad_fast_fft; g_pad_fast_fft = on ? 1 : 0; return old; }
 int g_pad_own_xy = 1;        // hand-written strided (x, y) passes with the fused multiply (n0, n1 in 64/128/256)
+int g_pad_pipe = 1;          // (z, y) passes of a plane as items of one persistent kernel, handed over through the L2 (zy_pipe.cuh)
+int g_pad_pipe_lpi = 0, g_pad_pipe_tpi = 0;
 extern "C" int pad_set_option(const char* name, int value) {
     int* slot = nullptr;
     if (!name) { pad_set_error("pad_set_option: null name"); return -1; }
     if (!strcmp(name, "fast_fft")) slot = &g_pad_fast_fft;
     else if (!strcmp(name, "own_xy")) slot = &g_pad_own_xy;
+    else if (!strcmp(name, "pipe")) slot = &g_pad_pipe;
+    else if (!strcmp(name, "pipe_lpi")) slot = &g_pad_pipe_lpi;
+    else if (!strcmp(name, "pipe_tpi")) slot = &g_pad_pipe_tpi;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }
     const int old = *slot;
     *slot = value;
@@ -248,6 +253,8 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     if (p->xy_ready) cufftDestroy(p->xy);
     if (p->xy_work) cudaFree(p->xy_work);
     for (int i = 0; i < 4; ++i) if (p->zbuf[i]) cudaFree(p->zbuf[i]);
+    if (p->pipe_ctl) cudaFree(p->pipe_ctl);
+    if (p->pipe_part) cudaFree(p->pipe_part);
     cudaFree(p->partials);
     cudaFree(p->scal);
     delete p;

@@ -38,7 +38,7 @@ def get_stress(box_vecs, den, functional, requires_grad=False):
         raise NotImplementedError('second derivatives (requires_grad=True) are outside the B200 hot path')
     from . import _density_opt
     name = getattr(functional, '__qualname__', '') or getattr(functional, '__name__', '')
-    T = _density_opt.describe_terms([functional]) if name not in ('IonElectron', 'IonIon') else None
+    T = _density_opt.describe_terms([functional], den.device) if name not in ('IonElectron', 'IonIon') else None
     if T is None:
         raise NotImplementedError('get_stress: only native functionals of (box_vecs, den) have an analytic stress here')
     return _density_opt.stress_terms(box_vecs, den, T)
@@ -66,21 +66,57 @@ def wavevecs(box_vecs, shape):
     return kx, ky, kz, kx.pow(2) + ky.pow(2) + kz.pow(2)
 
 
+def hermitian_symmetrize(spec, shape):
+    """Hermitian part of a half spectrum on its two self-conjugate planes (j2 = 0, and j2 = n2/2 for even n2):
+    S(p) <- (S(p) + conj S(pbar)) / 2, pbar = (-j0, -j1, j2).
+
+    The multipliers of ``wavevecs`` (Nyquist index made positive on axes 0, 1) are not Hermitian on even grids, so
+    ``i k F`` and, on skewed cells, ``k^2 F`` are not the transform of a real field.  The reference's CPU ``irfftn``
+    (c2c over axes 0, 1, then c2r over axis 2) silently keeps exactly this Hermitian part; cuFFT's c2r is undefined
+    for such input.  Making it explicit gives the reference's numbers on any backend."""
+    n2 = int(shape[2])
+    planes = [0] + ([n2 // 2] if n2 % 2 == 0 and n2 > 1 else [])
+    out = spec.clone()
+    for j2 in planes:
+        P = spec[:, :, j2]
+        partner = torch.roll(torch.flip(P, (0, 1)), (1, 1), (0, 1)).conj()
+        out[:, :, j2] = 0.5 * (P + partner)
+    return out
+
+
+def _irfftn(spec, shape):
+    """irfftn with the reference's CPU semantics on every device (see hermitian_symmetrize)."""
+    return torch.fft.irfftn(hermitian_symmetrize(spec, shape), tuple(int(n) for n in shape))
+
+
+def hermitian_symmetrize_nodes(spec, shape):
+    """hermitian_symmetrize for a stack of half spectra (n0, n1, n2/2 + 1, n_nodes)"""
+    n2 = int(shape[2])
+    planes = [0] + ([n2 // 2] if n2 % 2 == 0 and n2 > 1 else [])
+    out = spec.clone()
+    for j2 in planes:
+        P = spec[:, :, j2]
+        partner = torch.roll(torch.flip(P, (0, 1)), (1, 1), (0, 1)).conj()
+        out[:, :, j2] = 0.5 * (P + partner)
+    return out
+
+
 def grad_i(ki, f):
-    """functional_tools.py:166-183 (explicit k_i tensor; library FFT -- compatibility helper)."""
-    return torch.fft.irfftn(1j * ki * torch.fft.rfftn(f), f.shape)
+    """functional_tools.py:166-183 (explicit k_i tensor, library FFT: compatibility helper for user functionals;
+    the native path is ``spectral_gradient`` / pad_gradient)."""
+    return _irfftn(1j * ki * torch.fft.rfftn(f), f.shape)
 
 
 def grad_dot_grad(kx, ky, kz, f):
     """functional_tools.py:186-206"""
     F = torch.fft.rfftn(f)
-    g = [torch.fft.irfftn(1j * k * F, f.shape) for k in (kx, ky, kz)]
+    g = [_irfftn(1j * k * F, f.shape) for k in (kx, ky, kz)]
     return g[0] * g[0] + g[1] * g[1] + g[2] * g[2]
 
 
 def laplacian(k2, f):
     """functional_tools.py:209-227"""
-    return torch.fft.irfftn(-k2 * torch.fft.rfftn(f), f.shape)
+    return _irfftn(-k2 * torch.fft.rfftn(f), f.shape)
 
 
 def reduced_gradient(kx, ky, kz, den):
@@ -173,5 +209,5 @@ def field_dependent_convolution(k, f_tilde, g, xis, kappa, mode='arithmetic'):
     native path instead."""
     nodes = xi_nodes(xis.min().item(), xis.max().item(), kappa, mode, device=xis.device)
     g_ft = torch.fft.rfftn(g).unsqueeze(3)
-    conv = torch.fft.irfftn(f_tilde(k, nodes) * g_ft, s=g.shape, dim=(0, 1, 2))
+    conv = torch.fft.irfftn(hermitian_symmetrize_nodes(f_tilde(k, nodes) * g_ft, g.shape), s=g.shape, dim=(0, 1, 2))
     return interpolate_kernel(nodes, conv, xis)

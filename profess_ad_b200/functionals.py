@@ -50,10 +50,9 @@ class _NativeEnergy(torch.autograd.Function):
         return E
 
     @staticmethod
-    def backward(ctx, grad_out):
+    @torch.autograd.function.once_differentiable      # the potential is a constant here: a second derivative must raise,
+    def backward(ctx, grad_out):                      # not silently drop the native terms (create_graph=True)
         (v,) = ctx.saved_tensors
-        if grad_out.requires_grad:
-            raise NotImplementedError('professad_b200: double backward through a native functional is not supported')
         return v * (grad_out * ctx.dV), None, None, None
 
 
@@ -259,7 +258,11 @@ class WangGovindCarter99(KineticFunctional):
         for name, val in (('alpha', alpha), ('beta', beta), ('gamma', gamma), ('kappa', kappa)):
             setattr(self, name, torch.nn.Parameter(torch.tensor([val], dtype=torch.double)))
         self.initialize()
-        self._args = tuple(float(x) for x in (alpha, beta, gamma, kappa))
+
+    @property
+    def _args(self):
+        """(alpha, beta, gamma, kappa) as they are NOW (load_state_dict / .data edits count, as in the reference)"""
+        return tuple(float(p.item()) for p in (self.alpha, self.beta, self.gamma, self.kappa))
 
     def forward(self, box_vecs, den):
         a, b, g, k = self._args
@@ -328,7 +331,7 @@ WangGovindCarter98._pad_term = ('wt', _A98, _B98, _native.PART_ALL)
 pbe_exchange._pad_term = ('pbe', 1)
 pbe_correlation._pad_term = ('pbe', 2)
 PerdewBurkeErnzerhof._pad_term = ('pbe', 3)
-WangGovindCarter99._pad_term_of = lambda self: ('wgc99',) + self._args
+WangGovindCarter99._pad_term_of = lambda self, device=None: ('wgc99',) + self._args
 
 
 # ----------------------------------------------------------------------------------------------
@@ -363,15 +366,23 @@ class _HuangCarterFamily(KineticFunctional):
     mode = 'geometric'
     _variant = 0
 
-    def _pad_term_of(self):
-        """Descriptor for the fused evaluator / device-resident optimiser (_density_opt.describe_terms)."""
+    def _pad_term_of(self, device=None):
+        """Descriptor for the fused evaluator / device-resident optimiser (_density_opt.describe_terms).  The table
+        travels as a raw device pointer: it must live on the device the terms are evaluated on."""
         if self.mode not in ('geometric', 'arithmetic'):
             return None
-        table = self.kernel
-        if table.device.type != 'cuda' or table.dtype != torch.double or not table.is_contiguous():
+        if device is None:
             if not torch.cuda.is_available():
                 return None
-            table = table.to(device=torch.device('cuda', torch.cuda.current_device()), dtype=torch.double).contiguous()
+            device = torch.device('cuda', torch.cuda.current_device())
+        device = torch.device(device)
+        if device.type != 'cuda':
+            return None
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        table = self.kernel
+        if table.device != device or table.dtype != torch.double or not table.is_contiguous():
+            table = table.to(device=device, dtype=torch.double).contiguous()
             self.kernel = table
         p0, p1 = self._params()
         return ('hc', self._variant, p0, p1, float(self.beta.item()), float(self.kappa),

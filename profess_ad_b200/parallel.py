@@ -274,7 +274,7 @@ def optimize_density(box_vecs, den_local, v_ext_local, terms, n_elec, ntol=1e-7,
     from . import _density_opt
     if current() is None:
         raise RuntimeError('parallel.optimize_density must be called inside a parallel.slab(...) context')
-    T = _density_opt.describe_terms(terms)
+    T = _density_opt.describe_terms(terms, den_local.device)
     if T is None:
         raise NotImplementedError('parallel.optimize_density needs every term to be a native functional')
     return _density_opt.run(box_vecs, den_local, v_ext_local, T, n_elec, ntol, n_conv_cond_count, n_method,

@@ -313,7 +313,9 @@ class System():
     def forces(self, units='Ha/b'):
         """F = -dE/dR at fixed density (system.py:623-643, 913-925): the IonElectron part is one native
         reciprocal-space reduction per ion (pad_ion_forces), the IonIon part autograd through the real-space pair
-        sum.  Like the reference, exact structure factors are differentiated even if v_ext came from PME."""
+        sum.  Deviation from the reference: when ``pme_order`` is set the reference differentiates the particle-mesh
+        structure factor (system.py:913-925 goes through __potential_from_ions with pme_order); here the forces are
+        always those of the EXACT structure factor, i.e. the PME interpolation error is not differentiated."""
         if units not in ('Ha/b', 'eV/a'):
             raise ValueError('Parameter \'units\' can only be \'Ha/b\' or \'eV/a\'')
         names = [_term_name(f) for f in self.__terms]
@@ -334,7 +336,7 @@ class System():
         names = [_term_name(f) for f in self.__terms]
         sig = torch.zeros((3, 3), dtype=torch.double, device=self.__device)
         if plain:
-            T = _density_opt.describe_terms(plain)
+            T = _density_opt.describe_terms(plain, self.__device)
             if T is None:
                 raise NotImplementedError('System.stress: analytic stresses exist for the native functionals only '
                                           '(user-defined Python terms need autograd through box_vecs)')
@@ -458,6 +460,7 @@ class System():
                 box, frac = parameterized_geometry(params.detach())
             self.__box_vecs = box.detach().to(self.__device).double().clone()
             self.__frac_ion_coords = frac.detach().to(self.__device).double().clone()
+            self.__Eion_cache = None        # the cached ion-ion energy belongs to the last closure's (line-search) geometry
             self.__update_ionic_potential()
             self.detach()
             self.optimize_density(**den_opt_inputs)
@@ -543,7 +546,8 @@ class System():
             if current_E < uniform_E:
                 self.set_density(current_den)
 
-        T = _density_opt.describe_terms(self.__terms) if (potentials is None and self.use_native_optimizer) else None
+        T = (_density_opt.describe_terms(self.__terms, self.__device)
+             if (potentials is None and self.use_native_optimizer) else None)
         if T is not None:
             self.__optimize_density_native(T, ntol, n_conv_cond_count, n_method, n_step_size, n_maxiter, conv_target,
                                            n_verbose)

@@ -210,3 +210,52 @@ def test_full_size_properties_256():
             lhs = (Ep - Em) / (2 * eps)
             rhs = (V2 * delta).sum().item() * dV
             assert abs(lhs - rhs) <= 1e-7 * abs(rhs) + 1e-12, (name, lhs, rhs)
+
+
+@pytest.mark.parametrize('shape,lpi,tpi', [((64, 128, 128), 0, 0), ((128, 256, 256), 0, 0), ((64, 256, 128), 16, 1),
+                                           ((64, 128, 256), 32, 7), ((256, 128, 128), 64, 3)])
+def test_pipelined_zy_kernels_match_per_pass_kernels(shape, lpi, tpi):
+    """Software-pipelined (z, y) kernels (csrc/zy_pipe.cuh: z items and y items of an x-plane in ONE persistent kernel,
+    plane handed over through the L2) against the one-kernel-per-pass path, for the plain transforms, WGC99 and the
+    Wang-Teter family, with several item sizes; the watchdog word of the control block must stay 0."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native as nat
+    lib = nat.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=sum(shape) + lpi, L=9.0)
+    b, d = box.to(dev), den.to(dev)
+    plan = nat.get_plan(b, d)
+    nzh, nzp = shape[2] // 2 + 1, shape[2] // 2 + 8
+    res = {}
+    for pipe in (1, 0):
+        olds = [lib.pad_set_option(b'pipe', pipe), lib.pad_set_option(b'pipe_lpi', lpi), lib.pad_set_option(b'pipe_tpi', tpi)]
+        try:
+            assert lib.pad_pipe_supported(plan.handle) == pipe
+            spec = torch.zeros(shape[0], shape[1], nzp, dtype=torch.complex128, device=dev)
+            nat.check(lib.pad_rfft3_fast(plan.handle, nat.ptr(d), nat.ptr(spec), None, nat.stream_ptr(dev)))
+            ref = torch.fft.rfftn(d)
+            assert ((spec[:, :, :nzh] - ref).abs().max() / ref.abs().max()).item() < 1e-14, pipe
+            assert spec[:, :, nzh:].abs().max().item() == 0.0
+            back = torch.empty_like(d)
+            nat.check(lib.pad_irfft3_fast(plan.handle, nat.ptr(spec.clone()), nat.ptr(back), nat.stream_ptr(dev)))
+            assert ((back / d.numel() - d).abs().max() / d.abs().max()).item() < 1e-14, pipe
+            out = {}
+            for name, f in (('WGC99', F.WangGovindCarter99().forward), ('WT', F.WangTeter), ('WGC98', F.WangGovindCarter98)):
+                for rep in range(3):        # the control block must come back clean launch after launch
+                    E, V = F.energy_and_potential(b, d, f)
+                out[name] = (E.item(), V.clone())
+            res[pipe] = out
+            if pipe:
+                assert lib.pad_pipe_status(plan.handle, nat.stream_ptr(dev)) == 0
+        finally:
+            for nm, o in zip((b'pipe', b'pipe_lpi', b'pipe_tpi'), olds):
+                lib.pad_set_option(nm, o)
+    for name in res[1]:
+        e1, v1 = res[1][name]
+        e0, v0 = res[0][name]
+        assert abs(e1 - e0) <= 2e-14 * abs(e0), (name, e1, e0)
+        assert ((v1 - v0).abs().max() / v0.abs().max()).item() < 1e-13, name
+    E_ref, V_ref = orc.energy_and_potential(box, den, orc.WangGovindCarter99())
+    assert abs(res[1]['WGC99'][0] - E_ref.item()) <= 1e-10 * abs(E_ref.item())
+    assert ((res[1]['WGC99'][1].cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9

@@ -287,3 +287,24 @@ def test_elastic_averages_and_crystal_constructors():
     assert frac.shape == (2, 3) and abs(torch.linalg.det(lat).abs().item() / 2 - 16.8) < 1e-10
     with pytest.raises(ValueError):
         X.face_centered_cubic(16.8, 'nope')
+
+
+def test_hermitian_symmetrize_is_the_cpu_irfftn_semantics():
+    """functional_tools.hermitian_symmetrize makes explicit what the reference's CPU irfftn does with the non-Hermitian
+    i*k*F on even grids: applied before a CPU irfftn it must change nothing, and the symmetrised half spectrum must be the
+    transform of a real field (rfftn(irfftn(S)) == S)."""
+    import torch
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functional_tools as T
+    for shape in [(8, 6, 10), (7, 9, 5), (6, 8, 7), (4, 4, 4)]:
+        box, den = orc.synth_rough(shape, seed=1)
+        g = orc.Grid(box, shape)
+        kx, ky, kz, k2 = T.wavevecs(box, shape)
+        for c, k in enumerate((kx, ky, kz)):
+            ref = g.grad(den)[c]
+            assert ((T.grad_i(k, den) - ref).abs().max() / ref.abs().max()).item() < 1e-14
+            S = T.hermitian_symmetrize(1j * k * torch.fft.rfftn(den), shape)
+            back = torch.fft.rfftn(torch.fft.irfftn(S, shape))
+            assert ((back - S).abs().max() / S.abs().max()).item() < 1e-13
+        ref = g.laplacian(den)
+        assert ((T.laplacian(k2, den) - ref).abs().max() / ref.abs().max()).item() < 1e-14
