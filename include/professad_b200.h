@@ -62,7 +62,9 @@ int pad_set_fast_fft(int on);
 /* tuning switches (process-wide): "fast_fft" (as above), "own_xy" (1: hand-written strided x/y passes with the
  * reciprocal-space multiply fused into the x pass; 0: batched 2-D cuFFT), "pipe" (1: the z and y passes of an x-plane run
  * as items of ONE persistent kernel and hand the plane over through the L2, csrc/zy_pipe.cuh; 0: one kernel per pass),
- * "pipe_lpi" / "pipe_tpi" (lines per z item / tiles per y item, 0: default).  Returns the previous value, -1 on error. */
+ * "pipe_lpi" / "pipe_tpi" (lines per z item / tiles per y item, 0: default), "fuse_terms" (1: pad_eval_total evaluates
+ * IonElectron / LDA exchange / PZ correlation inside the WGC99 mid pass and Hartree as a fourth field of its second
+ * transform batch; 0: one call per term).  Returns the previous value, -1 on error. */
 int pad_set_option(const char* name, int value);
 /* Live per-stage device timing (CUDA events on the launch stream between the kernels of the fused WGC99
  * pipeline).  pad_profile_begin() switches it on and clears the sums; pad_profile_end() switches it off and

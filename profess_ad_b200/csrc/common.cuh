@@ -265,6 +265,7 @@ int pad_fft_forward_many(pad_plan* p, const double* const* in, cufftDoubleComple
 int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* const* out, int n, cudaStream_t s);
 extern int g_pad_own_xy;
 extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
+extern int g_pad_fuse_terms;       // 1: pad_eval_total folds local terms + Hartree into the WGC99 pipeline where it can
 extern int g_pad_pipe_lpi;         // lines per z item (0: default)
 extern int g_pad_pipe_tpi;         // tiles per y item (0: default)
 extern int g_pad_profile;          // 1: record CUDA events between pipeline stages (pad_profile_begin/end)
@@ -275,8 +276,18 @@ int pad_wgc99_fast_supported(const pad_plan* p);
 int pad_wt_fast_supported(const pad_plan* p);
 int pad_wt_fast(pad_plan* p, const double* den, double alpha, double beta, double* E_out, double* v_out, int accumulate,
                 cudaStream_t s);
+// extra terms evaluated inside the WGC99 pipeline (fused term list): local terms in the mid pass, Hartree as a fourth
+// field of the second batch
+struct pad_wgc_extras {
+    int local_mask;            // PAD_LOCAL_LDAX | PAD_LOCAL_PZC | PAD_LOCAL_IONEL (not TF: WGC99 carries its own)
+    const double* v_ext;       // for PAD_LOCAL_IONEL
+    int hartree;
+};
+int pad_wgc99_total_supported(const pad_plan* p);
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,
-                   double* v_out, int accumulate, cudaStream_t s);
+                   double* v_out, int accumulate, cudaStream_t s, const pad_wgc_extras* ex);
+int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
+                      double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex);
 
 // finalize: E_out (+)= sum_t coef[t] * (sum over blocks of partials[t]); optionally store raw sums
 struct FinalizeArgs {

@@ -80,15 +80,28 @@ __device__ __forceinline__ cd w16(int m) {
     return cd{c, DIR < 0 ? -s : s};
 }
 
+// constant twiddles exp(DIR * 2 pi i m / 32), m < 16
+template <int DIR>
+__device__ __forceinline__ cd w32(int m) {
+    constexpr double c[9] = {1.0, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524, 0.70710678118654752,
+                             0.55557023301960218, 0.38268343236508977, 0.19509032201612825, 0.0};
+    const int q = m & 15;
+    const double co = q <= 8 ? c[q] : -c[16 - q];
+    const double si = q <= 8 ? c[8 - q] : c[q - 8];
+    return cd{co, DIR < 0 ? -si : si};
+}
+
 // register slot that holds natural output index k after fft_reg<R>
 template <int R>
 __device__ __forceinline__ constexpr int fft_slot(int k) {
-    return R == 16 ? (k >> 2) + 4 * (k & 3) : R == 8 ? (k >> 2) + 2 * (k & 3) : k;
+    return R == 32 ? (((k & 15) >> 2) + 4 * (k & 3)) + 16 * (k >> 4)
+         : R == 16 ? (k >> 2) + 4 * (k & 3) : R == 8 ? (k >> 2) + 2 * (k & 3) : k;
 }
 // natural output index held by register slot r (inverse of fft_slot)
 template <int R>
 __device__ __forceinline__ constexpr int fft_nat(int r) {
-    return R == 16 ? (r >> 2) + 4 * (r & 3) : R == 8 ? (r >> 1) + 4 * (r & 1) : r;
+    return R == 32 ? (((r & 15) >> 2) + 4 * (r & 3)) + 16 * (r >> 4)
+         : R == 16 ? (r >> 2) + 4 * (r & 3) : R == 8 ? (r >> 1) + 4 * (r & 1) : r;
 }
 
 template <int R, int DIR>
@@ -106,8 +119,23 @@ __device__ __forceinline__ void fft_reg(cd* v) {
         v[7] = cmul(v[7], w16<DIR>(6));      // W8^3
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) fft2<DIR>(v[2 * k2], v[2 * k2 + 1]);
+    } else if constexpr (R == 32) {
+        // n = n1 + 2 n2: two 16-point transforms (even, odd inputs), twiddle, radix-2; slot s holds A[nat16(s)],
+        // so X[nat16(s)] goes to slot s and X[nat16(s) + 16] to slot 16 + s
+        cd a[16], b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { a[j] = v[2 * j]; b[j] = v[2 * j + 1]; }
+        fft_reg<16, DIR>(a);
+        fft_reg<16, DIR>(b);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int k = fft_nat<16>(s);
+            const cd t = k == 0 ? b[s] : (k == 8 ? mul_i<DIR>(b[s]) : cmul(b[s], w32<DIR>(k)));
+            v[s] = a[s] + t;
+            v[16 + s] = a[s] - t;
+        }
     } else {
-        static_assert(R == 16, "fft_reg: R must be 2, 4, 8 or 16");
+        static_assert(R == 16, "fft_reg: R must be 2, 4, 8, 16 or 32");
         // n = n1 + 4 n2 ; k = k2 + 4 k1
 #pragma unroll
         for (int n1 = 0; n1 < 4; ++n1) fft4<DIR>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
@@ -177,7 +205,8 @@ __device__ __forceinline__ int line_fft_out_index(int t, int slot) {
 // ---------------------------------------------------------------------------------------------
 template <int M, int TPL, int DIR>
 __device__ __forceinline__ void line_fft8(cd* v, cd* S, int t, const cd* __restrict__ tw1) {
-    static_assert((M == 64 && TPL == 8) || (M == 128 && TPL == 16), "line_fft8: (M, TPL) must be (64, 8) or (128, 16)");
+    static_assert((M == 64 && TPL == 8) || (M == 128 && TPL == 16) || (M == 256 && TPL == 32),
+                  "line_fft8: (M, TPL) must be (64, 8), (128, 16) or (256, 32)");
     fft_reg<8, DIR>(v);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -190,6 +219,22 @@ __device__ __forceinline__ void line_fft8(cd* v, cd* S, int t, const cd* __restr
     if constexpr (TPL == 8) {
 #pragma unroll
         for (int t2 = 0; t2 < 8; ++t2) v[t2] = S[t * (TPL + 1) + t2];
+    } else if constexpr (TPL == 32) {
+        // 32-point FFT per k1 shared by the four lanes (k1, h): lane h computes the outputs k2 = 4 m + h as an 8-point
+        // FFT of u[t'] = (sum_q y[t' + 8 q] W4^{q h}) W32^{t' h}
+        const int k1 = t & 7, h = t >> 3;
+        const bool odd = h & 1, neg = h & 2;
+#pragma unroll
+        for (int t2 = 0; t2 < 8; ++t2) {
+            const cd y0 = S[k1 * (TPL + 1) + t2], y1 = S[k1 * (TPL + 1) + t2 + 8];
+            const cd y2 = S[k1 * (TPL + 1) + t2 + 16], y3 = S[k1 * (TPL + 1) + t2 + 24];
+            const cd A = odd ? y0 - y2 : y0 + y2;
+            const cd Bq = y1 - y3, Bs = y1 + y3;
+            const cd B = odd ? mul_i<DIR>(Bq) : Bs;
+            cd u = neg ? A - B : A + B;
+            if (t2 != 0) u = cmul(u, tw_dir<DIR>(tw1[(M / 32) * t2 * h]));      // W32^{t2 h}; h = 0: tw1[0] = 1
+            v[t2] = u;
+        }
     } else {
         const int k1 = t & 7, h = t >> 3;
 #pragma unroll

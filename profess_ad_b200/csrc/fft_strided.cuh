@@ -1,7 +1,7 @@
 // Strided-axis (x or y) complex FFT passes over the padded half-spectrum layout spec[x][y][nzp],
 // with the reciprocal-space multiply fused between the forward and the inverse x transform.
 //
-// Tile = L points along the transformed axis x 8 consecutive z columns (128-byte row segments).
+// Tile = L points along the transformed axis (L = 64 ... 512) x 8 consecutive z columns (128-byte row segments).
 // TPL threads share a line; thread (t, c) owns the points n = t + TPL j of column c, so one warp-wide
 // 16-byte load touches 4 rows x 128 contiguous bytes.  The L-point FFT is two register radix stages
 // (fft_reg) around one shared-memory exchange; the result comes out in natural order across
@@ -19,15 +19,16 @@
 
 template <int L>
 struct SPass {
-    static constexpr int TPL = (L == 256) ? 16 : 8;      // threads per line
-    static constexpr int EPT = L / TPL;                  // points per thread: 16 (L = 256, 128), 8 (L = 64)
-    static constexpr int G = EPT / TPL;                  // second-stage FFTs per thread: 1, 2, 1
+    static constexpr int TPL = (L >= 256) ? 16 : 8;      // threads per line
+    static constexpr int EPT = L / TPL;                  // points per thread: 32 (L = 512), 16 (L = 256, 128), 8 (L = 64)
+    static constexpr int G = EPT / TPL;                  // second-stage FFTs per thread: 2, 1, 2, 1
     static constexpr int ZC = 8;                         // z columns per tile
     static constexpr int TILE_THREADS = TPL * ZC;        // 128, 64, 64
     static constexpr int THREADS = 128;
     static constexpr int TPC = THREADS / TILE_THREADS;   // tiles per CTA
     static constexpr int TILE_CD = L * ZC;               // complex numbers per tile
-    static_assert(L == 256 || L == 128 || L == 64, "strided pass: L must be 64, 128 or 256");
+    static constexpr int CTAS_PER_SM = (L == 512) ? 2 : 4;   // plain pass: 32 complex points per thread need > 128 registers
+    static_assert(L == 512 || L == 256 || L == 128 || L == 64, "strided pass: L must be 64, 128, 256 or 512");
 };
 
 // natural index along the line held by register slot s after tile_fft
@@ -130,7 +131,7 @@ struct SPassFields {
 //  plain pass: in-place FFT along the strided axis for nf fields
 // ------------------------------------------------------------------------------------------------
 template <int L, int DIR>
-__global__ void __launch_bounds__(128, 4) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
+__global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -187,7 +188,7 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 //  the remaining inverse transforms, the stores and the next tile's first forward transforms.
 // ------------------------------------------------------------------------------------------------
 template <int L, int NF, class Mix>
-__global__ void __launch_bounds__(128, (L >= 128) ? 2 : 3) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
+__global__ void __launch_bounds__(128, (L >= 512) ? 1 : (L >= 128) ? 2 : 3) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);

@@ -17,6 +17,7 @@
 #include "fft_strided.cuh"
 #include "zy_pipe.cuh"
 #include "fastmath.cuh"
+#include "xc.cuh"
 
 namespace {
 
@@ -654,10 +655,11 @@ __global__ void __launch_bounds__(PAD_THREADS) pipe_finalize_kernel(const double
     }
 }
 
+inline bool spass_len_ok(int n) { return n == 64 || n == 128 || n == 256 || n == 512; }
 inline bool pipe_len_ok(int n) { return n == 128 || n == 256; }
 bool pipe_shape(const pad_plan* p) {
-    return g_pad_pipe && g_pad_own_xy && !p->dist && (p->n2 == 128 || p->n2 == 256) && pipe_len_ok(p->n1) &&
-           (p->n0 == 64 || p->n0 == 128 || p->n0 == 256) && p->n0 <= PIPE_MAX_PLANES;
+    return g_pad_pipe && g_pad_own_xy && !p->dist && (p->n2 == 128 || p->n2 == 256 || p->n2 == 512) && pipe_len_ok(p->n1) &&
+           spass_len_ok(p->n0) && p->n0 <= PIPE_MAX_PLANES;
 }
 
 int pipe_prepare(pad_plan* p, int lines_per_iter, ZYGeom* g) {
@@ -820,7 +822,6 @@ int get_zbuf(pad_plan* p, int i, cd** out) {
 // ------------------------------------------------------------------------------------------------
 //  own strided passes (fft_strided.cuh): launchers
 // ------------------------------------------------------------------------------------------------
-inline bool spass_len_ok(int n) { return n == 64 || n == 128 || n == 256; }
 bool own_xy_shape(const pad_plan* p) { return spass_len_ok(p->n0) && spass_len_ok(p->n1); }
 
 SPassGeom spass_geom(const pad_plan* p, int axis) {
@@ -864,6 +865,7 @@ int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fiel
         SPASS_CASE(64)
         SPASS_CASE(128)
         SPASS_CASE(256)
+        SPASS_CASE(512)
     }
 #undef SPASS_CASE
     pad_set_error("strided FFT pass: length %d not supported", L);
@@ -902,6 +904,7 @@ int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
         case 64: return launch_xmix_L<64, NF>(p, s, f, g, mix);
         case 128: return launch_xmix_L<128, NF>(p, s, f, g, mix);
         case 256: return launch_xmix_L<256, NF>(p, s, f, g, mix);
+        case 512: return launch_xmix_L<512, NF>(p, s, f, g, mix);
     }
     pad_set_error("fused x pass: length %d not supported", p->n0);
     return PAD_ERR_ARG;
@@ -935,6 +938,19 @@ struct MixLaplace {                    // -k^2 / N   (functional_tools.py:209-22
     }
     __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
 };
+struct MixCoulomb {                    // 4 pi / (k^2 N), 0 at k = 0   (functionals.py:49-72)
+    double inv_n;
+    typedef double Coef;
+    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+        if (!live) return 0.0;
+        const KPoint k = make_kpoint_at(g, kx, ky, z);
+        return inv_n * sym_even(k, [](double x, double y, double w) {
+                   const double k2 = x * x + y * y + w * w;
+                   return k2 != 0.0 ? 4.0 * kPi / k2 : 0.0;
+               });
+    }
+    __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
+};
 struct MixScale {                      // plain 1/N (round-trip tests)
     double m;
     typedef double Coef;
@@ -942,13 +958,14 @@ struct MixScale {                      // plain 1/N (round-trip tests)
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 
-bool fast_shape(const pad_plan* p) { return !p->dist && (p->n2 == 128 || p->n2 == 256); }
+bool fast_shape(const pad_plan* p) { return !p->dist && (p->n2 == 128 || p->n2 == 256 || p->n2 == 512); }
 
-// dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16)}
-#define ZDISPATCH(p, CALL)                                             \
-    do {                                                               \
-        if ((p)->n2 == 256) { constexpr int M = 128, TPL = 16; CALL; } \
-        else { constexpr int M = 64, TPL = 8; CALL; }                  \
+// dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16), (256, 32)}
+#define ZDISPATCH(p, CALL)                                                  \
+    do {                                                                    \
+        if ((p)->n2 == 512) { constexpr int M = 256, TPL = 32; CALL; }      \
+        else if ((p)->n2 == 256) { constexpr int M = 128, TPL = 16; CALL; } \
+        else { constexpr int M = 64, TPL = 8; CALL; }                       \
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -1016,6 +1033,25 @@ struct GenWgcP {
     }
 };
 
+// second forward batch of the fused term list: P, P theta, P theta^2 / 2 and the density itself (for the Hartree term)
+struct GenWgcP4 {
+    static constexpr int NST = 2, NIN = 2;
+    const double* scal;
+    __device__ void stage(const double2* in, double* a, double* b) const {
+        a[0] = in[0].x; a[1] = in[1].x;
+        b[0] = in[0].y; b[1] = in[1].y;
+    }
+    template <int F>
+    __device__ double field(const double* s) const {
+        if constexpr (F == 0) return s[1];
+        else if constexpr (F == 3) return s[0];
+        else {
+            const double th = s[0] - scal[S_NREF];
+            return F == 1 ? s[1] * th : 0.5 * s[1] * th * th;
+        }
+    }
+};
+
 // WGC99 mid pass: u1, u2, u3, lap(chi) -> energy densities, first half of the potential, P
 struct MidOut {
     double v, P, e_tf, e_vw, e_nl;
@@ -1076,6 +1112,93 @@ struct PostWgcMid {
     }
 };
 
+// ---- fused term list (system.py:759-772 with WGC99 as the kinetic term): the local terms LDA exchange, Perdew-Zunger
+//      correlation and IonElectron ride on the mid pass (they need n, n^(1/3), log n: all there), the Hartree term
+//      is a fourth field of the second batch (n -> 4 pi / k^2 -> v_H, E_H = 1/2 sum n v_H) -----------------------------
+struct MidOutT {
+    double v, P, e_tf, e_vw, e_nl, e_loc;
+};
+__device__ __noinline__ MidOutT wgc_mid_point_total(double n, double n_ref, double alpha, double u1, double u2, double u3,
+                                                   double lap, int mask, double vext) {
+    MidOutT o;
+    const double th = n - n_ref;
+    const double conv = u1 + th * (u2 + 0.5 * th * u3);
+    double e_loc = 0.0, v_loc = 0.0;
+    if (fm_ok(n)) {
+        const double l = fm_log(n);
+        o.P = fm_exp(alpha * l);
+        const double c2 = fm_exp((2.0 / 3.0) * l);
+        const double y = fm_rsqrt(n);
+        const double chi = fm_sqrt_from_rsqrt(n, y);
+        const double inv_n = y * y;
+        o.e_tf = kCTF * n * c2;
+        o.e_vw = chi * lap;
+        o.e_nl = o.P * conv;
+        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * o.P * inv_n * conv + o.P * (u2 + th * u3));
+        if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
+            const double c13 = c2 * c2 * inv_n;                       // n^(1/3)
+            if (mask & PAD_LOCAL_LDAX) { e_loc += kCX * n * c13; v_loc += (4.0 / 3.0) * kCX * c13; }
+            if (mask & PAD_LOCAL_PZC) {
+                // pz_correlation (xc.cuh, functionals.py:1515-1521) with rs = kRS13 n^(-1/3) and log rs from the log above
+                const double A = 0.0311, B = -0.048, C = 0.002, D = -0.0116;
+                const double ga = -0.1423, b1 = 1.0529, b2 = 0.3334;
+                const double rs = kRS13 * c2 * inv_n;
+                if (rs < 1.0) {
+                    const double lr = -0.47747065276706023 - (1.0 / 3.0) * l;
+                    e_loc += n * (A * lr + B + C * rs * lr + D * rs);
+                    v_loc += lr * (A + (2.0 / 3.0) * C * rs) + (B - A / 3.0) + rs / 3.0 * (2.0 * D - C);
+                } else {
+                    const double sr = sqrt(rs);
+                    const double dn = 1.0 + b1 * sr + b2 * rs;
+                    const double idn = 1.0 / dn;
+                    e_loc += n * ga * idn;
+                    v_loc += ga * (1.0 + (7.0 / 6.0) * b1 * sr + (4.0 / 3.0) * b2 * rs) * (idn * idn);
+                }
+            }
+        }
+    } else {
+        o.P = exp(alpha * log(n));
+        const double c = cbrt(n);
+        const double chi = n != 0.0 ? sqrt(n) : 0.0;
+        o.e_tf = kCTF * n * c * c;
+        o.e_vw = chi * lap;
+        o.e_nl = o.P * conv;
+        double v = (5.0 / 3.0) * kCTF * c * c;
+        if (n != 0.0) v += -0.5 * lap / chi;
+        v += kCTF * (alpha * o.P / n * conv + o.P * (u2 + th * u3));
+        o.v = v;
+        if (mask & PAD_LOCAL_LDAX) { e_loc += kCX * n * c; v_loc += (4.0 / 3.0) * kCX * c; }
+        if (mask & PAD_LOCAL_PZC) { const PZ r = pz_correlation(n, c); e_loc += r.e; v_loc += r.v; }
+    }
+    if (mask & PAD_LOCAL_IONEL) { e_loc += n * vext; v_loc += vext; }
+    o.e_loc = e_loc;
+    o.v += v_loc;
+    return o;
+}
+
+struct PostWgcMidT {                           // NRED = 4: TF, vW, non-local, local terms
+    static constexpr bool kDen = true, kVin = false;
+    static constexpr int NST = 2;
+    const double* scal;
+    double* v_out;
+    const double* v_ext;                       // IonElectron (may be null when the bit is not set)
+    double alpha;
+    int accumulate, mask;
+    __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc, double* sta, double* stb) const {
+        double2 vo = make_double2(0.0, 0.0), ve = make_double2(0.0, 0.0);
+        if (accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+        if (mask & PAD_LOCAL_IONEL) ve = *reinterpret_cast<const double2*>(v_ext + g);
+        const double n_ref = scal[S_NREF];
+        const MidOutT a = wgc_mid_point_total(n.x, n_ref, alpha, u0[0], u0[1], u0[2], u0[3], mask, ve.x);
+        const MidOutT b = wgc_mid_point_total(n.y, n_ref, alpha, u1[0], u1[1], u1[2], u1[3], mask, ve.y);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl; acc[3] += a.e_loc;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl; acc[3] += b.e_loc;
+        sta[0] = n.x; sta[1] = a.P;
+        stb[0] = n.y; stb[1] = b.P;
+        *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+    }
+};
+
 // WGC99 final pass: g1, g2, g3 -> second half of the potential
 __device__ __noinline__ double wgc_fin_point(double n, double n_ref, double beta, double g1, double g2, double g3) {
     const double th = n - n_ref;
@@ -1101,6 +1224,21 @@ struct PostWgcFin {
         const double n_ref = scal[S_NREF];
         v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]);
         v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]);
+        *reinterpret_cast<double2*>(v_out + g) = v;
+    }
+};
+
+struct PostWgcFinH {                           // final pass of the fused term list: + Hartree potential, NRED = 1: sum n v_H
+    static constexpr bool kDen = true, kVin = true;
+    static constexpr int NST = 0;
+    const double* scal;
+    double* v_out;
+    double beta;
+    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double* acc, double*, double*) const {
+        const double n_ref = scal[S_NREF];
+        v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]) + u0[3];
+        v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]) + u1[3];
+        acc[0] += n.x * u0[3] + n.y * u1[3];
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
 };
@@ -1184,7 +1322,7 @@ extern "C" int pad_pipe_status(pad_plan* p, void* stream) {
 // out: padded half-spectrum (n0, n1, nzp) complex; returns nzp through *nzp_out
 extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_padded, int* nzp_out, void* stream) {
     if (!p || !in || !out_cplx_padded) { pad_set_error("pad_rfft3_fast: null argument"); return PAD_ERR_ARG; }
-    if (!fast_shape(p)) { pad_set_error("pad_rfft3_fast: n2 = %d not supported (128, 256)", p->n2); return PAD_ERR_ARG; }
+    if (!fast_shape(p)) { pad_set_error("pad_rfft3_fast: n2 = %d not supported (128, 256, 512)", p->n2); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
@@ -1204,7 +1342,7 @@ extern "C" int pad_rfft3_fast(pad_plan* p, const double* in, double* out_cplx_pa
 // in: padded half-spectrum (destroyed); out: real field, unnormalised (N x the inverse)
 extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out, void* stream) {
     if (!p || !in_cplx_padded || !out) { pad_set_error("pad_irfft3_fast: null argument"); return PAD_ERR_ARG; }
-    if (!fast_shape(p)) { pad_set_error("pad_irfft3_fast: n2 = %d not supported (128, 256)", p->n2); return PAD_ERR_ARG; }
+    if (!fast_shape(p)) { pad_set_error("pad_irfft3_fast: n2 = %d not supported (128, 256, 512)", p->n2); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     PAD_TRY(ensure_twiddles(p->device));
@@ -1226,8 +1364,11 @@ extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out,
 // =================================================================================================
 int pad_wgc99_fast_supported(const pad_plan* p) { return fast_shape(p) ? 1 : 0; }
 
+int pad_wgc99_total_supported(const pad_plan* p) { return fast_shape(p) && pipe_shape(p) ? 1 : 0; }
+
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,
-                   double* v_out, int accumulate, cudaStream_t s) {
+                   double* v_out, int accumulate, cudaStream_t s, const pad_wgc_extras* ex) {
+    if (ex && !(pipe_shape(p) && v_out)) { pad_set_error("pad_wgc99_fast: fused term list needs the pipelined kernels and a potential"); return PAD_ERR_ARG; }
     PAD_TRY(ensure_twiddles(p->device));
     if (!(g_pad_own_xy && own_xy_shape(p))) PAD_TRY(ensure_xy(p, s));
     cd* B[4];
@@ -1259,10 +1400,37 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
         a.sums_out = nullptr;
         a.E_out = E_out;
-        PostWgcMid mid{scal, v_out, nullptr, alpha, accumulate, 1};
-        GenWgcP genP{scal};
-        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 3, PostWgcMid, 3>(p, s, mid, genP, B, den, nullptr, E_out ? &a : nullptr))));
-        pad_stage_mark("[y-inv (4) + z-c2r + energy/v1 + gen P.. + z-r2c + y-fwd (3)]", s);
+        if (ex) {
+            // fused term list: local terms in the mid pass, Hartree as the fourth field of the second batch
+            a.nterms = 4; a.coef[3] = p->dV;
+            PostWgcMidT mid{scal, v_out, ex->v_ext, alpha, accumulate, ex->local_mask};
+            if (ex->hartree) {
+                ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 4, PostWgcMidT, 4>(p, s, mid, GenWgcP4{scal}, B, den, nullptr, E_out ? &a : nullptr))));
+                pad_stage_mark("[y-inv (4) + z-c2r + energy/v1/local + gen P..,n + z-r2c + y-fwd (4)]", s);
+                PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
+                pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
+                cd* one[1] = {B[3]};
+                PAD_TRY((launch_xmix<1>(p, s, one, MixCoulomb{p->geom.inv_n})));
+                pad_stage_mark("x-fwd * (4 pi / k^2) * x-inv (1 field)", s);
+                FinalizeArgs h;
+                h.nblocks = 0; h.nterms = 1; h.accumulate = 1;
+                for (int t = 0; t < PAD_MAX_RED; ++t) h.coef[t] = 0.0;
+                h.coef[0] = 0.5 * p->dV;
+                h.sums_out = nullptr;
+                h.E_out = E_out;
+                PostWgcFinH fin{scal, v_out, beta};
+                ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 1, PostWgcFinH, 0>(p, s, fin, GenNone{}, B, den, v_out, E_out ? &h : nullptr))));
+                pad_stage_mark("[y-inv (4) + z-c2r + v2 + Hartree]", s);
+                return PAD_OK;
+            }
+            ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 4, PostWgcMidT, 3>(p, s, mid, GenWgcP{scal}, B, den, nullptr, E_out ? &a : nullptr))));
+            pad_stage_mark("[y-inv (4) + z-c2r + energy/v1/local + gen P.. + z-r2c + y-fwd (3)]", s);
+        } else {
+            PostWgcMid mid{scal, v_out, nullptr, alpha, accumulate, 1};
+            GenWgcP genP{scal};
+            ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 3, PostWgcMid, 3>(p, s, mid, genP, B, den, nullptr, E_out ? &a : nullptr))));
+            pad_stage_mark("[y-inv (4) + z-c2r + energy/v1 + gen P.. + z-r2c + y-fwd (3)]", s);
+        }
         PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
         pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
         PostWgcFin fin{scal, v_out, beta};
@@ -1560,7 +1728,7 @@ extern "C" int pad_dbg_fastmath(const double* x, size_t n, double e, double* out
 extern "C" int pad_fft_axis_fast(pad_plan* p, double* cplx_padded, int axis, int dir, void* stream) {
     if (!p || !cplx_padded || (axis != 0 && axis != 1)) { pad_set_error("pad_fft_axis_fast: bad argument"); return PAD_ERR_ARG; }
     if (!spass_len_ok(axis == 0 ? p->n0 : p->n1)) {
-        pad_set_error("pad_fft_axis_fast: axis length %d not supported (64, 128, 256)", axis == 0 ? p->n0 : p->n1);
+        pad_set_error("pad_fft_axis_fast: axis length %d not supported (64, 128, 256, 512)", axis == 0 ? p->n0 : p->n1);
         return PAD_ERR_ARG;
     }
     PAD_CUDA(cudaSetDevice(p->device));

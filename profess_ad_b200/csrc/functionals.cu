@@ -601,7 +601,16 @@ int pad_stress_wgc99_nl(pad_plan* p, const double* den, double alpha, double bet
 
 extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa,
                               double* E_out, double* v_out, int accumulate, void* stream) {
+    return pad_eval_wgc99_ex(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, nullptr);
+}
+
+int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
+                      double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex) {
     PAD_TRY(check_common(p, den, "pad_eval_wgc99"));
+    if (ex && !(g_pad_fast_fft && pad_wgc99_total_supported(p) && v_out)) {
+        pad_set_error("pad_eval_wgc99_ex: the fused term list needs the pipelined FFT kernels");
+        return PAD_ERR_ARG;
+    }
     cudaStream_t s = as_stream(stream);
     double *R[4];
     cufftDoubleComplex* C[4];
@@ -650,7 +659,7 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
     pad_stage_mark("sum(n) -> n_ref, kernel cache check", s);
     if (g_pad_fast_fft && pad_wgc99_fast_supported(p))
-        return pad_wgc99_fast(p, den, alpha, beta, p->wgc_kern4, E_out, v_out, accumulate, s);
+        return pad_wgc99_fast(p, den, alpha, beta, p->wgc_kern4, E_out, v_out, accumulate, s, ex);
 
     // --- forward fields: a = n^beta, a theta, a theta^2 / 2, chi --------------------------------
     double *Ra = R[0], *Rb = R[1], *Rc = R[2], *Rx = R[3];

@@ -424,6 +424,16 @@ extern "C" int pad_eval_total(pad_plan* p, const pad_terms* T, const double* den
                               double* v_out, void* stream) {
     if (!p || !T || !den) { pad_set_error("pad_eval_total: null argument"); return PAD_ERR_ARG; }
     int acc = 0;
+    if (T->kinetic == 2 && v_out && g_pad_fast_fft && g_pad_fuse_terms && pad_wgc99_total_supported(p) && !(T->local_mask & PAD_LOCAL_TF) &&
+        (T->local_mask || T->hartree)) {
+        // ONE pass over the grid for the whole list: the local terms ride on the WGC99 mid pass, the Hartree term is a
+        // fourth field of its second transform batch (csrc/fftz.cu)
+        if ((T->local_mask & PAD_LOCAL_IONEL) && !v_ext) { pad_set_error("pad_eval_total: IonElectron needs v_ext"); return PAD_ERR_ARG; }
+        pad_wgc_extras ex{T->local_mask, v_ext, T->hartree};
+        PAD_TRY(pad_eval_wgc99_ex(p, den, T->alpha, T->beta, T->gamma, T->kappa, E_out, v_out, 0, stream, &ex));
+        if (T->pbe) PAD_TRY(pad_eval_pbe(p, den, T->pbe, E_out, v_out, 1, stream));
+        return PAD_OK;
+    }
     if (T->local_mask) {
         PAD_TRY(pad_eval_local(p, den, v_ext, T->local_mask, E_out, v_out, acc, stream));
         acc = 1;

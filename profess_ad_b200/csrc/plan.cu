@@ -16,12 +16,14 @@ extern "C" int pad_set_fast_fft(int on) { const int old = g_pad_fast_fft; g_pad_
 int g_pad_own_xy = 1;        // hand-written strided (x, y) passes with the fused multiply (n0, n1 in 64/128/256)
 int g_pad_pipe = 1;          // (z, y) passes of a plane as items of one persistent kernel, handed over through the L2 (zy_pipe.cuh)
 int g_pad_pipe_lpi = 0, g_pad_pipe_tpi = 0;
+int g_pad_fuse_terms = 1;
 extern "C" int pad_set_option(const char* name, int value) {
     int* slot = nullptr;
     if (!name) { pad_set_error("pad_set_option: null name"); return -1; }
     if (!strcmp(name, "fast_fft")) slot = &g_pad_fast_fft;
     else if (!strcmp(name, "own_xy")) slot = &g_pad_own_xy;
     else if (!strcmp(name, "pipe")) slot = &g_pad_pipe;
+    else if (!strcmp(name, "fuse_terms")) slot = &g_pad_fuse_terms;
     else if (!strcmp(name, "pipe_lpi")) slot = &g_pad_pipe_lpi;
     else if (!strcmp(name, "pipe_tpi")) slot = &g_pad_pipe_tpi;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }

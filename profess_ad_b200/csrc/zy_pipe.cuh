@@ -50,6 +50,7 @@ struct PipeSched {                    // thread-0 registers
     unsigned t0, t1, t2;
 };
 
+#ifndef PAD_HOST_EMU      // (tests/host_emu: the scheduler runs on host threads with these two replaced by std::atomic loads)
 __device__ __forceinline__ unsigned pipe_ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -60,6 +61,7 @@ __device__ __forceinline__ unsigned pipe_ld_relaxed(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 template <int NSTAGE>
 __device__ __forceinline__ void pipe_begin(PipeCtl* c, PipeSched& ps) {

@@ -13,7 +13,7 @@ def _plan(box, den):
     return _native.get_plan(box, den), _native
 
 
-@pytest.mark.parametrize('shape', [(6, 10, 128), (12, 9, 256), (5, 4, 256), (16, 16, 128)])
+@pytest.mark.parametrize('shape', [(6, 10, 128), (12, 9, 256), (5, 4, 256), (16, 16, 128), (6, 10, 512), (3, 4, 512)])
 def test_fast_rfft3_matches_library(shape):
     dev = torch.device('cuda:0')
     gen = torch.Generator().manual_seed(sum(shape))
@@ -38,7 +38,7 @@ def test_fast_rfft3_matches_library(shape):
 
 
 @pytest.mark.parametrize('shape,axis', [((64, 128, 128), 0), ((64, 128, 128), 1), ((256, 64, 128), 0), ((128, 256, 256), 1),
-                                        ((128, 64, 256), 0), ((64, 64, 128), 1)])
+                                        ((128, 64, 256), 0), ((64, 64, 128), 1), ((512, 64, 128), 0), ((64, 512, 128), 1)])
 def test_strided_axis_pass_matches_library(shape, axis):
     """Own strided x / y pass (csrc/fft_strided.cuh) against torch.fft on the live columns; padding untouched."""
     dev = torch.device('cuda:0')
@@ -59,7 +59,8 @@ def test_strided_axis_pass_matches_library(shape, axis):
         assert (work[:, :, nzh:] == 123.0).all()
 
 
-@pytest.mark.parametrize('shape', [(64, 64, 128), (128, 64, 256), (64, 128, 128), (256, 128, 128), (64, 256, 256)])
+@pytest.mark.parametrize('shape', [(64, 64, 128), (128, 64, 256), (64, 128, 128), (256, 128, 128), (64, 256, 256),
+                                   (64, 512, 128), (512, 128, 128), (64, 64, 512), (128, 128, 512)])
 def test_fast_rfft3_own_xy(shape):
     """Full own 3-D transform (z pass + strided y and x passes, Nyquist column packed 8 lines per tile)."""
     dev = torch.device('cuda:0')
@@ -81,7 +82,8 @@ def test_fast_rfft3_own_xy(shape):
 
 
 @pytest.mark.parametrize('shape,seed', [((10, 12, 128), 31), ((9, 8, 256), 32), ((4, 6, 256), 33),
-                                        ((64, 64, 128), 34), ((64, 128, 256), 35), ((128, 64, 128), 36)])
+                                        ((64, 64, 128), 34), ((64, 128, 256), 35), ((128, 64, 128), 36),
+                                        ((64, 64, 512), 37), ((512, 64, 128), 38), ((64, 512, 128), 39)])
 def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     from oracle import ofdft_oracle as orc
     import profess_ad_b200.functionals as F
@@ -259,3 +261,41 @@ def test_pipelined_zy_kernels_match_per_pass_kernels(shape, lpi, tpi):
     E_ref, V_ref = orc.energy_and_potential(box, den, orc.WangGovindCarter99())
     assert abs(res[1]['WGC99'][0] - E_ref.item()) <= 1e-10 * abs(E_ref.item())
     assert ((res[1]['WGC99'][1].cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9
+
+
+@pytest.mark.parametrize('shape,terms', [((64, 128, 128), 'IHWP'), ((128, 128, 256), 'IHWP'), ((64, 128, 128), 'HW'), ((64, 128, 128), 'IWP'),
+                                         ((64, 128, 128), 'IHWB')])
+def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms):
+    """pad_eval_total with WGC99 as the kinetic term: IonElectron / LDA-x / PZ-c folded into the WGC99 mid pass, Hartree as a
+    fourth field of its second transform batch (system.py:759-772 in ONE sweep) against the term-by-term calls and the oracle."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _density_opt as D, _native as nat
+    lib = nat.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=sum(shape) + len(terms), L=9.0)
+    v_ext = -0.2 * torch.rand(*shape, dtype=torch.double, generator=torch.Generator().manual_seed(5))
+    b, d, vx = box.to(dev), den.to(dev), v_ext.to(dev)
+    table = {'I': (F.IonElectron, None), 'H': (F.Hartree, orc.Hartree), 'W': (F.WangGovindCarter99().forward, orc.WangGovindCarter99()),
+             'P': (F.PerdewZunger, orc.PerdewZunger), 'B': (F.PerdewBurkeErnzerhof, orc.PerdewBurkeErnzerhof)}
+    T = D.describe_terms([table[c][0] for c in terms])
+    out = {}
+    for fuse in (1, 0):
+        old = lib.pad_set_option(b'fuse_terms', fuse)
+        try:
+            for _ in range(2):
+                E, v = D.eval_total(b, d, vx if 'I' in terms else None, T)
+            out[fuse] = (E.item(), v.clone())
+        finally:
+            lib.pad_set_option(b'fuse_terms', old)
+    assert abs(out[1][0] - out[0][0]) <= 1e-12 * abs(out[0][0]), (out[1][0], out[0][0])
+    assert ((out[1][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11
+    E_ref, V_ref = 0.0, torch.zeros_like(den)
+    for c in terms:
+        if c == 'I':
+            e, v = orc.energy_and_potential(box, den, lambda bb, nn: orc.IonElectron(bb, nn, v_ext))
+        else:
+            e, v = orc.energy_and_potential(box, den, table[c][1])
+        E_ref, V_ref = E_ref + e.item(), V_ref + v
+    assert abs(out[1][0] - E_ref) <= 1e-10 * abs(E_ref)
+    assert ((out[1][1].cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9
