@@ -214,7 +214,8 @@ int pad_eval_total(pad_plan* plan, const pad_terms* terms, const double* den, co
 /* Analytic stress sigma_ij = (1/vol) dE/d eps_ij of the terms of a pad_terms descriptor (everything except
  * IonElectron, see pad_ion_stress): replaces get_stress / System.__compute_stress (functional_tools.py:73-100,
  * system.py:927-935; formulas tests/tools_for_tests.py:212-472).  stress_out: DEVICE, 9 doubles, overwritten.
- * Not available for kinetic == 2 (WangGovindCarter99). */
+ * Every kinetic kind is covered: Wang-Teter family, WangGovindCarter99 (kernel regenerated for the strained cell) and the
+ * Huang-Carter family (xi-node list held fixed, as the reference's autograd sees it, functional_tools.py:408-416). */
 int pad_stress_terms(pad_plan* plan, const pad_terms* terms, const double* den, double* stress_out, void* stream);
 
 /* ---- chi-parametrisation (system.py:830-854): n = N chi^2 / int chi^2 and the projected gradient

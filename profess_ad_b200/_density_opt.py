@@ -107,8 +107,6 @@ def eval_total(box_vecs, den, v_ext, T, want_potential=True):
 def stress_terms(box_vecs, den, T):
     """Analytic stress (3, 3) in Ha/bohr^3 of a described term list without its IonElectron part (pad_stress_terms)."""
     _native.require_cuda(den)
-    if T.kinetic == 3:
-        raise NotImplementedError('stress of the Huang-Carter family is not available')
     den = den.detach().contiguous()
     plan = _native.get_plan(box_vecs, den)
     out = torch.empty(9, dtype=torch.double, device=den.device)

@@ -110,6 +110,45 @@ __device__ __forceinline__ double sym_even(const KPoint& p, M mult) {
     return m;
 }
 
+// |k|^2 along a line of the half spectrum with fixed (j1, j2) and running j0: k(p) = f0 b0 + C, C = f1 b1 + f2 b2, so
+// |k|^2 = f0^2 |b0|^2 + 2 f0 (b0.C) + |C|^2 -- two FMAs per point instead of a make_kpoint_at; same for the Hermitian
+// partner pbar = (-j0, -j1, j2) (Nyquist indices keep their sign) that special points average with (sym_even).
+struct KLine {
+    double B00, d, cc, db, ccb;
+    int n0, half0;
+    bool e0, selfconj, nyq12;
+};
+__device__ __forceinline__ KLine make_kline(const KGeom& g, int j1, int j2) {
+    KLine L;
+    const double f1 = (double)(j1 <= g.n1 / 2 ? j1 : j1 - g.n1), f2 = (double)j2;
+    const bool nyq1 = g.e1 && (j1 == g.n1 / 2), nyq2 = g.e2 && (j2 == g.n2 / 2);
+    const double q1 = nyq1 ? f1 : -f1;
+    const double cx = f1 * g.b[3] + f2 * g.b[6], cy = f1 * g.b[4] + f2 * g.b[7], cz = f1 * g.b[5] + f2 * g.b[8];
+    const double px = q1 * g.b[3] + f2 * g.b[6], py = q1 * g.b[4] + f2 * g.b[7], pz = q1 * g.b[5] + f2 * g.b[8];
+    L.B00 = g.b[0] * g.b[0] + g.b[1] * g.b[1] + g.b[2] * g.b[2];
+    L.d = g.b[0] * cx + g.b[1] * cy + g.b[2] * cz;
+    L.cc = cx * cx + cy * cy + cz * cz;
+    L.db = g.b[0] * px + g.b[1] * py + g.b[2] * pz;
+    L.ccb = px * px + py * py + pz * pz;
+    L.n0 = g.n0; L.half0 = g.n0 / 2; L.e0 = g.e0;
+    L.selfconj = (j2 == 0) || nyq2;
+    L.nyq12 = nyq1 || nyq2;
+    return L;
+}
+// sym_even for a multiplier that depends on k only through |k|^2
+template <class M>
+__device__ __forceinline__ double kline_sym_even(const KLine& L, int j0, M mult_of_k2) {
+    const double f0 = (double)(j0 <= L.half0 ? j0 : j0 - L.n0);
+    const double k2 = fma(f0, fma(f0, L.B00, 2.0 * L.d), L.cc);
+    double m = mult_of_k2(k2);
+    const bool nyq0 = L.e0 && (j0 == L.half0);
+    if (L.selfconj && (L.nyq12 || nyq0)) {
+        const double q0 = nyq0 ? f0 : -f0;
+        m = 0.5 * (m + mult_of_k2(fma(q0, fma(q0, L.B00, 2.0 * L.db), L.ccb)));
+    }
+    return m;
+}
+
 // Effective wave-vector for the gradient multiplier i*k_c:  (k(p) - k(pbar)) / 2 on special points.
 __device__ __forceinline__ void sym_kvec(const KPoint& p, double& kx, double& ky, double& kz) {
     kx = p.kx; ky = p.ky; kz = p.kz;
@@ -305,6 +344,9 @@ int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s);
 // CTAs are finished (all-reduced on slab plans) and added to the row-major 3 x 3 device tensor `sig`:
 // sig_ij += c_t T_ij + c_iso iso delta_ij
 int pad_stress_accumulate(pad_plan* p, cudaStream_t s, int nblocks, double c_iso, double c_t, double* sig);
+// hc.cu: stress of the non-local term of the Huang-Carter family, added to sig[9]
+int pad_stress_hc_nl(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa, int geometric,
+                     const double* table_dev, int n_eta, double* sig, cudaStream_t s);
 // functionals.cu (needs the WGC99 series constants of that translation unit): non-local WGC99 stress, added to sig[9]
 int pad_stress_wgc99_nl(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* sig,
                         cudaStream_t s);

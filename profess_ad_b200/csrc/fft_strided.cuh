@@ -176,8 +176,9 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 // ------------------------------------------------------------------------------------------------
 //  x pass with fused multiply:  NF coupled fields.  The transformed axis is axis 0, the outer axis is
 //  axis 1.  Mix concept:
-//      typename Mix::Coef
-//      Coef  fetch(kg, kx, ky, z, pidx)     multiplier data of one k-point (pidx = padded index (kx n1 + ky) nzp + z)
+//      typename Mix::Coef;  Mix::kRing   multiplier slots kept in flight ahead of their use (8 for table reads, 1 for computed ones)
+//      Line  line(kg, ky, z)                per-thread constants of the tile column (e.g. a KLine for |k|^2 along kx)
+//      Coef  fetch(line, kx, pidx, live)    multiplier data of one k-point (pidx = padded index (kx n1 + ky) nzp + z)
 //      void  apply(coef, q[NF])             edits the NF spectral values in place
 //
 //  Per tile every field has one shared-memory buffer B[f] of L x 8 complex.  It is, in turn, the landing
@@ -187,8 +188,12 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 //  left the buffer, the loads of field f of the CTA's NEXT tile are issued into it, so they fly during
 //  the remaining inverse transforms, the stores and the next tile's first forward transforms.
 // ------------------------------------------------------------------------------------------------
+// CTAs per SM the fused x pass is compiled for: a single field leaves room for more resident tiles (latency hiding)
+template <int L, int NF>
+constexpr int xmix_ctas_per_sm() { return L >= 512 ? 1 : (NF == 1 ? 3 : (L >= 128 ? 2 : 3)); }
+
 template <int L, int NF, class Mix>
-__global__ void __launch_bounds__(128, (L >= 512) ? 1 : (L >= 128) ? 2 : 3) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
+__global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -240,19 +245,20 @@ __global__ void __launch_bounds__(128, (L >= 512) ? 1 : (L >= 128) ? 2 : 3) xmix
         // multiply; all mixed spectra go back to the parking rows.  The multiplier data comes from global
         // memory: keep PF slots of it in flight.
         {
-            constexpr int PF = 8;      // measured at 256^3: 8 in flight, no L2 hints: 269 us; 4 + prefetch.L2 hints: 283 us
+            constexpr int PF = Mix::kRing;      // table-driven mixes: 8 slots in flight (measured at 256^3: 269 us; 4 + prefetch.L2 hints: 283 us); computed multipliers: 1
+            const typename Mix::Line kl = mix.line(kg, cur.o, cur.z);
             typename Mix::Coef ring[PF];
 #pragma unroll
             for (int s = 0; s < PF; ++s) {
                 const int kx = spass_out_index<L>(t, s);
-                ring[s] = mix.fetch(kg, kx, cur.o, cur.z, prow + (size_t)kx * kxs, cur.live);
+                ring[s] = mix.fetch(kl, kx, prow + (size_t)kx * kxs, cur.live);
             }
 #pragma unroll
             for (int s = 0; s < P::EPT; ++s) {
                 const typename Mix::Coef coef = ring[s % PF];
                 if (s + PF < P::EPT) {
                     const int kxn = spass_out_index<L>(t, s + PF < P::EPT ? s + PF : s);
-                    ring[s % PF] = mix.fetch(kg, kxn, cur.o, cur.z, prow + (size_t)kxn * kxs, cur.live);
+                    ring[s % PF] = mix.fetch(kl, kxn, prow + (size_t)kxn * kxs, cur.live);
                 }
                 cd q[NF];
 #pragma unroll

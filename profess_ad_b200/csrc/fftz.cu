@@ -219,183 +219,18 @@ struct ZSpec {
     const cd* f[4];
 };
 
-//   Post::kDen / Post::kVin          the post-op reads the density / the previous potential at its points
-//   post.apply(g, n, vold, u0[NF], u1[NF], acc, sta[NST], stb[NST])   for the points g and g + 1 (n, vold: double2);
-//   Post::NST staged values per point go on to a forward transform in the pipelined kernels (zinv_item), else unused
-template <int M, int TPL, int NF, int NRED, class Post>
-__global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, ZSpec in, const double* __restrict__ den,
-                                                     const double* __restrict__ vin, int nlines, int nzp,
-                                                     double* __restrict__ partials) {
-    using L = ZLayout<M, TPL>;
-    constexpr int LPW = L::kLinesPerWarp;
-    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
-    constexpr int G = NF + NREAL;                              // cp.async groups per line
-    constexpr int kLineBytes = L::inv_line_bytes(NF, NREAL);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd* tw1 = reinterpret_cast<cd*>(smem_raw);
-    cd* tw2 = tw1 + M;
-    load_twiddles<M>(tw1, tw2);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int sub = lane / TPL, t = lane % TPL;
-    unsigned char* slot = smem_raw + L::kTwBytes + (size_t)(warp * LPW + sub) * kLineBytes;
-    cd* S = reinterpret_cast<cd*>(slot);
-    cd* spec = S + L::kScratch;                                // [NF][kSpecLine]
-    double2* rland = reinterpret_cast<double2*>(spec + NF * L::kSpecLine);   // [NREAL][M] pairs
-    const int stride = gridDim.x * wpb * LPW;
-    double acc[NRED > 0 ? NRED : 1];
-#pragma unroll
-    for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
-
-    auto issue_spec = [&](int f, int line) {
-        if (line < nlines) {
-            const cd* src = in.f[f] + (size_t)line * nzp + t;
-            cd* dst = spec + f * L::kSpecLine + t;
-#pragma unroll
-            for (int i = 0; i < (M + TPL) / TPL; ++i)
-                if (t + TPL * i <= M) cp_async16(dst + TPL * i, src + TPL * i);
-        }
-        cp_async_commit();
-    };
-    auto issue_real = [&](int q, const double* base, int line) {
-        if (line < nlines) {
-            const double2* src = reinterpret_cast<const double2*>(base + (size_t)line * (2 * M)) + t;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cp_async16(rland + q * M + t + TPL * j, src + TPL * j);
-        }
-        cp_async_commit();
-    };
-    auto issue_all = [&](int line) {
-#pragma unroll
-        for (int f = 0; f < NF; ++f) issue_spec(f, line);
-        if constexpr (Post::kDen) issue_real(0, den, line);
-        if constexpr (Post::kVin) issue_real(Post::kDen ? 1 : 0, vin, line);
-    };
-
-    int line0 = (blockIdx.x * wpb + warp) * LPW;
-    issue_all(line0 + sub);
-    for (; line0 < nlines; line0 += stride) {
-        const int line = line0 + sub;
-        const bool live = line < nlines;
-        const int next = line + stride;
-        const size_t base = (size_t)line * (2 * M);
-        cd res[NF][8];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            cp_async_wait<G - 1>();
-            __syncwarp();                                      // the line was copied by all lanes of its group
-            zinv_field<M, TPL>(spec + f * L::kSpecLine, res[f], S, tw1, tw2, t);   // ends with __syncwarp: all reads of spec[f] done
-            issue_spec(f, next);
-        }
-        double2 nn[8], vv[8];
-        if constexpr (Post::kDen) {
-            cp_async_wait<G - 1>();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) nn[r] = rland[t + TPL * fft_nat<8>(r)];      // own chunks
-            issue_real(0, den, next);
-        }
-        if constexpr (Post::kVin) {
-            cp_async_wait<G - 1>();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) vv[r] = rland[(Post::kDen ? M : 0) + t + TPL * fft_nat<8>(r)];
-            issue_real(Post::kDen ? 1 : 0, vin, next);
-        }
-        if (live) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                double u0[NF], u1[NF];
-#pragma unroll
-                for (int f = 0; f < NF; ++f) { u0[f] = res[f][r].x; u1[f] = res[f][r].y; }
-                double sta[Post::NST > 0 ? Post::NST : 1], stb[Post::NST > 0 ? Post::NST : 1];
-                post.apply(base + 2 * (t + TPL * fft_nat<8>(r)), Post::kDen ? nn[r] : make_double2(0.0, 0.0),
-                           Post::kVin ? vv[r] : make_double2(0.0, 0.0), u0, u1, acc, sta, stb);
-            }
-        }
-    }
-    cp_async_wait<0>();
-    if constexpr (NRED > 0) {
-        __shared__ double red[NRED][4];
-#pragma unroll
-        for (int r = 0; r < NRED; ++r) {
-            const double w = warp_sum(acc[r]);
-            if (lane == 0) red[r][warp] = w;
-        }
-        __syncthreads();
-        if (threadIdx.x < NRED) {
-            double s = 0.0;
-            for (int w = 0; w < wpb; ++w) s += red[threadIdx.x][w];
-            partials[(size_t)threadIdx.x * PAD_MAX_BLOCKS + blockIdx.x] = s;
-        }
-    }
-}
-
-inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
-    int b = (nlines + lines_per_block - 1) / lines_per_block;
-    const int cap = 148 * blocks_per_sm;
-    if (b > cap) b = cap;
-    if (b > PAD_MAX_BLOCKS) b = PAD_MAX_BLOCKS;
-    return b < 1 ? 1 : b;
-}
-
+// forward z work of a CTA: the lines line_begin + warp LPW + k stride < line_end (global line index = x n1 + y)
 template <int M, int TPL, int NF, class Gen>
-int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3) {
-    constexpr int warps = 4;
-    using L = ZLayout<M, TPL>;
-    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::fwd_line_bytes(Gen::NIN);
-    auto kern = zfwd_kernel<M, TPL, NF, Gen>;
-    static bool attr_done[64] = {false};
-    if (!attr_done[p->device & 63]) {
-        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done[p->device & 63] = true;
-    }
-    const int nlines = p->n0 * p->n1;
-    ZIn in{{in0, in1}};
-    kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, in, o0, o1, o2, o3, nlines, p->nzp);
-    ++g_pad_launches;
-    PAD_CUDA(cudaGetLastError());
-    return PAD_OK;
-}
-
-template <int M, int TPL, int NF, int NRED, class Post>
-int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
-                const double* den, const double* vin, int* grid_out) {
-    constexpr int warps = 4;
-    using L = ZLayout<M, TPL>;
-    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
-    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::inv_line_bytes(NF, NREAL);
-    auto kern = zinv_kernel<M, TPL, NF, NRED, Post>;
-    static bool attr_done[64] = {false};
-    if (!attr_done[p->device & 63]) {
-        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done[p->device & 63] = true;
-    }
-    const int nlines = p->n0 * p->n1;
-    constexpr int by_smem = (227 * 1024) / (smem + 1024);
-    const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < 2 ? by_smem : 2);
-    ZSpec in{{i0, i1, i2, i3}};
-    kern<<<grid, warps * 32, smem, s>>>(post, in, den, vin, nlines, p->nzp, p->partials);
-    ++g_pad_launches;
-    if (grid_out) *grid_out = grid;
-    PAD_CUDA(cudaGetLastError());
-    return PAD_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-//  software-pipelined (z, y) kernels (zy_pipe.cuh): the z passes above as ITEMS over a group of lines of one
-//  x-plane, next to the y items of that plane
-// ------------------------------------------------------------------------------------------------
-// forward z item: lines [line_begin, line_end) (global line index = x n1 + y)
-template <int M, int TPL, int NF, class Gen>
-__device__ __forceinline__ void zfwd_item(const Gen& gen, const ZIn& in, const SPassFields& out, int line_begin, int line_end, int nzp,
-                                          unsigned char* zarea, const cd* tw1, const cd* tw2) {
+__device__ __forceinline__ void zfwd_item(const Gen& gen, const ZIn& in, const SPassFields& out, int line_begin, int line_end, int stride,
+                                          int nzp, unsigned char* zarea, const cd* tw1, const cd* tw2) {
     using L = ZLayout<M, TPL>;
     constexpr int LPW = L::kLinesPerWarp, NST = Gen::NST, NIN = Gen::NIN;
     constexpr int kLineBytes = L::fwd_line_bytes(NIN);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
     unsigned char* slot = zarea + (size_t)(warp * LPW + sub) * kLineBytes;
     cd* S = reinterpret_cast<cd*>(slot);
     double2* land = reinterpret_cast<double2*>(slot + (L::kScratch > M + 1 ? L::kScratch : M + 2) * 16);   // [NIN][M] pairs
-    const int stride = wpb * LPW;
     auto issue = [&](int line) {
         if (line < line_end) {
 #pragma unroll
@@ -440,21 +275,20 @@ __device__ __forceinline__ void zfwd_item(const Gen& gen, const ZIn& in, const S
 //   post.apply(g, n, vold, u0[NF], u1[NF], acc, sta[NST], stb[NST])
 template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
 __device__ __forceinline__ void zinv_item(const Post& post, const GenF& genf, const SPassFields& spec, const double* __restrict__ den,
-                                          const double* __restrict__ vin, int line_begin, int line_end, int nzp, unsigned char* zarea,
-                                          const cd* tw1, const cd* tw2, double* acc) {
+                                          const double* __restrict__ vin, int line_begin, int line_end, int stride, int nzp,
+                                          unsigned char* zarea, const cd* tw1, const cd* tw2, double* acc) {
     using L = ZLayout<M, TPL>;
     constexpr int LPW = L::kLinesPerWarp;
     constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
     constexpr int G = NF + NREAL;
     constexpr int kLineBytes = L::inv_line_bytes(NF, NREAL);
     constexpr int NST = Post::NST > 0 ? Post::NST : 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / TPL, t = lane % TPL;
     unsigned char* slot = zarea + (size_t)(warp * LPW + sub) * kLineBytes;
     cd* S = reinterpret_cast<cd*>(slot);
     cd* sp = S + L::kScratch;                                  // [NF][kSpecLine]
     double2* rland = reinterpret_cast<double2*>(sp + NF * L::kSpecLine);   // [NREAL][M] pairs
-    const int stride = wpb * LPW;
 
     auto issue_spec = [&](int f, int line) {
         if (line < line_end) {
@@ -529,6 +363,7 @@ __device__ __forceinline__ void zinv_item(const Post& post, const GenF& genf, co
             zfwd_field<M, TPL, 0>(genf, sa, sb, S, tw1, tw2, t, spec.f[0] + orow, live);
             if constexpr (NFW > 1) zfwd_field<M, TPL, 1>(genf, sa, sb, S, tw1, tw2, t, spec.f[1] + orow, live);
             if constexpr (NFW > 2) zfwd_field<M, TPL, 2>(genf, sa, sb, S, tw1, tw2, t, spec.f[2] + orow, live);
+            if constexpr (NFW > 3) zfwd_field<M, TPL, 3>(genf, sa, sb, S, tw1, tw2, t, spec.f[3] + orow, live);
         }
     }
     cp_async_wait<0>();
@@ -540,6 +375,100 @@ struct GenNone {                       // placeholder GenF of inverse kernels wi
     template <int F>
     __device__ double field(const double* s) const { return s[0]; }
 };
+
+//   Post::kDen / Post::kVin          the post-op reads the density / the previous potential at its points
+//   post.apply(g, n, vold, u0[NF], u1[NF], acc, sta[NST], stb[NST])   for the points g and g + 1 (n, vold: double2)
+// NFW > 0: NFW fields generated by GenF from the post-op's staged values are transformed forward again and written over
+// the lines of spec.f[0..NFW-1] (WGC99: the mid pass and the forward z pass of the second batch in one kernel -- P never
+// travels through HBM)
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
+__global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, GenF genf, SPassFields spec, const double* __restrict__ den,
+                                                     const double* __restrict__ vin, int nlines, int nzp,
+                                                     double* __restrict__ partials) {
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tw1 = reinterpret_cast<cd*>(smem_raw);
+    cd* tw2 = tw1 + M;
+    load_twiddles<M>(tw1, tw2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
+    zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, blockIdx.x * wpb * LPW, nlines, gridDim.x * wpb * LPW, nzp,
+                                                 smem_raw + L::kTwBytes, tw1, tw2, acc);
+    if constexpr (NRED > 0) {
+        __shared__ double red[NRED][4];
+#pragma unroll
+        for (int r = 0; r < NRED; ++r) {
+            const double w = warp_sum(acc[r]);
+            if (lane == 0) red[r][warp] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x < NRED) {
+            double s = 0.0;
+            for (int w = 0; w < wpb; ++w) s += red[threadIdx.x][w];
+            partials[(size_t)threadIdx.x * PAD_MAX_BLOCKS + blockIdx.x] = s;
+        }
+    }
+}
+
+inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
+    int b = (nlines + lines_per_block - 1) / lines_per_block;
+    const int cap = 148 * blocks_per_sm;
+    if (b > cap) b = cap;
+    if (b > PAD_MAX_BLOCKS) b = PAD_MAX_BLOCKS;
+    return b < 1 ? 1 : b;
+}
+
+template <int M, int TPL, int NF, class Gen>
+int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3) {
+    constexpr int warps = 4;
+    using L = ZLayout<M, TPL>;
+    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::fwd_line_bytes(Gen::NIN);
+    auto kern = zfwd_kernel<M, TPL, NF, Gen>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const int nlines = p->n0 * p->n1;
+    ZIn in{{in0, in1}};
+    kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, in, o0, o1, o2, o3, nlines, p->nzp);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+template <int M, int TPL, int NF, int NRED, class Post, int NFW = 0, class GenF = GenNone>
+int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
+                const double* den, const double* vin, int* grid_out, GenF genf = GenF{}) {
+    constexpr int warps = 4;
+    using L = ZLayout<M, TPL>;
+    constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
+    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::inv_line_bytes(NF, NREAL);
+    auto kern = zinv_kernel<M, TPL, NF, NRED, Post, NFW, GenF>;
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const int nlines = p->n0 * p->n1;
+    constexpr int by_smem = (227 * 1024) / (smem + 1024);
+    const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < 2 ? by_smem : 2);
+    SPassFields in;
+    in.f[0] = const_cast<cd*>(i0); in.f[1] = const_cast<cd*>(i1); in.f[2] = const_cast<cd*>(i2); in.f[3] = const_cast<cd*>(i3);
+    kern<<<grid, warps * 32, smem, s>>>(post, genf, in, den, vin, nlines, p->nzp, p->partials);
+    ++g_pad_launches;
+    if (grid_out) *grid_out = grid;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  software-pipelined (z, y) kernels (zy_pipe.cuh): the z passes above as ITEMS over a group of lines of one
+//  x-plane, next to the y items of that plane
+// ------------------------------------------------------------------------------------------------
 
 template <int M, int LY>
 __device__ __forceinline__ cd* pipe_tables(unsigned char* smem_raw, cd*& tw1, cd*& tw2, cd*& twy) {
@@ -566,7 +495,7 @@ __global__ void __launch_bounds__(128, 4) zy_fwd_kernel(Gen gen, ZIn in, SPassFi
         if (it.stage < 0) break;
         if (it.stage == 0) {
             const int l0 = it.plane * g.n1 + it.sub * g.lpi;
-            zfwd_item<M, TPL, NF>(gen, in, out, l0, l0 + g.lpi, g.nzp, reinterpret_cast<unsigned char*>(work), tw1, tw2);
+            zfwd_item<M, TPL, NF>(gen, in, out, l0, l0 + g.lpi, 4 * (32 / TPL), g.nzp, reinterpret_cast<unsigned char*>(work), tw1, tw2);
         } else {
             const int w0 = it.sub * g.tpi;
             ytile_item_direct<LY, -1, true>(out, NF, g, it.plane, w0, min(w0 + g.tpi, ntiles), ntiles, work, twy);
@@ -604,7 +533,7 @@ __global__ void __launch_bounds__(128, 2) yz_inv_kernel(Post post, GenF genf, SP
 #pragma unroll
             for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
             const int l0 = it.plane * g.n1 + it.sub * g.lpi;
-            zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, l0, l0 + g.lpi, g.nzp,
+            zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, l0, l0 + g.lpi, 4 * (32 / TPL), g.nzp,
                                                          reinterpret_cast<unsigned char*>(work), tw1, tw2, acc);
             if constexpr (NRED > 0) {
 #pragma unroll
@@ -883,7 +812,8 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     }
     // persistent CTAs: the kernel prefetches its next tile while it finishes the current one
     constexpr int by_smem = (227 * 1024) / (smem + 1024);
-    constexpr int per_sm = (L >= 128) ? (by_smem < 2 ? by_smem : 2) : (by_smem < 3 ? by_smem : 3);
+    constexpr int want_sm = xmix_ctas_per_sm<L, NF>();
+    constexpr int per_sm = by_smem < want_sm ? by_smem : want_sm;
     static_assert(per_sm >= 1, "fused x pass: tile buffers do not fit in shared memory");
     const long long tiles = spass_tiles(g);
     long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
@@ -912,9 +842,12 @@ int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
 
 // reciprocal-space multipliers for the fused x pass (Mix concept: fft_strided.cuh)
 struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:968-981), kernels pre-scaled by 1/N
+    static constexpr int kRing = 8;
     const double2* K4;                 // [(kx n1 + ky) nzp + z][2]: (W0, K1), (K2, K3)
     struct Coef { double2 a, b; };
-    __device__ __forceinline__ Coef fetch(const KGeom&, int, int, int, size_t pidx, bool live) const {
+    struct Line {};
+    __device__ __forceinline__ Line line(const KGeom&, int, int) const { return Line{}; }
+    __device__ __forceinline__ Coef fetch(const Line&, int, size_t pidx, bool live) const {
         Coef c;
         c.a = c.b = make_double2(0.0, 0.0);
         if (live) { c.a = __ldcs(K4 + 2 * pidx); c.b = __ldcs(K4 + 2 * pidx + 1); }
@@ -929,32 +862,37 @@ struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:9
     }
 };
 struct MixLaplace {                    // -k^2 / N   (functional_tools.py:209-227)
+    static constexpr int kRing = 1;
     double inv_n;
     typedef double Coef;
-    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+    typedef KLine Line;
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return make_kline(g, ky, z); }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t, bool live) const {
         if (!live) return 0.0;
-        const KPoint k = make_kpoint_at(g, kx, ky, z);
-        return -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
+        return -inv_n * kline_sym_even(l, kx, [](double k2) { return k2; });
     }
     __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
 };
 struct MixCoulomb {                    // 4 pi / (k^2 N), 0 at k = 0   (functionals.py:49-72)
+    static constexpr int kRing = 1;
     double inv_n;
     typedef double Coef;
-    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t, bool live) const {
+    typedef KLine Line;
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return make_kline(g, ky, z); }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t, bool live) const {
         if (!live) return 0.0;
-        const KPoint k = make_kpoint_at(g, kx, ky, z);
-        return inv_n * sym_even(k, [](double x, double y, double w) {
-                   const double k2 = x * x + y * y + w * w;
-                   return k2 != 0.0 ? 4.0 * kPi / k2 : 0.0;
-               });
+        // k = 0 is the only point with k2 == 0 exactly (f0 = 0 and C = 0); anything else is > 0
+        return inv_n * kline_sym_even(l, kx, [](double k2) { return k2 > 0.0 ? 4.0 * kPi / k2 : 0.0; });
     }
     __device__ __forceinline__ void apply(const Coef& m, cd* q) const { q[0] = cd{q[0].x * m, q[0].y * m}; }
 };
 struct MixScale {                      // plain 1/N (round-trip tests)
+    static constexpr int kRing = 1;
     double m;
     typedef double Coef;
-    __device__ __forceinline__ Coef fetch(const KGeom&, int, int, int, size_t, bool) const { return m; }
+    struct Line {};
+    __device__ __forceinline__ Line line(const KGeom&, int, int) const { return Line{}; }
+    __device__ __forceinline__ Coef fetch(const Line&, int, size_t, bool) const { return m; }
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 
@@ -1364,80 +1302,125 @@ extern "C" int pad_irfft3_fast(pad_plan* p, double* in_cplx_padded, double* out,
 // =================================================================================================
 int pad_wgc99_fast_supported(const pad_plan* p) { return fast_shape(p) ? 1 : 0; }
 
-int pad_wgc99_total_supported(const pad_plan* p) { return fast_shape(p) && pipe_shape(p) ? 1 : 0; }
+int pad_wgc99_total_supported(const pad_plan* p) { return fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
 
+namespace {
+FinalizeArgs wgc_energy_args(const pad_plan* p, int nblocks, int nterms, int accumulate, double* E_out) {
+    FinalizeArgs a;
+    a.nblocks = nblocks; a.nterms = nterms; a.accumulate = accumulate;
+    for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
+    a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV; a.coef[3] = p->dV;
+    a.sums_out = nullptr;
+    a.E_out = E_out;
+    return a;
+}
+
+// inverse y pass + [z c2r + post-op (+ gen + z r2c of NFW new fields) ] + forward y pass of the new fields: one pipelined
+// kernel, or y^-1 | fused z kernel | y as three launches
+template <int NF, int NRED, class Post, int NFW, class GenF>
+int wgc_inverse_stage(pad_plan* p, cudaStream_t s, bool piped, Post post, GenF genf, cd* const* B, const double* den, const double* vin,
+                      const FinalizeArgs* fin, const char* mark_yinv, const char* mark_z, const char* mark_yfwd, const char* mark_piped) {
+    if (piped) {
+        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, NF, NRED, Post, NFW>(p, s, post, genf, B, den, vin, fin))));
+        pad_stage_mark(mark_piped, s);
+        return PAD_OK;
+    }
+    PAD_TRY(launch_spass(p, s, 1, +1, B, NF));
+    pad_stage_mark(mark_yinv, s);
+    int grid = 1;
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, NF, NRED, Post, NFW, GenF>(p, s, post, B[0], B[1], B[2], NF > 3 ? B[3] : nullptr, den, vin, &grid, genf))));
+    pad_stage_mark(mark_z, s);
+    if (NRED > 0 && fin) {
+        FinalizeArgs a = *fin;
+        a.nblocks = grid;
+        pad_launch_finalize(p, a, s);
+    }
+    if (NFW > 0) {
+        PAD_TRY(launch_spass(p, s, 1, -1, B, NFW));
+        pad_stage_mark(mark_yfwd, s);
+    }
+    return PAD_OK;
+}
+}  // namespace
+
+// ex != null: the fused term list (local terms in the mid pass, Hartree as a fourth field of the second batch)
 int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, const double* kern, double* E_out,
                    double* v_out, int accumulate, cudaStream_t s, const pad_wgc_extras* ex) {
-    if (ex && !(pipe_shape(p) && v_out)) { pad_set_error("pad_wgc99_fast: fused term list needs the pipelined kernels and a potential"); return PAD_ERR_ARG; }
     PAD_TRY(ensure_twiddles(p->device));
-    if (!(g_pad_own_xy && own_xy_shape(p))) PAD_TRY(ensure_xy(p, s));
+    const bool own = g_pad_own_xy && own_xy_shape(p);
+    const bool want_v = v_out != nullptr;
+    if (ex && !(own && want_v)) { pad_set_error("pad_wgc99_fast: the fused term list needs the own (x, y) passes and a potential"); return PAD_ERR_ARG; }
+    if (!own) PAD_TRY(ensure_xy(p, s));
     cd* B[4];
     for (int i = 0; i < 4; ++i) PAD_TRY(get_zbuf(p, i, &B[i]));
-    double* Pbuf;
-    PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
     const double* scal = p->scal;
     const double inv_n = p->geom.inv_n;
     const KGeom geom = p->geom;
-    const bool want_v = v_out != nullptr;
-
-    GenWgcA genA{scal, beta};
-    const bool own = g_pad_own_xy && own_xy_shape(p);
     const MixWgc mixw{reinterpret_cast<const double2*>(kern)};
-    if (pipe_shape(p) && want_v) {
-        // five launches: [gen + z + y] -> x.mix.x^-1 (+ the Laplacian field) -> [y^-1 + z^-1 + mid + gen + z + y] -> x.mix.x^-1 -> [y^-1 + z^-1 + fin]
-        ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, 4>(p, s, genA, den, nullptr, B))));
-        pad_stage_mark("[gen a,a.th,a.th2,chi + z-r2c + y-fwd] (4 fields)", s);
+    GenWgcA genA{scal, beta};
+
+    if (own && want_v) {
+        // [gen + z + y] -> x.mix.x^-1 (+ Laplacian field) -> [y^-1 + z^-1 + mid + gen + z + y] -> x.mix.x^-1 (+ Coulomb field)
+        //   -> [y^-1 + z^-1 + fin]; the bracketed groups are ONE pipelined kernel each (option "pipe") or y | z | y launches
+        //   with the mid pass and the forward z pass of the second batch in one kernel
+        const bool piped = pipe_shape(p);
+        if (piped) {
+            ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, 4>(p, s, genA, den, nullptr, B))));
+            pad_stage_mark("[gen a,a.th,a.th2,chi + z-r2c + y-fwd] (4 fields)", s);
+        } else {
+            ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, den, nullptr, B[0], B[1], B[2], B[3]))));
+            pad_stage_mark("gen a,a.th,a.th2,chi + z-r2c (4 fields)", s);
+            PAD_TRY(launch_spass(p, s, 1, -1, B, 4));
+            pad_stage_mark("y-fwd (4 fields)", s);
+        }
         PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
         pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
         {
             cd* one[1] = {B[3]};
-            PAD_TRY((launch_xmix<1>(p, s, one, MixLaplace{p->geom.inv_n})));
+            PAD_TRY((launch_xmix<1>(p, s, one, MixLaplace{inv_n})));
             pad_stage_mark("x-fwd * (-k^2) * x-inv (1 field)", s);
         }
-        FinalizeArgs a;
-        a.nblocks = 0; a.nterms = 3; a.accumulate = accumulate;
-        for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
-        a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
-        a.sums_out = nullptr;
-        a.E_out = E_out;
-        if (ex) {
-            // fused term list: local terms in the mid pass, Hartree as the fourth field of the second batch
-            a.nterms = 4; a.coef[3] = p->dV;
+        const bool hartree = ex && ex->hartree;
+        const FinalizeArgs a = wgc_energy_args(p, 0, ex ? 4 : 3, accumulate, E_out);
+        const FinalizeArgs* fa = E_out ? &a : nullptr;
+        if (ex && hartree) {
             PostWgcMidT mid{scal, v_out, ex->v_ext, alpha, accumulate, ex->local_mask};
-            if (ex->hartree) {
-                ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 4, PostWgcMidT, 4>(p, s, mid, GenWgcP4{scal}, B, den, nullptr, E_out ? &a : nullptr))));
-                pad_stage_mark("[y-inv (4) + z-c2r + energy/v1/local + gen P..,n + z-r2c + y-fwd (4)]", s);
-                PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
-                pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
-                cd* one[1] = {B[3]};
-                PAD_TRY((launch_xmix<1>(p, s, one, MixCoulomb{p->geom.inv_n})));
-                pad_stage_mark("x-fwd * (4 pi / k^2) * x-inv (1 field)", s);
-                FinalizeArgs h;
-                h.nblocks = 0; h.nterms = 1; h.accumulate = 1;
-                for (int t = 0; t < PAD_MAX_RED; ++t) h.coef[t] = 0.0;
-                h.coef[0] = 0.5 * p->dV;
-                h.sums_out = nullptr;
-                h.E_out = E_out;
-                PostWgcFinH fin{scal, v_out, beta};
-                ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 1, PostWgcFinH, 0>(p, s, fin, GenNone{}, B, den, v_out, E_out ? &h : nullptr))));
-                pad_stage_mark("[y-inv (4) + z-c2r + v2 + Hartree]", s);
-                return PAD_OK;
-            }
-            ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 4, PostWgcMidT, 3>(p, s, mid, GenWgcP{scal}, B, den, nullptr, E_out ? &a : nullptr))));
-            pad_stage_mark("[y-inv (4) + z-c2r + energy/v1/local + gen P.. + z-r2c + y-fwd (3)]", s);
+            PAD_TRY((wgc_inverse_stage<4, 4, PostWgcMidT, 4>(p, s, piped, mid, GenWgcP4{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
+                                                            "z-c2r (4) + energy/v1/local + gen P..,n + z-r2c (4)", "y-fwd (4 fields)",
+                                                            "[y-inv (4) + z-c2r + energy/v1/local + gen P..,n + z-r2c + y-fwd (4)]")));
+        } else if (ex) {
+            PostWgcMidT mid{scal, v_out, ex->v_ext, alpha, accumulate, ex->local_mask};
+            PAD_TRY((wgc_inverse_stage<4, 4, PostWgcMidT, 3>(p, s, piped, mid, GenWgcP{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
+                                                            "z-c2r (4) + energy/v1/local + gen P.. + z-r2c (3)", "y-fwd (3 fields)",
+                                                            "[y-inv (4) + z-c2r + energy/v1/local + gen P.. + z-r2c + y-fwd (3)]")));
         } else {
             PostWgcMid mid{scal, v_out, nullptr, alpha, accumulate, 1};
-            GenWgcP genP{scal};
-            ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 4, 3, PostWgcMid, 3>(p, s, mid, genP, B, den, nullptr, E_out ? &a : nullptr))));
-            pad_stage_mark("[y-inv (4) + z-c2r + energy/v1 + gen P.. + z-r2c + y-fwd (3)]", s);
+            PAD_TRY((wgc_inverse_stage<4, 3, PostWgcMid, 3>(p, s, piped, mid, GenWgcP{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
+                                                           "z-c2r (4) + energy/v1 + gen P.. + z-r2c (3)", "y-fwd (3 fields)",
+                                                           "[y-inv (4) + z-c2r + energy/v1 + gen P.. + z-r2c + y-fwd (3)]")));
         }
         PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
         pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
-        PostWgcFin fin{scal, v_out, beta};
-        ZDISPATCH(p, PAD_TRY((launch_yz_inv<M, TPL, 3, 0, PostWgcFin, 0>(p, s, fin, GenNone{}, B, den, v_out, nullptr))));
-        pad_stage_mark("[y-inv (3) + z-c2r + v2]", s);
+        if (hartree) {
+            cd* one[1] = {B[3]};
+            PAD_TRY((launch_xmix<1>(p, s, one, MixCoulomb{inv_n})));
+            pad_stage_mark("x-fwd * (4 pi / k^2) * x-inv (1 field)", s);
+            FinalizeArgs h = wgc_energy_args(p, 0, 1, 1, E_out);
+            h.coef[0] = 0.5 * p->dV;
+            PostWgcFinH fin{scal, v_out, beta};
+            PAD_TRY((wgc_inverse_stage<4, 1, PostWgcFinH, 0>(p, s, piped, fin, GenNone{}, B, den, v_out, E_out ? &h : nullptr, "y-inv (4 fields)",
+                                                            "z-c2r (4 fields) + v2 + Hartree", "", "[y-inv (4) + z-c2r + v2 + Hartree]")));
+        } else {
+            PostWgcFin fin{scal, v_out, beta};
+            PAD_TRY((wgc_inverse_stage<3, 0, PostWgcFin, 0>(p, s, piped, fin, GenNone{}, B, den, v_out, nullptr, "y-inv (3 fields)",
+                                                           "z-c2r (3 fields) + v2", "", "[y-inv (3) + z-c2r + v2]")));
+        }
         return PAD_OK;
     }
+
+    // energy only, or (x, y) lengths the own strided passes do not cover: one kernel per pass, cuFFT for (x, y) if needed
+    double* Pbuf;
+    PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, genA, den, nullptr, B[0], B[1], B[2], B[3]))));
     pad_stage_mark("gen a,a.th,a.th2,chi + z-r2c (4 fields)", s);
     if (own) {
@@ -1447,7 +1430,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         cd *CA = B[0], *CB = B[1], *CC = B[2], *CX = B[3];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw.apply(mixw.fetch(geom, 0, 0, 0, pidx, true), q);
+            mixw.apply(mixw.fetch(MixWgc::Line{}, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
             const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
             const cd X = CX[pidx];
@@ -1460,33 +1443,23 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     PostWgcMid mid{scal, v_out, Pbuf, alpha, accumulate, want_v ? 1 : 0};
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 4, 3>(p, s, mid, B[0], B[1], B[2], B[3], den, nullptr, &grid))));
     pad_stage_mark("z-c2r (4 fields) + energy/v1/P", s);
-    if (E_out) {
-        FinalizeArgs a;
-        a.nblocks = grid; a.nterms = 3; a.accumulate = accumulate;
-        for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
-        a.coef[0] = p->dV; a.coef[1] = -0.5 * p->dV; a.coef[2] = kCTF * p->dV;
-        a.sums_out = nullptr;
-        a.E_out = E_out;
-        pad_launch_finalize(p, a, s);
-    }
+    if (E_out) pad_launch_finalize(p, wgc_energy_args(p, grid, 3, accumulate, E_out), s);
     if (!want_v) return PAD_OK;
 
     GenWgcP genP{scal};
     ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, genP, den, Pbuf, B[0], B[1], B[2], nullptr))));
     pad_stage_mark("gen P,P.th,P.th2 + z-r2c (3 fields)", s);
-    if (own) {
-        PAD_TRY((xy_convolve_own<3>(p, s, B, nullptr, mixw)));
-    } else {
-        for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
+    for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], -1));
+    {
         cd *CA = B[0], *CB = B[1], *CC = B[2];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw.apply(mixw.fetch(geom, 0, 0, 0, pidx, true), q);
+            mixw.apply(mixw.fetch(MixWgc::Line{}, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
         });
         PAD_CUDA(cudaGetLastError());
-        for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     }
+    for (int i = 0; i < 3; ++i) PAD_TRY(xy_exec(p, s, B[i], +1));
     PostWgcFin fin{scal, v_out, beta};
     ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, fin, B[0], B[1], B[2], nullptr, den, v_out, nullptr))));
     pad_stage_mark("z-c2r (3 fields) + v2", s);
@@ -1548,16 +1521,18 @@ __global__ void wt_key_kernel(double* scal) { scal[S_WT_KEY] = scal[S_N0]; }
 
 template <bool TWO>
 struct MixWt {                         // fields 0 (, 1): Lindhard kernel / N;  last field: -k^2 / N
+    static constexpr int kRing = 8;
     const double* scal;
     const double* table;               // [(kx n1 + ky) nzp + z]
     double inv_n;
     struct Coef { double nl, lap; };
-    __device__ __forceinline__ Coef fetch(const KGeom& g, int kx, int ky, int z, size_t pidx, bool live) const {
+    typedef KLine Line;
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return make_kline(g, ky, z); }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const {
         Coef c{0.0, 0.0};
         if (!live) return c;
         c.nl = __ldcs(table + pidx);
-        const KPoint k = make_kpoint_at(g, kx, ky, z);
-        c.lap = -inv_n * sym_even(k, [](double x, double y, double w) { return x * x + y * y + w * w; });
+        c.lap = -inv_n * kline_sym_even(l, kx, [](double k2) { return k2; });
         return c;
     }
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const {

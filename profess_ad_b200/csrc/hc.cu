@@ -16,6 +16,12 @@
 //                + E_xi xi_n  - 2 div(E_xi xi_sigma grad n) ],    E_xi = -3 F K / xi + F dK/dxi
 // FFT count: 12 + 2 n_xi including the 2 of vW.
 //
+// Stress (pad_stress_hc_nl, formula validated against autograd in tests/analytic_model.py:stress_huang_carter_nonlocal):
+//   sigma_ab = (1/vol) [ delta_ab (E_NL - int v_NL n) - sum_r (dE/dg_a) g_b
+//                        - sum_j sum_k w (omega'(|k|/xi_j) / xi_j) (k_a k_b / |k|) Re[conj(W_j^) g^] / N ]
+// with g = grad n, dE/dg_a = 2 E_xi xi_sigma g_a dV, W_j = C_HC dV F w_j, g^ = rfftn(n^beta): the evaluation below run
+// once more with three reductions hooked in.
+//
 // The node list depends on min/max of xi, which the reference reads on the host
 // (functional_tools.py:408-416); this entry point does the same single device->host read of two doubles.
 #include <vector>
@@ -157,9 +163,16 @@ int pad_allreduce_max_bits_raw(pad_plan* p, unsigned long long* mm, cudaStream_t
 
 }  // namespace
 
-extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa,
-                           int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out,
-                           int accumulate, int* n_nodes_out, void* stream) {
+__global__ void k_add_iso(double* sig, const double* E, double c) {
+    const double v = c * E[0];
+    sig[0] += v; sig[4] += v; sig[8] += v;
+}
+
+// sig != null: stress mode -- only the non-local term is evaluated (E_out / v_out must then be scratch: a device double and
+// a ZEROED field), and its stress is ADDED to the 9 device doubles sig
+static int hc_impl(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa,
+                   int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out,
+                   int accumulate, int* n_nodes_out, void* stream, double* sig) {
     if (!p || !den || !table_dev) { pad_set_error("pad_eval_hc: null argument"); return PAD_ERR_ARG; }
     if (variant != 0 && variant != 1) { pad_set_error("pad_eval_hc: variant must be 0 (HC) or 1 (revHC)"); return PAD_ERR_ARG; }
     if (n_eta < 3) { pad_set_error("pad_eval_hc: kernel table too short"); return PAD_ERR_ARG; }
@@ -173,7 +186,7 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
     const KGeom geom = p->geom;
 
     // TF + vW first (they also own rbuf 0/cbuf 0 while they run)
-    PAD_TRY(pad_eval_wt(p, den, 1.0, 1.0, PAD_PART_TF | PAD_PART_VW, E_out, v_out, accumulate, stream));
+    if (!sig) PAD_TRY(pad_eval_wt(p, den, 1.0, 1.0, PAD_PART_TF | PAD_PART_VW, E_out, v_out, accumulate, stream));
 
     double* R[6];
     cufftDoubleComplex* C[4];
@@ -325,6 +338,24 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
         PAD_TRY(pad_fft_forward(p, Wj, C[1], s));
         cufftDoubleComplex *Cj = C[1], *Acc = C[2];
         const double xi_j = nodes[j];
+        if (sig) {      // - sum_k w (omega'(eta_j) / xi_j) (k_a k_b / |k|) Re[conj(W_j^) g^] C_HC dV / (N vol)
+            const cufftDoubleComplex* Gs = C[0];
+            auto fs = [=] __device__(size_t i, double(&acc)[7]) {
+                const KPoint k = make_kpoint(geom, (uint32_t)i);
+                const double ka = kabs3(k.kx, k.ky, k.kz);
+                if (ka == 0.0) return;
+                double val, slope;
+                table_lookup_slope(T, ka / xi_j, val, slope);
+                const cufftDoubleComplex w = Cj[i], gq = Gs[i];
+                const bool edge = k.j2 == 0 || (geom.e2 && k.j2 == geom.n2 / 2);
+                const double t = (edge ? 1.0 : 2.0) * slope / xi_j * (w.x * gq.x + w.y * gq.y) / ka;
+                acc[1] += t * k.kx * k.kx; acc[2] += t * k.ky * k.ky; acc[3] += t * k.kz * k.kz;
+                acc[4] += t * k.kx * k.ky; acc[5] += t * k.kx * k.kz; acc[6] += t * k.ky * k.kz;
+            };
+            ew_kernel<7, decltype(fs)><<<gridk, PAD_THREADS, 0, s>>>(nk, fs, p->partials);
+            ++g_pad_launches;
+            PAD_TRY(pad_stress_accumulate(p, s, gridk, 0.0, -kCHC * inv_n * inv_n, sig));
+        }
         auto fk = [=] __device__(uint32_t idx, const KPoint& k) {
             const double m = inv_n * sym_even(k, [&](double kx, double ky, double kz) { return table_lookup(T, kabs3(kx, ky, kz) / xi_j); });
             const cufftDoubleComplex c = Cj[idx];
@@ -340,6 +371,19 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
     PAD_TRY(pad_fft_inverse(p, C[2], Adj, s));
 
     // ---- xi-dependence: E_xi xi_n - 2 div(E_xi xi_sigma grad n) ------------------------------------
+    if (sig) {      // - sum_r (dE/dg_a) g_b / vol,  dE/dg_a = 2 E_xi xi_sigma g_a dV
+        auto f = [=] __device__(size_t i, double(&acc)[7]) {
+            const double gx = Gx[i], gy = Gy[i], gz = Gz[i];
+            double xi, xn, xs;
+            xi_of(variant, p0, p1, den[i], gx * gx + gy * gy + gz * gz, xi, xn, xs);
+            const double w = 2.0 * Ex[i] * xs;
+            acc[1] += w * gx * gx; acc[2] += w * gy * gy; acc[3] += w * gz * gz;
+            acc[4] += w * gx * gy; acc[5] += w * gx * gz; acc[6] += w * gy * gz;
+        };
+        ew_kernel<7, decltype(f)><<<grid, PAD_THREADS, 0, s>>>(N, f, p->partials);
+        ++g_pad_launches;
+        PAD_TRY(pad_stress_accumulate(p, s, grid, 0.0, -inv_n, sig));
+    }
     {
         auto f = [=] __device__(size_t i, double(&)[1]) {
             const double gx = Gx[i], gy = Gy[i], gz = Gz[i];
@@ -373,6 +417,32 @@ extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p
         ew_kernel<0, decltype(f)><<<grid, PAD_THREADS, 0, s>>>(N, f, p->partials);
         ++g_pad_launches;
     }
+    if (sig) {      // delta_ab (E_NL - int v_NL n) / vol
+        auto f = [=] __device__(size_t i, double(&acc)[7]) { acc[0] += v_out[i] * den[i]; };
+        ew_kernel<7, decltype(f)><<<grid, PAD_THREADS, 0, s>>>(N, f, p->partials);
+        ++g_pad_launches;
+        PAD_TRY(pad_stress_accumulate(p, s, grid, -inv_n, 0.0, sig));
+        k_add_iso<<<1, 1, 0, s>>>(sig, E_out, 1.0 / p->vol);
+        ++g_pad_launches;
+    }
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
+}
+
+extern "C" int pad_eval_hc(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa,
+                           int geometric, const double* table_dev, int n_eta, double* E_out, double* v_out,
+                           int accumulate, int* n_nodes_out, void* stream) {
+    return hc_impl(p, den, variant, p0, p1, beta, kappa, geometric, table_dev, n_eta, E_out, v_out, accumulate, n_nodes_out, stream,
+                   nullptr);
+}
+
+// stress of the non-local Huang-Carter term, added to sig[9] (device).  Scratch: real field 7 (v_NL), scalar slot S_TMP0 + 4.
+int pad_stress_hc_nl(pad_plan* p, const double* den, int variant, double p0, double p1, double beta, double kappa, int geometric,
+                     const double* table_dev, int n_eta, double* sig, cudaStream_t s) {
+    double* vtmp;
+    PAD_TRY(pad_get_rbuf(p, 7, &vtmp));
+    PAD_CUDA(cudaMemsetAsync(vtmp, 0, sizeof(double) * p->N, s));
+    double* Etmp = p->scal + S_TMP0 + 4;
+    PAD_CUDA(cudaMemsetAsync(Etmp, 0, sizeof(double), s));
+    return hc_impl(p, den, variant, p0, p1, beta, kappa, geometric, table_dev, n_eta, Etmp, vtmp, 1, nullptr, (void*)s, sig);
 }

@@ -14,7 +14,7 @@ extern "C" unsigned long long pad_fft_exec_count(void) { return g_pad_fft_execs;
 int g_pad_fast_fft = 1;      // hand-written fused FFT pipeline where the grid allows it (0: plain cuFFT 3-D + separate elementwise kernels)
 extern "C" int pad_set_fast_fft(int on) { const int old = g_pad_fast_fft; g_pad_fast_fft = on ? 1 : 0; return old; }
 int g_pad_own_xy = 1;        // hand-written strided (x, y) passes with the fused multiply (n0, n1 in 64/128/256)
-int g_pad_pipe = 1;          // (z, y) passes of a plane as items of one persistent kernel, handed over through the L2 (zy_pipe.cuh)
+int g_pad_pipe = 0;          // (z, y) passes of a plane as items of one persistent kernel, handed over through the L2 (zy_pipe.cuh)
 int g_pad_pipe_lpi = 0, g_pad_pipe_tpi = 0;
 int g_pad_fuse_terms = 1;
 extern "C" int pad_set_option(const char* name, int value) {

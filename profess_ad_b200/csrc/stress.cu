@@ -16,7 +16,7 @@
 //                             the derivative with the kernel regenerated for the strained cell (the reference's autograd
 //                             with a fresh kernel; with a kernel cached at the same cell the reference silently drops the
 //                             kernel's own eta-dependence, functionals.py:961-966)
-// The Huang-Carter family is not covered.
+//   HuangCarter / RevisedHuangCarter NL : pad_stress_hc_nl (hc.cu)
 #include "common.cuh"
 #include "xc.cuh"
 
@@ -70,7 +70,6 @@ int pad_stress_accumulate(pad_plan* p, cudaStream_t s, int nblocks, double c_iso
 
 extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* den, double* stress_out, void* stream) {
     if (!p || !T || !den || !stress_out) { pad_set_error("pad_stress_terms: null argument"); return PAD_ERR_ARG; }
-    if (T->kinetic == 3) { pad_set_error("pad_stress_terms: no stress for the Huang-Carter family"); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     const KGeom geom = p->geom;
@@ -83,7 +82,8 @@ extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* d
 
     // ---- local terms (IonElectron is handled by pad_ion_stress) ------------------------------------------
     // WangGovindCarter99 = TF + vW + its own non-local term (functionals.py:983-985)
-    int parts = T->kinetic == 1 ? T->kinetic_parts : (T->kinetic == 2 ? (PAD_PART_TF | PAD_PART_VW) : 0);
+    // HuangCarter / RevisedHuangCarter = TF + vW + their non-local term too (functionals.py:1267-1269)
+    int parts = T->kinetic == 1 ? T->kinetic_parts : (T->kinetic >= 2 ? (PAD_PART_TF | PAD_PART_VW) : 0);
     // ThomasFermi can appear as a term of its own and inside a Wang-Teter style functional: count both
     const double tfc = ((T->local_mask & PAD_LOCAL_TF) ? 1.0 : 0.0) + ((parts & PAD_PART_TF) ? 1.0 : 0.0);
     const bool tf = tfc != 0.0;
@@ -136,6 +136,9 @@ extern "C" int pad_stress_terms(pad_plan* p, const pad_terms* T, const double* d
 
     // ---- non-local term of the Wang-Teter family ---------------------------------------------------------------
     if (T->kinetic == 2) PAD_TRY(pad_stress_wgc99_nl(p, den, T->alpha, T->beta, T->gamma, T->kappa, stress_out, s));
+    if (T->kinetic == 3)
+        PAD_TRY(pad_stress_hc_nl(p, den, T->hc_variant, T->hc_p0, T->hc_p1, T->beta, T->kappa, T->hc_geometric, T->hc_table_dev, T->hc_n_eta,
+                                 stress_out, s));
     if (parts & PAD_PART_NL) {
         const double alpha = T->alpha, beta = T->beta;
         PAD_TRY(pad_get_rbuf(p, 0, &R[0]));

@@ -263,9 +263,10 @@ def test_pipelined_zy_kernels_match_per_pass_kernels(shape, lpi, tpi):
     assert ((res[1]['WGC99'][1].cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9
 
 
-@pytest.mark.parametrize('shape,terms', [((64, 128, 128), 'IHWP'), ((128, 128, 256), 'IHWP'), ((64, 128, 128), 'HW'), ((64, 128, 128), 'IWP'),
-                                         ((64, 128, 128), 'IHWB')])
-def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms):
+@pytest.mark.parametrize('shape,terms,pipe', [((64, 128, 128), 'IHWP', 0), ((128, 128, 256), 'IHWP', 0), ((64, 128, 128), 'HW', 0),
+                                              ((64, 64, 128), 'IWP', 0), ((64, 128, 128), 'IHWB', 0), ((64, 128, 128), 'IHWP', 1),
+                                              ((64, 128, 128), 'IWP', 1)])
+def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms, pipe):
     """pad_eval_total with WGC99 as the kinetic term: IonElectron / LDA-x / PZ-c folded into the WGC99 mid pass, Hartree as a
     fourth field of its second transform batch (system.py:759-772 in ONE sweep) against the term-by-term calls and the oracle."""
     from oracle import ofdft_oracle as orc
@@ -282,12 +283,14 @@ def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms):
     out = {}
     for fuse in (1, 0):
         old = lib.pad_set_option(b'fuse_terms', fuse)
+        old_pipe = lib.pad_set_option(b'pipe', pipe)
         try:
             for _ in range(2):
                 E, v = D.eval_total(b, d, vx if 'I' in terms else None, T)
             out[fuse] = (E.item(), v.clone())
         finally:
             lib.pad_set_option(b'fuse_terms', old)
+            lib.pad_set_option(b'pipe', old_pipe)
     assert abs(out[1][0] - out[0][0]) <= 1e-12 * abs(out[0][0]), (out[1][0], out[0][0])
     assert ((out[1][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11
     E_ref, V_ref = 0.0, torch.zeros_like(den)

@@ -43,3 +43,13 @@ def test_pipe_scheduler_on_host_threads(tmp_path):
     (tmp_path / 'sched_part.h').write_text(src[a:b])
     out = _build_and_run(tmp_path, 'pipe_sched.cpp', extra_includes=[str(tmp_path)])
     assert 'bad = 0' in out
+
+
+def test_kline_matches_kpoint_on_host(tmp_path):
+    """|k|^2 along an x line from per-line constants (KLine, used by the fused x pass) == make_kpoint_at + sym_even."""
+    src = open(os.path.join(CSRC, 'common.cuh')).read()
+    a = src.index('struct KGeom {')
+    b = src.index('// Effective wave-vector for the gradient multiplier')
+    (tmp_path / 'kgeom_part.h').write_text(src[a:b])
+    out = _build_and_run(tmp_path, 'kline.cpp', extra_includes=[str(tmp_path)])
+    assert 'kline worst' in out
