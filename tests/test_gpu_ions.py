@@ -228,3 +228,24 @@ def test_slab_stress(golden_dir, potentials_dir):
     ref = g['stress_WangTeter'] + g['stress_PerdewBurkeErnzerhof'] + g['stress_Hartree'] + g['stress_IonElectron']
     for st in out:
         assert _rel(st, ref) < 1e-10
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_huang_carter_stress_matches_reference(case, golden_dir, potentials_dir):
+    """Stress of HuangCarter / RevisedHuangCarter (TF + vW + non-local term, csrc/hc.cu:pad_stress_hc_nl) against the
+    unmodified reference's autograd through box_vecs (tests/golden/hc_stress.npz, make_golden_hc_stress.py; the omega(eta)
+    table injected on both sides), and the same through System.stress()."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200.functional_tools import get_stress
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    hs = np.load(os.path.join(golden_dir, 'hc_stress.npz'))
+    tab = np.load(os.path.join(golden_dir, 'hc_table.npz'))
+    b, d = box.to(DEV), den.to(DEV)
+    for name, f in (('HC', F.HuangCarter(tuple(hs['hc_args']), kernel=torch.from_numpy(tab['hc']))),
+                    ('revHC', F.RevisedHuangCarter(tuple(hs['revhc_args']), kernel=torch.from_numpy(tab['revhc'])))):
+        E = f.forward(b, d).item()
+        assert abs(E - float(hs[f'{case}_{name}_E'])) <= 1e-10 * abs(E)
+        st = get_stress(b, d, f.forward).cpu().numpy()
+        ref = hs[f'{case}_{name}']
+        assert _rel(st, ref) < 1e-9, (name, st, ref)
+        assert np.abs(st - st.T).max() <= 1e-12 * np.abs(st).max()
