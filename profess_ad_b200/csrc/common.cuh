@@ -304,6 +304,9 @@ int pad_fft_forward_many(pad_plan* p, const double* const* in, cufftDoubleComple
 int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* const* out, int n, cudaStream_t s);
 extern int g_pad_own_xy;
 extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
+extern int g_pad_zinv_stream;      // 1: streamed inverse z kernel (results folded as they arrive, 3 CTAs/SM), 0: batch form
+extern int g_pad_fuse_mid;         // 1: WGC99 mid pass and the forward z pass of the second batch in one kernel
+extern int g_pad_fold_table;       // 1: orthorhombic cells read only the |kx|, |ky| quarter of the WGC99 kernel table
 extern int g_pad_fuse_terms;       // 1: pad_eval_total folds local terms + Hartree into the WGC99 pipeline where it can
 extern int g_pad_pipe_lpi;         // lines per z item (0: default)
 extern int g_pad_pipe_tpi;         // tiles per y item (0: default)

@@ -77,6 +77,8 @@ struct ZLayout {
     static constexpr int kSpecLine = M + 2;                           // cd per staged half-spectrum line (M + 1 used)
     static constexpr int kLinesPerWarp = 32 / TPL;
     __host__ __device__ static constexpr int inv_line_bytes(int nf, int nreal) { return (kScratch + nf * kSpecLine) * 16 + nreal * 2 * M * 8; }
+    // streamed inverse pass: scratch | two spectral landing buffers (ring) | one density line
+    __host__ __device__ static constexpr int stream_line_bytes(bool kden) { return (kScratch + 2 * kSpecLine) * 16 + (kden ? 2 * M * 8 : 0); }
     __host__ __device__ static constexpr int fwd_line_bytes(int nin) { return (kScratch > M + 1 ? kScratch : M + 2) * 16 + nin * 2 * M * 8; }
 };
 
@@ -369,6 +371,129 @@ __device__ __forceinline__ void zinv_item(const Post& post, const GenF& genf, co
     cp_async_wait<0>();
 }
 
+// Streamed inverse z work: like zinv_item, but the NF spectral lines of a real-space line pass through a ring of TWO
+// landing buffers and every inverse result is FOLDED into Post::NACC per-point accumulators as soon as it exists
+// (WGC99: conv = u1 + th u2 + th^2 u3 / 2 and w = u2 + th u3 instead of u1, u2, u3), the last field goes to the post-op
+// directly.  A thread then holds 2 NACC + 4 doubles per point instead of 2 NF + 2, and a line slot 8.4 KB of shared
+// memory instead of 12.5 KB: three CTAs (12 warps) per SM instead of two -- the pass is bound by dependent-issue latency,
+// so resident warps are what it needs.
+//   Ctx  post.begin()                                   per-thread constants
+//   post.fold<F>(ctx, n, u, acc[NACC])                  field F < NF - 1 at one real point with density n
+//   post.finish(ctx, g, n2, accA, accB, uA, uB, red, sta, stb)   points g, g + 1: accumulators, last field, sums, staged values
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
+__device__ __forceinline__ void zinv_item_stream(const Post& post, const GenF& genf, const SPassFields& spec, const double* __restrict__ den,
+                                                 int line_begin, int line_end, int stride, int nzp, unsigned char* zarea,
+                                                 const cd* tw1, const cd* tw2, double* acc) {
+    using L = ZLayout<M, TPL>;
+    constexpr int LPW = L::kLinesPerWarp;
+    constexpr int kLineBytes = L::stream_line_bytes(Post::kDen);
+    constexpr int NACC = Post::NACC > 0 ? Post::NACC : 1;
+    constexpr int NST = Post::NST > 0 ? Post::NST : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / TPL, t = lane % TPL;
+    unsigned char* slot = zarea + (size_t)(warp * LPW + sub) * kLineBytes;
+    cd* S = reinterpret_cast<cd*>(slot);
+    cd* sp = S + L::kScratch;                                  // [2][kSpecLine]
+    double2* rland = reinterpret_cast<double2*>(sp + 2 * L::kSpecLine);
+    const typename Post::Ctx ctx = post.begin();
+
+    auto issue_spec = [&](int f, int line, int buf) {
+        if (line < line_end) {
+            const cd* src = spec.f[f] + (size_t)line * nzp + t;
+            cd* dst = sp + buf * L::kSpecLine + t;
+#pragma unroll
+            for (int i = 0; i < (M + TPL) / TPL; ++i)
+                if (t + TPL * i <= M) cp_async16(dst + TPL * i, src + TPL * i);
+        }
+        cp_async_commit();
+    };
+    auto issue_real = [&](int line) {
+        if (Post::kDen && line < line_end) {
+            const double2* src = reinterpret_cast<const double2*>(den + (size_t)line * (2 * M)) + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async16(rland + t + TPL * j, src + TPL * j);
+        }
+        cp_async_commit();
+    };
+    // commit order (oldest first) at the top of every line: S0, R, S1  (NF = 1: S0, R)
+    int line0 = line_begin + warp * LPW;
+    issue_spec(0, line0 + sub, 0);
+    issue_real(line0 + sub);
+    if constexpr (NF > 1) issue_spec(1, line0 + sub, 1);
+    int par = 0;          // ring position of the line's first field (flips from line to line when NF is odd)
+    for (; line0 < line_end; line0 += stride) {
+        const int line = line0 + sub;
+        const bool live = line < line_end;
+        const int next = line + stride;
+        const size_t base = (size_t)line * (2 * M);
+        double aA[NACC][8], aB[NACC][8];
+        double2 nn[8];
+        cd res[8];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            if constexpr (NF == 1) cp_async_wait<0>();
+            else if (f == NF - 1) cp_async_wait<2>();
+            else cp_async_wait<1>();
+            __syncwarp();
+            const int buf = NF == 1 ? 0 : ((par + f) & 1);
+            zinv_field<M, TPL>(sp + buf * L::kSpecLine, res, S, tw1, tw2, t);      // ends with __syncwarp: the buffer is free
+            if constexpr (NF == 1) {
+                issue_spec(0, next, 0);
+                issue_real(next);
+            } else {
+                if (f + 2 < NF) issue_spec(f + 2, line, buf);
+                else issue_spec(f + 2 - NF, next, buf);
+            }
+            if (f < NF - 1) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const double2 n2 = Post::kDen ? rland[t + TPL * fft_nat<8>(r)] : make_double2(0.0, 0.0);
+                    double a[NACC], b[NACC];
+#pragma unroll
+                    for (int q = 0; q < NACC; ++q) { a[q] = aA[q][r]; b[q] = aB[q][r]; }
+                    if (f == 0) post.template fold<0>(ctx, n2.x, res[r].x, a), post.template fold<0>(ctx, n2.y, res[r].y, b);
+                    else if (f == 1) post.template fold<1>(ctx, n2.x, res[r].x, a), post.template fold<1>(ctx, n2.y, res[r].y, b);
+                    else post.template fold<2>(ctx, n2.x, res[r].x, a), post.template fold<2>(ctx, n2.y, res[r].y, b);
+#pragma unroll
+                    for (int q = 0; q < NACC; ++q) { aA[q][r] = a[q]; aB[q][r] = b[q]; }
+                }
+            }
+            if (NF > 1 && f == NF - 2) {
+                // the density line moves to registers for the post-op, its landing zone takes the next line's
+#pragma unroll
+                for (int r = 0; r < 8; ++r) nn[r] = Post::kDen ? rland[t + TPL * fft_nat<8>(r)] : make_double2(0.0, 0.0);
+                issue_real(next);
+            }
+        }
+        if constexpr (NF == 1) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) nn[r] = make_double2(0.0, 0.0);
+        }
+        double sa[NST][8], sb[NST][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double a[NACC], b[NACC], st0[NST], st1[NST];
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) { a[q] = aA[q][r]; b[q] = aB[q][r]; }
+#pragma unroll
+            for (int q = 0; q < NST; ++q) { st0[q] = 1.0; st1[q] = 1.0; }
+            if (live) post.finish(ctx, base + 2 * (t + TPL * fft_nat<8>(r)), nn[r], a, b, res[r].x, res[r].y, acc, st0, st1);
+#pragma unroll
+            for (int q = 0; q < NST; ++q) { sa[q][fft_nat<8>(r)] = st0[q]; sb[q][fft_nat<8>(r)] = st1[q]; }
+        }
+        if constexpr (NFW > 0) {
+            __syncwarp();
+            const size_t orow = (size_t)(live ? line : line_begin) * nzp;
+            zfwd_field<M, TPL, 0>(genf, sa, sb, S, tw1, tw2, t, spec.f[0] + orow, live);
+            if constexpr (NFW > 1) zfwd_field<M, TPL, 1>(genf, sa, sb, S, tw1, tw2, t, spec.f[1] + orow, live);
+            if constexpr (NFW > 2) zfwd_field<M, TPL, 2>(genf, sa, sb, S, tw1, tw2, t, spec.f[2] + orow, live);
+            if constexpr (NFW > 3) zfwd_field<M, TPL, 3>(genf, sa, sb, S, tw1, tw2, t, spec.f[3] + orow, live);
+        }
+        if constexpr (NF > 1) par = (par + NF) & 1;
+    }
+    cp_async_wait<0>();
+}
+
 struct GenNone {                       // placeholder GenF of inverse kernels without a forward part
     static constexpr int NST = 1, NIN = 1;
     __device__ void stage(const double2*, double*, double*) const {}
@@ -381,10 +506,12 @@ struct GenNone {                       // placeholder GenF of inverse kernels wi
 // NFW > 0: NFW fields generated by GenF from the post-op's staged values are transformed forward again and written over
 // the lines of spec.f[0..NFW-1] (WGC99: the mid pass and the forward z pass of the second batch in one kernel -- P never
 // travels through HBM)
-template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF>
-__global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, GenF genf, SPassFields spec, const double* __restrict__ den,
-                                                     const double* __restrict__ vin, int nlines, int nzp,
-                                                     double* __restrict__ partials) {
+// STREAM: zinv_item_stream (spectral lines through a two-buffer ring, results folded as they arrive; 3 CTAs per SM) instead
+// of zinv_item (all NF lines landed and transformed before the post-op; 2 CTAs per SM)
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF, bool STREAM>
+__global__ void __launch_bounds__(128, STREAM ? 3 : 2) zinv_kernel(Post post, GenF genf, SPassFields spec, const double* __restrict__ den,
+                                                                  const double* __restrict__ vin, int nlines, int nzp,
+                                                                  double* __restrict__ partials) {
     using L = ZLayout<M, TPL>;
     constexpr int LPW = L::kLinesPerWarp;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -395,8 +522,12 @@ __global__ void __launch_bounds__(128, 2) zinv_kernel(Post post, GenF genf, SPas
     double acc[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int r = 0; r < (NRED > 0 ? NRED : 1); ++r) acc[r] = 0.0;
-    zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, blockIdx.x * wpb * LPW, nlines, gridDim.x * wpb * LPW, nzp,
-                                                 smem_raw + L::kTwBytes, tw1, tw2, acc);
+    if constexpr (STREAM)
+        zinv_item_stream<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, blockIdx.x * wpb * LPW, nlines, gridDim.x * wpb * LPW,
+                                                            nzp, smem_raw + L::kTwBytes, tw1, tw2, acc);
+    else
+        zinv_item<M, TPL, NF, NRED, Post, NFW, GenF>(post, genf, spec, den, vin, blockIdx.x * wpb * LPW, nlines, gridDim.x * wpb * LPW, nzp,
+                                                     smem_raw + L::kTwBytes, tw1, tw2, acc);
     if constexpr (NRED > 0) {
         __shared__ double red[NRED][4];
 #pragma unroll
@@ -440,14 +571,15 @@ int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const d
     return PAD_OK;
 }
 
-template <int M, int TPL, int NF, int NRED, class Post, int NFW = 0, class GenF = GenNone>
-int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
-                const double* den, const double* vin, int* grid_out, GenF genf = GenF{}) {
+template <int M, int TPL, int NF, int NRED, class Post, int NFW, class GenF, bool STREAM>
+int launch_zinv_impl(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
+                     const double* den, const double* vin, int* grid_out, GenF genf) {
     constexpr int warps = 4;
     using L = ZLayout<M, TPL>;
     constexpr int NREAL = (Post::kDen ? 1 : 0) + (Post::kVin ? 1 : 0);
-    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::inv_line_bytes(NF, NREAL);
-    auto kern = zinv_kernel<M, TPL, NF, NRED, Post, NFW, GenF>;
+    constexpr int line_bytes = STREAM ? L::stream_line_bytes(Post::kDen) : L::inv_line_bytes(NF, NREAL);
+    constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * line_bytes;
+    auto kern = zinv_kernel<M, TPL, NF, NRED, Post, NFW, GenF, STREAM>;
     static bool attr_done[64] = {false};
     if (!attr_done[p->device & 63]) {
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -455,7 +587,8 @@ int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* 
     }
     const int nlines = p->n0 * p->n1;
     constexpr int by_smem = (227 * 1024) / (smem + 1024);
-    const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < 2 ? by_smem : 2);
+    constexpr int want = STREAM ? 3 : 2;
+    const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < want ? by_smem : want);
     SPassFields in;
     in.f[0] = const_cast<cd*>(i0); in.f[1] = const_cast<cd*>(i1); in.f[2] = const_cast<cd*>(i2); in.f[3] = const_cast<cd*>(i3);
     kern<<<grid, warps * 32, smem, s>>>(post, genf, in, den, vin, nlines, p->nzp, p->partials);
@@ -463,6 +596,14 @@ int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* 
     if (grid_out) *grid_out = grid;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
+}
+
+template <int M, int TPL, int NF, int NRED, class Post, int NFW = 0, class GenF = GenNone>
+int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
+                const double* den, const double* vin, int* grid_out, GenF genf = GenF{}) {
+    if (g_pad_zinv_stream)
+        return launch_zinv_impl<M, TPL, NF, NRED, Post, NFW, GenF, true>(p, s, post, i0, i1, i2, i3, den, vin, grid_out, genf);
+    return launch_zinv_impl<M, TPL, NF, NRED, Post, NFW, GenF, false>(p, s, post, i0, i1, i2, i3, den, vin, grid_out, genf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -844,13 +985,26 @@ int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
 struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:968-981), kernels pre-scaled by 1/N
     static constexpr int kRing = 8;
     const double2* K4;                 // [(kx n1 + ky) nzp + z][2]: (W0, K1), (K2, K3)
+    int fold;                          // orthorhombic cell: K(kx, ky, kz) = K(|kx|, |ky|, kz) bit for bit, so only the quarter
+                                       // kx <= n0/2, ky <= n1/2 of the table is ever read (72 of 285 MB at 256^3: L2 sized)
     struct Coef { double2 a, b; };
-    struct Line {};
-    __device__ __forceinline__ Line line(const KGeom&, int, int) const { return Line{}; }
-    __device__ __forceinline__ Coef fetch(const Line&, int, size_t pidx, bool live) const {
+    struct Line { size_t prow, kxs; int n0; };
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const {
+        const int fy = ky <= g.n1 - ky ? ky : g.n1 - ky;
+        return Line{(size_t)fy * g.nzp_pad + z, (size_t)g.n1 * g.nzp_pad, g.n0};
+    }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const {
         Coef c;
         c.a = c.b = make_double2(0.0, 0.0);
-        if (live) { c.a = __ldcs(K4 + 2 * pidx); c.b = __ldcs(K4 + 2 * pidx + 1); }
+        if (live) {
+            if (fold) {
+                const int fx = kx <= l.n0 - kx ? kx : l.n0 - kx;
+                pidx = l.prow + (size_t)fx * l.kxs;
+                c.a = __ldg(K4 + 2 * pidx); c.b = __ldg(K4 + 2 * pidx + 1);
+            } else {
+                c.a = __ldcs(K4 + 2 * pidx); c.b = __ldcs(K4 + 2 * pidx + 1);
+            }
+        }
         return c;
     }
     __device__ __forceinline__ void apply(const Coef& k, cd* q) const {
@@ -922,6 +1076,15 @@ struct PostStore {                     // plain c2r of one real field
     double* out;
     __device__ void apply(size_t g, double2, double2, const double* u0, const double* u1, double*, double*, double*) const {
         *reinterpret_cast<double2*>(out + g) = make_double2(u0[0], u1[0]);
+    }
+    // streamed kernel
+    static constexpr int NACC = 0;
+    typedef int Ctx;
+    __device__ Ctx begin() const { return 0; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double, double*) const {}
+    __device__ void finish(const Ctx&, size_t g, double2, const double*, const double*, double uA, double uB, double*, double*, double*) const {
+        *reinterpret_cast<double2*>(out + g) = make_double2(uA, uB);
     }
 };
 
@@ -1025,6 +1188,45 @@ __device__ __noinline__ MidOut wgc_mid_point(double n, double n_ref, double alph
     return o;
 }
 
+// streamed kernels: the three convolution fields are folded as they arrive into  conv = u1 + th u2 + th^2 u3 / 2  and
+// w = u2 + th u3  (th = n - n_ref); both the mid and the final pass need exactly these two combinations
+struct WgcCtx {
+    double n_ref;
+};
+template <int F>
+__device__ __forceinline__ void wgc_fold(const WgcCtx& c, double n, double u, double* a) {
+    const double th = n - c.n_ref;
+    if constexpr (F == 0) { a[0] = u; a[1] = 0.0; }
+    else if constexpr (F == 1) { a[0] = fma(th, u, a[0]); a[1] = u; }
+    else { a[0] = fma(0.5 * th * th, u, a[0]); a[1] = fma(th, u, a[1]); }
+}
+__device__ __noinline__ MidOut wgc_mid_point_cw(double n, double alpha, double conv, double w, double lap) {
+    MidOut o;
+    if (fm_ok(n)) {
+        const double l = fm_log(n);
+        o.P = fm_exp(alpha * l);
+        const double c2 = fm_exp((2.0 / 3.0) * l);
+        const double y = fm_rsqrt(n);
+        const double chi = fm_sqrt_from_rsqrt(n, y);
+        o.e_tf = kCTF * n * c2;
+        o.e_vw = chi * lap;
+        o.e_nl = o.P * conv;
+        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * o.P * (y * y) * conv + o.P * w);
+        return o;
+    }
+    o.P = exp(alpha * log(n));
+    const double c = cbrt(n);
+    const double chi = n != 0.0 ? sqrt(n) : 0.0;
+    o.e_tf = kCTF * n * c * c;
+    o.e_vw = chi * lap;
+    o.e_nl = o.P * conv;
+    double v = (5.0 / 3.0) * kCTF * c * c;
+    if (n != 0.0) v += -0.5 * lap / chi;
+    v += kCTF * (alpha * o.P / n * conv + o.P * w);
+    o.v = v;
+    return o;
+}
+
 struct PostWgcMid {
     static constexpr bool kDen = true, kVin = false;
     static constexpr int NST = 2;              // staged for the second forward batch (GenWgcP): n, P = n^alpha
@@ -1048,6 +1250,27 @@ struct PostWgcMid {
             if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
         }
     }
+    // streamed kernel: fields u1, u2, u3 folded, lap(chi) last
+    static constexpr int NACC = 2;
+    typedef WgcCtx Ctx;
+    __device__ Ctx begin() const { return WgcCtx{scal[S_NREF]}; }
+    template <int F>
+    __device__ void fold(const Ctx& c, double n, double u, double* a) const { wgc_fold<F>(c, n, u, a); }
+    __device__ void finish(const Ctx&, size_t g, double2 n, const double* aA, const double* aB, double lapA, double lapB, double* acc,
+                           double* sta, double* stb) const {
+        double2 vo = make_double2(0.0, 0.0);
+        if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+        const MidOut a = wgc_mid_point_cw(n.x, alpha, aA[0], aA[1], lapA);
+        const MidOut b = wgc_mid_point_cw(n.y, alpha, aB[0], aB[1], lapB);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
+        sta[0] = n.x; sta[1] = a.P;
+        stb[0] = n.y; stb[1] = b.P;
+        if (want_v) {
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+            if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
+        }
+    }
 };
 
 // ---- fused term list (system.py:759-772 with WGC99 as the kinetic term): the local terms LDA exchange, Perdew-Zunger
@@ -1056,11 +1279,9 @@ struct PostWgcMid {
 struct MidOutT {
     double v, P, e_tf, e_vw, e_nl, e_loc;
 };
-__device__ __noinline__ MidOutT wgc_mid_point_total(double n, double n_ref, double alpha, double u1, double u2, double u3,
-                                                   double lap, int mask, double vext) {
+__device__ __noinline__ MidOutT wgc_mid_point_total_cw(double n, double alpha, double conv, double wsum, double lap, int mask,
+                                                      double vext) {
     MidOutT o;
-    const double th = n - n_ref;
-    const double conv = u1 + th * (u2 + 0.5 * th * u3);
     double e_loc = 0.0, v_loc = 0.0;
     if (fm_ok(n)) {
         const double l = fm_log(n);
@@ -1072,7 +1293,7 @@ __device__ __noinline__ MidOutT wgc_mid_point_total(double n, double n_ref, doub
         o.e_tf = kCTF * n * c2;
         o.e_vw = chi * lap;
         o.e_nl = o.P * conv;
-        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * o.P * inv_n * conv + o.P * (u2 + th * u3));
+        o.v = (5.0 / 3.0) * kCTF * c2 - 0.5 * lap * y + kCTF * (alpha * o.P * inv_n * conv + o.P * wsum);
         if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
             const double c13 = c2 * c2 * inv_n;                       // n^(1/3)
             if (mask & PAD_LOCAL_LDAX) { e_loc += kCX * n * c13; v_loc += (4.0 / 3.0) * kCX * c13; }
@@ -1103,7 +1324,7 @@ __device__ __noinline__ MidOutT wgc_mid_point_total(double n, double n_ref, doub
         o.e_nl = o.P * conv;
         double v = (5.0 / 3.0) * kCTF * c * c;
         if (n != 0.0) v += -0.5 * lap / chi;
-        v += kCTF * (alpha * o.P / n * conv + o.P * (u2 + th * u3));
+        v += kCTF * (alpha * o.P / n * conv + o.P * wsum);
         o.v = v;
         if (mask & PAD_LOCAL_LDAX) { e_loc += kCX * n * c; v_loc += (4.0 / 3.0) * kCX * c; }
         if (mask & PAD_LOCAL_PZC) { const PZ r = pz_correlation(n, c); e_loc += r.e; v_loc += r.v; }
@@ -1114,12 +1335,19 @@ __device__ __noinline__ MidOutT wgc_mid_point_total(double n, double n_ref, doub
     return o;
 }
 
+__device__ __forceinline__ MidOutT wgc_mid_point_total(double n, double n_ref, double alpha, double u1, double u2, double u3,
+                                                      double lap, int mask, double vext) {
+    const double th = n - n_ref;
+    return wgc_mid_point_total_cw(n, alpha, u1 + th * (u2 + 0.5 * th * u3), u2 + th * u3, lap, mask, vext);
+}
+
 struct PostWgcMidT {                           // NRED = 4: TF, vW, non-local, local terms
     static constexpr bool kDen = true, kVin = false;
     static constexpr int NST = 2;
     const double* scal;
     double* v_out;
     const double* v_ext;                       // IonElectron (may be null when the bit is not set)
+    double* P_out;                             // null: P stays on chip (forward part fused)
     double alpha;
     int accumulate, mask;
     __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc, double* sta, double* stb) const {
@@ -1134,6 +1362,26 @@ struct PostWgcMidT {                           // NRED = 4: TF, vW, non-local, l
         sta[0] = n.x; sta[1] = a.P;
         stb[0] = n.y; stb[1] = b.P;
         *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+        if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
+    }
+    static constexpr int NACC = 2;
+    typedef WgcCtx Ctx;
+    __device__ Ctx begin() const { return WgcCtx{scal[S_NREF]}; }
+    template <int F>
+    __device__ void fold(const Ctx& c, double n, double u, double* a) const { wgc_fold<F>(c, n, u, a); }
+    __device__ void finish(const Ctx&, size_t g, double2 n, const double* aA, const double* aB, double lapA, double lapB, double* acc,
+                           double* sta, double* stb) const {
+        double2 vo = make_double2(0.0, 0.0), ve = make_double2(0.0, 0.0);
+        if (accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+        if (mask & PAD_LOCAL_IONEL) ve = *reinterpret_cast<const double2*>(v_ext + g);
+        const MidOutT a = wgc_mid_point_total_cw(n.x, alpha, aA[0], aA[1], lapA, mask, ve.x);
+        const MidOutT b = wgc_mid_point_total_cw(n.y, alpha, aB[0], aB[1], lapB, mask, ve.y);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl; acc[3] += a.e_loc;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl; acc[3] += b.e_loc;
+        sta[0] = n.x; sta[1] = a.P;
+        stb[0] = n.y; stb[1] = b.P;
+        *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+        if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
     }
 };
 
@@ -1152,6 +1400,19 @@ __device__ __noinline__ double wgc_fin_point(double n, double n_ref, double beta
     return kCTF * (da * g1 + (da * th + a) * g2 + (0.5 * da * th * th + a * th) * g3);
 }
 
+__device__ __noinline__ double wgc_fin_point_cw(double n, double beta, double s1, double s2) {
+    double a, da;
+    if (fm_ok(n)) {
+        const double l = fm_log(n);
+        a = fm_exp(beta * l);
+        da = beta * fm_exp((beta - 1.0) * l);
+    } else {
+        a = exp(beta * log(n));
+        da = beta * a / n;
+    }
+    return kCTF * (da * s1 + a * s2);
+}
+
 struct PostWgcFin {
     static constexpr bool kDen = true, kVin = true;
     static constexpr int NST = 0;
@@ -1162,6 +1423,22 @@ struct PostWgcFin {
         const double n_ref = scal[S_NREF];
         v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]);
         v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]);
+        *reinterpret_cast<double2*>(v_out + g) = v;
+    }
+    // streamed kernel: g1, g2 folded, g3 last; the first half of the potential is read from v_out itself
+    static constexpr int NACC = 2;
+    typedef WgcCtx Ctx;
+    __device__ Ctx begin() const { return WgcCtx{scal[S_NREF]}; }
+    template <int F>
+    __device__ void fold(const Ctx& c, double n, double u, double* a) const { wgc_fold<F>(c, n, u, a); }
+    __device__ void finish(const Ctx& c, size_t g, double2 n, const double* aA, const double* aB, double g3A, double g3B, double*,
+                           double*, double*) const {
+        double2 v = *reinterpret_cast<const double2*>(v_out + g);
+        double a[2] = {aA[0], aA[1]}, b[2] = {aB[0], aB[1]};
+        wgc_fold<2>(c, n.x, g3A, a);
+        wgc_fold<2>(c, n.y, g3B, b);
+        v.x += wgc_fin_point_cw(n.x, beta, a[0], a[1]);
+        v.y += wgc_fin_point_cw(n.y, beta, b[0], b[1]);
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
 };
@@ -1177,6 +1454,19 @@ struct PostWgcFinH {                           // final pass of the fused term l
         v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]) + u0[3];
         v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]) + u1[3];
         acc[0] += n.x * u0[3] + n.y * u1[3];
+        *reinterpret_cast<double2*>(v_out + g) = v;
+    }
+    static constexpr int NACC = 2;
+    typedef WgcCtx Ctx;
+    __device__ Ctx begin() const { return WgcCtx{scal[S_NREF]}; }
+    template <int F>
+    __device__ void fold(const Ctx& c, double n, double u, double* a) const { wgc_fold<F>(c, n, u, a); }
+    __device__ void finish(const Ctx&, size_t g, double2 n, const double* aA, const double* aB, double vhA, double vhB, double* acc,
+                           double*, double*) const {
+        double2 v = *reinterpret_cast<const double2*>(v_out + g);
+        v.x += wgc_fin_point_cw(n.x, beta, aA[0], aA[1]) + vhA;
+        v.y += wgc_fin_point_cw(n.y, beta, aB[0], aB[1]) + vhB;
+        acc[0] += n.x * vhA + n.y * vhB;
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
 };
@@ -1356,7 +1646,10 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     const double* scal = p->scal;
     const double inv_n = p->geom.inv_n;
     const KGeom geom = p->geom;
-    const MixWgc mixw{reinterpret_cast<const double2*>(kern)};
+    // fold only where the fused x pass reads the table (own passes); the k-space kernel of the cuFFT (x, y) fallback indexes it plainly
+    const bool ortho = p->recip[1] == 0.0 && p->recip[2] == 0.0 && p->recip[3] == 0.0 && p->recip[5] == 0.0 && p->recip[6] == 0.0 &&
+                       p->recip[7] == 0.0;
+    const MixWgc mixw{reinterpret_cast<const double2*>(kern), (g_pad_fold_table && ortho && own) ? 1 : 0};
     GenWgcA genA{scal, beta};
 
     if (own && want_v) {
@@ -1383,16 +1676,46 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         const bool hartree = ex && ex->hartree;
         const FinalizeArgs a = wgc_energy_args(p, 0, ex ? 4 : 3, accumulate, E_out);
         const FinalizeArgs* fa = E_out ? &a : nullptr;
-        if (ex && hartree) {
-            PostWgcMidT mid{scal, v_out, ex->v_ext, alpha, accumulate, ex->local_mask};
+        if (ex && !g_pad_fuse_mid && !piped) {
+            // local terms in the mid pass; P = n^alpha goes through HBM to a separate (16 warps / SM) forward z kernel that
+            // also transforms the density itself when the Hartree term is wanted
+            double* Pbuf;
+            PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
+            PostWgcMidT mid{scal, v_out, ex->v_ext, Pbuf, alpha, accumulate, ex->local_mask};
+            PAD_TRY((wgc_inverse_stage<4, 4, PostWgcMidT, 0>(p, s, false, mid, GenNone{}, B, den, nullptr, fa, "y-inv (4 fields)",
+                                                            "z-c2r (4 fields) + energy/v1/local/P", "", "")));
+            if (hartree) {
+                ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, GenWgcP4{scal}, den, Pbuf, B[0], B[1], B[2], B[3]))));
+                pad_stage_mark("gen P,P.th,P.th2,n + z-r2c (4 fields)", s);
+                PAD_TRY(launch_spass(p, s, 1, -1, B, 4));
+                pad_stage_mark("y-fwd (4 fields)", s);
+            } else {
+                ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, GenWgcP{scal}, den, Pbuf, B[0], B[1], B[2], nullptr))));
+                pad_stage_mark("gen P,P.th,P.th2 + z-r2c (3 fields)", s);
+                PAD_TRY(launch_spass(p, s, 1, -1, B, 3));
+                pad_stage_mark("y-fwd (3 fields)", s);
+            }
+        } else if (ex && hartree) {
+            PostWgcMidT mid{scal, v_out, ex->v_ext, nullptr, alpha, accumulate, ex->local_mask};
             PAD_TRY((wgc_inverse_stage<4, 4, PostWgcMidT, 4>(p, s, piped, mid, GenWgcP4{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
                                                             "z-c2r (4) + energy/v1/local + gen P..,n + z-r2c (4)", "y-fwd (4 fields)",
                                                             "[y-inv (4) + z-c2r + energy/v1/local + gen P..,n + z-r2c + y-fwd (4)]")));
         } else if (ex) {
-            PostWgcMidT mid{scal, v_out, ex->v_ext, alpha, accumulate, ex->local_mask};
+            PostWgcMidT mid{scal, v_out, ex->v_ext, nullptr, alpha, accumulate, ex->local_mask};
             PAD_TRY((wgc_inverse_stage<4, 4, PostWgcMidT, 3>(p, s, piped, mid, GenWgcP{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
                                                             "z-c2r (4) + energy/v1/local + gen P.. + z-r2c (3)", "y-fwd (3 fields)",
                                                             "[y-inv (4) + z-c2r + energy/v1/local + gen P.. + z-r2c + y-fwd (3)]")));
+        } else if (!g_pad_fuse_mid && !piped) {
+            // mid pass and the forward z pass of the second batch as two kernels: P = n^alpha travels through HBM
+            double* Pbuf;
+            PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
+            PostWgcMid mid{scal, v_out, Pbuf, alpha, accumulate, 1};
+            PAD_TRY((wgc_inverse_stage<4, 3, PostWgcMid, 0>(p, s, false, mid, GenNone{}, B, den, nullptr, fa, "y-inv (4 fields)",
+                                                           "z-c2r (4 fields) + energy/v1/P", "", "")));
+            ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, GenWgcP{scal}, den, Pbuf, B[0], B[1], B[2], nullptr))));
+            pad_stage_mark("gen P,P.th,P.th2 + z-r2c (3 fields)", s);
+            PAD_TRY(launch_spass(p, s, 1, -1, B, 3));
+            pad_stage_mark("y-fwd (3 fields)", s);
         } else {
             PostWgcMid mid{scal, v_out, nullptr, alpha, accumulate, 1};
             PAD_TRY((wgc_inverse_stage<4, 3, PostWgcMid, 3>(p, s, piped, mid, GenWgcP{scal}, B, den, nullptr, fa, "y-inv (4 fields)",
@@ -1430,7 +1753,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         cd *CA = B[0], *CB = B[1], *CC = B[2], *CX = B[3];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw.apply(mixw.fetch(MixWgc::Line{}, 0, pidx, true), q);
+            mixw.apply(mixw.fetch(MixWgc::Line{0, 0, 0}, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
             const double m = -inv_n * sym_even(k, [](double kx, double ky, double kz) { return kx * kx + ky * ky + kz * kz; });
             const cd X = CX[pidx];
@@ -1454,7 +1777,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         cd *CA = B[0], *CB = B[1], *CC = B[2];
         launch_ksp(p, s, [=] __device__(uint32_t idx, size_t pidx, const KPoint& k) {
             cd q[3] = {CA[pidx], CB[pidx], CC[pidx]};
-            mixw.apply(mixw.fetch(MixWgc::Line{}, 0, pidx, true), q);
+            mixw.apply(mixw.fetch(MixWgc::Line{0, 0, 0}, 0, pidx, true), q);
             CA[pidx] = q[0]; CB[pidx] = q[1]; CC[pidx] = q[2];
         });
         PAD_CUDA(cudaGetLastError());
@@ -1525,14 +1848,23 @@ struct MixWt {                         // fields 0 (, 1): Lindhard kernel / N;  
     const double* scal;
     const double* table;               // [(kx n1 + ky) nzp + z]
     double inv_n;
+    int fold;                          // orthorhombic cell: read only the |kx|, |ky| quarter of the table (see MixWgc)
     struct Coef { double nl, lap; };
-    typedef KLine Line;
-    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return make_kline(g, ky, z); }
+    struct Line { KLine kl; size_t prow, kxs; };
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const {
+        const int fy = ky <= g.n1 - ky ? ky : g.n1 - ky;
+        return Line{make_kline(g, ky, z), (size_t)fy * g.nzp_pad + z, (size_t)g.n1 * g.nzp_pad};
+    }
     __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const {
         Coef c{0.0, 0.0};
         if (!live) return c;
-        c.nl = __ldcs(table + pidx);
-        c.lap = -inv_n * kline_sym_even(l, kx, [](double k2) { return k2; });
+        if (fold) {
+            const int fx = kx <= l.kl.n0 - kx ? kx : l.kl.n0 - kx;
+            c.nl = __ldg(table + l.prow + (size_t)fx * l.kxs);
+        } else {
+            c.nl = __ldcs(table + pidx);
+        }
+        c.lap = -inv_n * kline_sym_even(l.kl, kx, [](double k2) { return k2; });
         return c;
     }
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const {
@@ -1599,6 +1931,24 @@ struct PostWt {
             *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
         }
     }
+    // streamed kernel: the convolution(s) are kept as they are, lap(chi) last
+    static constexpr int NACC = TWO ? 2 : 1;
+    struct Ctx { double n0a; };
+    __device__ Ctx begin() const { return Ctx{scal[S_TMP0 + 2]}; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double u, double* a) const { a[F < NACC ? F : 0] = u; }
+    __device__ void finish(const Ctx& c, size_t g, double2 n, const double* aA, const double* aB, double lapA, double lapB, double* acc,
+                           double*, double*) const {
+        const WtOut a = wt_point(n.x, alpha, beta, TWO, c.n0a, aA[0], TWO ? aA[NACC - 1] : aA[0], lapA);
+        const WtOut b = wt_point(n.y, alpha, beta, TWO, c.n0a, aB[0], TWO ? aB[NACC - 1] : aB[0], lapB);
+        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
+        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
+        if (want_v) {
+            double2 vo = make_double2(0.0, 0.0);
+            if (accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+        }
+    }
 };
 
 template <bool TWO>
@@ -1628,10 +1978,12 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     }
     pad_stage_mark("WT: Lindhard table check", s);
     GenWt<TWO> gen{scal, alpha, beta};
+    const int wt_fold = (g_pad_fold_table && p->recip[1] == 0.0 && p->recip[2] == 0.0 && p->recip[3] == 0.0 && p->recip[5] == 0.0 &&
+                         p->recip[6] == 0.0 && p->recip[7] == 0.0) ? 1 : 0;
     if (pipe_shape(p)) {
         ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, NF>(p, s, gen, den, nullptr, B))));
         pad_stage_mark("WT: [gen fields + z-r2c + y-fwd]", s);
-        PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n})));
+        PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n, wt_fold})));
         pad_stage_mark("WT: x-fwd * (Lindhard | -k^2) * x-inv", s);
         FinalizeArgs a;
         a.nblocks = 0; a.nterms = 3; a.accumulate = accumulate;
@@ -1648,7 +2000,7 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     pad_stage_mark("WT: gen fields + z-r2c", s);
     PAD_TRY(launch_spass(p, s, 1, -1, B, NF));
     pad_stage_mark("WT: y-fwd", s);
-    PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n})));
+    PAD_TRY((launch_xmix<NF>(p, s, B, MixWt<TWO>{scal, p->wt_kern, p->geom.inv_n, wt_fold})));
     pad_stage_mark("WT: x-fwd * (Lindhard | -k^2) * x-inv", s);
     PAD_TRY(launch_spass(p, s, 1, +1, B, NF));
     pad_stage_mark("WT: y-inv", s);

@@ -17,6 +17,9 @@ int g_pad_own_xy = 1;        // hand-written strided (x, y) passes with the fuse
 int g_pad_pipe = 0;          // (z, y) passes of a plane as items of one persistent kernel, handed over through the L2 (zy_pipe.cuh)
 int g_pad_pipe_lpi = 0, g_pad_pipe_tpi = 0;
 int g_pad_fuse_terms = 1;
+int g_pad_fold_table = 1;
+int g_pad_zinv_stream = 0;     // measured at 256^3: the streamed form (12 warps/SM, 168 registers) is 7-13 % slower than the batch form
+int g_pad_fuse_mid = 0;        // measured: mid + forward z in one 8-warp kernel 508 us, as two kernels 348 + 135 us
 extern "C" int pad_set_option(const char* name, int value) {
     int* slot = nullptr;
     if (!name) { pad_set_error("pad_set_option: null name"); return -1; }
@@ -24,6 +27,9 @@ extern "C" int pad_set_option(const char* name, int value) {
     else if (!strcmp(name, "own_xy")) slot = &g_pad_own_xy;
     else if (!strcmp(name, "pipe")) slot = &g_pad_pipe;
     else if (!strcmp(name, "fuse_terms")) slot = &g_pad_fuse_terms;
+    else if (!strcmp(name, "fold_table")) slot = &g_pad_fold_table;
+    else if (!strcmp(name, "zinv_stream")) slot = &g_pad_zinv_stream;
+    else if (!strcmp(name, "fuse_mid")) slot = &g_pad_fuse_mid;
     else if (!strcmp(name, "pipe_lpi")) slot = &g_pad_pipe_lpi;
     else if (!strcmp(name, "pipe_tpi")) slot = &g_pad_pipe_tpi;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }
