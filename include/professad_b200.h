@@ -181,6 +181,12 @@ typedef struct pad_species {
 } pad_species;
 /* v_ext(r) = irfftn(sum_s v_s(|k|) S_s(k)) / vol over the plan's grid; v_ext_out: N doubles */
 int pad_ionic_potential(pad_plan* plan, const pad_species* species, int n_species, double* v_ext_out, void* stream);
+/* Particle-mesh Ewald variants (System(pme_order=n), system.py:183-205 -> structure_factor_spline, ion_utils.py:218-286):
+ * B-spline spreading + one r2c + exponential-spline factors instead of the O(N_k N_ion) exact structure factor.  order: even,
+ * 2..32.  Not on slab plans.  pad_pme_structure_factor returns S(k) itself (n0 x n1 x (n2/2+1) complex), the quantity the
+ * reference's tests/test_particle_mesh_ewald.py:46-63 compares with the exact structure factor. */
+int pad_ionic_potential_pme(pad_plan* plan, const pad_species* species, int n_species, int order, double* v_ext_out, void* stream);
+int pad_pme_structure_factor(pad_plan* plan, const double* frac_dev, int n_ions, int order, double* S_out_cplx, void* stream);
 /* F_I = -d/dR_I of IonElectron(den, v_ext[R]) at fixed density, Cartesian, Ha/bohr; forces_out: DEVICE,
  * 3 * (total number of ions) doubles in species order */
 int pad_ion_forces(pad_plan* plan, const pad_species* species, int n_species, const double* den, double* forces_out,
@@ -217,6 +223,17 @@ int pad_eval_total(pad_plan* plan, const pad_terms* terms, const double* den, co
  * Every kinetic kind is covered: Wang-Teter family, WangGovindCarter99 (kernel regenerated for the strained cell) and the
  * Huang-Carter family (xi-node list held fixed, as the reference's autograd sees it, functional_tools.py:408-416). */
 int pad_stress_terms(pad_plan* plan, const pad_terms* terms, const double* den, double* stress_out, void* stream);
+
+/* ---- ion-ion interaction: replaces ion_interaction_sum (ion_utils.py:293-333; torch_nl pair list + autograd) with a
+ *      direct sweep over (ion j, image shift) candidates per ion i and closed-form derivatives.  box_host: 9 doubles (rows =
+ *      lattice vectors); cart_dev: n x 3 Cartesian coordinates (DEVICE); charges_dev: n (DEVICE); charge_total: their sum.
+ *      E_out_dev: 1 double.  dcart_dev (n x 3) = dE/dcoords, dbox_dev (9) = dE/dbox_vecs AT FIXED coords (what autograd needs
+ *      for a function of the two tensors; the stress follows through coords = frac @ box_vecs) -- either may be null.
+ *      work_dev: pad_ion_ion_work_doubles(...) doubles of DEVICE scratch.  Reference vectors: tests/test_ion_utils.py:12-147. */
+size_t pad_ion_ion_work_doubles(const double* box_host, int n, double Rc);
+int pad_ion_ion(const double* box_host, const double* cart_dev, const double* charges_dev, int n, double charge_total,
+                double Rc, double Rd, double* E_out_dev, double* dcart_dev, double* dbox_dev, double* work_dev, int device,
+                void* stream);
 
 /* ---- chi-parametrisation (system.py:830-854): n = N chi^2 / int chi^2 and the projected gradient
  *      dE/dchi_ijk = dV (N/Ntilde) 2 chi (v - mu), mu = int v n / N.  grad_out = N doubles. -------- */

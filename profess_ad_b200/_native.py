@@ -57,9 +57,13 @@ SIGNATURES = {
     'pad_eval_total': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     # pad_species* is passed as a ctypes array of _density_opt-style Structures
     'pad_ionic_potential': (_int, [_vp, _vp, _int, _vp, _vp]),
+    'pad_ionic_potential_pme': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
+    'pad_pme_structure_factor': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
     'pad_ion_forces': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'pad_ion_stress': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
     'pad_stress_terms': (_int, [_vp, _vp, _vp, _vp, _vp]),
+    'pad_ion_ion_work_doubles': (ctypes.c_size_t, [_c_double_p, _int, _dbl]),
+    'pad_ion_ion': (_int, [_c_double_p, _vp, _vp, _int, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _int, _vp]),
     'pad_chi_to_density': (_int, [_vp, _vp, _dbl, _vp, _vp]),
     'pad_chi_project': (_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
     'pad_denopt_create': (_int, [ctypes.POINTER(_vp), _vp, _vp, _vp]),

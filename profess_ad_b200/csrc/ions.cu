@@ -411,3 +411,193 @@ extern "C" int pad_ion_stress(pad_plan* p, const pad_species* species, int n_spe
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
 }
+
+// =================================================================================================
+//  Particle-mesh Ewald structure factor (Essmann et al. 1995): replaces structure_factor_spline (ion_utils.py:218-286)
+//  -- cardinal B-spline spreading of the ions onto the grid (cardinal_b_spline_values, ion_utils.py:140-204), one r2c,
+//  Euler exponential-spline factors b_a(m) (exponential_spline_b, ion_utils.py:207-215):
+//      S(k) = conj( b_0(j0) b_1(j1) b_2(j2) rfftn(Q)(k) ),   Q[(i - floor(u_a)) mod N_a ...] += prod_a M_n(u_a - floor(u_a) + i_a)
+//  O(N_ion order^3 + N log N) instead of O(N_k N_ion).  The spreading uses fp64 atomicAdd: the order of the (few)
+//  additions into a grid point varies from run to run, i.e. S is reproducible to rounding, not bit for bit.
+// =================================================================================================
+namespace {
+
+constexpr int PME_MAX_ORDER = 32;
+
+// M_n(x + i), i < n, by the Cox-de Boor recursion of cardinal_b_spline_values (x in [0, 1))
+__host__ __device__ inline void bspline_weights(double x, int order, double* M /* [PME_MAX_ORDER] */) {
+    for (int i = 0; i < order; ++i) M[i] = 0.0;
+    M[0] = x;
+    M[1] = 1.0 - x;
+    for (int n = 3; n <= order; ++n) {
+        double prev = 0.0;          // M_{n-1}[i-1]
+        for (int i = 0; i < n; ++i) {
+            const double cur = i < n - 1 ? M[i] : 0.0;          // M_{n-1}[i] (zero beyond its support)
+            const double left = (x + (double)i) * cur;
+            const double right = i >= 1 ? ((double)n - x - (double)i) * prev : 0.0;
+            M[i] = (left + right) / (double)(n - 1);
+            prev = cur;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pme_spread(const double* __restrict__ frac, int n_ions, int order, int N0, int N1, int N2,
+                                                   double* __restrict__ Q) {
+    __shared__ double w[3][PME_MAX_ORDER];
+    __shared__ int fl[3];
+    for (int ion = blockIdx.x; ion < n_ions; ion += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const int a = threadIdx.x;
+            const int N = a == 0 ? N0 : (a == 1 ? N1 : N2);
+            double f = frac[3 * ion + a];
+            f -= floor(f);
+            f -= floor(f);
+            const double u = f * (double)N;
+            const double fu = floor(u);
+            fl[a] = (int)fu;
+            bspline_weights(u - fu, order, w[a]);
+        }
+        __syncthreads();
+        const int total = order * order * order;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int i = e / (order * order), j = (e / order) % order, k = e % order;
+            int a0 = (i - fl[0]) % N0, a1 = (j - fl[1]) % N1, a2 = (k - fl[2]) % N2;
+            if (a0 < 0) a0 += N0;
+            if (a1 < 0) a1 += N1;
+            if (a2 < 0) a2 += N2;
+            atomicAdd(Q + ((size_t)a0 * N1 + a1) * N2 + a2, w[0][i] * w[1][j] * w[2][k]);
+        }
+    }
+}
+
+// host: b(m) = exp(2 pi i m (n - 1) / N) / sum_i M_n(i) exp(2 pi i m (i - 1) / N),  m < count
+void pme_b_table(int count, int N, int order, std::vector<double2>& out) {
+    double M[PME_MAX_ORDER];
+    bspline_weights(0.0, order, M);
+    out.resize(count);
+    for (int m = 0; m < count; ++m) {
+        double dr = 0.0, di = 0.0;
+        for (int i = 0; i < order; ++i) {
+            const double ph = 2.0 * kPi * (double)m * (double)(i - 1) / (double)N;
+            dr += M[i] * cos(ph);
+            di += M[i] * sin(ph);
+        }
+        const double ph = 2.0 * kPi * (double)m * (double)(order - 1) / (double)N;
+        const double nr = cos(ph), ni = sin(ph), d2 = dr * dr + di * di;
+        out[m] = make_double2((nr * dr + ni * di) / d2, (ni * dr - nr * di) / d2);
+    }
+}
+
+// G(k) (+)= v_s(|k|) conj(b0 b1 b2 Qhat(k)) / vol, Hermitian part on the special points (as k_ion_spectrum);
+// raw: plain S(k) into out, no potential factor, no symmetrisation
+__global__ void __launch_bounds__(PAD_THREADS) k_pme_spectrum(KGeom g, uint32_t nk, UniformTable T, double z, const double2* __restrict__ Qh,
+                                                            const double2* __restrict__ b0, const double2* __restrict__ b1,
+                                                            const double2* __restrict__ b2, double inv_vol, int accumulate, int raw,
+                                                            double2* __restrict__ out) {
+    const uint32_t stride = gridDim.x * PAD_THREADS;
+    for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
+        const KPoint p = make_kpoint(g, idx);
+        auto S_at = [&](int j0, int j1, int j2) {
+            const double2 q = Qh[((size_t)j0 * g.n1 + j1) * g.nzh + j2];
+            const double2 b = cmul(cmul(b0[j0], b1[j1]), b2[j2]);
+            const double2 t = cmul(b, q);
+            return make_double2(t.x, -t.y);
+        };
+        const double2 S = S_at(p.j0, p.j1, p.j2);
+        double2 G;
+        if (raw) {
+            G = S;
+        } else {
+            const double f = recpot_value(T, z, p.kx, p.ky, p.kz);
+            G = make_double2(f * S.x, f * S.y);
+            if (p.special) {
+                const double2 Sb = S_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2);
+                const double fb = recpot_value(T, z, p.px, p.py, p.pz);
+                G.x = 0.5 * (G.x + fb * Sb.x);
+                G.y = 0.5 * (G.y - fb * Sb.y);
+            }
+            G.x *= inv_vol; G.y *= inv_vol;
+        }
+        double2 o = accumulate ? out[idx] : make_double2(0.0, 0.0);
+        o.x += G.x; o.y += G.y;
+        out[idx] = o;
+    }
+}
+
+// spread + r2c + b tables of one species; Qhat in cbuf 1, b tables in *btab (device, caller frees)
+int pme_prepare(pad_plan* p, const double* frac_dev, int n_ions, int order, cudaStream_t s, cufftDoubleComplex** Qh, double2** btab) {
+    if (p->dist) { pad_set_error("particle-mesh Ewald structure factor: not available on slab plans (use the exact one)"); return PAD_ERR_ARG; }
+    if (order < 2 || order > PME_MAX_ORDER || (order & 1)) { pad_set_error("Requires even order 2 <= n <= %d", PME_MAX_ORDER); return PAD_ERR_ARG; }
+    double* Q;
+    PAD_TRY(pad_get_rbuf(p, 0, &Q));
+    PAD_TRY(pad_get_cbuf(p, 1, Qh));
+    PAD_CUDA(cudaMemsetAsync(Q, 0, sizeof(double) * p->N, s));
+    if (n_ions > 0) {
+        k_pme_spread<<<n_ions < 148 * 8 ? n_ions : 148 * 8, 128, 0, s>>>(frac_dev, n_ions, order, p->n0, p->n1, p->n2, Q);
+        ++g_pad_launches;
+    }
+    PAD_TRY(pad_fft_forward(p, Q, *Qh, s));
+    std::vector<double2> h0, h1, h2, all;
+    pme_b_table(p->n0, p->n0, order, h0);
+    pme_b_table(p->n1, p->n1, order, h1);
+    pme_b_table(p->nzh, p->n2, order, h2);
+    all.insert(all.end(), h0.begin(), h0.end());
+    all.insert(all.end(), h1.begin(), h1.end());
+    all.insert(all.end(), h2.begin(), h2.end());
+    PAD_CUDA(cudaMalloc(btab, sizeof(double2) * all.size()));
+    PAD_CUDA(cudaMemcpyAsync(*btab, all.data(), sizeof(double2) * all.size(), cudaMemcpyHostToDevice, s));
+    PAD_CUDA(cudaStreamSynchronize(s));       // `all` is pageable host memory that dies with this frame
+    return PAD_OK;
+}
+
+}  // namespace
+
+// S(k) of the particle-mesh scheme over the half spectrum (n0, n1, n2/2 + 1), complex: what structure_factor_spline returns
+extern "C" int pad_pme_structure_factor(pad_plan* p, const double* frac_dev, int n_ions, int order, double* S_out_cplx, void* stream) {
+    if (!p || !frac_dev || !S_out_cplx || n_ions < 1) { pad_set_error("pad_pme_structure_factor: bad argument"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cufftDoubleComplex* Qh;
+    double2* bt = nullptr;
+    PAD_TRY(pme_prepare(p, frac_dev, n_ions, order, s, &Qh, &bt));
+    UniformTable T{};
+    k_pme_spectrum<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, T, 0.0, reinterpret_cast<const double2*>(Qh), bt,
+                                                            bt + p->n0, bt + p->n0 + p->n1, 0.0, 0, 1,
+                                                            reinterpret_cast<double2*>(S_out_cplx));
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    PAD_CUDA(cudaStreamSynchronize(s));
+    cudaFree(bt);
+    return PAD_OK;
+}
+
+// v_ext with particle-mesh structure factors: System.__potential_from_ions with pme_order (system.py:183-205)
+extern "C" int pad_ionic_potential_pme(pad_plan* p, const pad_species* species, int n_species, int order, double* v_ext_out,
+                                       void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ionic_potential_pme"));
+    if (!v_ext_out) { pad_set_error("pad_ionic_potential_pme: null output"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cufftDoubleComplex* G;
+    PAD_TRY(pad_get_cbuf(p, 0, &G));
+    for (int sI = 0; sI < n_species; ++sI) {
+        IonScratch W;
+        UniformTable T;
+        pad_species tab_only = species[sI];
+        tab_only.n_ions = 0;                                    // only the table slopes are needed, no phase tables
+        PAD_TRY(prepare_species(p, tab_only, s, W, T));
+        cufftDoubleComplex* Qh;
+        double2* bt = nullptr;
+        PAD_TRY(pme_prepare(p, species[sI].frac_dev, species[sI].n_ions, order, s, &Qh, &bt));
+        k_pme_spectrum<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, T, species[sI].z,
+                                                                reinterpret_cast<const double2*>(Qh), bt, bt + p->n0, bt + p->n0 + p->n1,
+                                                                1.0 / p->vol, sI > 0, 0, reinterpret_cast<double2*>(G));
+        ++g_pad_launches;
+        PAD_CUDA(cudaGetLastError());
+        PAD_CUDA(cudaStreamSynchronize(s));
+        cudaFree(bt);
+    }
+    PAD_TRY(pad_fft_inverse(p, G, v_ext_out, s));
+    return PAD_OK;
+}

@@ -98,9 +98,10 @@ def _pad_species_array(species, device):
     return arr, keep
 
 
-def ionic_potential(box_vecs, shape, species):
-    """v_ext on the grid from the ion positions, one C-ABI call (pad_ionic_potential): exact structure factor x
-    interpolated local pseudopotential -> c2r.  ``species`` = [(recpot path, (n, 3) fractional coordinates), ...].
+def ionic_potential(box_vecs, shape, species, pme_order=None):
+    """v_ext on the grid from the ion positions, one C-ABI call: structure factor x interpolated local pseudopotential
+    -> c2r.  ``species`` = [(recpot path, (n, 3) fractional coordinates), ...].  ``pme_order`` None: exact structure factor
+    (pad_ionic_potential); even n: particle-mesh Ewald of that spline order (pad_ionic_potential_pme).
     Inside ``parallel.slab(...)`` ``shape`` is the LOCAL slab shape and the local slab of v_ext is returned.
     Replaces System.__potential_from_ions (system.py:183-205)."""
     from . import _native
@@ -109,7 +110,12 @@ def ionic_potential(box_vecs, shape, species):
     _native.require_cuda(v_ext, 'box_vecs')
     plan = _native.get_plan(box_vecs, v_ext)
     arr, keep = _pad_species_array(species, dev)
-    _native.check(plan.lib.pad_ionic_potential(plan.handle, arr, len(species), _native.ptr(v_ext), _native.stream_ptr(dev)))
+    if pme_order is None:
+        _native.check(plan.lib.pad_ionic_potential(plan.handle, arr, len(species), _native.ptr(v_ext), _native.stream_ptr(dev)))
+    else:
+        assert (pme_order % 2 == 0) & (pme_order >= 2), 'Requires even order n ≥ 2'
+        _native.check(plan.lib.pad_ionic_potential_pme(plan.handle, arr, len(species), int(pme_order), _native.ptr(v_ext),
+                                                       _native.stream_ptr(dev)))
     del keep
     return v_ext
 
@@ -211,8 +217,23 @@ def exponential_spline_b(m, N, order):
 
 
 def structure_factor_spline(box_vecs, shape, cart_ion_coords, order):
-    """Particle-mesh Ewald structure factor (ion_utils.py:218-286; Essmann et al. 1995): B-spline
-    charge spreading as ONE scatter-add over (ion, order^3 stencil), FFT, exponential-spline factors."""
+    """Particle-mesh Ewald structure factor (ion_utils.py:218-286; Essmann et al. 1995).  CUDA tensors: native spreading
+    kernel + r2c + exponential-spline factors (pad_pme_structure_factor); CPU tensors (host-side checks): the torch
+    restatement below -- B-spline charge spreading as ONE scatter-add over (ion, order^3 stencil), FFT, b factors."""
+    if cart_ion_coords.is_cuda and not cart_ion_coords.requires_grad and not box_vecs.requires_grad and order <= 32:
+        from . import _native
+        dev = cart_ion_coords.device
+        frac = torch.matmul(cart_ion_coords, torch.linalg.inv(box_vecs)).double().contiguous()
+        probe = torch.empty(tuple(int(n) for n in shape), dtype=torch.double, device=dev)
+        plan = _native.get_plan(box_vecs, probe)
+        S = torch.empty((int(shape[0]), int(shape[1]), int(shape[2]) // 2 + 1), dtype=torch.complex128, device=dev)
+        _native.check(plan.lib.pad_pme_structure_factor(plan.handle, _native.ptr(frac), int(frac.shape[0]), int(order), _native.ptr(S),
+                                                        _native.stream_ptr(dev)))
+        return S
+    return _structure_factor_spline_torch(box_vecs, shape, cart_ion_coords, order)
+
+
+def _structure_factor_spline_torch(box_vecs, shape, cart_ion_coords, order):
     N0, N1, N2 = (int(s) for s in shape)
     frac = torch.matmul(cart_ion_coords, torch.linalg.inv(box_vecs))
     frac = frac - torch.floor(frac)
@@ -275,9 +296,52 @@ def _pair_list(box_vecs, coords, Rc, chunk=None):
     return torch.cat(out_i), torch.cat(out_j), torch.cat(out_s)
 
 
+class _IonIonSum(torch.autograd.Function):
+    """ion_interaction_sum on the device (csrc/ionion.cu): E, and in backward dE/dcoords and dE/dbox_vecs at fixed coords."""
+
+    @staticmethod
+    def forward(ctx, box_vecs, coords, charges, Rc, Rd):
+        from . import _native
+        lib = _native.load_library()
+        dev = coords.device
+        box_h = (ctypes.c_double * 9)(*[float(x) for x in box_vecs.detach().double().cpu().reshape(-1)])
+        c = coords.detach().double().contiguous()
+        z = charges.detach().to(device=dev, dtype=torch.double).contiguous()
+        n = int(c.shape[0])
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        E = torch.empty((), dtype=torch.double, device=dev)
+        dcart = torch.empty_like(c) if need else None
+        dbox = torch.empty(9, dtype=torch.double, device=dev) if need else None
+        nwork = int(lib.pad_ion_ion_work_doubles(box_h, n, float(Rc)))
+        if nwork == 0:
+            raise ValueError('Lattice vector matrix is not invertible.')
+        work = torch.empty(nwork, dtype=torch.double, device=dev)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        _native.check(lib.pad_ion_ion(box_h, _native.ptr(c), _native.ptr(z), n, float(z.sum().item()), float(Rc), float(Rd),
+                                      _native.ptr(E), _native.ptr(dcart), _native.ptr(dbox), _native.ptr(work), idx,
+                                      _native.stream_ptr(dev)))
+        if need:
+            ctx.save_for_backward(dcart, dbox)
+        ctx.box_device = box_vecs.device
+        return E
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        dcart, dbox = ctx.saved_tensors
+        g_box = (grad_out * dbox.reshape(3, 3)).to(ctx.box_device) if ctx.needs_input_grad[0] else None
+        g_cart = grad_out * dcart if ctx.needs_input_grad[1] else None
+        return g_box, g_cart, None, None, None
+
+
 def ion_interaction_sum(box_vecs, coords, charges, Rc, Rd):
     """Real-space damped pairwise electrostatic sum in a neutralising background
-    (ion_utils.py:293-333; Phys. Rev. Materials 2, 013806)."""
+    (ion_utils.py:293-333; Phys. Rev. Materials 2, 013806).  CUDA tensors: one native sweep over the (ion, image) candidates
+    with closed-form derivatives (pad_ion_ion); CPU tensors (host-side checks only): the pair-list restatement below."""
+    if coords.is_cuda:
+        Rc_f = float(Rc.item()) if torch.is_tensor(Rc) else float(Rc)
+        Rd_f = float(Rd.item()) if torch.is_tensor(Rd) else float(Rd)
+        return _IonIonSum.apply(box_vecs, coords, charges, Rc_f, Rd_f)
     mi, mj, shifts = _pair_list(box_vecs, coords, Rc)
     rho = torch.sum(charges) / torch.abs(torch.linalg.det(box_vecs))
     Zi, Zj = charges[mi], charges[mj]

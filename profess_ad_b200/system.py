@@ -140,9 +140,10 @@ class System():
 
     def __potential_from_ions(self, cart_ion_coords):
         """system.py:183-205.  Exact structure factor (pme_order None, the reference's default): one native call
-        that never materialises the N_k x N_ion phases; particle-mesh Ewald orders use the torch spline path."""
-        if self.__pme_order is None and self.__N_ions > 0:
-            return ionic_potential(self.__box_vecs, self.__shape, self.__species())
+        that never materialises the N_k x N_ion phases; particle-mesh Ewald orders up to 32: native B-spline spreading
+        + r2c (pad_ionic_potential_pme); higher orders: the torch spline path."""
+        if self.__N_ions > 0 and (self.__pme_order is None or self.__pme_order <= 32):
+            return ionic_potential(self.__box_vecs, self.__shape, self.__species(), self.__pme_order)
         kx, ky, kz, k2 = wavevecs(self.__box_vecs, self.__shape)
         k = torch.sqrt(k2)
         v_ext = torch.zeros(self.__shape, dtype=torch.double, device=self.__device)

@@ -1,0 +1,72 @@
+"""Particle-mesh Ewald structure factor on the device (csrc/ions.cu: k_pme_spread / k_pme_spectrum) against the exact
+structure factor (the reference's tests/test_particle_mesh_ewald.py:46-63), against the torch restatement, and through
+System(pme_order=...) (test4 of that file: same energy, density, forces as with exact structure factors)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def test_structure_factor_low_k_matches_exact():
+    from profess_ad_b200 import ion_utils as IU
+    shape = (35, 36, 37)
+    box = torch.tensor([[4.9, 0.1, 0.2], [-0.2, 5.0, 0.3], [0.3, -0.1, 5.1]], dtype=torch.double, device=DEV)
+    cart = torch.tensor([[0, 0, 0], [2, 0.1, 0.2], [0.3, 1, 2]], dtype=torch.double, device=DEV)
+    S = IU.structure_factor(box, shape, cart).cpu().numpy()
+    Sp = IU.structure_factor_spline(box, shape, cart, 20).cpu().numpy()
+    t = 10
+    for sl in ((slice(None, t), slice(None, t)), (slice(None, t), slice(-t, None)), (slice(-t, None), slice(None, t)),
+               (slice(-t, None), slice(-t, None))):
+        assert np.allclose(S[sl[0], sl[1], :t], Sp[sl[0], sl[1], :t])
+
+
+@pytest.mark.parametrize('shape,order', [((20, 21, 22), 4), ((20, 21, 22), 12), ((16, 12, 18), 8), ((35, 36, 37), 20), ((24, 24, 24), 2)])
+def test_native_spreading_equals_torch_restatement(shape, order):
+    from profess_ad_b200 import ion_utils as IU
+    gen = torch.Generator().manual_seed(order)
+    box = (7.5 * torch.eye(3, dtype=torch.double) + 0.1 * torch.rand(3, 3, dtype=torch.double, generator=gen)).to(DEV)
+    frac = torch.rand(7, 3, dtype=torch.double, generator=gen) * 3 - 1           # also outside [0, 1): wrapped
+    cart = frac.to(DEV) @ box
+    a = IU.structure_factor_spline(box, shape, cart, order)
+    b = IU._structure_factor_spline_torch(box, shape, cart, order)
+    assert ((a - b).abs().max() / b.abs().max()).item() < 1e-12
+
+
+def test_pme_ionic_potential_and_system(potentials_dir):
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import ion_utils as IU
+    from profess_ad_b200.functional_tools import wavevecs
+    from profess_ad_b200.system import System
+    pot = os.path.join(potentials_dir, 'li.gga.recpot')
+    shape, L = (25, 25, 25), 6.96
+    box = L * torch.eye(3, dtype=torch.double)
+    frac = torch.tensor([[0, 0, 0], [0.5, 0.5, 0.5]], dtype=torch.double)
+    # native PME v_ext == torch lattice_sum with the spline structure factor (reference semantics)
+    b = box.to(DEV)
+    v = IU.ionic_potential(b, shape, [(pot, frac.to(DEV))], pme_order=20)
+    k = torch.sqrt(wavevecs(b, shape)[3])
+    v_t = IU.lattice_sum(b, shape, (frac @ box).to(DEV), IU.interpolate_recpot(pot, k), 20)
+    assert ((v - v_t).abs().max() / v_t.abs().max()).item() < 1e-11
+    # a skewed, even grid: the Hermitian part on the self-conjugate planes matters
+    gen = torch.Generator().manual_seed(2)
+    box2 = (L * torch.eye(3, dtype=torch.double) + 0.3 * torch.rand(3, 3, dtype=torch.double, generator=gen)).to(DEV)
+    shape2 = (24, 20, 22)
+    v = IU.ionic_potential(box2, shape2, [(pot, frac.to(DEV))], pme_order=8)
+    k = torch.sqrt(wavevecs(box2, shape2)[3])
+    v_t = IU.lattice_sum(box2, shape2, frac.to(DEV) @ box2, IU.interpolate_recpot(pot, k), 8)
+    assert ((v - v_t).abs().max() / v_t.abs().max()).item() < 1e-11
+    # tests/test_particle_mesh_ewald.py:65-89
+    terms = [F.IonIon, F.IonElectron, F.Hartree, F.WangTeter, F.PerdewBurkeErnzerhof]
+    res = []
+    for order in (None, 20):
+        s = System(box, shape, [['Li', pot, frac]], terms, units='b', coord_type='fractional', pme_order=order)
+        s.optimize_density()
+        res.append((s.energy('eV'), s.density().cpu().numpy(), s.forces().cpu().numpy(), s.stress().cpu().numpy()))
+    assert np.allclose(res[0][0], res[1][0])
+    assert np.allclose(res[0][1], res[1][1])
+    assert np.allclose(res[0][2], res[1][2], atol=1e-8)
+    assert np.allclose(res[0][3], res[1][3])

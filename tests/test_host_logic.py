@@ -308,3 +308,18 @@ def test_hermitian_symmetrize_is_the_cpu_irfftn_semantics():
             assert ((back - S).abs().max() / S.abs().max()).item() < 1e-13
         ref = g.laplacian(den)
         assert ((T.laplacian(k2, den) - ref).abs().max() / ref.abs().max()).item() < 1e-14
+
+
+def test_ion_ion_pair_list_restatement_against_castep_energies(golden_dir):
+    """ion_interaction_sum (pair-list restatement, CPU tensors) against the reference's known answers: CASTEP energies of
+    Al, Si and SiO2 (tests/test_ion_utils.py:12-72 of the reference, tests/golden/ion_ion_castep.json)."""
+    import json
+    import torch
+    from profess_ad_b200 import ion_utils
+    doc = json.load(open(os.path.join(golden_dir, 'ion_ion_castep.json')))
+    for c in doc['cases'][:3]:
+        box = torch.tensor(c['box'], dtype=torch.double)
+        cart = torch.tensor(c['frac'], dtype=torch.double) @ box
+        z = torch.tensor(c['charges'], dtype=torch.double)
+        E = ion_utils.ion_interaction_sum(box, cart, z, 12 * c['h_max'], 2 * c['h_max'])
+        assert abs(E.item() - c['E']) / len(c['charges']) < 1e-10, c['name']
