@@ -65,12 +65,14 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError('nvcc failed')
-    link = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'shared', '-lcufft',
+    tmp = LIB + '.tmp'
+    link = [nvcc, '-shared', '-o', tmp] + objs + ['-cudart', 'shared', '-lcufft',
                                                    '-gencode', 'arch=compute_100a,code=sm_100a']
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(' '.join(link) + '\n' + r.stdout + '\n')
         raise RuntimeError('link failed')
+    os.replace(tmp, LIB)        # atomic: a snapshot of the tree (gpurun) never sees a half-written library
     return LIB
 
 

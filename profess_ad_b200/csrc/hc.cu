@@ -322,19 +322,24 @@ static int hc_impl(pad_plan* p, const double* den, int variant, double p0, doubl
 
     // ---- adjoint convolutions: sum_j omega_j rfft(W_j), W_j = F w_j ----------------------------------
     PAD_CUDA(cudaMemsetAsync(C[2], 0, sizeof(cufftDoubleComplex) * nk, s));
-    // every conv_j is dead once K and dK/dxi are formed, so W_j is written in its place
-    for (int j = 0; j < nn; ++j) {
-        double* Wj = conv + (size_t)j * Ns;
+    // every conv_j is dead once K and dK/dxi are formed, so W_j is written in its place -- all n_xi fields in ONE sweep:
+    // the node search, the Hermite weights and n^(8/3 - beta) / xi^3 are evaluated once per voxel instead of once per node
+    {
         auto f = [=] __device__(size_t i, double(&)[1]) {
             const double n = den[i], xi = Xi[i];
             const NodeWeights nw = node_weights(nodes_dev, nn, xi);
-            const int q = j - (nw.i - 1);
-            double w = 0.0;
-            if (q >= 0 && q < 4) w = nw.w[q];
-            Wj[i] = w != 0.0 ? w * exp((8.0 / 3.0 - beta) * log(n)) / (xi * xi * xi) : 0.0;
+            const double F = exp((8.0 / 3.0 - beta) * log(n)) / (xi * xi * xi);
+            for (int j = 0; j < nn; ++j) {
+                const int q = j - (nw.i - 1);
+                const double w = q == 0 ? nw.w[0] : q == 1 ? nw.w[1] : q == 2 ? nw.w[2] : q == 3 ? nw.w[3] : 0.0;
+                conv[(size_t)j * Ns + i] = w != 0.0 ? w * F : 0.0;
+            }
         };
         ew_kernel<0, decltype(f)><<<grid, PAD_THREADS, 0, s>>>(N, f, p->partials);
         ++g_pad_launches;
+    }
+    for (int j = 0; j < nn; ++j) {
+        double* Wj = conv + (size_t)j * Ns;
         PAD_TRY(pad_fft_forward(p, Wj, C[1], s));
         cufftDoubleComplex *Cj = C[1], *Acc = C[2];
         const double xi_j = nodes[j];

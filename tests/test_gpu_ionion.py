@@ -71,4 +71,3 @@ def test_system_energy_forces_stress_with_ion_ion(golden_dir, potentials_dir):
     assert np.abs(s.forces('Ha/b').cpu().numpy() - g['forces_Ha_b']).max() <= 1e-9 * np.abs(g['forces_Ha_b']).max()
     st = s.stress('Ha/b3').cpu().numpy()
     assert np.abs(st - g['stress_Ha_b3']).max() <= 1e-9 * np.abs(g['stress_Ha_b3']).max()
-    assert abs(s._System__Eion_cache - float(g['E_ion_Ha'])) < 1e-10
