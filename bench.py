@@ -229,6 +229,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
+    (first-touch puts the pages there): with 8 ranks staging 134 MB per step each through host memory, buffers on the
+    far socket halve the per-rank PCIe rate.  Returns what was done, for the JSON line."""
+    info = {'gpu': index}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(':')[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read().strip())
+        info['numa_node'] = node
+        if node >= 0:
+            cpus = set()
+            for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & set(os.sched_getaffinity(0))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info['cpus_bound'] = len(allowed)
+    except Exception as e:      # noqa: BLE001 -- placement is an optimisation, never a failure
+        info['error'] = repr(e)
+    return info
+
+
 # --------------------------------------------------------------------------------------------------
 #  B200 arm
 # --------------------------------------------------------------------------------------------------
@@ -240,6 +270,7 @@ def run_gpu(args):
         raise RuntimeError('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # high-priority NCCL stream: in the slab block the exchange of one field runs while the FFT kernels of the next one
@@ -402,7 +433,9 @@ def run_gpu(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': npts * 8, 'd2h_bytes_per_step': npts * 8 + 8,
                     'how': 'profess_ad_b200.streaming.HostPipeline: H2D / evaluate / D2H of consecutive steps on 3 streams, 2 device buffers',
-                    'serial_value': e2e_serial, 'repeats': e2e_repeats},
+                    'serial_value': e2e_serial, 'repeats': e2e_repeats,
+                    'per_rank_host_link_GBps_each_way': (e2e_value / world) * npts * 8 / 1e9,
+                    'numa': numa},
             'gpu_launches': launches + fft_execs,
             'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

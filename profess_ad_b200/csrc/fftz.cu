@@ -91,7 +91,7 @@ __device__ __forceinline__ void load_twiddles(cd* tw1, cd* tw2) {
         const double2 w2 = g_fft_tw[e * (FFT_TW_N / (2 * M))];
         tw2[e] = cd{w2.x, w2.y};
     }
-    __syncthreads();
+    fm_load_tables();          // log / exp tables of fastmath.cuh (ends with __syncthreads)
 }
 
 // forward: field F generated from the staged values, packed FFT, real post-processing, store
@@ -601,8 +601,10 @@ int launch_zinv_impl(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const
 template <int M, int TPL, int NF, int NRED, class Post, int NFW = 0, class GenF = GenNone>
 int launch_zinv(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const cd* i1, const cd* i2, const cd* i3,
                 const double* den, const double* vin, int* grid_out, GenF genf = GenF{}) {
+#ifdef PAD_BUILD_ZINV_STREAM      // measured 7-13 % slower than the batch form at 256^3: not built by default
     if (g_pad_zinv_stream)
         return launch_zinv_impl<M, TPL, NF, NRED, Post, NFW, GenF, true>(p, s, post, i0, i1, i2, i3, den, vin, grid_out, genf);
+#endif
     return launch_zinv_impl<M, TPL, NF, NRED, Post, NFW, GenF, false>(p, s, post, i0, i1, i2, i3, den, vin, grid_out, genf);
 }
 
@@ -1089,6 +1091,29 @@ struct PostStore {                     // plain c2r of one real field
 };
 
 // n^e for the first forward pass
+// the same for the two points of a packed pair in ONE call: the two dependent chains (log polynomial, exp polynomial)
+// are independent of each other, so the scheduler interleaves them -- the out-of-line per-point functions of round 1 were
+// half of the inverse z kernel's instructions and mostly stalled on their own results (ncu: 'wait' on DFMA chains)
+__device__ __noinline__ double2 pow_pos_pair(double2 n, double e) {
+    if (fm_ok(n.x) && fm_ok(n.y)) {
+        const double lx = fm_log(n.x), ly = fm_log(n.y);
+        return make_double2(fm_exp(e * lx), fm_exp(e * ly));
+    }
+    return make_double2(exp(e * log(n.x)), exp(e * log(n.y)));
+}
+// two exponents, one log per point
+__device__ __noinline__ void pow2_pos_pair(double2 n, double e1, double e2, double2& p1, double2& p2) {
+    if (fm_ok(n.x) && fm_ok(n.y)) {
+        const double lx = fm_log(n.x), ly = fm_log(n.y);
+        p1 = make_double2(fm_exp(e1 * lx), fm_exp(e1 * ly));
+        p2 = make_double2(fm_exp(e2 * lx), fm_exp(e2 * ly));
+        return;
+    }
+    const double lx = log(n.x), ly = log(n.y);
+    p1 = make_double2(exp(e1 * lx), exp(e1 * ly));
+    p2 = make_double2(exp(e2 * lx), exp(e2 * ly));
+}
+
 __device__ __noinline__ double pow_pos_ool(double n, double e) {
     if (fm_ok(n)) return fm_exp(e * fm_log(n));
     return exp(e * log(n));
@@ -1100,8 +1125,9 @@ struct GenWgcA {
     const double* scal;
     double beta;
     __device__ void stage(const double2* in, double* a, double* b) const {
-        a[0] = in[0].x; a[1] = pow_pos_ool(in[0].x, beta);
-        b[0] = in[0].y; b[1] = pow_pos_ool(in[0].y, beta);
+        const double2 pw = pow_pos_pair(in[0], beta);
+        a[0] = in[0].x; a[1] = pw.x;
+        b[0] = in[0].y; b[1] = pw.y;
     }
     template <int F>
     __device__ double field(const double* s) const {
@@ -1227,6 +1253,38 @@ __device__ __noinline__ MidOut wgc_mid_point_cw(double n, double alpha, double c
     return o;
 }
 
+// both points of a packed pair in one call (see pow_pos_pair); energy densities summed over the pair
+struct MidOut2 {
+    double2 v, P;
+    double e_tf, e_vw, e_nl;
+};
+__device__ __noinline__ MidOut2 wgc_mid_pair(double2 n, double n_ref, double alpha, double2 u1, double2 u2, double2 u3, double2 lap) {
+    MidOut2 o;
+    if (fm_ok(n.x) && fm_ok(n.y)) {
+        const double thx = n.x - n_ref, thy = n.y - n_ref;
+        const double wx = u2.x + thx * u3.x, wy = u2.y + thy * u3.y;
+        const double cvx = u1.x + thx * (u2.x + 0.5 * thx * u3.x), cvy = u1.y + thy * (u2.y + 0.5 * thy * u3.y);
+        const double lx = fm_log(n.x), ly = fm_log(n.y);
+        const double Px = fm_exp(alpha * lx), Py = fm_exp(alpha * ly);
+        const double c2x = fm_exp((2.0 / 3.0) * lx), c2y = fm_exp((2.0 / 3.0) * ly);
+        const double yx = fm_rsqrt(n.x), yy = fm_rsqrt(n.y);
+        const double chx = fm_sqrt_from_rsqrt(n.x, yx), chy = fm_sqrt_from_rsqrt(n.y, yy);
+        o.P = make_double2(Px, Py);
+        o.e_tf = kCTF * (n.x * c2x + n.y * c2y);
+        o.e_vw = chx * lap.x + chy * lap.y;
+        o.e_nl = Px * cvx + Py * cvy;
+        o.v.x = (5.0 / 3.0) * kCTF * c2x - 0.5 * lap.x * yx + kCTF * (alpha * Px * (yx * yx) * cvx + Px * wx);
+        o.v.y = (5.0 / 3.0) * kCTF * c2y - 0.5 * lap.y * yy + kCTF * (alpha * Py * (yy * yy) * cvy + Py * wy);
+        return o;
+    }
+    const MidOut a = wgc_mid_point(n.x, n_ref, alpha, u1.x, u2.x, u3.x, lap.x);
+    const MidOut b = wgc_mid_point(n.y, n_ref, alpha, u1.y, u2.y, u3.y, lap.y);
+    o.v = make_double2(a.v, b.v);
+    o.P = make_double2(a.P, b.P);
+    o.e_tf = a.e_tf + b.e_tf; o.e_vw = a.e_vw + b.e_vw; o.e_nl = a.e_nl + b.e_nl;
+    return o;
+}
+
 struct PostWgcMid {
     static constexpr bool kDen = true, kVin = false;
     static constexpr int NST = 2;              // staged for the second forward batch (GenWgcP): n, P = n^alpha
@@ -1239,15 +1297,14 @@ struct PostWgcMid {
         double2 vo = make_double2(0.0, 0.0);
         if (want_v && accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
         const double n_ref = scal[S_NREF];
-        const MidOut a = wgc_mid_point(n.x, n_ref, alpha, u0[0], u0[1], u0[2], u0[3]);
-        const MidOut b = wgc_mid_point(n.y, n_ref, alpha, u1[0], u1[1], u1[2], u1[3]);
-        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
-        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
-        sta[0] = n.x; sta[1] = a.P;
-        stb[0] = n.y; stb[1] = b.P;
+        const MidOut2 o = wgc_mid_pair(n, n_ref, alpha, make_double2(u0[0], u1[0]), make_double2(u0[1], u1[1]), make_double2(u0[2], u1[2]),
+                                       make_double2(u0[3], u1[3]));
+        acc[0] += o.e_tf; acc[1] += o.e_vw; acc[2] += o.e_nl;
+        sta[0] = n.x; sta[1] = o.P.x;
+        stb[0] = n.y; stb[1] = o.P.y;
         if (want_v) {
-            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
-            if (P_out) *reinterpret_cast<double2*>(P_out + g) = make_double2(a.P, b.P);
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + o.v.x, vo.y + o.v.y);
+            if (P_out) *reinterpret_cast<double2*>(P_out + g) = o.P;
         }
     }
     // streamed kernel: fields u1, u2, u3 folded, lap(chi) last
@@ -1413,6 +1470,18 @@ __device__ __noinline__ double wgc_fin_point_cw(double n, double beta, double s1
     return kCTF * (da * s1 + a * s2);
 }
 
+__device__ __noinline__ double2 wgc_fin_pair(double2 n, double n_ref, double beta, double2 g1, double2 g2, double2 g3) {
+    if (fm_ok(n.x) && fm_ok(n.y)) {
+        const double thx = n.x - n_ref, thy = n.y - n_ref;
+        const double lx = fm_log(n.x), ly = fm_log(n.y);
+        const double ax = fm_exp(beta * lx), ay = fm_exp(beta * ly);
+        const double dax = beta * fm_exp((beta - 1.0) * lx), day = beta * fm_exp((beta - 1.0) * ly);
+        return make_double2(kCTF * (dax * g1.x + (dax * thx + ax) * g2.x + (0.5 * dax * thx * thx + ax * thx) * g3.x),
+                            kCTF * (day * g1.y + (day * thy + ay) * g2.y + (0.5 * day * thy * thy + ay * thy) * g3.y));
+    }
+    return make_double2(wgc_fin_point(n.x, n_ref, beta, g1.x, g2.x, g3.x), wgc_fin_point(n.y, n_ref, beta, g1.y, g2.y, g3.y));
+}
+
 struct PostWgcFin {
     static constexpr bool kDen = true, kVin = true;
     static constexpr int NST = 0;
@@ -1421,8 +1490,9 @@ struct PostWgcFin {
     double beta;
     __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double*, double*, double*) const {
         const double n_ref = scal[S_NREF];
-        v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]);
-        v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]);
+        const double2 f = wgc_fin_pair(n, n_ref, beta, make_double2(u0[0], u1[0]), make_double2(u0[1], u1[1]), make_double2(u0[2], u1[2]));
+        v.x += f.x;
+        v.y += f.y;
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
     // streamed kernel: g1, g2 folded, g3 last; the first half of the potential is read from v_out itself
@@ -1451,8 +1521,9 @@ struct PostWgcFinH {                           // final pass of the fused term l
     double beta;
     __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double* acc, double*, double*) const {
         const double n_ref = scal[S_NREF];
-        v.x += wgc_fin_point(n.x, n_ref, beta, u0[0], u0[1], u0[2]) + u0[3];
-        v.y += wgc_fin_point(n.y, n_ref, beta, u1[0], u1[1], u1[2]) + u1[3];
+        const double2 f = wgc_fin_pair(n, n_ref, beta, make_double2(u0[0], u1[0]), make_double2(u0[1], u1[1]), make_double2(u0[2], u1[2]));
+        v.x += f.x + u0[3];
+        v.y += f.y + u1[3];
         acc[0] += n.x * u0[3] + n.y * u1[3];
         *reinterpret_cast<double2*>(v_out + g) = v;
     }
@@ -1801,8 +1872,11 @@ struct GenWt {
     const double* scal;
     double alpha, beta;
     __device__ void stage(const double2* in, double* a, double* b) const {
-        a[0] = in[0].x; a[1] = pow_pos_ool(in[0].x, beta); a[2] = TWO ? pow_pos_ool(in[0].x, alpha) : a[1];
-        b[0] = in[0].y; b[1] = pow_pos_ool(in[0].y, beta); b[2] = TWO ? pow_pos_ool(in[0].y, alpha) : b[1];
+        double2 pb, pa;
+        if (TWO) pow2_pos_pair(in[0], beta, alpha, pb, pa);
+        else pa = pb = pow_pos_pair(in[0], beta);
+        a[0] = in[0].x; a[1] = pb.x; a[2] = pa.x;
+        b[0] = in[0].y; b[1] = pb.y; b[2] = pa.y;
     }
     template <int F>
     __device__ double field(const double* s) const {
@@ -1910,6 +1984,35 @@ __device__ __noinline__ WtOut wt_point(double n, double alpha, double beta, bool
     return o;
 }
 
+struct WtOut2 {
+    double2 v;
+    double e_tf, e_vw, e_nl;
+};
+// both points of a packed pair in one call (independent chains interleave, see pow_pos_pair)
+__device__ __noinline__ WtOut2 wt_pair(double2 n, double alpha, double beta, bool two, double n0a, double2 conv_b, double2 conv_a,
+                                      double2 lap) {
+    WtOut2 o;
+    if (fm_ok(n.x) && fm_ok(n.y)) {
+        const double lx = fm_log(n.x), ly = fm_log(n.y);
+        const double pbx = fm_exp(beta * lx), pby = fm_exp(beta * ly);
+        const double pax = two ? fm_exp(alpha * lx) : pbx, pay = two ? fm_exp(alpha * ly) : pby;
+        const double c2x = fm_exp((2.0 / 3.0) * lx), c2y = fm_exp((2.0 / 3.0) * ly);
+        const double yx = fm_rsqrt(n.x), yy = fm_rsqrt(n.y);
+        const double chx = fm_sqrt_from_rsqrt(n.x, yx), chy = fm_sqrt_from_rsqrt(n.y, yy);
+        o.e_tf = kCTF * (n.x * c2x + n.y * c2y);
+        o.e_vw = chx * lap.x + chy * lap.y;
+        o.e_nl = (pax - n0a) * conv_b.x + (pay - n0a) * conv_b.y;
+        o.v.x = (5.0 / 3.0) * kCTF * c2x - 0.5 * lap.x * yx + kCTF * (alpha * pax * conv_b.x + beta * pbx * conv_a.x) * (yx * yx);
+        o.v.y = (5.0 / 3.0) * kCTF * c2y - 0.5 * lap.y * yy + kCTF * (alpha * pay * conv_b.y + beta * pby * conv_a.y) * (yy * yy);
+        return o;
+    }
+    const WtOut a = wt_point(n.x, alpha, beta, two, n0a, conv_b.x, conv_a.x, lap.x);
+    const WtOut b = wt_point(n.y, alpha, beta, two, n0a, conv_b.y, conv_a.y, lap.y);
+    o.v = make_double2(a.v, b.v);
+    o.e_tf = a.e_tf + b.e_tf; o.e_vw = a.e_vw + b.e_vw; o.e_nl = a.e_nl + b.e_nl;
+    return o;
+}
+
 template <bool TWO>
 struct PostWt {
     static constexpr bool kDen = true, kVin = false;
@@ -1921,14 +2024,13 @@ struct PostWt {
     __device__ void apply(size_t g, double2 n, double2, const double* u0, const double* u1, double* acc, double*, double*) const {
         constexpr int L = TWO ? 2 : 1;
         const double n0a = scal[S_TMP0 + 2];
-        const WtOut a = wt_point(n.x, alpha, beta, TWO, n0a, u0[0], TWO ? u0[1] : u0[0], u0[L]);
-        const WtOut b = wt_point(n.y, alpha, beta, TWO, n0a, u1[0], TWO ? u1[1] : u1[0], u1[L]);
-        acc[0] += a.e_tf; acc[1] += a.e_vw; acc[2] += a.e_nl;
-        acc[0] += b.e_tf; acc[1] += b.e_vw; acc[2] += b.e_nl;
+        const WtOut2 o = wt_pair(n, alpha, beta, TWO, n0a, make_double2(u0[0], u1[0]),
+                                 TWO ? make_double2(u0[1], u1[1]) : make_double2(u0[0], u1[0]), make_double2(u0[L], u1[L]));
+        acc[0] += o.e_tf; acc[1] += o.e_vw; acc[2] += o.e_nl;
         if (want_v) {
             double2 vo = make_double2(0.0, 0.0);
             if (accumulate) vo = *reinterpret_cast<const double2*>(v_out + g);
-            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + a.v, vo.y + b.v);
+            *reinterpret_cast<double2*>(v_out + g) = make_double2(vo.x + o.v.x, vo.y + o.v.y);
         }
     }
     // streamed kernel: the convolution(s) are kept as they are, lap(chi) last
@@ -2031,6 +2133,7 @@ int pad_wt_fast(pad_plan* p, const double* den, double alpha, double beta, doubl
 // fastmath.cuh against the library functions: out[0..n) = fm_exp(e * fm_log(x)), out[n..2n) = sqrt via fm_rsqrt,
 // out[2n..3n) = fm_rsqrt(x)^2 (used as 1/x); ref[...] the same from exp/log, sqrt and division
 __global__ void fastmath_probe_kernel(const double* x, size_t n, double e, double* out, double* ref) {
+    fm_load_tables();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const double v = x[i];
         const double y = fm_rsqrt(v);

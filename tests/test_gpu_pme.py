@@ -33,7 +33,14 @@ def test_native_spreading_equals_torch_restatement(shape, order):
     cart = frac.to(DEV) @ box
     a = IU.structure_factor_spline(box, shape, cart, order)
     b = IU._structure_factor_spline_torch(box, shape, cart, order)
-    assert ((a - b).abs().max() / b.abs().max()).item() < 1e-12
+    # the exponential-spline factors b(m) grow like (pi / 2)^order towards the Nyquist frequencies and amplify the rounding of the
+    # spread charges (fused multiply-adds in the kernel's Cox-de Boor recursion, another FFT) by the same factor
+    tol = 1e-12 if order <= 8 else 1e-8
+    err = ((a - b).abs().max() / b.abs().max()).item()
+    assert err < tol, err
+    t = 6                      # the low-frequency corner, where b = O(1): rounding level
+    err_low = ((a[:t, :t, :t] - b[:t, :t, :t]).abs().max() / b[:t, :t, :t].abs().max()).item()
+    assert err_low < 1e-12, err_low
 
 
 def test_pme_ionic_potential_and_system(potentials_dir):
