@@ -136,7 +136,16 @@ class _WolfeSearch:
 class LBFGSNew(Optimizer):
 
     def __init__(self, params, lr=1, max_iter=10, max_eval=None, tolerance_grad=1e-5, tolerance_change=1e-9,
-                 history_size=7, line_search_fn=False, batch_mode=False):
+                 history_size=7, line_search_fn=False, batch_mode=False, max_step=None):
+        # max_step (not in the reference; None = the reference's behaviour exactly): restart guard.  When a quasi-Newton
+        # move would change some component of the variable by more than max_step, the history is dropped and the move is
+        # the first-iteration steepest-descent step instead.  The geometry drivers call step() once per outer iteration
+        # with a NEW objective (re-optimised density), so the pair (s, y) formed across two calls mixes a tiny s with a y
+        # that is dominated by the change of objective; when that pair happens to be nearly orthogonal (y.s -> 0+) it
+        # passes the curvature test and scales the direction by 1 / cos^2 -- the reference then throws the ions across
+        # many cells and never recovers.  The guard only acts on such moves; all other iterates are unchanged.
+        self._max_step = None if max_step is None else float(max_step)
+        self.restarts = 0
         if batch_mode:
             raise NotImplementedError('LBFGSNew: batch mode (stochastic training) is outside the density / geometry '
                                       'optimisation path')
@@ -248,6 +257,13 @@ class LBFGSNew(Optimizer):
                 if math.isnan(t):
                     print('Warning: stepsize nan')
                     t = lr
+            if self._max_step is not None and float(d.abs().max()) * abs(t) > self._max_step:
+                self.restarts += 1
+                self._order = []
+                self._H = 1.0
+                d = g.neg()
+                t = min(1.0, 1.0 / g_l1) * lr
+                gtd = float(torch.dot(g, d))
             self._x.data.add_(d.view_as(self._x.data), alpha=t)
             if it != max_iter:
                 loss = closure()

@@ -370,7 +370,11 @@ class System():
                           g_step_size=0.1, g_maxiter=1000, g_verbose=False, **den_opt_kwargs):
         """Minimise the energy over the fractional ionic coordinates (``ftol`` in eV/A, None = ions fixed) and / or
         the lattice vectors (``stol`` in eV/A^3, None = cell fixed); system.py:937-1068.  Same optimisers, closure
-        and stop rule; the gradients come from the analytic forces and stress instead of autograd."""
+        and stop rule; the gradients come from the analytic forces and stress instead of autograd.  ``g_max_step``
+        (extra keyword, default 1.0; None = the reference's unguarded behaviour): L-BFGS restart guard, see LBFGSNew --
+        a move of more than one whole cell (fractional coordinates) or 1 bohr (lattice-vector components) per inner
+        iteration is replaced by a steepest-descent restart."""
+        den_opt_kwargs.setdefault('g_max_step', 1.0)
         if (ftol is None) and (stol is None):
             raise ValueError('At least one of \'stol\' or \'ftol\' cannot be \'None\'')
         n_f = 3 * self.__N_ions if ftol is not None else 0
@@ -395,6 +399,7 @@ class System():
         parametrisation by autograd."""
         den_opt_inputs = {'ntol': 1e-10, 'n_conv_cond_count': 3, 'n_method': 'LBFGS', 'n_step_size': 0.1,
                           'n_maxiter': 1000, 'conv_target': 'dE', 'n_verbose': False, 'from_uniform': False}
+        g_max_step = den_opt_kwargs.pop('g_max_step', None)
         den_opt_inputs.update(den_opt_kwargs)
         if (ftol is None) and (stol is None):
             raise ValueError('At least one of \'stol\' or \'ftol\' cannot be \'None\'')
@@ -404,9 +409,9 @@ class System():
         elif g_method == 'TPGD':
             optimizer = TPGD([params], lr=g_step_size)
         elif g_method == 'LBFGSlinesearch':
-            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6, line_search_fn=True)
+            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6, line_search_fn=True, max_step=g_max_step)
         elif g_method == 'LBFGS':
-            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6)
+            optimizer = LBFGSNew([params], lr=g_step_size, history_size=8, max_iter=6, max_step=g_max_step)
         else:
             raise ValueError('Only \'LBFGSlinesearch\', \'LBFGS\', \'RPROP\' or \'TPGD\' recognized for \'g_method\'')
         state = {'chi': None}
