@@ -290,6 +290,7 @@ enum {
     S_NREF = 2,         // WGC99 reference density kappa * round(N_elec) / vol
     S_NREF_KEY = 3,     // n_ref the cached WGC99 kernel was built for
     S_WT_KEY = 4,       // n0 the cached Lindhard kernel table of the fused Wang-Teter pipeline was built for
+    S_CTR = 5,          // two 32-bit arrival counters of "last CTA finishes the job" kernels (zero between launches)
     S_TMP0 = 8,         // 8 slots of per-call temporaries
     S_E_PARTS = 16      // component energies
 };

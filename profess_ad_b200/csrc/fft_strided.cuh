@@ -17,14 +17,22 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 
-template <int L>
+// WIDE (L = 512 only, used by the fused x pass): 32 threads per line with 16 points each instead of 16 threads with 32 points --
+// twice the warps per tile and half the registers per thread (a 32-point register FFT plus its temporaries does not fit
+// next to the parked spectra: 1 CTA of 4 warps per SM, measured 1 TB/s).  The line is split 512 = 16 (j, registers) x 32 (t):
+// a 16-point register FFT over j, the twiddle, one shared-memory exchange, then the 32-point FFT over t of every k_j is
+// shared by the two threads (k_j, h): thread h computes the outputs k_t = 2 m + h as a 16-point register FFT of
+// (y[t'] +- y[t' + 16]) W32^{t' h}.  The result is distributed over the threads exactly like the input:
+// thread t, slot r holds X[t + 32 fft_nat<16>(r)].
+template <int L, bool WIDE = false>
 struct SPass {
-    static constexpr int TPL = (L >= 256) ? 16 : 8;      // threads per line
-    static constexpr int EPT = L / TPL;                  // points per thread: 32 (L = 512), 16 (L = 256, 128), 8 (L = 64)
-    static constexpr int G = EPT / TPL;                  // second-stage FFTs per thread: 2, 1, 2, 1
+    static_assert(!WIDE || L == 512, "strided pass: the wide layout exists for L = 512 only");
+    static constexpr int TPL = WIDE ? 32 : ((L >= 256) ? 16 : 8);      // threads per line
+    static constexpr int EPT = L / TPL;                  // points per thread: 32 (L = 512), 16 (L = 256, 128, wide 512), 8 (L = 64)
+    static constexpr int G = WIDE ? 1 : EPT / TPL;       // second-stage FFTs per thread: 2, 1, 2, 1
     static constexpr int ZC = 8;                         // z columns per tile
-    static constexpr int TILE_THREADS = TPL * ZC;        // 128, 64, 64
-    static constexpr int THREADS = 128;
+    static constexpr int TILE_THREADS = TPL * ZC;        // 128, 64, 64; wide: 256
+    static constexpr int THREADS = WIDE ? 256 : 128;
     static constexpr int TPC = THREADS / TILE_THREADS;   // tiles per CTA
     static constexpr int TILE_CD = L * ZC;               // complex numbers per tile
     static constexpr int CTAS_PER_SM = (L == 512) ? 2 : 4;   // plain pass: 32 complex points per thread need > 128 registers
@@ -32,43 +40,67 @@ struct SPass {
 };
 
 // natural index along the line held by register slot s after tile_fft
-template <int L>
+template <int L, bool WIDE = false>
 __device__ __forceinline__ int spass_out_index(int t, int s) {
-    using P = SPass<L>;
-    return (t + P::TPL * (s / P::TPL)) + P::EPT * fft_nat<P::TPL>(s % P::TPL);
+    using P = SPass<L, WIDE>;
+    if constexpr (WIDE) return t + P::TPL * fft_nat<16>(s);
+    else return (t + P::TPL * (s / P::TPL)) + P::EPT * fft_nat<P::TPL>(s % P::TPL);
 }
 // register slot (after tile_fft) that holds the input j of a following tile_fft: k = t + TPL j
-template <int L>
+template <int L, bool WIDE = false>
 __device__ __forceinline__ constexpr int spass_slot_of_input(int j) {
-    using P = SPass<L>;
+    using P = SPass<L, WIDE>;
+    if constexpr (WIDE) return fft_slot<16>(j);
     // k = t + TPL g + EPT k2 = t + TPL (g + G k2)  ->  j = g + G k2
-    return (j % P::G) * P::TPL + fft_slot<P::TPL>(j / P::G);
+    else return (j % P::G) * P::TPL + fft_slot<P::TPL>(j / P::G);
 }
 
 // In: v[j] = z[t + TPL j].  Out: v[s] = Z[spass_out_index(t, s)].  S: tile scratch of L * 8 cd.  tw[e] = exp(-2 pi i e / L).
-template <int L, int DIR>
+template <int L, int DIR, bool WIDE = false>
 __device__ __forceinline__ void tile_fft(cd* v, cd* S, int t, int c, const cd* __restrict__ tw) {
-    using P = SPass<L>;
-    fft_reg<P::EPT, DIR>(v);
+    using P = SPass<L, WIDE>;
+    if constexpr (WIDE) {
+        fft_reg<16, DIR>(v);
 #pragma unroll
-    for (int r = 0; r < P::EPT; ++r) {
-        const int k1 = fft_nat<P::EPT>(r);
-        cd a = v[r];
-        if (k1 != 0) a = cmul(a, tw_dir<DIR>(tw[t * k1]));
-        S[(k1 * P::TPL + t) * P::ZC + c] = a;
+        for (int r = 0; r < 16; ++r) {
+            const int kj = fft_nat<16>(r);
+            cd a = v[r];
+            if (kj != 0) a = cmul(a, tw_dir<DIR>(tw[t * kj]));
+            S[(kj * 32 + t) * P::ZC + c] = a;
+        }
+        __syncthreads();
+        const int kj = t & 15, h = t >> 4;
+#pragma unroll
+        for (int t2 = 0; t2 < 16; ++t2) {
+            const cd lo = S[(kj * 32 + t2) * P::ZC + c], hi = S[(kj * 32 + t2 + 16) * P::ZC + c];
+            cd u = h ? lo - hi : lo + hi;
+            if (t2 != 0) u = cmul(u, tw_dir<DIR>(tw[h * (L / 32) * t2]));      // W32^{t2 h}; h = 0: tw[0] = 1
+            v[t2] = u;
+        }
+        fft_reg<16, DIR>(v);
+        __syncthreads();
+    } else {
+        fft_reg<P::EPT, DIR>(v);
+#pragma unroll
+        for (int r = 0; r < P::EPT; ++r) {
+            const int k1 = fft_nat<P::EPT>(r);
+            cd a = v[r];
+            if (k1 != 0) a = cmul(a, tw_dir<DIR>(tw[t * k1]));
+            S[(k1 * P::TPL + t) * P::ZC + c] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < P::G; ++g) {
+            const int k1 = t + P::TPL * g;
+            cd u[P::TPL];
+#pragma unroll
+            for (int t2 = 0; t2 < P::TPL; ++t2) u[t2] = S[(k1 * P::TPL + t2) * P::ZC + c];
+            fft_reg<P::TPL, DIR>(u);
+#pragma unroll
+            for (int r = 0; r < P::TPL; ++r) v[g * P::TPL + r] = u[r];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-#pragma unroll
-    for (int g = 0; g < P::G; ++g) {
-        const int k1 = t + P::TPL * g;
-        cd u[P::TPL];
-#pragma unroll
-        for (int t2 = 0; t2 < P::TPL; ++t2) u[t2] = S[(k1 * P::TPL + t2) * P::ZC + c];
-        fft_reg<P::TPL, DIR>(u);
-#pragma unroll
-        for (int r = 0; r < P::TPL; ++r) v[g * P::TPL + r] = u[r];
-    }
-    __syncthreads();
 }
 
 template <int L>
@@ -190,11 +222,15 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 // ------------------------------------------------------------------------------------------------
 // CTAs per SM the fused x pass is compiled for: a single field leaves room for more resident tiles (latency hiding)
 template <int L, int NF>
-constexpr int xmix_ctas_per_sm() { return L >= 512 ? 1 : (NF == 1 ? 3 : (L >= 128 ? 2 : 3)); }
+constexpr int xmix_ctas_per_sm() { return L >= 512 ? (NF == 1 ? 2 : 1) : (NF == 1 ? 3 : (L >= 128 ? 2 : 3)); }
+template <int L>
+inline constexpr bool kXmixWide = (L == 512);
 
 template <int L, int NF, class Mix>
-__global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
-    using P = SPass<L>;
+__global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_per_sm<L, NF>()))
+    xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
+    constexpr bool W = kXmixWide<L>;
+    using P = SPass<L, W>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
     spass_load_twiddles<L>(tw);
@@ -236,7 +272,7 @@ __global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SP
             cd* Bf = own + f * P::TILE_CD;
 #pragma unroll
             for (int j = 0; j < P::EPT; ++j) v[j] = cur.live ? Bf[j * ROWSTEP] : cd{0.0, 0.0};
-            tile_fft<L, -1>(v, B0 + f * P::TILE_CD, t, c, tw);
+            tile_fft<L, -1, W>(v, B0 + f * P::TILE_CD, t, c, tw);
             if (f < NF - 1) {
 #pragma unroll
                 for (int s = 0; s < P::EPT; ++s) Bf[s * ROWSTEP] = v[s];
@@ -250,14 +286,14 @@ __global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SP
             typename Mix::Coef ring[PF];
 #pragma unroll
             for (int s = 0; s < PF; ++s) {
-                const int kx = spass_out_index<L>(t, s);
+                const int kx = spass_out_index<L, W>(t, s);
                 ring[s] = mix.fetch(kl, kx, prow + (size_t)kx * kxs, cur.live);
             }
 #pragma unroll
             for (int s = 0; s < P::EPT; ++s) {
                 const typename Mix::Coef coef = ring[s % PF];
                 if (s + PF < P::EPT) {
-                    const int kxn = spass_out_index<L>(t, s + PF < P::EPT ? s + PF : s);
+                    const int kxn = spass_out_index<L, W>(t, s + PF < P::EPT ? s + PF : s);
                     ring[s % PF] = mix.fetch(kl, kxn, prow + (size_t)kxn * kxs, cur.live);
                 }
                 cd q[NF];
@@ -275,13 +311,13 @@ __global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SP
             cd* Bf = own + f * P::TILE_CD;
             cd u[P::EPT];
 #pragma unroll
-            for (int j = 0; j < P::EPT; ++j) u[j] = Bf[spass_slot_of_input<L>(j) * ROWSTEP];
-            tile_fft<L, +1>(u, B0 + f * P::TILE_CD, t, c, tw);
+            for (int j = 0; j < P::EPT; ++j) u[j] = Bf[spass_slot_of_input<L, W>(j) * ROWSTEP];
+            tile_fft<L, +1, W>(u, B0 + f * P::TILE_CD, t, c, tw);
             issue(f, nxt);
             if (cur.live) {
                 cd* base = fields.f[f] + cur.off;
 #pragma unroll
-                for (int s = 0; s < P::EPT; ++s) base[(size_t)spass_out_index<L>(t, s) * xs] = u[s];
+                for (int s = 0; s < P::EPT; ++s) base[(size_t)spass_out_index<L, W>(t, s) * xs] = u[s];
             }
         }
         cur = nxt;
@@ -289,7 +325,7 @@ __global__ void __launch_bounds__(128, xmix_ctas_per_sm<L, NF>()) xmix_kernel(SP
     cp_async_wait<0>();
 }
 
-template <int L>
+template <int L, bool WIDE = false>
 constexpr int spass_smem_bytes(int tile_buffers) {
-    return (L + SPass<L>::TPC * SPass<L>::TILE_CD * tile_buffers) * 16;
+    return (L + SPass<L, WIDE>::TPC * SPass<L, WIDE>::TILE_CD * tile_buffers) * 16;
 }

@@ -947,7 +947,8 @@ int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fiel
 template <int L, int NF, class Mix>
 int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix) {
     auto kern = xmix_kernel<L, NF, Mix>;
-    constexpr int smem = spass_smem_bytes<L>(NF);
+    using P = SPass<L, kXmixWide<L>>;
+    constexpr int smem = spass_smem_bytes<L, kXmixWide<L>>(NF);
     static bool attr_done[64] = {false};
     if (!attr_done[p->device & 63]) {
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -959,9 +960,9 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     constexpr int per_sm = by_smem < want_sm ? by_smem : want_sm;
     static_assert(per_sm >= 1, "fused x pass: tile buffers do not fit in shared memory");
     const long long tiles = spass_tiles(g);
-    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    long long grid = (tiles + P::TPC - 1) / P::TPC;
     if (grid > 148 * per_sm) grid = 148 * per_sm;
-    kern<<<(unsigned)grid, 128, smem, s>>>(f, g, p->geom, mix);
+    kern<<<(unsigned)grid, P::THREADS, smem, s>>>(f, g, p->geom, mix);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;

@@ -410,13 +410,67 @@ __device__ __forceinline__ void wgc_w(double eta, double& w0, double& w1, double
     wgc_w_t<false>(eta, w0, w1, w2, w3);
 }
 
-__global__ void wgc_scalars_kernel(double* scal, double alpha, double beta, double kappa, double dV, double vol) {
+__device__ __forceinline__ void wgc_scalars(double* scal, double alpha, double beta, double kappa, double dV, double vol) {
     // N_elec = round(mean(n) vol) (functionals.py:952; Python round = half-to-even = rint)
     const double n_elec = rint(scal[S_SUM_RHO] * dV);
     const double n_ref = kappa * n_elec / vol;
     scal[S_NREF] = n_ref;
     scal[S_TMP0 + 0] = 1.0 / (2.0 * cbrt(k3Pi2 * n_ref));
     scal[S_TMP0 + 1] = 20.0 * pow(n_ref, 5.0 / 3.0 - alpha - beta);
+}
+
+// sum of the density and the scalars derived from it in ONE launch (single-GPU plans): 16-byte loads with four
+// independent partial sums per thread (the generic ew_kernel sum runs at 2.3 TB/s: one dependent add per 8-byte load),
+// then the last CTA to arrive adds the per-CTA partials in a fixed order -- deterministic for a fixed grid -- and derives
+// n_ref and the kernel scalars, which used to be two more one-CTA launches.  ctr: a zeroed word the last CTA resets.
+constexpr int kSumThreads = 256;
+constexpr int kSumBlocks = 148 * 4;
+__global__ void __launch_bounds__(kSumThreads) wgc_sum_scalars_kernel(const double* __restrict__ den, size_t n, double* __restrict__ partials,
+                                                                     unsigned* ctr, double* scal, double alpha, double beta,
+                                                                     double kappa, double dV, double vol) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const size_t n2 = n / 2;                    // den is 16-byte aligned (checked by the caller)
+    const double2* d2 = reinterpret_cast<const double2*>(den);
+    const size_t stride = (size_t)gridDim.x * kSumThreads;
+    size_t i = (size_t)blockIdx.x * kSumThreads + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        const double2 u0 = __ldcs(d2 + i), u1 = __ldcs(d2 + i + stride), u2 = __ldcs(d2 + i + 2 * stride), u3 = __ldcs(d2 + i + 3 * stride);
+        a0 += u0.x + u0.y; a1 += u1.x + u1.y; a2 += u2.x + u2.y; a3 += u3.x + u3.y;
+    }
+    for (; i < n2; i += stride) { const double2 u = d2[i]; a0 += u.x + u.y; }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) a1 += den[n - 1];
+    double v = warp_sum((a0 + a1) + (a2 + a3));
+    __shared__ double sm[kSumThreads / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double w = 0.0;
+        for (int k = 0; k < kSumThreads / 32; ++k) w += sm[k];
+        partials[blockIdx.x] = w;
+        __threadfence();
+        last = atomicAdd(ctr, 1u) + 1u == gridDim.x;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double w = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kSumThreads) w += __ldcg(partials + b);
+    w = warp_sum(w);
+    if (lane == 0) sm[warp] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < kSumThreads / 32; ++k) t += sm[k];
+        scal[S_SUM_RHO] = t;
+        wgc_scalars(scal, alpha, beta, kappa, dV, vol);
+        *ctr = 0u;
+    }
+}
+
+__global__ void wgc_scalars_kernel(double* scal, double alpha, double beta, double kappa, double dV, double vol) {
+    wgc_scalars(scal, alpha, beta, kappa, dV, vol);
 }
 
 // kern layout: [W0 | K1 | K2 | K3], each Nk doubles, pre-multiplied by 1/N
@@ -448,9 +502,17 @@ __global__ void __launch_bounds__(PAD_THREADS) wgc_build_kernel(KGeom g, uint32_
             o[1] = make_double2(sc * out[2], sc * out[3]);
         }
     }
+    // the last CTA to finish records the reference density the table now belongs to (every CTA has read the old key by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* ctr = reinterpret_cast<unsigned*>(scal + S_CTR) + 1;
+        __threadfence();
+        if (atomicAdd(ctr, 1u) + 1u == gridDim.x) {
+            scal[S_NREF_KEY] = n_ref;
+            *ctr = 0u;
+        }
+    }
 }
-
-__global__ void wgc_key_kernel(double* scal) { scal[S_NREF_KEY] = scal[S_NREF]; }
 
 static void wgc_host_series(double alpha, double beta, double gamma, WgcSeries* S) {
     // functionals.py:817-843 (coefficient recursions) and :853-875 (homogeneous-solution constants)
@@ -621,12 +683,18 @@ int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta,
 
     // --- reference density and kernel -----------------------------------------------------------
     pad_stage_begin(s);
-    launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
-    PAD_CHECK_LAUNCH();
-    const double one[1] = {1.0};
-    finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
-    wgc_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, kappa, p->dV, p->vol);
-    ++g_pad_launches;
+    if (!p->dist && (reinterpret_cast<uintptr_t>(den) & 15) == 0) {
+        wgc_sum_scalars_kernel<<<kSumBlocks, kSumThreads, 0, s>>>(den, p->N, p->partials, reinterpret_cast<unsigned*>(scal + S_CTR), scal,
+                                                                 alpha, beta, kappa, p->dV, p->vol);
+        ++g_pad_launches;
+    } else {
+        launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) { acc[0] += den[i]; });
+        PAD_CHECK_LAUNCH();
+        const double one[1] = {1.0};
+        finalize(p, s, 1, one, nullptr, 0, scal + S_SUM_RHO);
+        wgc_scalars_kernel<<<1, 1, 0, s>>>(scal, alpha, beta, kappa, p->dV, p->vol);
+        ++g_pad_launches;
+    }
     PAD_CHECK_LAUNCH();
     if (!p->wgc_kern) {
         PAD_CUDA(cudaMalloc(&p->wgc_kern, sizeof(double) * 4 * nk));
@@ -652,9 +720,7 @@ int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta,
     // (it changes when the electron number does): a one-wave grid is enough for the check, and still rebuilds the
     // kernel (grid-stride, slower) in the rare case that the key differs
     wgc_build_kernel<<<same ? 148 : pad_grid_for(nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)nk, kern, p->wgc_kern4, scal, same ? 0 : 1);
-    PAD_CHECK_LAUNCH();
-    wgc_key_kernel<<<1, 1, 0, s>>>(scal);
-    g_pad_launches += 2;
+    ++g_pad_launches;
     PAD_CHECK_LAUNCH();
     const double *W0 = kern, *K1 = kern + nk, *K2 = kern + 2 * nk, *K3 = kern + 3 * nk;
     pad_stage_mark("sum(n) -> n_ref, kernel cache check", s);

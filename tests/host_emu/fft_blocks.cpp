@@ -7,40 +7,9 @@ thread_local std::barrier<>* g_warp_barrier = nullptr;
 thread_local std::barrier<>* g_block_barrier = nullptr;
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #include "fft_core.cuh"
-// only the tile FFT part of fft_strided.cuh is host-testable: paste the needed pieces
-template <int L>
-struct SPass {
-    static constexpr int TPL = (L >= 256) ? 16 : 8;
-    static constexpr int EPT = L / TPL;
-    static constexpr int G = EPT / TPL;
-    static constexpr int ZC = 8;
-    static constexpr int TILE_THREADS = TPL * ZC;
-    static constexpr int THREADS = 128;
-    static constexpr int TPC = THREADS / TILE_THREADS;
-    static constexpr int TILE_CD = L * ZC;
-};
-template <int L> inline int spass_out_index(int t, int s) { using P = SPass<L>; return (t + P::TPL * (s / P::TPL)) + P::EPT * fft_nat<P::TPL>(s % P::TPL); }
-template <int L> constexpr int spass_slot_of_input(int j) { using P = SPass<L>; return (j % P::G) * P::TPL + fft_slot<P::TPL>(j / P::G); }
-template <int L, int DIR>
-inline void tile_fft(cd* v, cd* S, int t, int c, const cd* tw) {
-    using P = SPass<L>;
-    fft_reg<P::EPT, DIR>(v);
-    for (int r = 0; r < P::EPT; ++r) {
-        const int k1 = fft_nat<P::EPT>(r);
-        cd a = v[r];
-        if (k1 != 0) a = cmul(a, tw_dir<DIR>(tw[t * k1]));
-        S[(k1 * P::TPL + t) * P::ZC + c] = a;
-    }
-    __syncthreads();
-    for (int g = 0; g < P::G; ++g) {
-        const int k1 = t + P::TPL * g;
-        cd u[P::TPL];
-        for (int t2 = 0; t2 < P::TPL; ++t2) u[t2] = S[(k1 * P::TPL + t2) * P::ZC + c];
-        fft_reg<P::TPL, DIR>(u);
-        for (int r = 0; r < P::TPL; ++r) v[g * P::TPL + r] = u[r];
-    }
-    __syncthreads();
-}
+// the tile FFT part of fft_strided.cuh (SPass, spass_out_index, spass_slot_of_input, tile_fft), cut out of the real header by
+// tests/test_host_emulation.py
+#include "tile_part.h"
 #include <complex>
 #include <cstdio>
 #include <thread>
@@ -51,8 +20,8 @@ static void dft(const std::vector<C>& in, std::vector<C>& out, int dir) {
     int n = in.size(); out.assign(n, 0);
     for (int k = 0; k < n; ++k) { C s = 0; for (int j = 0; j < n; ++j) s += in[j] * std::polar(1.0, dir * 2 * M_PI * ((j * k) % n) / n); out[k] = s; }
 }
-template <int L, int DIR> double test_tile() {
-    using P = SPass<L>;
+template <int L, int DIR, bool WIDE = false> double test_tile() {
+    using P = SPass<L, WIDE>;
     std::mt19937 g(L); std::uniform_real_distribution<double> u(-1, 1);
     std::vector<std::vector<C>> in(8, std::vector<C>(L)), ref(8);
     for (int c = 0; c < 8; ++c) { for (auto& x : in[c]) x = C(u(g), u(g)); dft(in[c], ref[c], DIR); }
@@ -67,12 +36,12 @@ template <int L, int DIR> double test_tile() {
         const int t = tid / 8, c = tid % 8;
         cd v[P::EPT];
         for (int j = 0; j < P::EPT; ++j) v[j] = cd{in[c][t + P::TPL * j].real(), in[c][t + P::TPL * j].imag()};
-        tile_fft<L, DIR>(v, S, t, c, tw);
-        for (int s = 0; s < P::EPT; ++s) err[tid] = std::max(err[tid], std::abs(C(v[s].x, v[s].y) - ref[c][spass_out_index<L>(t, s)]));
+        tile_fft<L, DIR, WIDE>(v, S, t, c, tw);
+        for (int s = 0; s < P::EPT; ++s) err[tid] = std::max(err[tid], std::abs(C(v[s].x, v[s].y) - ref[c][spass_out_index<L, WIDE>(t, s)]));
         // inverse fed from the forward's slots: u[j] = v[slot_of_input(j)] must be Z[t + TPL j]
         for (int j = 0; j < P::EPT; ++j) {
-            const int s = spass_slot_of_input<L>(j);
-            if (spass_out_index<L>(t, s) != t + P::TPL * j) err[tid] = 1e9;
+            const int s = spass_slot_of_input<L, WIDE>(j);
+            if (spass_out_index<L, WIDE>(t, s) != t + P::TPL * j) err[tid] = 1e9;
         }
     });
     for (auto& x : th) x.join();
@@ -118,5 +87,6 @@ int main() {
     chk("tile 128", std::max(test_tile<128, -1>(), test_tile<128, 1>()));
     chk("tile 256", std::max(test_tile<256, -1>(), test_tile<256, 1>()));
     chk("tile 512", std::max(test_tile<512, -1>(), test_tile<512, 1>()));
+    chk("tile 512 wide", std::max(test_tile<512, -1, true>(), test_tile<512, 1, true>()));
     return worst != 0;
 }

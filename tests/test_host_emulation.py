@@ -29,8 +29,12 @@ def _build_and_run(tmp_path, source, extra_includes=()):
 
 
 def test_fft_building_blocks_on_host_threads(tmp_path):
-    out = _build_and_run(tmp_path, 'fft_blocks.cpp')
-    assert 'tile 512' in out and 'line 256/32' in out
+    src = open(os.path.join(CSRC, 'fft_strided.cuh')).read()
+    a = src.index('template <int L, bool WIDE = false>\nstruct SPass {')
+    b = src.index('template <int L>\n__device__ __forceinline__ void spass_load_twiddles')
+    (tmp_path / 'tile_part.h').write_text(src[a:b])
+    out = _build_and_run(tmp_path, 'fft_blocks.cpp', extra_includes=[str(tmp_path)])
+    assert 'tile 512 wide' in out and 'line 256/32' in out
 
 
 def test_pipe_scheduler_on_host_threads(tmp_path):
