@@ -90,11 +90,14 @@ int pad_plan_destroy(pad_plan* plan);
  *      and return 0.  Python binds it to torch.distributed (NCCL over NVLink).  Every functional entry point
  *      below then takes LOCAL slabs (den, v: n0/world x n1 x n2) and returns GLOBAL energies on every rank;
  *      pad_denopt_* keeps each rank's slab of chi, the gradient and the L-BFGS history and all-reduces the
- *      inner products of an iteration in one batch.  Not available on slab plans: the fused FFT pipeline. ---- */
+ *      inner products of an iteration in one batch.  The fused FFT pipeline runs on slab plans once
+ *      pad_plan_set_slab_fast_buffers has been called. ---- */
 #define PAD_COMM_ALL_TO_ALL 0
 #define PAD_COMM_ALL_REDUCE 1
 #define PAD_COMM_ALL_REDUCE_MAX 2
 #define PAD_COMM_ALL_TO_ALL_2 3          /* as PAD_COMM_ALL_TO_ALL, on the second buffer pair (pad_plan_set_overlap_buffers) */
+#define PAD_COMM_ALL_TO_ALL_FAST 16      /* + 8 * dst + src: exchange slab_fast buffer `src` -> `dst` (pad_plan_set_slab_fast_buffers),
+                                           `count` complex128 per peer */
 #define PAD_COMM_SCRATCH 64
 typedef int (*pad_comm_fn)(void* user, int op, long long count, void* stream);
 int pad_plan_create_slab(pad_plan** plan, const double* box_host, const int* global_shape_host, int device,
@@ -105,6 +108,14 @@ int pad_plan_create_slab(pad_plan** plan, const double* box_host, const int* glo
  * (`fn` is then called with THAT stream and op PAD_COMM_ALL_TO_ALL / PAD_COMM_ALL_TO_ALL_2) while the local FFTs of the
  * neighbouring fields run on the caller's stream. */
 int pad_plan_set_overlap_buffers(pad_plan* plan, void* send_buf2, void* recv_buf2);
+/* Buffers for the fused FFT pipeline on a slab plan (functional_tools.py:381-423 / functionals.py:941-985 on one grid over several
+ * GPUs): six caller-owned device buffers of pad_slab_fast_elements(plan) complex128 each -- four spectrum fields and two exchange
+ * stagings.  With them (and n0, n1 in {64 ... 512}, n2 in {128, 256, 512}) WangGovindCarter99 and the Wang-Teter family run the
+ * hand-written z / y / x passes on the slabs: the y pass stores its rows blocked by destination rank, so the all-to-all (op
+ * PAD_COMM_ALL_TO_ALL_FAST + 8 * dst + src, issued on the plan's communication stream field by field while the neighbouring
+ * fields' passes run) needs no pack / unpack kernel, and the kernel mix is fused into the x pass of the transposed layout. */
+size_t pad_slab_fast_elements(const pad_plan* plan);
+int pad_plan_set_slab_fast_buffers(pad_plan* plan, void* const* six_buffers);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
 size_t pad_plan_workspace_bytes(const pad_plan* plan);
 

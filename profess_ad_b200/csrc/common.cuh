@@ -275,6 +275,7 @@ struct pad_plan {
     // second exchange buffer pair + a communication stream: batches of transforms are software-pipelined so that the
     // all-to-all of one field runs while the local FFTs of its neighbours do (pad_fft_forward_many / _inverse_many)
     void *send_buf2, *recv_buf2;
+    void* slab_fast[6];          // fused pipeline on slabs: 4 spectrum buffers + 2 exchange stagings of n0_loc * n1 * nzp complex, owned by the caller
     cudaStream_t comm_stream;
     cudaEvent_t ev_ready[2], ev_a2a[2], ev_free[2];
     bool comm_ready;
@@ -344,6 +345,7 @@ void pad_launch_finalize(pad_plan* p, const FinalizeArgs& a, cudaStream_t s);
 // max: non-negative doubles held as their bit patterns (the atomicMax convention of the reduction kernels).
 int pad_allreduce_max_bits(pad_plan* p, unsigned long long* bits, int n, cudaStream_t s);
 int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s);
+int pad_ensure_comm_stream(pad_plan* p);      // plan-owned communication stream + the events of the pipelined exchanges
 // stress.cu: the 7 block-reduced sums [iso, xx, yy, zz, xy, xz, yz] left in p->partials by a kernel with `nblocks`
 // CTAs are finished (all-reduced on slab plans) and added to the row-major 3 x 3 device tensor `sig`:
 // sig_ij += c_t T_ij + c_iso iso delta_ij

@@ -191,6 +191,56 @@ __global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_kernel(SPass
 }
 
 // ------------------------------------------------------------------------------------------------
+//  slab plans: the y pass next to the all-to-all.  The transposition (n0_loc, n1, nzp) <-> (n0, n1_loc, nzp) moves, for every
+//  pair of ranks, the rows y of the partner's range of all local x-planes.  With the rows of a plane BLOCKED by owner rank,
+//      blocked[r][x_loc][y_l][z],   y = r n1_loc + y_l,
+//  the block sent to rank r is contiguous and what arrives from rank r is the x range of r in the transposed layout, so the
+//  exchange needs no pack / unpack pass of its own: the forward y pass stores its result rows blocked (BLK = 1), the inverse
+//  y pass loads its input rows blocked (BLK = 2); the other side of either is the natural local layout.  Out of place.
+// ------------------------------------------------------------------------------------------------
+struct SPassBlocked {
+    int rows;                  // n1_loc: rows per rank block
+    long long block_stride;    // complex elements between the blocks of consecutive ranks: n0_loc * n1_loc * nzp
+    long long outer_stride;    // complex elements between consecutive x-planes inside a block: n1_loc * nzp
+};
+
+template <int L, int DIR, int BLK>
+__global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_blocked_kernel(const cd* __restrict__ src, cd* __restrict__ dst,
+                                                                                 SPassGeom geo, SPassBlocked bl) {
+    using P = SPass<L>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tw = reinterpret_cast<cd*>(smem_raw);
+    spass_load_twiddles<L>(tw);
+    const int tile_in_cta = threadIdx.x / P::TILE_THREADS;
+    const int tid = threadIdx.x % P::TILE_THREADS;
+    const int t = tid / P::ZC, c = tid % P::ZC;
+    cd* S = tw + L + (size_t)tile_in_cta * P::TILE_CD;
+    const long long total = spass_tiles(geo);
+    for (long long w0 = (long long)blockIdx.x * P::TPC; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
+        const TileAt a = spass_locate(geo, w0 + tile_in_cta, total, c);
+        const long long nat = a.off;                                              // o * outer_stride + z
+        const long long blk = (long long)a.o * bl.outer_stride + a.z;
+        auto blocked_row = [&](int y) { const int r = y / bl.rows; return (long long)r * bl.block_stride + (long long)(y - r * bl.rows) * geo.axis_stride; };
+        cd v[P::EPT];
+#pragma unroll
+        for (int j = 0; j < P::EPT; ++j) {
+            const int y = t + P::TPL * j;
+            const long long off = BLK == 2 ? blk + blocked_row(y) : nat + (long long)y * geo.axis_stride;
+            v[j] = a.live ? src[off] : cd{0.0, 0.0};
+        }
+        tile_fft<L, DIR>(v, S, t, c, tw);
+        if (a.live) {
+#pragma unroll
+            for (int s = 0; s < P::EPT; ++s) {
+                const int y = spass_out_index<L>(t, s);
+                const long long off = BLK == 1 ? blk + blocked_row(y) : nat + (long long)y * geo.axis_stride;
+                dst[off] = v[s];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 //  asynchronous global -> shared copies (LDGSTS): each thread copies the elements it will read itself,
 //  so a cp.async.wait_group is all the synchronisation the consumer needs
 // ------------------------------------------------------------------------------------------------
@@ -259,8 +309,8 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
 
     for (; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
         const TileAt nxt = locate(w0 + (long long)gridDim.x * P::TPC);
-        const size_t prow = ((size_t)cur.o) * kg.nzp_pad + cur.z;         // + kx n1 nzp
-        const size_t kxs = (size_t)kg.n1 * kg.nzp_pad;
+        const size_t prow = ((size_t)cur.o) * kg.nzp_pad + cur.z;         // + kx n1_loc nzp  (tables cover the plan's own rows)
+        const size_t kxs = (size_t)kg.n1_loc * kg.nzp_pad;
         cd v[P::EPT];
         // forward transforms; every spectrum but the last is parked in its thread-owned rows
 #pragma unroll
@@ -282,7 +332,7 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
         // memory: keep PF slots of it in flight.
         {
             constexpr int PF = Mix::kRing;      // table-driven mixes: 8 slots in flight (measured at 256^3: 269 us; 4 + prefetch.L2 hints: 283 us); computed multipliers: 1
-            const typename Mix::Line kl = mix.line(kg, cur.o, cur.z);
+            const typename Mix::Line kl = mix.line(kg, cur.o + kg.j1_off, cur.z);      // global row index (slab plans: the rank's y range)
             typename Mix::Coef ring[PF];
 #pragma unroll
             for (int s = 0; s < PF; ++s) {

@@ -552,6 +552,9 @@ inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
     return b < 1 ? 1 : b;
 }
 
+// z lines of the plan's real-space block: slab plans hold n0_loc x-planes
+inline int z_lines(const pad_plan* p) { return (p->dist ? p->n0_loc : p->n0) * p->n1; }
+
 template <int M, int TPL, int NF, class Gen>
 int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3) {
     constexpr int warps = 4;
@@ -563,7 +566,7 @@ int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const d
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done[p->device & 63] = true;
     }
-    const int nlines = p->n0 * p->n1;
+    const int nlines = z_lines(p);
     ZIn in{{in0, in1}};
     kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, in, o0, o1, o2, o3, nlines, p->nzp);
     ++g_pad_launches;
@@ -585,7 +588,7 @@ int launch_zinv_impl(pad_plan* p, cudaStream_t s, Post post, const cd* i0, const
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done[p->device & 63] = true;
     }
-    const int nlines = p->n0 * p->n1;
+    const int nlines = z_lines(p);
     constexpr int by_smem = (227 * 1024) / (smem + 1024);
     constexpr int want = STREAM ? 3 : 2;
     const int grid = zgrid(nlines, warps * (32 / TPL), by_smem < want ? by_smem : want);
@@ -880,6 +883,11 @@ int xy_exec(pad_plan* p, cudaStream_t s, cd* spec, int dir) {
 
 int get_zbuf(pad_plan* p, int i, cd** out) {
     if (i < 0 || i >= 4) { pad_set_error("zbuf index %d", i); return PAD_ERR_ARG; }
+    if (p->dist) {          // slab plans: caller-owned buffers (the exchange callback has to know them)
+        if (!p->slab_fast[i]) { pad_set_error("slab plan: pad_plan_set_slab_fast_buffers has not been called"); return PAD_ERR_ARG; }
+        *out = reinterpret_cast<cd*>(p->slab_fast[i]);
+        return PAD_OK;
+    }
     const size_t bytes = sizeof(cd) * (size_t)p->n0 * p->n1 * p->nzp;
     if (!p->zbuf[i]) {
         PAD_CUDA(cudaMalloc(&p->zbuf[i], bytes));
@@ -898,10 +906,11 @@ bool own_xy_shape(const pad_plan* p) { return spass_len_ok(p->n0) && spass_len_o
 
 SPassGeom spass_geom(const pad_plan* p, int axis) {
     SPassGeom g;
-    const long long row = p->nzp, plane = (long long)p->n1 * p->nzp;
+    // slab plans: the y pass sees the local layout (n0_loc, n1, nzp), the x pass the transposed one (n0, n1_loc, nzp)
+    const long long row = p->nzp, plane = (long long)(p->dist && axis == 0 ? p->n1_loc : p->n1) * p->nzp;
     g.axis_stride = axis == 0 ? plane : row;
     g.outer_stride = axis == 0 ? row : plane;
-    g.n_outer = axis == 0 ? p->n1 : p->n0;
+    g.n_outer = axis == 0 ? (p->dist ? p->n1_loc : p->n1) : (p->dist ? p->n0_loc : p->n0);
     g.nzh = p->nzh;
     return g;
 }
@@ -924,8 +933,98 @@ int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, co
     return PAD_OK;
 }
 
+template <int L, int DIR, int BLK>
+int launch_spass_blocked_L(pad_plan* p, cudaStream_t s, const cd* src, cd* dst, const SPassGeom& g, const SPassBlocked& bl) {
+    auto kern = spass_blocked_kernel<L, DIR, BLK>;
+    constexpr int smem = spass_smem_bytes<L>(1);
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const long long tiles = spass_tiles(g);
+    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    if (grid > (1 << 20)) grid = 1 << 20;
+    kern<<<(unsigned)grid, 128, smem, s>>>(src, dst, g, bl);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
+int launch_spass_blocked(pad_plan* p, cudaStream_t s, int dir, const cd* src, cd* dst) {
+    const SPassGeom g = spass_geom(p, 1);
+    const SPassBlocked bl{p->n1_loc, (long long)p->n0_loc * p->n1_loc * p->nzp, (long long)p->n1_loc * p->nzp};
+#define SPASS_BLK_CASE(LL)                                                                                   \
+    case LL:                                                                                                 \
+        return dir < 0 ? launch_spass_blocked_L<LL, -1, 1>(p, s, src, dst, g, bl) : launch_spass_blocked_L<LL, +1, 2>(p, s, src, dst, g, bl);
+    switch (p->n1) {
+        SPASS_BLK_CASE(64)
+        SPASS_BLK_CASE(128)
+        SPASS_BLK_CASE(256)
+        SPASS_BLK_CASE(512)
+    }
+#undef SPASS_BLK_CASE
+    pad_set_error("strided FFT pass: length %d not supported", p->n1);
+    return PAD_ERR_ARG;
+}
+
+// Slab plans, y axis: the pass and the transposition of a batch of fields, software-pipelined over the two stagings.
+//   forward:  fields[f] (local layout) --y pass, rows blocked by rank--> staging b --all-to-all--> fields[f] (transposed layout)
+//   inverse:  fields[f] (transposed)   --all-to-all--> staging b --y pass from blocked rows--> fields[f] (local layout)
+// The exchange of field f runs on the plan's communication stream while the pass of field f + 1 (forward) or f - 1 (inverse)
+// runs on `s`; fields[] must be slab_fast buffers 0..3 in order (the callback names them by index).
+int slab_ypass_exchange(pad_plan* p, cudaStream_t s, int dir, cd* const* fields, int nf) {
+    PAD_TRY(pad_ensure_comm_stream(p));
+    int idx[4];
+    for (int f = 0; f < nf; ++f) {
+        idx[f] = -1;
+        for (int i = 0; i < 4; ++i)
+            if (fields[f] == reinterpret_cast<cd*>(p->slab_fast[i])) idx[f] = i;
+        if (idx[f] < 0) { pad_set_error("slab y pass: field %d is not a registered slab_fast buffer", f); return PAD_ERR_ARG; }
+    }
+    cd* stg[2] = {reinterpret_cast<cd*>(p->slab_fast[4]), reinterpret_cast<cd*>(p->slab_fast[5])};
+    const long long count = (long long)p->n0_loc * p->n1_loc * p->nzp;
+    auto a2a = [&](int dst, int src) -> int {
+        return pad_slab_comm(p, PAD_COMM_ALL_TO_ALL_FAST + 8 * dst + src, count, p->comm_stream);
+    };
+    if (dir < 0) {
+        for (int f = 0; f < nf; ++f) {
+            const int b = f & 1;
+            if (f >= 2) PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));               // exchange f - 2 has left staging b
+            PAD_TRY(launch_spass_blocked(p, s, -1, fields[f], stg[b]));
+            PAD_CUDA(cudaEventRecord(p->ev_ready[b], s));
+            PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_ready[b], 0));
+            PAD_TRY(a2a(idx[f], 4 + b));
+            PAD_CUDA(cudaEventRecord(p->ev_a2a[b], p->comm_stream));
+        }
+        PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[0], 0));
+        if (nf > 1) PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[1], 0));
+        return PAD_OK;
+    }
+    // inverse: everything queued on `s` so far (the x pass) precedes the first exchange
+    PAD_CUDA(cudaEventRecord(p->ev_ready[0], s));
+    PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_ready[0], 0));
+    auto exchange = [&](int f) -> int {
+        const int b = f & 1;
+        if (f >= 2) PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_free[b], 0));    // the pass of field f - 2 has read staging b
+        PAD_TRY(a2a(4 + b, idx[f]));
+        PAD_CUDA(cudaEventRecord(p->ev_a2a[b], p->comm_stream));
+        return PAD_OK;
+    };
+    PAD_TRY(exchange(0));
+    for (int f = 0; f < nf; ++f) {
+        const int b = f & 1;
+        if (f + 1 < nf) PAD_TRY(exchange(f + 1));
+        PAD_CUDA(cudaStreamWaitEvent(s, p->ev_a2a[b], 0));
+        PAD_TRY(launch_spass_blocked(p, s, +1, stg[b], fields[f]));
+        PAD_CUDA(cudaEventRecord(p->ev_free[b], s));
+    }
+    return PAD_OK;
+}
+
 // in-place FFT of nf padded half-spectra along axis 0 (x) or 1 (y)
 int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf) {
+    if (p->dist && axis == 1) return slab_ypass_exchange(p, s, dir, fields, nf);
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < nf ? fields[i] : nullptr;
     const SPassGeom g = spass_geom(p, axis);
@@ -994,7 +1093,7 @@ struct MixWgc {                        // WGC99 3x3 kernel mix (functionals.py:9
     struct Line { size_t prow, kxs; int n0; };
     __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const {
         const int fy = ky <= g.n1 - ky ? ky : g.n1 - ky;
-        return Line{(size_t)fy * g.nzp_pad + z, (size_t)g.n1 * g.nzp_pad, g.n0};
+        return Line{(size_t)fy * g.nzp_pad + z, (size_t)g.n1_loc * g.nzp_pad, g.n0};
     }
     __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const {
         Coef c;
@@ -1053,7 +1152,13 @@ struct MixScale {                      // plain 1/N (round-trip tests)
     __device__ __forceinline__ void apply(const Coef& c, cd* q) const { q[0] = cd{q[0].x * c, q[0].y * c}; }
 };
 
-bool fast_shape(const pad_plan* p) { return !p->dist && (p->n2 == 128 || p->n2 == 256 || p->n2 == 512); }
+// single-GPU plans: any (n0, n1) (cuFFT does the (x, y) transform where the own strided passes do not cover the lengths);
+// slab plans: only with the own passes and registered buffers (the y pass carries the transposition)
+bool fast_shape(const pad_plan* p) {
+    if (!(p->n2 == 128 || p->n2 == 256 || p->n2 == 512)) return false;
+    if (!p->dist) return true;
+    return g_pad_own_xy && spass_len_ok(p->n0) && spass_len_ok(p->n1) && p->slab_fast[0] != nullptr;
+}
 
 // dispatch on n2: M = n2/2; (M, TPL) in {(64, 8), (128, 16), (256, 32)}
 #define ZDISPATCH(p, CALL)                                                  \
@@ -1721,7 +1826,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
     // fold only where the fused x pass reads the table (own passes); the k-space kernel of the cuFFT (x, y) fallback indexes it plainly
     const bool ortho = p->recip[1] == 0.0 && p->recip[2] == 0.0 && p->recip[3] == 0.0 && p->recip[5] == 0.0 && p->recip[6] == 0.0 &&
                        p->recip[7] == 0.0;
-    const MixWgc mixw{reinterpret_cast<const double2*>(kern), (g_pad_fold_table && ortho && own) ? 1 : 0};
+    const MixWgc mixw{reinterpret_cast<const double2*>(kern), (g_pad_fold_table && ortho && own && !p->dist) ? 1 : 0};      // (a slab holds only its own rows of the table)
     GenWgcA genA{scal, beta};
 
     if (own && want_v) {
@@ -1928,7 +2033,7 @@ struct MixWt {                         // fields 0 (, 1): Lindhard kernel / N;  
     struct Line { KLine kl; size_t prow, kxs; };
     __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const {
         const int fy = ky <= g.n1 - ky ? ky : g.n1 - ky;
-        return Line{make_kline(g, ky, z), (size_t)fy * g.nzp_pad + z, (size_t)g.n1 * g.nzp_pad};
+        return Line{make_kline(g, ky, z), (size_t)fy * g.nzp_pad + z, (size_t)g.n1_loc * g.nzp_pad};
     }
     __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const {
         Coef c{0.0, 0.0};
@@ -2066,7 +2171,7 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     {   // Lindhard table (padded layout), cached per lattice and n0
         bool fresh = false;
         if (!p->wt_kern) {
-            const size_t bytes = sizeof(double) * (size_t)p->n0 * p->n1 * p->nzp;
+            const size_t bytes = sizeof(double) * (size_t)p->n0 * (p->dist ? p->n1_loc : p->n1) * p->nzp;      // the plan's own rows
             PAD_CUDA(cudaMalloc(&p->wt_kern, bytes));
             PAD_CUDA(cudaMemsetAsync(p->wt_kern, 0, bytes, s));
             p->bytes_allocated += bytes;
@@ -2081,7 +2186,7 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     }
     pad_stage_mark("WT: Lindhard table check", s);
     GenWt<TWO> gen{scal, alpha, beta};
-    const int wt_fold = (g_pad_fold_table && p->recip[1] == 0.0 && p->recip[2] == 0.0 && p->recip[3] == 0.0 && p->recip[5] == 0.0 &&
+    const int wt_fold = (g_pad_fold_table && !p->dist && p->recip[1] == 0.0 && p->recip[2] == 0.0 && p->recip[3] == 0.0 && p->recip[5] == 0.0 &&
                          p->recip[6] == 0.0 && p->recip[7] == 0.0) ? 1 : 0;
     if (pipe_shape(p)) {
         ZDISPATCH(p, PAD_TRY((launch_zy_fwd<M, TPL, NF>(p, s, gen, den, nullptr, B))));

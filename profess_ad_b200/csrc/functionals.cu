@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(PAD_THREADS) wgc_build_kernel(KGeom g, uint32_
         const double sc = k.special ? 0.5 : 1.0;
         for (int c = 0; c < 4; ++c) kern[(size_t)c * nk + idx] = sc * out[c];
         if (kern4) {     // interleaved copy over the padded layout for the fused x pass (fft_strided.cuh)
-            double2* o = reinterpret_cast<double2*>(kern4) + 2 * (((size_t)k.j0 * g.n1 + k.j1) * g.nzp_pad + k.j2);
+            double2* o = reinterpret_cast<double2*>(kern4) + 2 * (((size_t)k.j0 * g.n1_loc + (k.j1 - g.j1_off)) * g.nzp_pad + k.j2);
             o[0] = make_double2(sc * out[0], sc * out[1]);
             o[1] = make_double2(sc * out[2], sc * out[3]);
         }
@@ -702,7 +702,7 @@ int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta,
         p->wgc_key[5] = 0.0;
     }
     if (!p->wgc_kern4 && pad_wgc99_fast_supported(p)) {
-        const size_t bytes = sizeof(double) * 4 * (size_t)p->n0 * p->n1 * p->nzp;
+        const size_t bytes = sizeof(double) * 4 * (size_t)p->n0 * (p->dist ? p->n1_loc : p->n1) * p->nzp;      // the plan's own rows
         PAD_CUDA(cudaMalloc(&p->wgc_kern4, bytes));
         PAD_CUDA(cudaMemsetAsync(p->wgc_kern4, 0, bytes, s));
         p->bytes_allocated += bytes;

@@ -415,7 +415,21 @@ extern "C" int pad_plan_set_overlap_buffers(pad_plan* p, void* send_buf2, void* 
     return PAD_OK;
 }
 
-static int ensure_comm_stream(pad_plan* p) {
+extern "C" size_t pad_slab_fast_elements(const pad_plan* p) {
+    return (p && p->dist) ? (size_t)p->n0_loc * p->n1 * p->nzp : 0;
+}
+extern "C" int pad_plan_set_slab_fast_buffers(pad_plan* p, void* const* six) {
+    if (!p || !p->dist || !six) { pad_set_error("pad_plan_set_slab_fast_buffers: needs a slab plan and six buffers"); return PAD_ERR_ARG; }
+    for (int i = 0; i < 6; ++i) {
+        if (!six[i]) { pad_set_error("pad_plan_set_slab_fast_buffers: buffer %d is null", i); return PAD_ERR_ARG; }
+        p->slab_fast[i] = six[i];
+    }
+    return PAD_OK;
+}
+
+int pad_ensure_comm_stream(pad_plan* p);
+static int ensure_comm_stream(pad_plan* p) { return pad_ensure_comm_stream(p); }
+int pad_ensure_comm_stream(pad_plan* p) {
     if (p->comm_ready) return PAD_OK;
     PAD_CUDA(cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {

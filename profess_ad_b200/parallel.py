@@ -118,7 +118,7 @@ class ThreadComm:
 class SlabPlan(_native.Plan):
     """``pad_plan`` for this rank's slab of a global grid."""
 
-    def __init__(self, box_host, global_shape, device_index, comm, overlap=True):
+    def __init__(self, box_host, global_shape, device_index, comm, overlap=True, fast=True):
         self.lib = _native.load_library()
         self.comm = comm
         self.global_shape = tuple(int(s) for s in global_shape)
@@ -138,6 +138,14 @@ class SlabPlan(_native.Plan):
         if self.overlap:
             self.send2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
             self.recv2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+        # fused FFT pipeline on the slabs (csrc/fftz.cu: own z / y / x passes, the y pass stores its rows blocked by
+        # destination rank so the exchange needs no pack kernel): four spectrum fields + two exchange stagings in the
+        # padded layout, registered with the library; the callback exchanges them by index
+        self.fast = []
+        if fast and all(n in (64, 128, 256, 512) for n in (n0, n1)) and n2 in (128, 256, 512):
+            nzp = n2 // 2 + 8
+            nfast = (n0 // comm.world) * n1 * nzp
+            self.fast = [torch.zeros(nfast, dtype=torch.complex128, device=dev) for _ in range(6)]
         streams = {}
 
         def callback(_user, op, count, stream):
@@ -163,6 +171,9 @@ class SlabPlan(_native.Plan):
                         self.comm.all_reduce(self.scratch[:count])
                     elif op == 2:
                         self.comm.all_reduce_max(self.scratch[:count])
+                    elif op >= 16:
+                        dst, src = divmod(op - 16, 8)
+                        self.comm.all_to_all(self.fast[dst], self.fast[src])
                     else:
                         raise ValueError(f'unknown communication op {op}')
                 return 0
@@ -180,6 +191,9 @@ class SlabPlan(_native.Plan):
                                                     _native.ptr(self.scratch), self._callback, None))
         if self.overlap:
             _native.check(self.lib.pad_plan_set_overlap_buffers(self.handle, _native.ptr(self.send2), _native.ptr(self.recv2)))
+        if self.fast:
+            arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.fast])
+            _native.check(self.lib.pad_plan_set_slab_fast_buffers(self.handle, arr))
         self.box = tuple(box_host)
         self._set_geometry()
 
