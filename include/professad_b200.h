@@ -115,6 +115,14 @@ int pad_plan_set_overlap_buffers(pad_plan* plan, void* send_buf2, void* recv_buf
  * PAD_COMM_ALL_TO_ALL_FAST + 8 * dst + src, issued on the plan's communication stream field by field while the neighbouring
  * fields' passes run) needs no pack / unpack kernel, and the kernel mix is fused into the x pass of the transposed layout. */
 size_t pad_slab_fast_elements(const pad_plan* plan);
+/* Same pipeline with the transposition fused into the passes (the B200 / NVSwitch form): base_ptrs[r] is rank r's symmetric
+ * allocation of 8 * pad_slab_fast_elements(plan) complex128 -- four spectrum fields in the local layout followed by the same four
+ * in the transposed layout -- mapped into THIS process (peer access over NVLink; torch symmetric memory in parallel.py).  The
+ * forward y pass then stores every result row straight into the owner rank's transposed buffer and the fused x pass stores its
+ * inverse transform straight into the owner ranks' local buffers; the only collective left is a barrier (fn with op
+ * PAD_COMM_BARRIER) between producer and consumer passes.  world <= 8. */
+#define PAD_COMM_BARRIER 4
+int pad_plan_set_slab_peer_buffers(pad_plan* plan, void* const* base_ptrs, int world);
 int pad_plan_set_slab_fast_buffers(pad_plan* plan, void* const* six_buffers);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
 size_t pad_plan_workspace_bytes(const pad_plan* plan);

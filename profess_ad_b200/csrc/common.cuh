@@ -275,6 +275,8 @@ struct pad_plan {
     // second exchange buffer pair + a communication stream: batches of transforms are software-pipelined so that the
     // all-to-all of one field runs while the local FFTs of its neighbours do (pad_fft_forward_many / _inverse_many)
     void *send_buf2, *recv_buf2;
+    bool slab_push;              // peer pointers registered (pad_plan_set_slab_peer_buffers): transposition by NVLink stores of the y / x passes
+    void *peer_B[4][8], *peer_T[4][8];      // [field][rank]: local-layout and transposed-layout spectrum buffers of every rank
     void* slab_fast[6];          // fused pipeline on slabs: 4 spectrum buffers + 2 exchange stagings of n0_loc * n1 * nzp complex, owned by the caller
     cudaStream_t comm_stream;
     cudaEvent_t ev_ready[2], ev_a2a[2], ev_free[2];

@@ -204,9 +204,17 @@ struct SPassBlocked {
     long long outer_stride;    // complex elements between consecutive x-planes inside a block: n1_loc * nzp
 };
 
+// BLK = 3: as BLK = 1, but the block of rank r is stored straight into rank r's transposed-layout buffer over NVLink (peer
+// pointers, symmetric memory): peers.p[r] + my_rank * block_stride is where "the block that came from me" lives over there.
+// The transfer then overlaps the transform tile by tile and there is neither a staging buffer nor a separate collective.
+struct SPassPeers {
+    cd* p[8];
+    int my_rank;
+};
+
 template <int L, int DIR, int BLK>
 __global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_blocked_kernel(const cd* __restrict__ src, cd* __restrict__ dst,
-                                                                                 SPassGeom geo, SPassBlocked bl) {
+                                                                                 SPassGeom geo, SPassBlocked bl, SPassPeers peers) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -233,8 +241,13 @@ __global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_blocked_kern
 #pragma unroll
             for (int s = 0; s < P::EPT; ++s) {
                 const int y = spass_out_index<L>(t, s);
-                const long long off = BLK == 1 ? blk + blocked_row(y) : nat + (long long)y * geo.axis_stride;
-                dst[off] = v[s];
+                if constexpr (BLK == 3) {
+                    const int r = y / bl.rows;
+                    peers.p[r][(long long)peers.my_rank * bl.block_stride + blk + (long long)(y - r * bl.rows) * geo.axis_stride] = v[s];
+                } else {
+                    const long long off = BLK == 1 ? blk + blocked_row(y) : nat + (long long)y * geo.axis_stride;
+                    dst[off] = v[s];
+                }
             }
         }
     }
@@ -276,9 +289,19 @@ constexpr int xmix_ctas_per_sm() { return L >= 512 ? (NF == 1 ? 2 : 1) : (NF == 
 template <int L>
 inline constexpr bool kXmixWide = (L == 512);
 
-template <int L, int NF, class Mix>
+// PUSH (slab plans with peer pointers): the result of the inverse x transform is not stored in place but straight into the
+// LOCAL-layout buffers (n0_loc, n1, nzp) of the ranks that own the x-planes -- the transposition back rides on the stores of
+// this kernel over NVLink, and the inverse y pass that follows is the ordinary local in-place pass.
+struct XmixPush {
+    cd* peer[4][8];            // [field][rank]: that rank's local-layout buffer of the field
+    int n0_loc_log2;           // x-planes per rank = 1 << n0_loc_log2
+    int n1;                    // rows of a local-layout plane
+    int y0;                    // first global row of this rank: rank * n1_loc
+};
+
+template <int L, int NF, class Mix, bool PUSH = false>
 __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_per_sm<L, NF>()))
-    xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix) {
+    xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix, XmixPush push) {
     constexpr bool W = kXmixWide<L>;
     using P = SPass<L, W>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -365,9 +388,19 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
             tile_fft<L, +1, W>(u, B0 + f * P::TILE_CD, t, c, tw);
             issue(f, nxt);
             if (cur.live) {
-                cd* base = fields.f[f] + cur.off;
+                if constexpr (PUSH) {
+                    const size_t rowz = (size_t)(push.y0 + cur.o) * kg.nzp_pad + cur.z;
 #pragma unroll
-                for (int s = 0; s < P::EPT; ++s) base[(size_t)spass_out_index<L, W>(t, s) * xs] = u[s];
+                    for (int s = 0; s < P::EPT; ++s) {
+                        const int x = spass_out_index<L, W>(t, s);
+                        const int r = x >> push.n0_loc_log2, xl = x - (r << push.n0_loc_log2);
+                        push.peer[f][r][(size_t)xl * push.n1 * kg.nzp_pad + rowz] = u[s];
+                    }
+                } else {
+                    cd* base = fields.f[f] + cur.off;
+#pragma unroll
+                    for (int s = 0; s < P::EPT; ++s) base[(size_t)spass_out_index<L, W>(t, s) * xs] = u[s];
+                }
             }
         }
         cur = nxt;

@@ -934,7 +934,8 @@ int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, co
 }
 
 template <int L, int DIR, int BLK>
-int launch_spass_blocked_L(pad_plan* p, cudaStream_t s, const cd* src, cd* dst, const SPassGeom& g, const SPassBlocked& bl) {
+int launch_spass_blocked_L(pad_plan* p, cudaStream_t s, const cd* src, cd* dst, const SPassGeom& g, const SPassBlocked& bl,
+                           const SPassPeers& peers = SPassPeers{}) {
     auto kern = spass_blocked_kernel<L, DIR, BLK>;
     constexpr int smem = spass_smem_bytes<L>(1);
     static bool attr_done[64] = {false};
@@ -945,7 +946,7 @@ int launch_spass_blocked_L(pad_plan* p, cudaStream_t s, const cd* src, cd* dst, 
     const long long tiles = spass_tiles(g);
     long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
     if (grid > (1 << 20)) grid = 1 << 20;
-    kern<<<(unsigned)grid, 128, smem, s>>>(src, dst, g, bl);
+    kern<<<(unsigned)grid, 128, smem, s>>>(src, dst, g, bl, peers);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
@@ -968,12 +969,53 @@ int launch_spass_blocked(pad_plan* p, cudaStream_t s, int dir, const cd* src, cd
     return PAD_ERR_ARG;
 }
 
+// index of a registered slab spectrum buffer (0..3), or -1
+int slab_field_index(const pad_plan* p, const cd* ptr) {
+    for (int i = 0; i < 4; ++i)
+        if (ptr == reinterpret_cast<const cd*>(p->slab_fast[i])) return i;
+    return -1;
+}
+
+// forward y pass of field `fi` with its result rows pushed into the owner ranks' transposed buffers
+int launch_spass_push(pad_plan* p, cudaStream_t s, int fi) {
+    const SPassGeom g = spass_geom(p, 1);
+    const SPassBlocked bl{p->n1_loc, (long long)p->n0_loc * p->n1_loc * p->nzp, (long long)p->n1_loc * p->nzp};
+    SPassPeers peers;
+    for (int r = 0; r < 8; ++r) peers.p[r] = r < p->world ? reinterpret_cast<cd*>(p->peer_T[fi][r]) : nullptr;
+    peers.my_rank = p->rank;
+    const cd* src = reinterpret_cast<const cd*>(p->peer_B[fi][p->rank]);
+    switch (p->n1) {
+        case 64: return launch_spass_blocked_L<64, -1, 3>(p, s, src, nullptr, g, bl, peers);
+        case 128: return launch_spass_blocked_L<128, -1, 3>(p, s, src, nullptr, g, bl, peers);
+        case 256: return launch_spass_blocked_L<256, -1, 3>(p, s, src, nullptr, g, bl, peers);
+        case 512: return launch_spass_blocked_L<512, -1, 3>(p, s, src, nullptr, g, bl, peers);
+    }
+    pad_set_error("strided FFT pass: length %d not supported", p->n1);
+    return PAD_ERR_ARG;
+}
+
+int launch_spass_local(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf);
+
 // Slab plans, y axis: the pass and the transposition of a batch of fields, software-pipelined over the two stagings.
 //   forward:  fields[f] (local layout) --y pass, rows blocked by rank--> staging b --all-to-all--> fields[f] (transposed layout)
 //   inverse:  fields[f] (transposed)   --all-to-all--> staging b --y pass from blocked rows--> fields[f] (local layout)
 // The exchange of field f runs on the plan's communication stream while the pass of field f + 1 (forward) or f - 1 (inverse)
 // runs on `s`; fields[] must be slab_fast buffers 0..3 in order (the callback names them by index).
 int slab_ypass_exchange(pad_plan* p, cudaStream_t s, int dir, cd* const* fields, int nf) {
+    if (p->slab_push) {
+        // peer pointers: forward = y pass with pushed rows, then a barrier (every rank's rows have arrived before the x pass
+        // reads the transposed buffers); inverse = barrier (every rank's x pass has pushed its planes), then the plain local pass
+        if (dir < 0) {
+            for (int f = 0; f < nf; ++f) {
+                const int fi = slab_field_index(p, fields[f]);
+                if (fi < 0) { pad_set_error("slab y pass: field %d is not a registered slab buffer", f); return PAD_ERR_ARG; }
+                PAD_TRY(launch_spass_push(p, s, fi));
+            }
+            return pad_slab_comm(p, PAD_COMM_BARRIER, 0, s);
+        }
+        PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER, 0, s));
+        return launch_spass_local(p, s, 1, +1, fields, nf);
+    }
     PAD_TRY(pad_ensure_comm_stream(p));
     int idx[4];
     for (int f = 0; f < nf; ++f) {
@@ -1025,6 +1067,10 @@ int slab_ypass_exchange(pad_plan* p, cudaStream_t s, int dir, cd* const* fields,
 // in-place FFT of nf padded half-spectra along axis 0 (x) or 1 (y)
 int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf) {
     if (p->dist && axis == 1) return slab_ypass_exchange(p, s, dir, fields, nf);
+    if (p->dist && p->slab_push) { pad_set_error("slab plan with peer buffers: a bare x pass is not part of the pipeline"); return PAD_ERR_ARG; }
+    return launch_spass_local(p, s, axis, dir, fields, nf);
+}
+int launch_spass_local(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fields, int nf) {
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < nf ? fields[i] : nullptr;
     const SPassGeom g = spass_geom(p, axis);
@@ -1043,9 +1089,9 @@ int launch_spass(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const* fiel
     return PAD_ERR_ARG;
 }
 
-template <int L, int NF, class Mix>
-int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix) {
-    auto kern = xmix_kernel<L, NF, Mix>;
+template <int L, int NF, class Mix, bool PUSH = false>
+int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix, const XmixPush& push = XmixPush{}) {
+    auto kern = xmix_kernel<L, NF, Mix, PUSH>;
     using P = SPass<L, kXmixWide<L>>;
     constexpr int smem = spass_smem_bytes<L, kXmixWide<L>>(NF);
     static bool attr_done[64] = {false};
@@ -1061,7 +1107,7 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     const long long tiles = spass_tiles(g);
     long long grid = (tiles + P::TPC - 1) / P::TPC;
     if (grid > 148 * per_sm) grid = 148 * per_sm;
-    kern<<<(unsigned)grid, P::THREADS, smem, s>>>(f, g, p->geom, mix);
+    kern<<<(unsigned)grid, P::THREADS, smem, s>>>(f, g, p->geom, mix, push);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
@@ -1073,6 +1119,28 @@ int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < NF ? fields[i] : nullptr;
     const SPassGeom g = spass_geom(p, 0);
+    if (p->dist && p->slab_push) {
+        // the fields live in the transposed buffers (the forward y passes pushed them there); results go to the owners' local buffers
+        XmixPush push;
+        for (int i = 0; i < NF; ++i) {
+            const int fi = slab_field_index(p, fields[i]);
+            if (fi < 0) { pad_set_error("fused x pass: field %d is not a registered slab buffer", i); return PAD_ERR_ARG; }
+            f.f[i] = reinterpret_cast<cd*>(p->peer_T[fi][p->rank]);
+            for (int r = 0; r < 8; ++r) push.peer[i][r] = r < p->world ? reinterpret_cast<cd*>(p->peer_B[fi][r]) : nullptr;
+        }
+        int lg = 0;
+        while ((1 << lg) < p->n0_loc) ++lg;
+        if ((1 << lg) != p->n0_loc) { pad_set_error("fused x pass on slabs: n0 / world = %d must be a power of two", p->n0_loc); return PAD_ERR_ARG; }
+        push.n0_loc_log2 = lg; push.n1 = p->n1; push.y0 = p->rank * p->n1_loc;
+        switch (p->n0) {
+            case 64: return launch_xmix_L<64, NF, Mix, true>(p, s, f, g, mix, push);
+            case 128: return launch_xmix_L<128, NF, Mix, true>(p, s, f, g, mix, push);
+            case 256: return launch_xmix_L<256, NF, Mix, true>(p, s, f, g, mix, push);
+            case 512: return launch_xmix_L<512, NF, Mix, true>(p, s, f, g, mix, push);
+        }
+        pad_set_error("fused x pass: length %d not supported", p->n0);
+        return PAD_ERR_ARG;
+    }
     switch (p->n0) {
         case 64: return launch_xmix_L<64, NF>(p, s, f, g, mix);
         case 128: return launch_xmix_L<128, NF>(p, s, f, g, mix);

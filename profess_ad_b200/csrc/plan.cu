@@ -427,6 +427,25 @@ extern "C" int pad_plan_set_slab_fast_buffers(pad_plan* p, void* const* six) {
     return PAD_OK;
 }
 
+extern "C" int pad_plan_set_slab_peer_buffers(pad_plan* p, void* const* base, int world) {
+    if (!p || !p->dist || !base || world != p->world || world > 8) {
+        pad_set_error("pad_plan_set_slab_peer_buffers: needs a slab plan, base pointers of all %d ranks and world <= 8", p ? p->world : 0);
+        return PAD_ERR_ARG;
+    }
+    const size_t each = (size_t)p->n0_loc * p->n1 * p->nzp * sizeof(double) * 2;
+    for (int r = 0; r < world; ++r) {
+        if (!base[r]) { pad_set_error("pad_plan_set_slab_peer_buffers: rank %d has no buffer", r); return PAD_ERR_ARG; }
+        for (int f = 0; f < 4; ++f) {
+            p->peer_B[f][r] = static_cast<char*>(base[r]) + (size_t)f * each;
+            p->peer_T[f][r] = static_cast<char*>(base[r]) + (size_t)(4 + f) * each;
+        }
+    }
+    for (int f = 0; f < 4; ++f) p->slab_fast[f] = p->peer_B[f][p->rank];
+    p->slab_fast[4] = p->slab_fast[5] = nullptr;
+    p->slab_push = true;
+    return PAD_OK;
+}
+
 int pad_ensure_comm_stream(pad_plan* p);
 static int ensure_comm_stream(pad_plan* p) { return pad_ensure_comm_stream(p); }
 int pad_ensure_comm_stream(pad_plan* p) {

@@ -56,6 +56,35 @@ class TorchDistComm:
     def all_reduce_max(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
 
+    def symmetric_buffer(self, numel, device):
+        """``numel`` complex128 of symmetric memory (torch.distributed._symmetric_memory: the same allocation on every rank,
+        mapped into every process of the node over NVLink).  Returns (tensor, [address of rank r's copy in THIS process]),
+        or None when the box cannot do it (no peer access; PAD_SLAB_PEER=0) -- the caller then uses the staged exchange."""
+        if os.environ.get('PAD_SLAB_PEER', '1') == '0' or self.world > 8:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(numel, dtype=torch.complex128, device=device)
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else self.dist.group.WORLD)
+            t.zero_()
+            self._symm = getattr(self, '_symm', []) + [(t, hdl)]
+            self._barrier_hdl = hdl
+            hdl.barrier()
+            return t, [int(p) for p in hdl.buffer_ptrs]
+        except Exception as e:      # noqa: BLE001 -- an optimisation, never a failure
+            self.symm_error = repr(e)
+            return None
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks (signal pads of the symmetric allocation; a 1-element all-reduce otherwise)."""
+        hdl = getattr(self, '_barrier_hdl', None)
+        if hdl is not None:
+            hdl.barrier()
+        else:
+            if not hasattr(self, '_one'):
+                self._one = torch.zeros(1, device='cuda')
+            self.dist.all_reduce(self._one, group=self.group)
+
 
 class SingleComm:
     """world = 1: the exchange is a copy (exercises the slab code path on one GPU)."""
@@ -68,6 +97,13 @@ class SingleComm:
         pass
 
     def all_reduce_max(self, t):
+        pass
+
+    def symmetric_buffer(self, numel, device):
+        t = torch.zeros(numel, dtype=torch.complex128, device=device)
+        return t, [t.data_ptr()]
+
+    def barrier(self):
         pass
 
 
@@ -114,6 +150,24 @@ class ThreadComm:
     def all_reduce_max(self, t):
         self.all_reduce(t, op=torch.maximum)
 
+    def symmetric_buffer(self, numel, device):
+        """The ranks are threads of one process on one GPU: every rank's buffer is directly addressable -- the peer-pointer
+        kernels run exactly as over NVLink."""
+        if os.environ.get('PAD_SLAB_PEER', '1') == '0':
+            return None
+        sh = self.shared
+        t = torch.zeros(numel, dtype=torch.complex128, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        sh.vals[self.rank] = t
+        sh.barrier.wait()
+        ptrs = [sh.vals[r].data_ptr() for r in range(self.world)]
+        sh.barrier.wait()
+        return t, ptrs
+
+    def barrier(self):
+        torch.cuda.current_stream().synchronize()
+        self.shared.barrier.wait()
+
 
 class SlabPlan(_native.Plan):
     """``pad_plan`` for this rank's slab of a global grid."""
@@ -141,11 +195,18 @@ class SlabPlan(_native.Plan):
         # fused FFT pipeline on the slabs (csrc/fftz.cu: own z / y / x passes, the y pass stores its rows blocked by
         # destination rank so the exchange needs no pack kernel): four spectrum fields + two exchange stagings in the
         # padded layout, registered with the library; the callback exchanges them by index
-        self.fast = []
+        # Preferred form (NVLink / NVSwitch): ONE symmetric allocation per rank holding the four fields in the local and in
+        # the transposed layout, mapped into every process -- the y and x passes then store their results straight into the
+        # owner ranks' buffers and the only collective left is a barrier.
+        self.fast, self.peer = [], None
         if fast and all(n in (64, 128, 256, 512) for n in (n0, n1)) and n2 in (128, 256, 512):
             nzp = n2 // 2 + 8
             nfast = (n0 // comm.world) * n1 * nzp
-            self.fast = [torch.zeros(nfast, dtype=torch.complex128, device=dev) for _ in range(6)]
+            sym = comm.symmetric_buffer(8 * nfast, dev) if hasattr(comm, 'symmetric_buffer') else None
+            if sym is not None:
+                self.peer = sym
+            else:
+                self.fast = [torch.zeros(nfast, dtype=torch.complex128, device=dev) for _ in range(6)]
         streams = {}
 
         def callback(_user, op, count, stream):
@@ -171,6 +232,8 @@ class SlabPlan(_native.Plan):
                         self.comm.all_reduce(self.scratch[:count])
                     elif op == 2:
                         self.comm.all_reduce_max(self.scratch[:count])
+                    elif op == 4:
+                        self.comm.barrier()
                     elif op >= 16:
                         dst, src = divmod(op - 16, 8)
                         self.comm.all_to_all(self.fast[dst], self.fast[src])
@@ -194,6 +257,9 @@ class SlabPlan(_native.Plan):
         if self.fast:
             arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.fast])
             _native.check(self.lib.pad_plan_set_slab_fast_buffers(self.handle, arr))
+        if self.peer is not None:
+            arr = (ctypes.c_void_p * comm.world)(*self.peer[1])
+            _native.check(self.lib.pad_plan_set_slab_peer_buffers(self.handle, arr, comm.world))
         self.box = tuple(box_host)
         self._set_geometry()
 

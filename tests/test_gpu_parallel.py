@@ -79,11 +79,15 @@ def test_slab_matches_oracle(world, shape):
         assert err < 1e-9, (name, world, err)
 
 
-@pytest.mark.parametrize('world,shape', [(1, (64, 64, 128)), (2, (64, 128, 128)), (4, (128, 64, 128)), (2, (64, 64, 256))])
-def test_slab_fused_pipeline_matches_single_gpu_and_oracle(world, shape):
-    """Grids the hand-written z / y / x passes cover: the slab plans run the fused pipeline (the y pass stores its rows blocked
-    by destination rank, all-to-all, kernel mix inside the x pass of the transposed layout) -- no cuFFT call -- and must give
-    what the single-GPU pipeline and the oracle give."""
+@pytest.mark.parametrize('world,shape,peer', [(1, (64, 64, 128), 1), (2, (64, 128, 128), 1), (4, (128, 64, 128), 1), (2, (64, 64, 256), 1),
+                                              (2, (128, 64, 128), 0), (4, (64, 128, 128), 0), (1, (64, 64, 128), 0)])
+def test_slab_fused_pipeline_matches_single_gpu_and_oracle(world, shape, peer, monkeypatch):
+    """Grids the hand-written z / y / x passes cover: the slab plans run the fused pipeline -- no cuFFT call -- and must give
+    what the single-GPU pipeline and the oracle give.  peer = 1: every rank's buffers are addressable by the others (symmetric
+    memory over NVLink; here: threads sharing the GPU), the y pass pushes its rows into the owners' transposed buffers and the
+    fused x pass pushes its planes back, barriers in between.  peer = 0: the y pass stores its rows blocked by destination
+    rank into a staging buffer and an all-to-all moves the blocks."""
+    monkeypatch.setenv('PAD_SLAB_PEER', str(peer))
     from oracle import ofdft_oracle as orc
     import profess_ad_b200.functionals as F
     from profess_ad_b200 import _native
