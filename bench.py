@@ -84,9 +84,12 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled every ~5 ms through NVML while the timed region runs
-    (nvidia-smi polling is too slow for a sub-second region)."""
+    """SM clock / throttle reasons sampled through NVML while the timed region runs (nvidia-smi polling is too slow for a
+    sub-second region).  NVML is initialised BEFORE the region and polled every 25 ms: every query takes the driver's lock, so
+    a tighter loop (5 ms in earlier rounds) -- or nvmlInit inside the region -- showed up as stalled kernel launches on some
+    boxes (3.8 instead of 2.2 ms per step with one sample taken)."""
     REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+    PERIOD = 0.025
 
     def __init__(self, index):
         self.index = index
@@ -97,35 +100,55 @@ class ClockSampler:
         self.err = None
         self.max_mhz = None
         self.power = []
-
-    def _run(self):
+        self.nvml = self.handle = None
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
+
+    def _sample(self):
+        pynvml, h = self.nvml, self.handle
+        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        try:
+            self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+
+    def _run(self):
+        try:
             while not self.stop_flag:
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                try:
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                try:
-                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                except Exception:
-                    pass
-                time.sleep(0.005)
+                time.sleep(self.PERIOD)
+                if not self.stop_flag:
+                    self._sample()
         except Exception as e:      # noqa: BLE001
             self.err = repr(e)
 
     def start(self):
+        if self.handle is None:
+            return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
     def stop(self):
+        """Call while the GPU is still busy with the last timed steps (before the closing synchronise): takes a final sample."""
         self.stop_flag = True
         if self.thread is not None:
             self.thread.join(timeout=2)
+        if self.handle is not None:
+            try:
+                for i in range(3):          # the launch loop runs far ahead of the GPU: these fall into the timed work
+                    self._sample()
+                    time.sleep(0.008)
+            except Exception as e:      # noqa: BLE001
+                self.err = repr(e)
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + str(self.err)]}
         sm = sorted(self.samples)
@@ -315,6 +338,7 @@ def run_gpu(args):
     for _ in range(args.steps):
         E, g = step_device()
     ev1.record()
+    clocks = sampler.stop() if rank == 0 else None      # the queue still holds timed steps: a sample under load
     barrier()
     launches = int(lib.pad_launch_count() - l0)
     fft_execs = int(lib.pad_fft_exec_count() - f0)
@@ -323,7 +347,6 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = t.item()
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
 
@@ -632,7 +655,8 @@ def slab_measure(n, functional, steps, warmup, overlap=None):
         fun, label = hc.forward, type(hc).__name__
     if overlap is None:
         overlap = os.environ.get('PAD_SLAB_OVERLAP', '1') != '0'
-    with parallel.slab((n, n, n), overlap=overlap):
+    path = {}
+    with parallel.slab((n, n, n), overlap=overlap) as ctx:
         def step():
             d = den.requires_grad_(True)
             E = fun(box, d)
@@ -655,6 +679,19 @@ def slab_measure(n, functional, steps, warmup, overlap=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item() / steps
         e_val = E.item()
+        plan = next(iter(ctx.plans.values()), None)
+        lib = plan.lib if plan is not None else None
+        fused = bool(plan is not None and lib.pad_fast_fft_supported(plan.handle)) and functional in ('wgc99',)
+        if fused and plan.peer is not None:
+            path = {'transforms': 'own z / y / x FFT passes per rank; the forward y pass stores its rows into the owner ranks\' transposed '
+                                  'buffers and the fused x pass (kernel mix inside) stores its planes into the owners\' local buffers '
+                                  'over NVLink (symmetric memory), barriers instead of all-to-alls', 'exchange': 'peer stores'}
+        elif fused:
+            path = {'transforms': 'own z / y / x FFT passes per rank, y pass stores rows blocked by destination rank, NCCL all-to-all '
+                                  'pipelined over two stagings', 'exchange': 'all_to_all_single'}
+        else:
+            path = {'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
+                    'exchange': 'all_to_all_single'}
     npts = n ** 3
     if hc is not None:
         n_fft = 12 + 2 * int(getattr(hc, 'last_n_nodes', 0))
@@ -669,8 +706,7 @@ def slab_measure(n, functional, steps, warmup, overlap=None):
         'data': 'synthetic',
         'config': {'workload': f'Al {4 * side ** 3}-atom supercell, {label} E+V, {n}^3 grid, slabs of {n // world} planes per GPU',
                    'n_fft': n_fft, 'grid': [n] * 3, 'energy_Ha': e_val,
-                   'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
-                   'exchange_overlap': bool(overlap)},
+                   'transforms': path.get('transforms'), 'exchange': path.get('exchange'), 'exchange_overlap': bool(overlap)},
         'roofline': {'bound': 'hbm', 'achieved': balg / (ms * 1e-3) / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
                      'frac': balg / (ms * 1e-3) / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_eval': balg, 'per': 'GPU',
@@ -757,7 +793,8 @@ def slab_block(world, steps, warmup):
                         'hbm_frac_per_gpu': m['roofline']['frac'], 'hbm_GBps_per_gpu': m['roofline']['achieved'],
                         'nvlink_GBps_each_way': m['roofline']['nvlink_GBps_each_way'],
                         'nvlink_frac_of_900': m['roofline']['nvlink_GBps_each_way'] / 900.0,
-                        'transforms': m['config']['transforms'], 'exchange_overlap': m['config']['exchange_overlap']})
+                        'transforms': m['config']['transforms'], 'exchange': m['config']['exchange'],
+                        'exchange_overlap': m['config']['exchange_overlap']})
         except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
             out.append({'workload': f'{fun} {n}^3', 'error': repr(e)})
         torch.cuda.empty_cache()
