@@ -335,10 +335,12 @@ def run_gpu(args):
     l0, f0 = lib.pad_launch_count(), lib.pad_fft_exec_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         E, g = step_device()
     ev1.record()
-    clocks = sampler.stop() if rank == 0 else None      # the queue still holds timed steps: a sample under load
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps       # CPU time to queue one step (no sync inside)
+    clocks = sampler.stop()      # every rank: the queue still holds timed steps, so these samples are taken under load
     barrier()
     launches = int(lib.pad_launch_count() - l0)
     fft_execs = int(lib.pad_fft_exec_count() - f0)
@@ -347,6 +349,18 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = t.item()
+    t = torch.tensor([host_enqueue_ms], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    host_enqueue_ms = t.item()
+    per_rank = None
+    if world > 1:
+        # the reported time is the MAX over the ranks; keep every rank's own figures beside it (which GPU was slow, and was it
+        # the GPU -- clock -- or its host process -- enqueue time)
+        mine = torch.tensor([ev0.elapsed_time(ev1) / args.steps, float(clocks.get('sm_mhz') or 0.0)], dtype=torch.double, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {'ms_per_step': [round(a[0].item(), 4) for a in allr], 'sm_mhz': [a[1].item() for a in allr]}
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
 
@@ -452,7 +466,7 @@ def run_gpu(args):
             'config': workload_config(),
             'config_detail': {'per_gpu': 'one independent system per GPU',
                               'l2': 'working set per evaluation (>= 2 GB of fields) exceeds the 126 MB L2',
-                              'energy_Ha': e_check, 'pipelined_zy_kernels': bool(int(os.environ.get('PAD_PIPE', '1')))},
+                              'energy_Ha': e_check, 'per_rank': per_rank},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': npts * 8, 'd2h_bytes_per_step': npts * 8 + 8,
                     'how': 'profess_ad_b200.streaming.HostPipeline: H2D / evaluate / D2H of consecutive steps on 3 streams, 2 device buffers',
@@ -460,7 +474,7 @@ def run_gpu(args):
                     'per_rank_host_link_GBps_each_way': (e2e_value / world) * npts * 8 / 1e9,
                     'numa': numa},
             'gpu_launches': launches + fft_execs,
-            'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs},
+            'launch_detail': {'own_kernels': launches, 'cufft_execs': fft_execs, 'host_enqueue_ms_per_step': host_enqueue_ms},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': NCU_TRAFFIC_256['evaluation'] if GRID == 256 else None,
                          'traffic_source': NCU_TRAFFIC_SOURCE,
