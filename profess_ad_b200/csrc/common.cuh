@@ -275,6 +275,16 @@ struct pad_plan {
     // second exchange buffer pair + a communication stream: batches of transforms are software-pipelined so that the
     // all-to-all of one field runs while the local FFTs of its neighbours do (pad_fft_forward_many / _inverse_many)
     void *send_buf2, *recv_buf2;
+    // CUDA graphs of whole evaluations (pad_eval_wgc99 / the fused term list): one instantiated graph per distinct argument set
+    struct GraphSlot {
+        unsigned long long key[14];
+        void* exec;                  // cudaGraphExec_t
+        unsigned long long launches; // kernels in the graph (pad_launch_count goes up by this per replay)
+        unsigned long long stamp;    // last use (LRU)
+        int state;                   // 0 empty, 1 argument set seen once (run directly), 2 captured, -1 capture failed: always direct
+    } graphs[16];
+    cudaStream_t graph_stream;   // private capture stream (the caller's may be the legacy default stream, which cannot capture)
+    unsigned long long graph_clock;
     bool slab_push;              // peer pointers registered (pad_plan_set_slab_peer_buffers): transposition by NVLink stores of the y / x passes
     void *peer_B[4][8], *peer_T[4][8];      // [field][rank]: local-layout and transposed-layout spectrum buffers of every rank
     void* slab_fast[6];          // fused pipeline on slabs: 4 spectrum buffers + 2 exchange stagings of n0_loc * n1 * nzp complex, owned by the caller
@@ -293,6 +303,7 @@ enum {
     S_NREF = 2,         // WGC99 reference density kappa * round(N_elec) / vol
     S_NREF_KEY = 3,     // n_ref the cached WGC99 kernel was built for
     S_WT_KEY = 4,       // n0 the cached Lindhard kernel table of the fused Wang-Teter pipeline was built for
+    S_GRAPH_E = 6,      // energy output of a replayed evaluation graph (copied to the caller's scalar after the launch)
     S_CTR = 5,          // two 32-bit arrival counters of "last CTA finishes the job" kernels (zero between launches)
     S_TMP0 = 8,         // 8 slots of per-call temporaries
     S_E_PARTS = 16      // component energies
@@ -309,6 +320,8 @@ int pad_fft_inverse_many(pad_plan* p, cufftDoubleComplex* const* in, double* con
 extern int g_pad_own_xy;
 extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
 extern int g_pad_zinv_stream;      // 1: streamed inverse z kernel (results folded as they arrive, 3 CTAs/SM), 0: batch form
+extern int g_pad_graphs;           // 1: repeated evaluations with the same arguments replay a CUDA graph
+extern unsigned long long g_pad_option_epoch;      // bumped by pad_set_option (part of the graph keys)
 extern int g_pad_fuse_mid;         // 1: WGC99 mid pass and the forward z pass of the second batch in one kernel
 extern int g_pad_fold_table;       // 1: orthorhombic cells read only the |kx|, |ky| quarter of the WGC99 kernel table
 extern int g_pad_fuse_terms;       // 1: pad_eval_total folds local terms + Hartree into the WGC99 pipeline where it can

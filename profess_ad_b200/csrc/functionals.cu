@@ -666,9 +666,84 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
     return pad_eval_wgc99_ex(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, nullptr);
 }
 
+static int wgc99_ex_direct(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
+                           double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex);
+
+// An evaluation is 14-16 dependent launches with no host decision that depends on device data, so a repeated call with the
+// same arguments (the optimiser's closure, a benchmark loop, a scan at fixed buffers) is replayed as ONE cudaGraphLaunch: the
+// host cost per evaluation drops from ~0.3 ms of launch calls to ~10 us and launch jitter of a busy host (8 ranks per node)
+// no longer reaches the GPU.  First call with an argument set: direct; second: captured on a private stream (the caller's may
+// be the legacy default stream) and instantiated; from then on replayed on the caller's stream.
 int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
                       double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex) {
     PAD_TRY(check_common(p, den, "pad_eval_wgc99"));
+    const bool eligible = g_pad_graphs && !p->dist && !g_pad_profile && g_pad_fast_fft && pad_wgc99_total_supported(p) && v_out && E_out;
+    if (!eligible) return wgc99_ex_direct(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, ex);
+    unsigned long long key[14];
+    auto bits = [](double x) { unsigned long long u; memcpy(&u, &x, 8); return u; };
+    // The energy scalar of a framework caller is a fresh 8-byte allocation per call whose address wanders through the allocator's
+    // small-block pool: inside the graph the energy goes to a scalar of the plan and one 8-byte copy hands it to the caller
+    // (not with accumulate: then E_out is an input as well, and its owner -- the optimiser -- keeps it fixed anyway)
+    double* E_in_graph = accumulate ? E_out : p->scal + S_GRAPH_E;
+    key[0] = (unsigned long long)(uintptr_t)den; key[1] = (unsigned long long)(uintptr_t)E_in_graph; key[2] = (unsigned long long)(uintptr_t)v_out;
+    key[3] = bits(alpha); key[4] = bits(beta); key[5] = bits(gamma); key[6] = bits(kappa);
+    key[7] = (unsigned long long)accumulate; key[8] = ex ? 1ull + (unsigned long long)ex->local_mask * 4ull + (ex->hartree ? 2ull : 0ull) : 0ull;
+    key[9] = ex ? (unsigned long long)(uintptr_t)ex->v_ext : 0ull;
+    key[10] = p->box_generation; key[11] = g_pad_option_epoch; key[12] = (unsigned long long)(uintptr_t)stream; key[13] = 0ull;
+    pad_plan::GraphSlot* slot = nullptr;
+    pad_plan::GraphSlot* victim = &p->graphs[0];
+    for (auto& g : p->graphs) {
+        if (g.state != 0 && memcmp(g.key, key, sizeof(key)) == 0) { slot = &g; break; }
+        if (g.state == 0 || (victim->state != 0 && g.stamp < victim->stamp)) victim = &g;
+    }
+    ++p->graph_clock;
+    cudaStream_t s = as_stream(stream);
+    if (slot && slot->state == 2) {
+        slot->stamp = p->graph_clock;
+        PAD_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(slot->exec), s));
+        if (E_in_graph != E_out) PAD_CUDA(cudaMemcpyAsync(E_out, E_in_graph, sizeof(double), cudaMemcpyDeviceToDevice, s));
+        g_pad_launches += slot->launches;
+        return PAD_OK;
+    }
+    if (!slot) {                      // new argument set: remember it, run directly
+        if (victim->exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(victim->exec));
+        memset(victim, 0, sizeof(*victim));
+        memcpy(victim->key, key, sizeof(key));
+        victim->state = 1;
+        victim->stamp = p->graph_clock;
+        return wgc99_ex_direct(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, ex);
+    }
+    slot->stamp = p->graph_clock;
+    if (slot->state != 1) return wgc99_ex_direct(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, ex);
+    // second call: capture
+    if (!p->graph_stream) PAD_CUDA(cudaStreamCreateWithFlags(&p->graph_stream, cudaStreamNonBlocking));
+    const unsigned long long l0 = g_pad_launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(p->graph_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        const int rc = wgc99_ex_direct(p, den, alpha, beta, gamma, kappa, E_in_graph, v_out, accumulate, p->graph_stream, ex);
+        const cudaError_t ce = cudaStreamEndCapture(p->graph_stream, &graph);
+        ok = rc == PAD_OK && ce == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();            // clear; this argument set runs directly from now on
+        g_pad_launches = l0;
+        slot->state = -1;
+        return wgc99_ex_direct(p, den, alpha, beta, gamma, kappa, E_out, v_out, accumulate, stream, ex);
+    }
+    slot->exec = exec;
+    slot->launches = g_pad_launches - l0;
+    slot->state = 2;
+    PAD_CUDA(cudaGraphLaunch(exec, s));
+    if (E_in_graph != E_out) PAD_CUDA(cudaMemcpyAsync(E_out, E_in_graph, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return PAD_OK;
+}
+
+static int wgc99_ex_direct(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
+                           double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex) {
     if (ex && !(g_pad_fast_fft && pad_wgc99_total_supported(p) && v_out)) {
         pad_set_error("pad_eval_wgc99_ex: the fused term list needs the pipelined FFT kernels");
         return PAD_ERR_ARG;

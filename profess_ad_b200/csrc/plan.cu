@@ -19,6 +19,8 @@ int g_pad_pipe_lpi = 0, g_pad_pipe_tpi = 0;
 int g_pad_fuse_terms = 1;
 int g_pad_fold_table = 1;
 int g_pad_zinv_stream = 0;     // measured at 256^3: the streamed form (12 warps/SM, 168 registers) is 7-13 % slower than the batch form
+int g_pad_graphs = 1;          // whole evaluations with unchanged arguments are captured once and replayed as ONE graph launch
+unsigned long long g_pad_option_epoch = 0;
 int g_pad_fuse_mid = 0;        // measured: mid + forward z in one 8-warp kernel 508 us, as two kernels 348 + 135 us
 extern "C" int pad_set_option(const char* name, int value) {
     int* slot = nullptr;
@@ -32,9 +34,11 @@ extern "C" int pad_set_option(const char* name, int value) {
     else if (!strcmp(name, "fuse_mid")) slot = &g_pad_fuse_mid;
     else if (!strcmp(name, "pipe_lpi")) slot = &g_pad_pipe_lpi;
     else if (!strcmp(name, "pipe_tpi")) slot = &g_pad_pipe_tpi;
+    else if (!strcmp(name, "graphs")) slot = &g_pad_graphs;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }
     const int old = *slot;
     *slot = value;
+    ++g_pad_option_epoch;
     return old;
 }
 
@@ -261,6 +265,9 @@ extern "C" int pad_plan_destroy(pad_plan* p) {
     if (p->xy_ready) cufftDestroy(p->xy);
     if (p->xy_work) cudaFree(p->xy_work);
     for (int i = 0; i < 4; ++i) if (p->zbuf[i]) cudaFree(p->zbuf[i]);
+    for (int i = 0; i < 16; ++i)
+        if (p->graphs[i].exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(p->graphs[i].exec));
+    if (p->graph_stream) cudaStreamDestroy(p->graph_stream);
     if (p->pipe_ctl) cudaFree(p->pipe_ctl);
     if (p->pipe_part) cudaFree(p->pipe_part);
     cudaFree(p->partials);

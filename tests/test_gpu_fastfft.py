@@ -302,3 +302,44 @@ def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms, pipe):
         E_ref, V_ref = E_ref + e.item(), V_ref + v
     assert abs(out[1][0] - E_ref) <= 1e-10 * abs(E_ref)
     assert ((out[1][1].cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9
+
+
+def test_repeated_evaluation_replays_a_cuda_graph_with_identical_results():
+    """pad_eval_wgc99 with unchanged arguments: direct on the first call, captured on the second, replayed as one graph launch
+    afterwards -- same bits every time, the launch counter keeps counting the kernels of the graph, a changed density BUFFER or
+    option 'graphs' = 0 goes back to direct launches, and a changed density in the SAME buffer is picked up by the replay."""
+    from oracle import ofdft_oracle as orc
+    from profess_ad_b200 import _native as nat
+    lib = nat.load_library()
+    dev = torch.device('cuda:0')
+    shape = (64, 64, 128)
+    box, den = orc.synth_rough(shape, seed=21, L=9.0)
+    b, d = box.to(dev), den.to(dev).contiguous()
+    plan = nat.get_plan(b, d)
+    a98, b98 = (5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6
+    E = torch.zeros((), dtype=torch.double, device=dev)
+    v = torch.zeros_like(d)
+
+    def call(dd):
+        l0 = lib.pad_launch_count()
+        nat.check(lib.pad_eval_wgc99(plan.handle, nat.ptr(dd), a98, b98, 2.7, 1.0, nat.ptr(E), nat.ptr(v), 0, nat.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        return E.item(), v.clone(), lib.pad_launch_count() - l0
+
+    runs = [call(d) for _ in range(5)]
+    for e, vv, n in runs[1:]:
+        assert e == runs[0][0] and torch.equal(vv, runs[0][1]) and n == runs[0][2] > 0
+    E_ref, V_ref = orc.energy_and_potential(box, den, orc.WangGovindCarter99())
+    assert abs(runs[-1][0] - E_ref.item()) <= 1e-10 * abs(E_ref.item())
+    # new contents in the same buffer: the replayed graph reads them (nothing about the data is baked in)
+    d.mul_(1.01)
+    e2, v2, _ = call(d)
+    d2 = d.clone()
+    e3, v3, _ = call(d2)              # different buffer: a direct evaluation
+    assert e2 == e3 and torch.equal(v2, v3) and e2 != runs[0][0]
+    old = lib.pad_set_option(b'graphs', 0)
+    try:
+        e4, v4, _ = call(d)
+    finally:
+        lib.pad_set_option(b'graphs', old)
+    assert e4 == e2 and torch.equal(v4, v2)
