@@ -1687,6 +1687,106 @@ struct PostWgcFin {
     }
 };
 
+// Tail of the fused term list: c2r of the Hartree potential (4 pi n / k^2, the fourth field of the second batch) with the local
+// terms of the list -- LDA exchange, Perdew-Zunger correlation, IonElectron -- evaluated on the same sweep.  A one-field inverse
+// pass has the fp64 issue slots to spare that the mid pass (four fields, 255 registers, 8 warps / SM) does not: with the local
+// terms inside the mid pass that kernel took 534 instead of 264 us at 256^3, and the four-field final pass 437 instead of
+// 199 us.  NRED = 2: sum n v_H, sum of the local energy densities.
+struct LocalOut {
+    double e, v;
+};
+__device__ __noinline__ LocalOut local_terms_point(double n, int mask, double vext) {
+    LocalOut o{0.0, 0.0};
+    if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
+        const double c = cbrt(n);
+        if (mask & PAD_LOCAL_LDAX) { o.e += kCX * n * c; o.v += (4.0 / 3.0) * kCX * c; }
+        if (mask & PAD_LOCAL_PZC) { const PZ r = pz_correlation(n, c); o.e += r.e; o.v += r.v; }
+    }
+    if (mask & PAD_LOCAL_IONEL) { o.e += n * vext; o.v += vext; }
+    return o;
+}
+// the same terms from one table log per point (fastmath.cuh): n^(1/3), rs, sqrt(rs), log rs all come from log n
+__device__ __forceinline__ LocalOut local_terms_fast(double n, int mask, double vext) {
+    if (!fm_ok(n)) return local_terms_point(n, mask, vext);
+    LocalOut o{0.0, 0.0};
+    if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
+        const double l = fm_log(n);
+        const double c13 = fm_exp((1.0 / 3.0) * l);                    // n^(1/3)
+        if (mask & PAD_LOCAL_LDAX) { o.e += kCX * n * c13; o.v += (4.0 / 3.0) * kCX * c13; }
+        if (mask & PAD_LOCAL_PZC) {
+            // pz_correlation (xc.cuh, functionals.py:1515-1521) with rs = kRS13 n^(-1/3)
+            const double A = 0.0311, B = -0.048, C = 0.002, D = -0.0116;
+            const double ga = -0.1423, b1 = 1.0529, b2 = 0.3334;
+            const double y3 = fm_rsqrt(c13);                          // n^(-1/6)
+            const double rs = kRS13 * (y3 * y3);
+            if (rs < 1.0) {
+                const double lr = -0.47747065276706023 - (1.0 / 3.0) * l;      // log rs
+                o.e += n * (A * lr + B + C * rs * lr + D * rs);
+                o.v += lr * (A + (2.0 / 3.0) * C * rs) + (B - A / 3.0) + rs / 3.0 * (2.0 * D - C);
+            } else {
+                const double sr = 0.78762331789974325 * y3;           // sqrt(rs) = sqrt(kRS13) n^(-1/6)
+                const double dn = 1.0 + b1 * sr + b2 * rs;
+                const double q = fm_rsqrt(dn);
+                const double idn = q * q;
+                o.e += n * ga * idn;
+                o.v += ga * (1.0 + (7.0 / 6.0) * b1 * sr + (4.0 / 3.0) * b2 * rs) * (idn * idn);
+            }
+        }
+    }
+    if (mask & PAD_LOCAL_IONEL) { o.e += n * vext; o.v += vext; }
+    return o;
+}
+
+// v += local terms, one block-reduced energy sum; two points per thread and iteration (16-byte accesses)
+__global__ void __launch_bounds__(PAD_THREADS) local_fast_kernel(const double* __restrict__ den, const double* __restrict__ v_ext,
+                                                                double* __restrict__ v, size_t n, int mask, double* __restrict__ partials) {
+    fm_load_tables();
+    double acc[1] = {0.0};
+    const size_t n2 = n / 2, stride = (size_t)gridDim.x * PAD_THREADS;
+    for (size_t i = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; i < n2; i += stride) {
+        const double2 d = reinterpret_cast<const double2*>(den)[i];
+        double2 ve = make_double2(0.0, 0.0);
+        if (mask & PAD_LOCAL_IONEL) ve = reinterpret_cast<const double2*>(v_ext)[i];
+        double2 vv = reinterpret_cast<double2*>(v)[i];
+        const LocalOut a = local_terms_fast(d.x, mask, ve.x), b = local_terms_fast(d.y, mask, ve.y);
+        acc[0] += a.e + b.e;
+        vv.x += a.v; vv.y += b.v;
+        reinterpret_cast<double2*>(v)[i] = vv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const LocalOut a = local_terms_fast(den[n - 1], mask, (mask & PAD_LOCAL_IONEL) ? v_ext[n - 1] : 0.0);
+        acc[0] += a.e;
+        v[n - 1] += a.v;
+    }
+    block_reduce_store<1>(acc, partials);
+}
+
+struct PostHartreeLocal {
+    static constexpr bool kDen = true, kVin = true;
+    static constexpr int NST = 0;
+    double* v_out;
+    const double* v_ext;                       // IonElectron (may be null when the bit is not set)
+    int mask;
+    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double* acc, double*, double*) const {
+        double2 ve = make_double2(0.0, 0.0);
+        if (mask & PAD_LOCAL_IONEL) ve = *reinterpret_cast<const double2*>(v_ext + g);
+        const LocalOut a = local_terms_point(n.x, mask, ve.x), b = local_terms_point(n.y, mask, ve.y);
+        acc[0] += n.x * u0[0] + n.y * u1[0];
+        acc[1] += a.e + b.e;
+        *reinterpret_cast<double2*>(v_out + g) = make_double2(v.x + u0[0] + a.v, v.y + u1[0] + b.v);
+    }
+    static constexpr int NACC = 0;
+    typedef int Ctx;
+    __device__ Ctx begin() const { return 0; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double, double*) const {}
+    __device__ void finish(const Ctx&, size_t g, double2 n, const double*, const double*, double uA, double uB, double* acc, double*,
+                           double*) const {
+        const double u0[1] = {uA}, u1[1] = {uB};
+        apply(g, n, *reinterpret_cast<const double2*>(v_out + g), u0, u1, acc, nullptr, nullptr);
+    }
+};
+
 struct PostWgcFinH {                           // final pass of the fused term list: + Hartree potential, NRED = 1: sum n v_H
     static constexpr bool kDen = true, kVin = true;
     static constexpr int NST = 0;
@@ -1921,6 +2021,72 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
         const bool hartree = ex && ex->hartree;
         const FinalizeArgs a = wgc_energy_args(p, 0, ex ? 4 : 3, accumulate, E_out);
         const FinalizeArgs* fa = E_out ? &a : nullptr;
+        if (ex && !g_pad_fuse_mid && !piped && g_pad_local_tail) {
+            // the plain (pair-optimised) WGC99 passes; the Hartree field rides along through y / x / y^-1 and is brought back by a
+            // one-field inverse z pass of its own that also evaluates the local terms (PostHartreeLocal)
+            double* Pbuf;
+            PAD_TRY(pad_get_rbuf(p, 7, &Pbuf));
+            const FinalizeArgs a3 = wgc_energy_args(p, 0, 3, accumulate, E_out);
+            PostWgcMid mid{scal, v_out, Pbuf, alpha, accumulate, 1};
+            PAD_TRY((wgc_inverse_stage<4, 3, PostWgcMid, 0>(p, s, false, mid, GenNone{}, B, den, nullptr, E_out ? &a3 : nullptr,
+                                                           "y-inv (4 fields)", "z-c2r (4 fields) + energy/v1/P", "", "")));
+            if (hartree) {
+                ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 4>(p, s, GenWgcP4{scal}, den, Pbuf, B[0], B[1], B[2], B[3]))));
+                pad_stage_mark("gen P,P.th,P.th2,n + z-r2c (4 fields)", s);
+            } else {
+                ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, GenWgcP{scal}, den, Pbuf, B[0], B[1], B[2], nullptr))));
+                pad_stage_mark("gen P,P.th,P.th2 + z-r2c (3 fields)", s);
+            }
+            const int nb = hartree ? 4 : 3;
+            PAD_TRY(launch_spass(p, s, 1, -1, B, nb));
+            pad_stage_mark(hartree ? "y-fwd (4 fields)" : "y-fwd (3 fields)", s);
+            PAD_TRY((launch_xmix<3>(p, s, B, mixw)));
+            pad_stage_mark("x-fwd * kernel-mix * x-inv (3 fields)", s);
+            if (hartree) {
+                cd* one[1] = {B[3]};
+                PAD_TRY((launch_xmix<1>(p, s, one, MixCoulomb{inv_n})));
+                pad_stage_mark("x-fwd * (4 pi / k^2) * x-inv (1 field)", s);
+            }
+            PAD_TRY(launch_spass(p, s, 1, +1, B, nb));
+            pad_stage_mark(hartree ? "y-inv (4 fields)" : "y-inv (3 fields)", s);
+            PostWgcFin fin{scal, v_out, beta};
+            ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, fin, B[0], B[1], B[2], nullptr, den, v_out, nullptr))));
+            pad_stage_mark("z-c2r (3 fields) + v2", s);
+            // The local terms: inside the Hartree tail they cost 305 us at 256^3 (8 warps / SM: the dependent chains of the
+            // transcendental functions have nothing to hide behind), in a full-occupancy elementwise kernel with the table
+            // log / exp far less -- option local_tail = 2 keeps them in the tail.
+            const bool aligned = ((reinterpret_cast<uintptr_t>(den) | reinterpret_cast<uintptr_t>(v_out) |
+                                   reinterpret_cast<uintptr_t>(ex->v_ext)) & 15) == 0;
+            const bool in_tail = hartree && (g_pad_local_tail == 2 || !aligned);
+            if (hartree) {
+                int grid = 1;
+                PostHartreeLocal tail{v_out, ex->v_ext, in_tail ? ex->local_mask : 0};
+                ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 2>(p, s, tail, B[3], nullptr, nullptr, nullptr, den, v_out, &grid))));
+                pad_stage_mark(in_tail ? "z-c2r (Hartree) + local terms" : "z-c2r (Hartree)", s);
+                if (E_out) {
+                    FinalizeArgs h = wgc_energy_args(p, grid, 2, 1, E_out);
+                    h.coef[0] = 0.5 * p->dV; h.coef[1] = p->dV;
+                    pad_launch_finalize(p, h, s);
+                }
+            }
+            if (ex->local_mask && !in_tail) {
+                if (aligned) {
+                    const int grid = pad_grid_for(p->N / 2);
+                    local_fast_kernel<<<grid, PAD_THREADS, 0, s>>>(den, ex->v_ext, v_out, p->N, ex->local_mask, p->partials);
+                    ++g_pad_launches;
+                    PAD_CUDA(cudaGetLastError());
+                    if (E_out) {
+                        FinalizeArgs h = wgc_energy_args(p, grid, 1, 1, E_out);
+                        h.coef[0] = p->dV;
+                        pad_launch_finalize(p, h, s);
+                    }
+                } else {
+                    PAD_TRY(pad_eval_local(p, den, ex->v_ext, ex->local_mask, E_out, v_out, 1, (void*)s));
+                }
+                pad_stage_mark("local terms", s);
+            }
+            return PAD_OK;
+        }
         if (ex && !g_pad_fuse_mid && !piped) {
             // local terms in the mid pass; P = n^alpha goes through HBM to a separate (16 warps / SM) forward z kernel that
             // also transforms the density itself when the Hartree term is wanted

@@ -281,18 +281,23 @@ def test_fused_term_list_matches_term_by_term_and_oracle(shape, terms, pipe):
              'P': (F.PerdewZunger, orc.PerdewZunger), 'B': (F.PerdewBurkeErnzerhof, orc.PerdewBurkeErnzerhof)}
     T = D.describe_terms([table[c][0] for c in terms])
     out = {}
-    for fuse in (1, 0):
+    # 1: fused list, local terms in the one-field Hartree inverse pass (default); 2: fused list, local terms inside the mid
+    # pass; 0: term by term
+    for variant, (fuse, tail) in {1: (1, 1), 2: (1, 0), 0: (0, 1)}.items():
         old = lib.pad_set_option(b'fuse_terms', fuse)
         old_pipe = lib.pad_set_option(b'pipe', pipe)
+        old_tail = lib.pad_set_option(b'local_tail', tail)
         try:
-            for _ in range(2):
+            for _ in range(3):          # direct, captured, replayed
                 E, v = D.eval_total(b, d, vx if 'I' in terms else None, T)
-            out[fuse] = (E.item(), v.clone())
+            out[variant] = (E.item(), v.clone())
         finally:
             lib.pad_set_option(b'fuse_terms', old)
             lib.pad_set_option(b'pipe', old_pipe)
-    assert abs(out[1][0] - out[0][0]) <= 1e-12 * abs(out[0][0]), (out[1][0], out[0][0])
-    assert ((out[1][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11
+            lib.pad_set_option(b'local_tail', old_tail)
+    for variant in (1, 2):
+        assert abs(out[variant][0] - out[0][0]) <= 1e-12 * abs(out[0][0]), (variant, out[variant][0], out[0][0])
+        assert ((out[variant][1] - out[0][1]).abs().max() / out[0][1].abs().max()).item() < 1e-11, variant
     E_ref, V_ref = 0.0, torch.zeros_like(den)
     for c in terms:
         if c == 'I':
