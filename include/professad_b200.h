@@ -123,6 +123,12 @@ size_t pad_slab_fast_elements(const pad_plan* plan);
  * PAD_COMM_BARRIER) between producer and consumer passes.  world <= 8. */
 #define PAD_COMM_BARRIER 4
 int pad_plan_set_slab_peer_buffers(pad_plan* plan, void* const* base_ptrs, int world);
+/* The same idea for the cuFFT slab path (every functional, any grid): recv_ptrs[r] / recv2_ptrs[r] are the addresses, in THIS
+ * process, of rank r's recv_buf / second receive buffer (pad_plan_set_overlap_buffers must have been called; both pairs live in
+ * symmetric memory).  The pack kernel of a forward transform then stores every element straight into the owner rank's receive
+ * buffer, an inverse transform copies its blocks there, and the all-to-all becomes a barrier (op PAD_COMM_BARRIER); consecutive
+ * transforms alternate between the two receive buffers, which is what makes one barrier per transform enough. */
+int pad_plan_set_slab_peer_recv(pad_plan* plan, void* const* recv_ptrs, void* const* recv2_ptrs, int world);
 int pad_plan_set_slab_fast_buffers(pad_plan* plan, void* const* six_buffers);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
 size_t pad_plan_workspace_bytes(const pad_plan* plan);

@@ -32,6 +32,7 @@ SIGNATURES = {
     'pad_slab_fast_elements': (ctypes.c_size_t, [_vp]),
     'pad_plan_set_slab_fast_buffers': (_int, [_vp, ctypes.POINTER(_vp)]),
     'pad_plan_set_slab_peer_buffers': (_int, [_vp, ctypes.POINTER(_vp), _int]),
+    'pad_plan_set_slab_peer_recv': (_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int]),
     'pad_plan_destroy': (_int, [_vp]),
     'pad_plan_set_box': (_int, [_vp, _c_double_p]),
     'pad_plan_workspace_bytes': (ctypes.c_size_t, [_vp]),

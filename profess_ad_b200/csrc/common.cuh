@@ -275,6 +275,9 @@ struct pad_plan {
     // second exchange buffer pair + a communication stream: batches of transforms are software-pipelined so that the
     // all-to-all of one field runs while the local FFTs of its neighbours do (pad_fft_forward_many / _inverse_many)
     void *send_buf2, *recv_buf2;
+    void* peer_recv[2][8];       // cuFFT slab path over peer memory: every rank's two receive buffers (pad_plan_set_slab_peer_recv)
+    bool recv_push;              // ... registered: the permute kernel stores straight into the owners' receive buffers
+    int recv_parity;             // receive buffer the next transform uses (alternating: see fft_forward_slab)
     // CUDA graphs of whole evaluations (pad_eval_wgc99 / the fused term list): one instantiated graph per distinct argument set
     struct GraphSlot {
         unsigned long long key[14];

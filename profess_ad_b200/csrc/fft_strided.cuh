@@ -214,7 +214,7 @@ struct SPassPeers {
 
 template <int L, int DIR, int BLK>
 __global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_blocked_kernel(const cd* __restrict__ src, cd* __restrict__ dst,
-                                                                                 SPassGeom geo, SPassBlocked bl, SPassPeers peers) {
+                                                                                 SPassGeom geo, SPassBlocked bl, const __grid_constant__ SPassPeers peers) {
     using P = SPass<L>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
@@ -301,7 +301,7 @@ struct XmixPush {
 
 template <int L, int NF, class Mix, bool PUSH = false>
 __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_per_sm<L, NF>()))
-    xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix, XmixPush push) {
+    xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix, const __grid_constant__ XmixPush push) {
     constexpr bool W = kXmixWide<L>;
     using P = SPass<L, W>;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -380,6 +380,51 @@ __global__ void __launch_bounds__(PAD_THREADS) slab_permute_kernel(const double2
     }
 }
 
+// peer form of the two permutes: the forward pack stores into the owners' receive buffers, the inverse copies its x-range blocks
+struct PeerRecv {
+    double2* p[8];
+};
+__global__ void __launch_bounds__(PAD_THREADS) slab_permute_push_kernel(const double2* __restrict__ src, const __grid_constant__ PeerRecv dst,
+                                                                        int n0_loc, int n1, int n1_loc, int nzh, int rank) {
+    const size_t total = (size_t)n0_loc * n1 * nzh;
+    for (size_t e = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * PAD_THREADS) {
+        const int k = (int)(e % nzh);
+        const size_t row = e / nzh;
+        const int j = (int)(row % n1);
+        const int i = (int)(row / n1);
+        const int r = j / n1_loc, jl = j - r * n1_loc;
+        dst.p[r][(((size_t)rank * n0_loc + i) * n1_loc + jl) * nzh + k] = src[e];     // block `rank` of rank r's (world, n0_loc, n1_loc, nzh)
+    }
+}
+__global__ void __launch_bounds__(PAD_THREADS) slab_block_push_kernel(const double2* __restrict__ src, const __grid_constant__ PeerRecv dst,
+                                                                      size_t block, int world, int rank) {
+    const size_t total = block * world;
+    for (size_t e = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * PAD_THREADS) {
+        const int r = (int)(e / block);
+        dst.p[r][(size_t)rank * block + (e - (size_t)r * block)] = src[e];
+    }
+}
+static PeerRecv peer_recv_of(const pad_plan* p, int b) {
+    PeerRecv d;
+    for (int r = 0; r < 8; ++r) d.p[r] = r < p->world ? reinterpret_cast<double2*>(p->peer_recv[b][r]) : nullptr;
+    return d;
+}
+
+extern "C" int pad_plan_set_slab_peer_recv(pad_plan* p, void* const* recv, void* const* recv2, int world) {
+    if (!p || !p->dist || !recv || !recv2 || world != p->world || world > 8 || !p->recv_buf2) {
+        pad_set_error("pad_plan_set_slab_peer_recv: needs a slab plan with overlap buffers and the receive buffers of all ranks (world <= 8)");
+        return PAD_ERR_ARG;
+    }
+    for (int r = 0; r < world; ++r) { p->peer_recv[0][r] = recv[r]; p->peer_recv[1][r] = recv2[r]; }
+    if (recv[p->rank] != p->recv_buf || recv2[p->rank] != p->recv_buf2) {
+        pad_set_error("pad_plan_set_slab_peer_recv: this rank's entries must be its own receive buffers");
+        return PAD_ERR_ARG;
+    }
+    p->recv_push = true;
+    p->recv_parity = 0;
+    return PAD_OK;
+}
+
 int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s) {
     const int rc = p->comm_fn(p->comm_user, op, count, (void*)s);
     if (rc != 0) {
@@ -392,6 +437,21 @@ int pad_slab_comm(pad_plan* p, int op, long long count, cudaStream_t s) {
 static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* out, cudaStream_t s) {
     PAD_TRY(ensure_fft_slab(p, s));
     PAD_CUFFT(cufftExecD2Z(p->d2z_yz, const_cast<double*>(in), out));                       // (n0_loc, n1, nzh)
+    if (p->recv_push) {
+        // Receive buffers alternate from transform to transform.  A rank enters the barrier of transform t after its x FFT of
+        // transform t - 1 (stream order), so once the barrier of t has let this rank through, every rank has consumed the buffer
+        // transform t + 1 is about to be pushed into: one barrier per transform is enough.
+        const int b = p->recv_parity;
+        p->recv_parity ^= 1;
+        slab_permute_push_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(out), peer_recv_of(p, b),
+                                                                            p->n0_loc, p->n1, p->n1_loc, p->nzh, p->rank);
+        PAD_CUDA(cudaGetLastError());
+        PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER, 0, s));
+        PAD_CUFFT(cufftExecZ2Z(p->z2z_x, reinterpret_cast<cufftDoubleComplex*>(b ? p->recv_buf2 : p->recv_buf), out, CUFFT_FORWARD));
+        g_pad_fft_execs += 2;
+        ++g_pad_launches;
+        return PAD_OK;
+    }
     slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(out),
         reinterpret_cast<double2*>(p->send_buf), p->n0_loc, p->n1, p->n1_loc, p->nzh, 1);
     PAD_CUDA(cudaGetLastError());
@@ -404,6 +464,24 @@ static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* o
 
 static int fft_inverse_slab(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
     PAD_TRY(ensure_fft_slab(p, s));
+    if (p->recv_push) {
+        const int b = p->recv_parity;
+        p->recv_parity ^= 1;
+        // x inverse into the send buffer (blocked by x range), blocks copied into the owners' receive buffers, barrier, unpack
+        PAD_CUFFT(cufftExecZ2Z(p->z2z_x, in, reinterpret_cast<cufftDoubleComplex*>(p->send_buf), CUFFT_INVERSE));
+        const size_t block = (size_t)p->n0_loc * p->n1_loc * p->nzh;
+        slab_block_push_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(p->send_buf), peer_recv_of(p, b),
+                                                                          block, p->world, p->rank);
+        PAD_CUDA(cudaGetLastError());
+        PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER, 0, s));
+        slab_permute_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(reinterpret_cast<const double2*>(b ? p->recv_buf2 : p->recv_buf),
+            reinterpret_cast<double2*>(in), p->n0_loc, p->n1, p->n1_loc, p->nzh, 0);
+        PAD_CUDA(cudaGetLastError());
+        PAD_CUFFT(cufftExecZ2D(p->z2d_yz, in, out));
+        g_pad_fft_execs += 2;
+        g_pad_launches += 2;
+        return PAD_OK;
+    }
     // x inverse into the send buffer: (n0, n1_loc, nzh) is already blocked by x range
     PAD_CUFFT(cufftExecZ2Z(p->z2z_x, in, reinterpret_cast<cufftDoubleComplex*>(p->send_buf), CUFFT_INVERSE));
     PAD_TRY(pad_slab_comm(p, PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, s)); // recv = (world, n0_loc, n1_loc, nzh)
@@ -469,7 +547,7 @@ int pad_ensure_comm_stream(pad_plan* p) {
     return PAD_OK;
 }
 
-static bool can_overlap(const pad_plan* p, int n) { return p->dist && p->world > 1 && p->send_buf2 && p->recv_buf2 && n >= 2; }
+static bool can_overlap(const pad_plan* p, int n) { return p->dist && p->world > 1 && p->send_buf2 && p->recv_buf2 && n >= 2 && !p->recv_push; }
 
 // exchange of buffer pair b on the communication stream: after the producer on `s` (ev_ready[b]) and, from the third
 // field on, after the consumer of the pair's previous contents (ev_free[b])

@@ -183,15 +183,21 @@ class SlabPlan(_native.Plan):
         self.device_index = device_index
         dev = torch.device('cuda', device_index)
         nk_loc = n0 * (n1 // comm.world) * (n2 // 2 + 1)
+        # cuFFT slab path over peer memory: both receive buffers in ONE symmetric allocation, so that the pack kernels of
+        # the other ranks can store straight into them (pad_plan_set_slab_peer_recv); plain tensors + all-to-all otherwise
+        self.recv_sym = None
+        if overlap and comm.world > 1 and hasattr(comm, 'symmetric_buffer'):
+            self.recv_sym = comm.symmetric_buffer(2 * nk_loc, dev)
         self.send = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
-        self.recv = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+        self.recv = self.recv_sym[0][:nk_loc] if self.recv_sym is not None else torch.empty(nk_loc, dtype=torch.complex128, device=dev)
         self.scratch = torch.zeros(COMM_SCRATCH, dtype=torch.double, device=dev)
         self.error = None
         # second exchange pair: lets the library overlap the all-to-all of one field with the FFTs of the next
         self.overlap = overlap and comm.world > 1
         if self.overlap:
             self.send2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
-            self.recv2 = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
+            self.recv2 = (self.recv_sym[0][nk_loc:] if self.recv_sym is not None
+                          else torch.empty(nk_loc, dtype=torch.complex128, device=dev))
         # fused FFT pipeline on the slabs (csrc/fftz.cu: own z / y / x passes, the y pass stores its rows blocked by
         # destination rank so the exchange needs no pack kernel): four spectrum fields + two exchange stagings in the
         # padded layout, registered with the library; the callback exchanges them by index
@@ -254,6 +260,11 @@ class SlabPlan(_native.Plan):
                                                     _native.ptr(self.scratch), self._callback, None))
         if self.overlap:
             _native.check(self.lib.pad_plan_set_overlap_buffers(self.handle, _native.ptr(self.send2), _native.ptr(self.recv2)))
+        if self.recv_sym is not None:
+            ptrs = self.recv_sym[1]
+            a1 = (ctypes.c_void_p * comm.world)(*ptrs)
+            a2 = (ctypes.c_void_p * comm.world)(*[q + 16 * nk_loc for q in ptrs])
+            _native.check(self.lib.pad_plan_set_slab_peer_recv(self.handle, a1, a2, comm.world))
         if self.fast:
             arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.fast])
             _native.check(self.lib.pad_plan_set_slab_fast_buffers(self.handle, arr))

@@ -64,9 +64,13 @@ def _evaluate_slabs(world, global_shape, box, den, make_f):
     return energies, torch.cat([o[1] for o in out], dim=0)
 
 
-@pytest.mark.parametrize('world,shape', [(1, (9, 10, 12)), (1, (8, 6, 7)), (2, (8, 6, 10)), (2, (12, 10, 9)), (4, (8, 12, 6))])
-def test_slab_matches_oracle(world, shape):
+@pytest.mark.parametrize('world,shape,peer', [(1, (9, 10, 12), 1), (1, (8, 6, 7), 1), (2, (8, 6, 10), 1), (2, (12, 10, 9), 0),
+                                              (4, (8, 12, 6), 1), (4, (8, 12, 6), 0)])
+def test_slab_matches_oracle(world, shape, peer, monkeypatch):
+    """peer = 1: the pack kernel of a transform stores straight into the other ranks' receive buffers (symmetric memory; here the
+    ranks are threads sharing the GPU) and a barrier replaces the all-to-all; peer = 0: staged all-to-all."""
     from oracle import ofdft_oracle as orc
+    monkeypatch.setenv('PAD_SLAB_PEER', str(peer))
     box, den = orc.synth_rough(shape, seed=17 + world, L=8.5)
     dV = abs(torch.linalg.det(box).item()) / den.numel()
     for name, make_f, make_o in _functionals():
