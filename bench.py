@@ -703,6 +703,9 @@ def slab_measure(n, functional, steps, warmup, overlap=None):
         elif fused:
             path = {'transforms': 'own z / y / x FFT passes per rank, y pass stores rows blocked by destination rank, NCCL all-to-all '
                                   'pipelined over two stagings', 'exchange': 'all_to_all_single'}
+        elif plan is not None and getattr(plan, 'recv_sym', None) is not None:
+            path = {'transforms': 'batched 2-D (y,z) cuFFT, pack kernel that stores straight into the owner ranks\' receive buffers over '
+                                  'NVLink (symmetric memory) + barrier, strided 1-D (x) cuFFT per 3-D transform', 'exchange': 'peer stores'}
         else:
             path = {'transforms': 'batched 2-D (y,z) cuFFT + NCCL all-to-all + strided 1-D (x) cuFFT per 3-D transform',
                     'exchange': 'all_to_all_single'}

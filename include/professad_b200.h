@@ -122,6 +122,7 @@ size_t pad_slab_fast_elements(const pad_plan* plan);
  * inverse transform straight into the owner ranks' local buffers; the only collective left is a barrier (fn with op
  * PAD_COMM_BARRIER) between producer and consumer passes.  world <= 8. */
 #define PAD_COMM_BARRIER 4
+#define PAD_COMM_BARRIER_2 5          /* the same on the plan's communication stream (a second signal channel: barriers of the two streams may be in flight together) */
 int pad_plan_set_slab_peer_buffers(pad_plan* plan, void* const* base_ptrs, int world);
 /* The same idea for the cuFFT slab path (every functional, any grid): recv_ptrs[r] / recv2_ptrs[r] are the addresses, in THIS
  * process, of rank r's recv_buf / second receive buffer (pad_plan_set_overlap_buffers must have been called; both pairs live in

@@ -277,6 +277,7 @@ struct pad_plan {
     void *send_buf2, *recv_buf2;
     void* peer_recv[2][8];       // cuFFT slab path over peer memory: every rank's two receive buffers (pad_plan_set_slab_peer_recv)
     bool recv_push;              // ... registered: the permute kernel stores straight into the owners' receive buffers
+    bool recv_after_pipeline;    // a pipelined batch has used the receive pair since the last single transform
     int recv_parity;             // receive buffer the next transform uses (alternating: see fft_forward_slab)
     // CUDA graphs of whole evaluations (pad_eval_wgc99 / the fused term list): one instantiated graph per distinct argument set
     struct GraphSlot {

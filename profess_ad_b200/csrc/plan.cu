@@ -438,6 +438,10 @@ static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* o
     PAD_TRY(ensure_fft_slab(p, s));
     PAD_CUFFT(cufftExecD2Z(p->d2z_yz, const_cast<double*>(in), out));                       // (n0_loc, n1, nzh)
     if (p->recv_push) {
+        if (p->recv_after_pipeline) {      // the pipelined batches use the pair in their own order: re-synchronise once
+            PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER, 0, s));
+            p->recv_after_pipeline = false;
+        }
         // Receive buffers alternate from transform to transform.  A rank enters the barrier of transform t after its x FFT of
         // transform t - 1 (stream order), so once the barrier of t has let this rank through, every rank has consumed the buffer
         // transform t + 1 is about to be pushed into: one barrier per transform is enough.
@@ -465,6 +469,10 @@ static int fft_forward_slab(pad_plan* p, const double* in, cufftDoubleComplex* o
 static int fft_inverse_slab(pad_plan* p, cufftDoubleComplex* in, double* out, cudaStream_t s) {
     PAD_TRY(ensure_fft_slab(p, s));
     if (p->recv_push) {
+        if (p->recv_after_pipeline) {
+            PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER, 0, s));
+            p->recv_after_pipeline = false;
+        }
         const int b = p->recv_parity;
         p->recv_parity ^= 1;
         // x inverse into the send buffer (blocked by x range), blocks copied into the owners' receive buffers, barrier, unpack
@@ -547,7 +555,7 @@ int pad_ensure_comm_stream(pad_plan* p) {
     return PAD_OK;
 }
 
-static bool can_overlap(const pad_plan* p, int n) { return p->dist && p->world > 1 && p->send_buf2 && p->recv_buf2 && n >= 2 && !p->recv_push; }
+static bool can_overlap(const pad_plan* p, int n) { return p->dist && p->world > 1 && p->send_buf2 && p->recv_buf2 && n >= 2; }
 
 // exchange of buffer pair b on the communication stream: after the producer on `s` (ev_ready[b]) and, from the third
 // field on, after the consumer of the pair's previous contents (ev_free[b])
@@ -555,7 +563,20 @@ static int exchange_async(pad_plan* p, int b, bool wait_free, cudaStream_t s) {
     PAD_CUDA(cudaEventRecord(p->ev_ready[b], s));
     PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_ready[b], 0));
     if (wait_free) PAD_CUDA(cudaStreamWaitEvent(p->comm_stream, p->ev_free[b], 0));
-    PAD_TRY(pad_slab_comm(p, b ? PAD_COMM_ALL_TO_ALL_2 : PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, p->comm_stream));
+    if (p->recv_push) {
+        // peer form: barrier (every rank's consumer of receive buffer b is done -- each rank enters it after its own ev_free[b]),
+        // blocks copied into the owners' receive buffers over NVLink, barrier (every rank's blocks have arrived)
+        PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER_2, 0, p->comm_stream));
+        const size_t block = (size_t)p->n0_loc * p->n1_loc * p->nzh;
+        slab_block_push_kernel<<<pad_grid_for(p->Nk), PAD_THREADS, 0, p->comm_stream>>>(
+            reinterpret_cast<const double2*>(b ? p->send_buf2 : p->send_buf), peer_recv_of(p, b), block, p->world, p->rank);
+        PAD_CUDA(cudaGetLastError());
+        ++g_pad_launches;
+        PAD_TRY(pad_slab_comm(p, PAD_COMM_BARRIER_2, 0, p->comm_stream));
+        p->recv_after_pipeline = true;
+    } else {
+        PAD_TRY(pad_slab_comm(p, b ? PAD_COMM_ALL_TO_ALL_2 : PAD_COMM_ALL_TO_ALL, (long long)p->n0_loc * p->n1_loc * p->nzh, p->comm_stream));
+    }
     PAD_CUDA(cudaEventRecord(p->ev_a2a[b], p->comm_stream));
     return PAD_OK;
 }

@@ -75,11 +75,11 @@ class TorchDistComm:
             self.symm_error = repr(e)
             return None
 
-    def barrier(self):
+    def barrier(self, channel=0):
         """Stream-ordered barrier over the ranks (signal pads of the symmetric allocation; a 1-element all-reduce otherwise)."""
         hdl = getattr(self, '_barrier_hdl', None)
         if hdl is not None:
-            hdl.barrier()
+            hdl.barrier(channel=channel)
         else:
             if not hasattr(self, '_one'):
                 self._one = torch.zeros(1, device='cuda')
@@ -103,7 +103,7 @@ class SingleComm:
         t = torch.zeros(numel, dtype=torch.complex128, device=device)
         return t, [t.data_ptr()]
 
-    def barrier(self):
+    def barrier(self, channel=0):
         pass
 
 
@@ -164,7 +164,7 @@ class ThreadComm:
         sh.barrier.wait()
         return t, ptrs
 
-    def barrier(self):
+    def barrier(self, channel=0):
         torch.cuda.current_stream().synchronize()
         self.shared.barrier.wait()
 
@@ -240,6 +240,8 @@ class SlabPlan(_native.Plan):
                         self.comm.all_reduce_max(self.scratch[:count])
                     elif op == 4:
                         self.comm.barrier()
+                    elif op == 5:
+                        self.comm.barrier(1)
                     elif op >= 16:
                         dst, src = divmod(op - 16, 8)
                         self.comm.all_to_all(self.fast[dst], self.fast[src])
