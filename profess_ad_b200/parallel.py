@@ -185,8 +185,13 @@ class SlabPlan(_native.Plan):
         nk_loc = n0 * (n1 // comm.world) * (n2 // 2 + 1)
         # cuFFT slab path over peer memory: both receive buffers in ONE symmetric allocation, so that the pack kernels of
         # the other ranks can store straight into them (pad_plan_set_slab_peer_recv); plain tensors + all-to-all otherwise
+        # (measured on 8 x B200, revHC 512^3 / PBE 1024^3: 2 GPUs 68.4 -> 59.8 ms with the peer form, but 8 GPUs 20.8 -> 22.4 /
+        #  32.7 -> 48.7 ms -- two barriers + a copy kernel per exchange, each a host callback, against ONE pipelined NCCL
+        #  all-to-all; so by default the peer form is used for world <= 2 only.  PAD_SLAB_PEER_RECV=1 / 0 overrides.)
         self.recv_sym = None
-        if overlap and comm.world > 1 and hasattr(comm, 'symmetric_buffer'):
+        want = os.environ.get('PAD_SLAB_PEER_RECV', '')
+        use_peer_recv = (want == '1') or (want != '0' and comm.world <= 2) or isinstance(comm, ThreadComm)
+        if use_peer_recv and overlap and comm.world > 1 and hasattr(comm, 'symmetric_buffer'):
             self.recv_sym = comm.symmetric_buffer(2 * nk_loc, dev)
         self.send = torch.empty(nk_loc, dtype=torch.complex128, device=dev)
         self.recv = self.recv_sym[0][:nk_loc] if self.recv_sym is not None else torch.empty(nk_loc, dtype=torch.complex128, device=dev)
