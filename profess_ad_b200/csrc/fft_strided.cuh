@@ -26,7 +26,7 @@
 // thread t, slot r holds X[t + 32 fft_nat<16>(r)].
 template <int L, bool WIDE = false>
 struct SPass {
-    static_assert(!WIDE || L == 512, "strided pass: the wide layout exists for L = 512 only");
+    static_assert(!WIDE || L == 512 || L == 256, "strided pass: the wide layout exists for L = 512 and 256");
     static constexpr int TPL = WIDE ? 32 : ((L >= 256) ? 16 : 8);      // threads per line
     static constexpr int EPT = L / TPL;                  // points per thread: 32 (L = 512), 16 (L = 256, 128, wide 512), 8 (L = 64)
     static constexpr int G = WIDE ? 1 : EPT / TPL;       // second-stage FFTs per thread: 2, 1, 2, 1
@@ -35,7 +35,7 @@ struct SPass {
     static constexpr int THREADS = WIDE ? 256 : 128;
     static constexpr int TPC = THREADS / TILE_THREADS;   // tiles per CTA
     static constexpr int TILE_CD = L * ZC;               // complex numbers per tile
-    static constexpr int CTAS_PER_SM = (L == 512) ? 2 : 4;   // plain pass: 32 complex points per thread need > 128 registers
+    static constexpr int CTAS_PER_SM = WIDE ? (L == 512 ? 2 : 4) : ((L == 512) ? 2 : 4);   // plain pass: 32 complex points per thread need > 128 registers
     static_assert(L == 512 || L == 256 || L == 128 || L == 64, "strided pass: L must be 64, 128, 256 or 512");
 };
 
@@ -43,14 +43,14 @@ struct SPass {
 template <int L, bool WIDE = false>
 __device__ __forceinline__ int spass_out_index(int t, int s) {
     using P = SPass<L, WIDE>;
-    if constexpr (WIDE) return t + P::TPL * fft_nat<16>(s);
+    if constexpr (WIDE) return t + P::TPL * fft_nat<P::EPT>(s);
     else return (t + P::TPL * (s / P::TPL)) + P::EPT * fft_nat<P::TPL>(s % P::TPL);
 }
 // register slot (after tile_fft) that holds the input j of a following tile_fft: k = t + TPL j
 template <int L, bool WIDE = false>
 __device__ __forceinline__ constexpr int spass_slot_of_input(int j) {
     using P = SPass<L, WIDE>;
-    if constexpr (WIDE) return fft_slot<16>(j);
+    if constexpr (WIDE) return fft_slot<P::EPT>(j);
     // k = t + TPL g + EPT k2 = t + TPL (g + G k2)  ->  j = g + G k2
     else return (j % P::G) * P::TPL + fft_slot<P::TPL>(j / P::G);
 }
@@ -60,24 +60,44 @@ template <int L, int DIR, bool WIDE = false>
 __device__ __forceinline__ void tile_fft(cd* v, cd* S, int t, int c, const cd* __restrict__ tw) {
     using P = SPass<L, WIDE>;
     if constexpr (WIDE) {
-        fft_reg<16, DIR>(v);
+        // L = EPT (registers, j) x 32 (threads, t): EPT = 16 (L = 512) or 8 (L = 256)
+        constexpr int E = P::EPT;
+        fft_reg<E, DIR>(v);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int kj = fft_nat<16>(r);
+        for (int r = 0; r < E; ++r) {
+            const int kj = fft_nat<E>(r);
             cd a = v[r];
             if (kj != 0) a = cmul(a, tw_dir<DIR>(tw[t * kj]));
             S[(kj * 32 + t) * P::ZC + c] = a;
         }
         __syncthreads();
-        const int kj = t & 15, h = t >> 4;
+        if constexpr (E == 16) {
+            // the 32-point FFT over t of every k_j is shared by two threads (k_j, h): outputs k_t = 2 m + h
+            const int kj = t & 15, h = t >> 4;
 #pragma unroll
-        for (int t2 = 0; t2 < 16; ++t2) {
-            const cd lo = S[(kj * 32 + t2) * P::ZC + c], hi = S[(kj * 32 + t2 + 16) * P::ZC + c];
-            cd u = h ? lo - hi : lo + hi;
-            if (t2 != 0) u = cmul(u, tw_dir<DIR>(tw[h * (L / 32) * t2]));      // W32^{t2 h}; h = 0: tw[0] = 1
-            v[t2] = u;
+            for (int t2 = 0; t2 < 16; ++t2) {
+                const cd lo = S[(kj * 32 + t2) * P::ZC + c], hi = S[(kj * 32 + t2 + 16) * P::ZC + c];
+                cd u = h ? lo - hi : lo + hi;
+                if (t2 != 0) u = cmul(u, tw_dir<DIR>(tw[h * (L / 32) * t2]));      // W32^{t2 h}; h = 0: tw[0] = 1
+                v[t2] = u;
+            }
+        } else {
+            // ... by four threads (k_j, h): outputs k_t = 4 m + h as an 8-point FFT of (sum_q y[t' + 8 q] W4^{q h}) W32^{t' h}
+            const int kj = t & 7, h = t >> 3;
+            const bool odd = h & 1, neg = h & 2;
+#pragma unroll
+            for (int t2 = 0; t2 < 8; ++t2) {
+                const cd y0 = S[(kj * 32 + t2) * P::ZC + c], y1 = S[(kj * 32 + t2 + 8) * P::ZC + c];
+                const cd y2 = S[(kj * 32 + t2 + 16) * P::ZC + c], y3 = S[(kj * 32 + t2 + 24) * P::ZC + c];
+                const cd A = odd ? y0 - y2 : y0 + y2;
+                const cd Bq = y1 - y3, Bs = y1 + y3;
+                const cd B = odd ? mul_i<DIR>(Bq) : Bs;
+                cd u = neg ? A - B : A + B;
+                if (t2 != 0) u = cmul(u, tw_dir<DIR>(tw[h * (L / 32) * t2]));
+                v[t2] = u;
+            }
         }
-        fft_reg<16, DIR>(v);
+        fft_reg<E, DIR>(v);
         __syncthreads();
     } else {
         fft_reg<P::EPT, DIR>(v);
@@ -162,9 +182,9 @@ struct SPassFields {
 // ------------------------------------------------------------------------------------------------
 //  plain pass: in-place FFT along the strided axis for nf fields
 // ------------------------------------------------------------------------------------------------
-template <int L, int DIR>
-__global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
-    using P = SPass<L>;
+template <int L, int DIR, bool WIDE = false>
+__global__ void __launch_bounds__((SPass<L, WIDE>::THREADS), (SPass<L, WIDE>::CTAS_PER_SM)) spass_kernel(SPassFields fields, int nf, SPassGeom geo) {
+    using P = SPass<L, WIDE>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);
     spass_load_twiddles<L>(tw);
@@ -182,10 +202,10 @@ __global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) spass_kernel(SPass
         cd v[P::EPT];
 #pragma unroll
         for (int j = 0; j < P::EPT; ++j) v[j] = a.live ? base[(long long)(t + P::TPL * j) * geo.axis_stride] : cd{0.0, 0.0};
-        tile_fft<L, DIR>(v, S, t, c, tw);
+        tile_fft<L, DIR, WIDE>(v, S, t, c, tw);
         if (a.live) {
 #pragma unroll
-            for (int s = 0; s < P::EPT; ++s) base[(long long)spass_out_index<L>(t, s) * geo.axis_stride] = v[s];
+            for (int s = 0; s < P::EPT; ++s) base[(long long)spass_out_index<L, WIDE>(t, s) * geo.axis_stride] = v[s];
         }
     }
 }

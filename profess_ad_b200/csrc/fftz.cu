@@ -915,19 +915,23 @@ SPassGeom spass_geom(const pad_plan* p, int axis) {
     return g;
 }
 
-template <int L, int DIR>
+template <int L, int DIR, bool WIDE = false>
 int launch_spass_L(pad_plan* p, cudaStream_t s, const SPassFields& f, int nf, const SPassGeom& g) {
-    auto kern = spass_kernel<L, DIR>;
-    constexpr int smem = spass_smem_bytes<L>(1);
+    if constexpr (L == 256 && !WIDE) {
+        if (g_pad_ywide) return launch_spass_L<L, DIR, true>(p, s, f, nf, g);
+    }
+    auto kern = spass_kernel<L, DIR, WIDE>;
+    using P = SPass<L, WIDE>;
+    constexpr int smem = spass_smem_bytes<L, WIDE>(1);
     static bool attr_done[64] = {false};
     if (!attr_done[p->device & 63]) {
         PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done[p->device & 63] = true;
     }
     const long long tiles = (long long)nf * spass_tiles(g);
-    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    long long grid = (tiles + P::TPC - 1) / P::TPC;
     if (grid > (1 << 20)) grid = 1 << 20;
-    kern<<<(unsigned)grid, 128, smem, s>>>(f, nf, g);
+    kern<<<(unsigned)grid, P::THREADS, smem, s>>>(f, nf, g);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;

@@ -88,5 +88,6 @@ int main() {
     chk("tile 256", std::max(test_tile<256, -1>(), test_tile<256, 1>()));
     chk("tile 512", std::max(test_tile<512, -1>(), test_tile<512, 1>()));
     chk("tile 512 wide", std::max(test_tile<512, -1, true>(), test_tile<512, 1, true>()));
+    chk("tile 256 wide", std::max(test_tile<256, -1, true>(), test_tile<256, 1, true>()));
     return worst != 0;
 }
