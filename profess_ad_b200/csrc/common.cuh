@@ -325,6 +325,7 @@ extern int g_pad_own_xy;
 extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
 extern int g_pad_zinv_stream;      // 1: streamed inverse z kernel (results folded as they arrive, 3 CTAs/SM), 0: batch form
 extern int g_pad_local_tail;       // 1: fused term list with the local terms in the one-field Hartree inverse pass (0: inside the mid pass)
+extern int g_pad_xone;             // 1: one-field x passes (-k^2, 4 pi / k^2) as the two-transform plain pass
 extern int g_pad_ywide;            // 1: y pass at L = 256 with 32 threads per line (8 points each)
 extern int g_pad_graphs;           // 1: repeated evaluations with the same arguments replay a CUDA graph
 extern unsigned long long g_pad_option_epoch;      // bumped by pad_set_option (part of the graph keys)

@@ -428,6 +428,47 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+//  x pass of ONE field with a computed multiplier (-k^2, 4 pi / k^2): nothing has to be parked, so it is the plain pass with
+//  two transforms per tile -- load, FFT, multiply in registers, inverse FFT straight from the forward's slots, store -- at the
+//  plain pass's occupancy (4 CTAs / SM) instead of the persistent three-buffer machinery of xmix_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int L, class Mix>
+__global__ void __launch_bounds__(128, SPass<L>::CTAS_PER_SM) xone_kernel(cd* __restrict__ field, SPassGeom geo, KGeom kg, Mix mix) {
+    using P = SPass<L>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* tw = reinterpret_cast<cd*>(smem_raw);
+    spass_load_twiddles<L>(tw);
+    const int tile_in_cta = threadIdx.x / P::TILE_THREADS;
+    const int tid = threadIdx.x % P::TILE_THREADS;
+    const int t = tid / P::ZC, c = tid % P::ZC;
+    cd* S = tw + L + (size_t)tile_in_cta * P::TILE_CD;
+    const long long total = spass_tiles(geo);
+    for (long long w0 = (long long)blockIdx.x * P::TPC; w0 < total; w0 += (long long)gridDim.x * P::TPC) {
+        const TileAt a = spass_locate(geo, w0 + tile_in_cta, total, c);
+        cd* base = field + a.off;
+        cd v[P::EPT];
+#pragma unroll
+        for (int j = 0; j < P::EPT; ++j) v[j] = a.live ? base[(long long)(t + P::TPL * j) * geo.axis_stride] : cd{0.0, 0.0};
+        tile_fft<L, -1>(v, S, t, c, tw);
+        const typename Mix::Line kl = mix.line(kg, a.o + kg.j1_off, a.z);
+#pragma unroll
+        for (int s = 0; s < P::EPT; ++s) {
+            cd q[1] = {v[s]};
+            mix.apply(mix.fetch(kl, spass_out_index<L>(t, s), 0, a.live), q);
+            v[s] = q[0];
+        }
+        cd u[P::EPT];
+#pragma unroll
+        for (int j = 0; j < P::EPT; ++j) u[j] = v[spass_slot_of_input<L>(j)];
+        tile_fft<L, +1>(u, S, t, c, tw);
+        if (a.live) {
+#pragma unroll
+            for (int s = 0; s < P::EPT; ++s) base[(long long)spass_out_index<L>(t, s) * geo.axis_stride] = u[s];
+        }
+    }
+}
+
 template <int L, bool WIDE = false>
 constexpr int spass_smem_bytes(int tile_buffers) {
     return (L + SPass<L, WIDE>::TPC * SPass<L, WIDE>::TILE_CD * tile_buffers) * 16;

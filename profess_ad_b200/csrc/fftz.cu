@@ -1117,9 +1117,38 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     return PAD_OK;
 }
 
+template <int L, class Mix>
+int launch_xone_L(pad_plan* p, cudaStream_t s, cd* field, const SPassGeom& g, Mix mix) {
+    auto kern = xone_kernel<L, Mix>;
+    constexpr int smem = spass_smem_bytes<L>(1);
+    static bool attr_done[64] = {false};
+    if (!attr_done[p->device & 63]) {
+        PAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[p->device & 63] = true;
+    }
+    const long long tiles = spass_tiles(g);
+    long long grid = (tiles + SPass<L>::TPC - 1) / SPass<L>::TPC;
+    if (grid > (1 << 20)) grid = 1 << 20;
+    kern<<<(unsigned)grid, 128, smem, s>>>(field, g, p->geom, mix);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    return PAD_OK;
+}
+
 // spec_f <- IFFT_x( mix( FFT_x(spec_0..NF-1) ) )
 template <int NF, class Mix>
 int launch_xmix(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
+    if constexpr (NF == 1 && Mix::kRing == 1) {
+        // one field, computed multiplier: the two-transform plain pass (single-GPU plans, L <= 256)
+        if (g_pad_xone && !p->dist && p->n0 <= 256) {
+            const SPassGeom g1 = spass_geom(p, 0);
+            switch (p->n0) {
+                case 64: return launch_xone_L<64>(p, s, fields[0], g1, mix);
+                case 128: return launch_xone_L<128>(p, s, fields[0], g1, mix);
+                case 256: return launch_xone_L<256>(p, s, fields[0], g1, mix);
+            }
+        }
+    }
     SPassFields f;
     for (int i = 0; i < 4; ++i) f.f[i] = i < NF ? fields[i] : nullptr;
     const SPassGeom g = spass_geom(p, 0);
