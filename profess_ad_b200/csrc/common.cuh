@@ -339,6 +339,8 @@ void pad_stage_begin(cudaStream_t s);
 void pad_stage_mark(const char* name, cudaStream_t s);
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
+int pad_hartree_fast_supported(const pad_plan* p);
+int pad_hartree_fast(pad_plan* p, const double* den, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_wt_fast_supported(const pad_plan* p);
 int pad_wt_fast(pad_plan* p, const double* den, double alpha, double beta, double* E_out, double* v_out, int accumulate,
                 cudaStream_t s);

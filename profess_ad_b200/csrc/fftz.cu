@@ -2495,6 +2495,36 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
     return PAD_OK;
 }
 
+// Hartree term alone (functionals.py:49-72) on the fused passes: [z r2c of n] -> y -> [x . 4 pi / (k^2 N) . x^-1] -> y^-1 ->
+// [z c2r + sum n v_H + potential]; v_out must be given (the energy-only call keeps the cuFFT route).  accumulate: v_out += v_H.
+int pad_hartree_fast_supported(const pad_plan* p) { return fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
+
+int pad_hartree_fast(pad_plan* p, const double* den, double* E_out, double* v_out, int accumulate, cudaStream_t s) {
+    PAD_TRY(ensure_twiddles(p->device));
+    cd* B[1];
+    PAD_TRY(get_zbuf(p, 0, &B[0]));
+    if (!accumulate) PAD_CUDA(cudaMemsetAsync(v_out, 0, sizeof(double) * p->N, s));
+    pad_stage_begin(s);
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, GenCopy{}, den, nullptr, B[0], nullptr, nullptr, nullptr))));
+    pad_stage_mark("Hartree: z-r2c", s);
+    PAD_TRY(launch_spass(p, s, 1, -1, B, 1));
+    pad_stage_mark("Hartree: y-fwd", s);
+    PAD_TRY((launch_xmix<1>(p, s, B, MixCoulomb{p->geom.inv_n})));
+    pad_stage_mark("Hartree: x-fwd * (4 pi / k^2) * x-inv", s);
+    PAD_TRY(launch_spass(p, s, 1, +1, B, 1));
+    pad_stage_mark("Hartree: y-inv", s);
+    int grid = 1;
+    PostHartreeLocal tail{v_out, nullptr, 0};
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 2>(p, s, tail, B[0], nullptr, nullptr, nullptr, den, v_out, &grid))));
+    pad_stage_mark("Hartree: z-c2r + energy + potential", s);
+    if (E_out) {
+        FinalizeArgs h = wgc_energy_args(p, grid, 2, accumulate, E_out);
+        h.coef[0] = 0.5 * p->dV; h.coef[1] = 0.0;
+        pad_launch_finalize(p, h, s);
+    }
+    return PAD_OK;
+}
+
 int pad_wt_fast_supported(const pad_plan* p) { return fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
 
 int pad_wt_fast(pad_plan* p, const double* den, double alpha, double beta, double* E_out, double* v_out, int accumulate,

@@ -103,6 +103,8 @@ extern "C" int pad_eval_hartree(pad_plan* p, const double* den, double* E_out, d
                                 void* stream) {
     PAD_TRY(check_common(p, den, "pad_eval_hartree"));
     cudaStream_t s = as_stream(stream);
+    if (g_pad_fast_fft && v_out && pad_hartree_fast_supported(p) && ((reinterpret_cast<uintptr_t>(den) | reinterpret_cast<uintptr_t>(v_out)) & 15) == 0)
+        return pad_hartree_fast(p, den, E_out, v_out, accumulate, s);
     cufftDoubleComplex* C0;
     double* R0;
     PAD_TRY(pad_get_cbuf(p, 0, &C0));

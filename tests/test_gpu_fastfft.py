@@ -108,6 +108,40 @@ def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
 
 
+@pytest.mark.parametrize('shape,seed', [((64, 64, 128), 51), ((128, 64, 256), 52), ((64, 64, 512), 53)])
+def test_hartree_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
+    """Hartree alone on the fused passes (z r2c -> y -> x . 4 pi / k^2 . x^-1 -> y^-1 -> z c2r + energy + potential), also
+    accumulating into an existing potential, against the cuFFT route and the oracle."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native as nat
+    lib = nat.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=seed, L=9.0)
+    E_ref, V_ref = orc.energy_and_potential(box, den, orc.Hartree)
+    b, d = box.to(dev), den.to(dev)
+    res = {}
+    for fast in (1, 0):
+        old = lib.pad_set_fast_fft(fast)
+        try:
+            f0 = lib.pad_fft_exec_count()
+            E, V = F.energy_and_potential(b, d, F.Hartree)
+            used_cufft = lib.pad_fft_exec_count() - f0
+            plan = nat.get_plan(b, d)
+            Eacc = torch.full((), 1.5, dtype=torch.double, device=dev)
+            vacc = torch.full_like(d, 0.25)
+            nat.check(lib.pad_eval_hartree(plan.handle, nat.ptr(d), nat.ptr(Eacc), nat.ptr(vacc), 1, nat.stream_ptr(dev)))
+        finally:
+            lib.pad_set_fast_fft(old)
+        assert (used_cufft == 0) == bool(fast)
+        assert abs(E.item() - E_ref.item()) <= 1e-10 * abs(E_ref.item()), fast
+        assert ((V.cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9, fast
+        assert abs(Eacc.item() - 1.5 - E.item()) <= 1e-12 * abs(E.item()) + 1e-15          # (1.5 + E rounds at 2e-16)
+        assert ((vacc - 0.25 - V).abs().max() / V.abs().max()).item() < 1e-12
+        res[fast] = E.item()
+    assert abs(res[1] - res[0]) <= 1e-12 * abs(res[0])
+
+
 @pytest.mark.parametrize('expo', [(5 + 5 ** 0.5) / 6, (5 - 5 ** 0.5) / 6, 2.0 / 3.0, -0.5393])
 def test_fast_math_accuracy(expo):
     """Table-driven pow / sqrt / reciprocal (csrc/fastmath.cuh) against torch fp64 over 60 decades."""

@@ -323,3 +323,42 @@ def test_ion_ion_pair_list_restatement_against_castep_energies(golden_dir):
         z = torch.tensor(c['charges'], dtype=torch.double)
         E = ion_utils.ion_interaction_sum(box, cart, z, 12 * c['h_max'], 2 * c['h_max'])
         assert abs(E.item() - c['E']) / len(c['charges']) < 1e-10, c['name']
+
+
+def test_lbfgs_restart_guard_replaces_runaway_moves_only():
+    """LBFGSNew(max_step=...): a quasi-Newton move that would change a component by more than max_step (the near-orthogonal
+    (s, y) pair formed across two step() calls with different objectives -- System.optimize_geometry) is replaced by a
+    steepest-descent restart; without such moves the iterates are those of the unguarded optimiser."""
+    import torch
+    from profess_ad_b200._optimizers.lbfgs.lbfgsnew import LBFGSNew
+
+    def run(max_step, poison):
+        x = torch.tensor([0.3, -0.2, 0.1], dtype=torch.double, requires_grad=True)
+        opt = LBFGSNew([x], lr=0.1, history_size=8, max_iter=6, max_step=max_step)
+        shift = [0.0]
+
+        def closure():
+            opt.zero_grad()
+            loss = ((x - 1.0) ** 2).sum() * 0.5 + shift[0] * x[0] - 3.0
+            loss.backward()
+            return loss
+        traj = []
+        for it in range(6):
+            if poison and it == 3:
+                # what the geometry driver's re-optimised density does: the objective changes between two step() calls,
+                # here so that the next (s, y) pair is almost orthogonal: y.s -> 0+
+                g_now = (x.detach() - 1.0)
+                s_vec = opt._d * opt._t
+                y_target = 1e-9 * s_vec / s_vec.norm() ** 2
+                shift[0] = float((y_target + opt._prev_g - g_now)[0]) if opt._prev_g is not None else 0.0
+            opt.step(closure)
+            traj.append(x.detach().clone())
+        return traj, opt.restarts
+
+    plain, r0 = run(None, False)
+    guarded, r1 = run(1.0, False)
+    assert r1 == 0 and all(torch.equal(a, b) for a, b in zip(plain, guarded))
+    _, r2 = run(1.0, True)
+    blown, _ = run(None, True)
+    safe, _ = run(1.0, True)
+    assert max(float(t.abs().max()) for t in safe) <= max(float(t.abs().max()) for t in blown)
