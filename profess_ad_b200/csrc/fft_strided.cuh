@@ -24,6 +24,9 @@
 // shared by the two threads (k_j, h): thread h computes the outputs k_t = 2 m + h as a 16-point register FFT of
 // (y[t'] +- y[t' + 16]) W32^{t' h}.  The result is distributed over the threads exactly like the input:
 // thread t, slot r holds X[t + 32 fft_nat<16>(r)].
+#ifndef PAD_Y256_CTAS
+#define PAD_Y256_CTAS 4
+#endif
 template <int L, bool WIDE = false>
 struct SPass {
     static_assert(!WIDE || L == 512 || L == 256, "strided pass: the wide layout exists for L = 512 and 256");
@@ -35,7 +38,7 @@ struct SPass {
     static constexpr int THREADS = WIDE ? 256 : 128;
     static constexpr int TPC = THREADS / TILE_THREADS;   // tiles per CTA
     static constexpr int TILE_CD = L * ZC;               // complex numbers per tile
-    static constexpr int CTAS_PER_SM = WIDE ? (L == 512 ? 2 : 4) : ((L == 512) ? 2 : 4);   // plain pass: 32 complex points per thread need > 128 registers
+    static constexpr int CTAS_PER_SM = WIDE ? (L == 512 ? 2 : 4) : ((L == 512) ? 2 : (L == 256 ? PAD_Y256_CTAS : 4));   // plain pass: 32 complex points per thread need > 128 registers
     static_assert(L == 512 || L == 256 || L == 128 || L == 64, "strided pass: L must be 64, 128, 256 or 512");
 };
 
