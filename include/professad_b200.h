@@ -213,6 +213,14 @@ int pad_ionic_potential(pad_plan* plan, const pad_species* species, int n_specie
  * reference's tests/test_particle_mesh_ewald.py:46-63 compares with the exact structure factor. */
 int pad_ionic_potential_pme(pad_plan* plan, const pad_species* species, int n_species, int order, double* v_ext_out, void* stream);
 int pad_pme_structure_factor(pad_plan* plan, const double* frac_dev, int n_ions, int order, double* S_out_cplx, void* stream);
+/* Forces and stress of the IonElectron term WITH the particle-mesh structure factor: what the reference's autograd gives when
+ * pme_order is set (system.py:913-935 through structure_factor_spline).  Forces: one r2c of the density, per species one k-space
+ * pass, one c2r and a gather of the B-spline derivative weights over every ion's order^3 stencil -- O(N log N + N_ion order^3);
+ * stress: pad_ion_stress with S(k) taken from the mesh (fixed fractional coordinates: S does not depend on the cell). */
+int pad_ion_forces_pme(pad_plan* plan, const pad_species* species, int n_species, int order, const double* den,
+                       double* forces_out, void* stream);
+int pad_ion_stress_pme(pad_plan* plan, const pad_species* species, int n_species, int order, const double* den,
+                       double* stress_out, int accumulate, void* stream);
 /* F_I = -d/dR_I of IonElectron(den, v_ext[R]) at fixed density, Cartesian, Ha/bohr; forces_out: DEVICE,
  * 3 * (total number of ions) doubles in species order */
 int pad_ion_forces(pad_plan* plan, const pad_species* species, int n_species, const double* den, double* forces_out,

@@ -65,6 +65,8 @@ SIGNATURES = {
     'pad_pme_structure_factor': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
     'pad_ion_forces': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'pad_ion_stress': (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp]),
+    'pad_ion_forces_pme': (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp]),
+    'pad_ion_stress_pme': (_int, [_vp, _vp, _int, _int, _vp, _vp, _int, _vp]),
     'pad_stress_terms': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'pad_ion_ion_work_doubles': (ctypes.c_size_t, [_c_double_p, _int, _dbl]),
     'pad_ion_ion': (_int, [_c_double_p, _vp, _vp, _int, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _int, _vp]),

@@ -525,6 +525,8 @@ __global__ void __launch_bounds__(PAD_THREADS) k_pme_spectrum(KGeom g, uint32_t 
     }
 }
 
+int pme_b_tables(pad_plan* p, int order, cudaStream_t s, double2** btab);
+
 // spread + r2c + b tables of one species; Qhat in cbuf 1, b tables in *btab (device, caller frees)
 int pme_prepare(pad_plan* p, const double* frac_dev, int n_ions, int order, cudaStream_t s, cufftDoubleComplex** Qh, double2** btab) {
     if (p->dist) { pad_set_error("particle-mesh Ewald structure factor: not available on slab plans (use the exact one)"); return PAD_ERR_ARG; }
@@ -538,6 +540,105 @@ int pme_prepare(pad_plan* p, const double* frac_dev, int n_ions, int order, cuda
         ++g_pad_launches;
     }
     PAD_TRY(pad_fft_forward(p, Q, *Qh, s));
+    return pme_b_tables(p, order, s, btab);
+}
+
+// weights and their derivatives with respect to x: d/dx M_n(x + i) = M_{n-1}(x + i) - M_{n-1}(x + i - 1)
+__device__ inline void bspline_weights_derivs(double x, int order, double* M, double* dM) {
+    for (int i = 0; i < order; ++i) M[i] = 0.0;
+    if (order == 2) {
+        M[0] = x; M[1] = 1.0 - x;
+        dM[0] = 1.0; dM[1] = -1.0;
+        return;
+    }
+    bspline_weights(x, order - 1, M);                    // M_{n-1}(x + i), i < n - 1 (M[n-1] = 0)
+    double prev = 0.0;
+    for (int i = 0; i < order; ++i) {
+        const double cur = i < order - 1 ? M[i] : 0.0;
+        dM[i] = cur - prev;
+        const double left = (x + (double)i) * cur;
+        const double right = i >= 1 ? ((double)order - x - (double)i) * prev : 0.0;
+        M[i] = (left + right) / (double)(order - 1);
+        prev = cur;
+    }
+}
+
+// A(k) = v_s(|k|) conj(b0 b1 b2 rho_hat(k)), Hermitian part on the special points: the unnormalised c2r of A is the field
+// Phi(r) = sum_k w_k Re[A(k) e^{ikr}] the spread charges are contracted with,  E = (dV / vol) sum_r Q(r) Phi(r)
+__global__ void __launch_bounds__(PAD_THREADS) k_pme_force_spectrum(KGeom g, uint32_t nk, UniformTable T, double z, const double2* __restrict__ R,
+                                                                  const double2* __restrict__ b0, const double2* __restrict__ b1,
+                                                                  const double2* __restrict__ b2, double2* __restrict__ out) {
+    const uint32_t stride = gridDim.x * PAD_THREADS;
+    for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
+        const KPoint p = make_kpoint(g, idx);
+        auto A_at = [&](int j0, int j1, int j2, double kx, double ky, double kz) {
+            const double2 r = R[((size_t)j0 * g.n1 + j1) * g.nzh + j2];
+            const double2 t = cmul(cmul(cmul(b0[j0], b1[j1]), b2[j2]), r);
+            const double f = recpot_value(T, z, kx, ky, kz);
+            return make_double2(f * t.x, -f * t.y);
+        };
+        double2 A = A_at(p.j0, p.j1, p.j2, p.kx, p.ky, p.kz);
+        if (p.special) {
+            const double2 Ab = A_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2, p.px, p.py, p.pz);
+            A.x = 0.5 * (A.x + Ab.x);
+            A.y = 0.5 * (A.y - Ab.y);
+        }
+        out[idx] = A;
+    }
+}
+
+// one CTA per ion: F_c = -(dV / vol) sum_a N_a (B^-1)_{ca} sum_stencil dW_a/du_a prod_{b != a} W_b Phi(grid point)
+__global__ void __launch_bounds__(128) k_pme_force_gather(const double* __restrict__ frac, int n_ions, int order, int N0, int N1, int N2,
+                                                         const double* __restrict__ Phi, double scale, double bi00, double bi01, double bi02,
+                                                         double bi10, double bi11, double bi12, double bi20, double bi21, double bi22,
+                                                         double* __restrict__ forces /* n_ions x 3 */) {
+    __shared__ double w[3][PME_MAX_ORDER], dw[3][PME_MAX_ORDER];
+    __shared__ int fl[3];
+    __shared__ double red[3][4];
+    for (int ion = blockIdx.x; ion < n_ions; ion += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const int a = threadIdx.x;
+            const int N = a == 0 ? N0 : (a == 1 ? N1 : N2);
+            double f = frac[3 * ion + a];
+            f -= floor(f);
+            f -= floor(f);
+            const double u = f * (double)N;
+            const double fu = floor(u);
+            fl[a] = (int)fu;
+            bspline_weights_derivs(u - fu, order, w[a], dw[a]);
+        }
+        __syncthreads();
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        const int total = order * order * order;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int i = e / (order * order), j = (e / order) % order, k = e % order;
+            int a0 = (i - fl[0]) % N0, a1 = (j - fl[1]) % N1, a2 = (k - fl[2]) % N2;
+            if (a0 < 0) a0 += N0;
+            if (a1 < 0) a1 += N1;
+            if (a2 < 0) a2 += N2;
+            const double ph = Phi[((size_t)a0 * N1 + a1) * N2 + a2];
+            g0 += dw[0][i] * w[1][j] * w[2][k] * ph;
+            g1 += w[0][i] * dw[1][j] * w[2][k] * ph;
+            g2 += w[0][i] * w[1][j] * dw[2][k] * ph;
+        }
+        g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { red[0][warp] = g0; red[1][warp] = g1; red[2][warp] = g2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // dE/du_a, u_a = N_a frac_a, frac = R B^-1  =>  dE/dR_c = sum_a N_a (B^-1)_{ca} dE/du_a
+            const double d0 = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) * (double)N0;
+            const double d1 = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) * (double)N1;
+            const double d2 = (red[2][0] + red[2][1] + red[2][2] + red[2][3]) * (double)N2;
+            forces[3 * ion + 0] = -scale * (bi00 * d0 + bi01 * d1 + bi02 * d2);
+            forces[3 * ion + 1] = -scale * (bi10 * d0 + bi11 * d1 + bi12 * d2);
+            forces[3 * ion + 2] = -scale * (bi20 * d0 + bi21 * d1 + bi22 * d2);
+        }
+    }
+}
+
+int pme_b_tables(pad_plan* p, int order, cudaStream_t s, double2** btab) {
     std::vector<double2> h0, h1, h2, all;
     pme_b_table(p->n0, p->n0, order, h0);
     pme_b_table(p->n1, p->n1, order, h1);
@@ -599,5 +700,125 @@ extern "C" int pad_ionic_potential_pme(pad_plan* p, const pad_species* species, 
         cudaFree(bt);
     }
     PAD_TRY(pad_fft_inverse(p, G, v_ext_out, s));
+    return PAD_OK;
+}
+
+
+// IonElectron forces with the particle-mesh structure factor: what the reference's autograd through structure_factor_spline gives
+// (system.py:913-925 with pme_order set).  E = (dV / vol) sum_r Q(r) Phi(r) with Q the B-spline charges (fixed stencil, weights
+// smooth in R) and Phi the unnormalised c2r of v_s conj(b rho_hat); one r2c of the density, and per species one k-space pass, one
+// c2r and one gather over the order^3 stencil of every ion: O(N log N + N_ion order^3) instead of O(N_k N_ion).
+extern "C" int pad_ion_forces_pme(pad_plan* p, const pad_species* species, int n_species, int order, const double* den,
+                                  double* forces_out, void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ion_forces_pme"));
+    if (!den || !forces_out) { pad_set_error("pad_ion_forces_pme: null argument"); return PAD_ERR_ARG; }
+    if (p->dist) { pad_set_error("particle-mesh Ewald forces: not available on slab plans (use the exact structure factor)"); return PAD_ERR_ARG; }
+    if (order < 2 || order > PME_MAX_ORDER || (order & 1)) { pad_set_error("Requires even order 2 <= n <= %d", PME_MAX_ORDER); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cufftDoubleComplex *R, *A;
+    double* Phi;
+    PAD_TRY(pad_get_cbuf(p, 0, &R));
+    PAD_TRY(pad_get_cbuf(p, 1, &A));
+    PAD_TRY(pad_get_rbuf(p, 0, &Phi));
+    PAD_TRY(pad_fft_forward(p, den, R, s));
+    double2* bt = nullptr;
+    PAD_TRY(pme_b_tables(p, order, s, &bt));
+    double inv[9], det;
+    {   // B^-1 of the lattice (rows = lattice vectors)
+        const double* m = p->box;
+        const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+        const double Aa = e * i - f * h, Bb = -(d * i - f * g), Cc = d * h - e * g;
+        det = a * Aa + b * Bb + c * Cc;
+        const double id = 1.0 / det;
+        inv[0] = Aa * id; inv[1] = -(b * i - c * h) * id; inv[2] = (b * f - c * e) * id;
+        inv[3] = Bb * id; inv[4] = (a * i - c * g) * id;  inv[5] = -(a * f - c * d) * id;
+        inv[6] = Cc * id; inv[7] = -(a * h - b * g) * id; inv[8] = (a * e - b * d) * id;
+    }
+    int ion_off = 0;
+    for (int sI = 0; sI < n_species; ++sI) {
+        const pad_species& sp = species[sI];
+        if (sp.n_ions == 0) continue;
+        IonScratch W;
+        UniformTable T;
+        pad_species tab_only = sp;
+        tab_only.n_ions = 0;
+        PAD_TRY(prepare_species(p, tab_only, s, W, T));
+        k_pme_force_spectrum<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->geom, (uint32_t)p->Nk, T, sp.z, reinterpret_cast<const double2*>(R), bt,
+                                                                      bt + p->n0, bt + p->n0 + p->n1, reinterpret_cast<double2*>(A));
+        PAD_CUDA(cudaGetLastError());
+        PAD_TRY(pad_fft_inverse(p, A, Phi, s));
+        k_pme_force_gather<<<sp.n_ions < 148 * 8 ? sp.n_ions : 148 * 8, 128, 0, s>>>(sp.frac_dev, sp.n_ions, order, p->n0, p->n1, p->n2, Phi,
+                                                                                 p->dV / p->vol, inv[0], inv[1], inv[2], inv[3], inv[4],
+                                                                                 inv[5], inv[6], inv[7], inv[8], forces_out + 3 * (size_t)ion_off);
+        g_pad_launches += 2;
+        PAD_CUDA(cudaGetLastError());
+        ion_off += sp.n_ions;
+    }
+    PAD_CUDA(cudaStreamSynchronize(s));
+    cudaFree(bt);
+    return PAD_OK;
+}
+
+// IonElectron stress with the particle-mesh structure factor (system.py:927-935 with pme_order): the ions keep their fractional
+// coordinates, so the spread charges and S(k) do not depend on the cell -- pad_ion_stress with S(k) from the mesh.
+extern "C" int pad_ion_stress_pme(pad_plan* p, const pad_species* species, int n_species, int order, const double* den,
+                                  double* stress_out, int accumulate, void* stream) {
+    PAD_TRY(check_species(p, species, n_species, "pad_ion_stress_pme"));
+    if (!den || !stress_out) { pad_set_error("pad_ion_stress_pme: null argument"); return PAD_ERR_ARG; }
+    PAD_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate) PAD_CUDA(cudaMemsetAsync(stress_out, 0, sizeof(double) * 9, s));
+    cufftDoubleComplex *R, *Sk;
+    PAD_TRY(pad_get_cbuf(p, 0, &R));
+    PAD_TRY(pad_get_cbuf(p, 2, &Sk));
+    PAD_TRY(pad_fft_forward(p, den, R, s));
+    const KGeom geom = p->geom;
+    const double inv_n = geom.inv_n;
+    for (int sI = 0; sI < n_species; ++sI) {
+        const pad_species& sp = species[sI];
+        if (sp.n_ions == 0) continue;
+        IonScratch W;
+        UniformTable T;
+        pad_species tab_only = sp;
+        tab_only.n_ions = 0;
+        PAD_TRY(prepare_species(p, tab_only, s, W, T));
+        cufftDoubleComplex* Qh;
+        double2* bt = nullptr;
+        PAD_TRY(pme_prepare(p, sp.frac_dev, sp.n_ions, order, s, &Qh, &bt));      // (uses real buffer 0 and complex buffer 1)
+        UniformTable T0{};
+        k_pme_spectrum<<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(geom, (uint32_t)p->Nk, T0, 0.0, reinterpret_cast<const double2*>(Qh), bt,
+                                                                bt + p->n0, bt + p->n0 + p->n1, 0.0, 0, 1, reinterpret_cast<double2*>(Sk));
+        ++g_pad_launches;
+        const cufftDoubleComplex *Rc = R, *Sc = Sk;
+        const double z = sp.z;
+        auto f = [=] __device__(size_t i, double(&acc)[7]) {
+            const KPoint k = make_kpoint(geom, (uint32_t)i);
+            const cufftDoubleComplex r = Rc[i], sk = Sc[i];
+            const bool edge = k.j2 == 0 || (geom.e2 && k.j2 == geom.n2 / 2);
+            const double re = (edge ? 1.0 : 2.0) * (sk.x * r.x + sk.y * r.y) * inv_n;
+            const double k2 = k.kx * k.kx + k.ky * k.ky + k.kz * k.kz;
+            double val, slope;
+            if (k2 == 0.0) {
+                table_lookup_slope(T, 0.0, val, slope);
+                acc[0] -= val * re;
+                return;
+            }
+            const double ka = sqrt(k2);
+            table_lookup_slope(T, ka, val, slope);
+            val -= 4.0 * kPi * z / k2;
+            slope += 8.0 * kPi * z / (k2 * ka);
+            acc[0] -= val * re;
+            const double t = -slope / ka * re;
+            acc[1] += t * k.kx * k.kx; acc[2] += t * k.ky * k.ky; acc[3] += t * k.kz * k.kz;
+            acc[4] += t * k.kx * k.ky; acc[5] += t * k.kx * k.kz; acc[6] += t * k.ky * k.kz;
+        };
+        ew_kernel<7, decltype(f)><<<pad_grid_for(p->Nk), PAD_THREADS, 0, s>>>(p->Nk, f, p->partials);
+        ++g_pad_launches;
+        PAD_TRY(pad_stress_accumulate(p, s, pad_grid_for(p->Nk), 1.0 / p->vol, 1.0 / p->vol, stress_out));
+        PAD_CUDA(cudaStreamSynchronize(s));
+        cudaFree(bt);
+    }
+    PAD_CUDA(cudaGetLastError());
     return PAD_OK;
 }

@@ -120,10 +120,11 @@ def ionic_potential(box_vecs, shape, species, pme_order=None):
     return v_ext
 
 
-def ion_electron_forces(box_vecs, den, species):
+def ion_electron_forces(box_vecs, den, species, pme_order=None):
     """-d IonElectron / d R_I at fixed density, (N_ion, 3) Cartesian in Ha/bohr (pad_ion_forces); the IonElectron
-    part of System.__compute_forces (system.py:913-925).  Inside ``parallel.slab(...)`` the partial sums of the
-    ranks are added here."""
+    part of System.__compute_forces (system.py:913-925).  ``pme_order`` (even, <= 32; single-GPU plans): the forces of the
+    particle-mesh structure factor -- what the reference's autograd gives when the System was built with pme_order
+    (pad_ion_forces_pme).  Inside ``parallel.slab(...)`` the partial sums of the ranks are added here."""
     from . import _native, parallel
     _native.require_cuda(den)
     den = den.detach().contiguous()
@@ -131,26 +132,36 @@ def ion_electron_forces(box_vecs, den, species):
     arr, keep = _pad_species_array(species, den.device)
     n_ions = sum(int(f.shape[0]) for _, f in species)
     forces = torch.zeros((n_ions, 3), dtype=torch.double, device=den.device)
+    ctx = parallel.current()
+    if pme_order is not None and ctx is None:
+        _native.check(plan.lib.pad_ion_forces_pme(plan.handle, arr, len(species), int(pme_order), _native.ptr(den), _native.ptr(forces),
+                                                  _native.stream_ptr(den.device)))
+        del keep
+        return forces
     _native.check(plan.lib.pad_ion_forces(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(forces),
                                           _native.stream_ptr(den.device)))
     del keep
-    ctx = parallel.current()
     if ctx is not None:
         ctx.comm.all_reduce(forces.view(-1))
     return forces
 
 
-def ion_electron_stress(box_vecs, den, species):
+def ion_electron_stress(box_vecs, den, species, pme_order=None):
     """IonElectron part of the stress, (3, 3) in Ha/bohr^3 (pad_ion_stress; system.py:927-935): ions at fixed
-    fractional coordinates, electron number conserved."""
-    from . import _native
+    fractional coordinates, electron number conserved.  ``pme_order``: with the particle-mesh structure factor
+    (pad_ion_stress_pme; single-GPU plans)."""
+    from . import _native, parallel
     _native.require_cuda(den)
     den = den.detach().contiguous()
     plan = _native.get_plan(box_vecs, den)
     arr, keep = _pad_species_array(species, den.device)
     out = torch.empty(9, dtype=torch.double, device=den.device)
-    _native.check(plan.lib.pad_ion_stress(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(out), 0,
-                                          _native.stream_ptr(den.device)))
+    if pme_order is not None and parallel.current() is None:
+        _native.check(plan.lib.pad_ion_stress_pme(plan.handle, arr, len(species), int(pme_order), _native.ptr(den), _native.ptr(out), 0,
+                                                  _native.stream_ptr(den.device)))
+    else:
+        _native.check(plan.lib.pad_ion_stress(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(out), 0,
+                                              _native.stream_ptr(den.device)))
     del keep
     return out.reshape(3, 3)
 

@@ -311,18 +311,21 @@ class System():
     def bulk_modulus(self, units='Ha/b3', requires_grad=False):
         self.__second_order('bulk_modulus')
 
+    def __native_pme_order(self):
+        """pme_order for the native force / stress kernels (orders the B-spline kernels cover), else None = exact."""
+        return self.__pme_order if (self.__pme_order is not None and self.__pme_order <= 32) else None
+
     def forces(self, units='Ha/b'):
         """F = -dE/dR at fixed density (system.py:623-643, 913-925): the IonElectron part is one native
-        reciprocal-space reduction per ion (pad_ion_forces), the IonIon part autograd through the real-space pair
-        sum.  Deviation from the reference: when ``pme_order`` is set the reference differentiates the particle-mesh
-        structure factor (system.py:913-925 goes through __potential_from_ions with pme_order); here the forces are
-        always those of the EXACT structure factor, i.e. the PME interpolation error is not differentiated."""
+        reciprocal-space reduction per ion (pad_ion_forces) or, when the System was built with ``pme_order``, the
+        derivative of the particle-mesh structure factor as in the reference (pad_ion_forces_pme: one c2r and a gather of
+        B-spline derivative weights); the IonIon part has closed forms (pad_ion_ion)."""
         if units not in ('Ha/b', 'eV/a'):
             raise ValueError('Parameter \'units\' can only be \'Ha/b\' or \'eV/a\'')
         names = [_term_name(f) for f in self.__terms]
         forces = torch.zeros((self.__N_ions, 3), dtype=torch.double, device=self.__device)
         if 'IonElectron' in names:
-            forces = forces + ion_electron_forces(self.__box_vecs, self.__den, self.__species())
+            forces = forces + ion_electron_forces(self.__box_vecs, self.__den, self.__species(), self.__native_pme_order())
         if 'IonIon' in names:
             cart = torch.matmul(self.__frac_ion_coords, self.__box_vecs).detach().requires_grad_(True)
             U = self.__ion_ion_interaction(cart)
@@ -343,7 +346,7 @@ class System():
                                           '(user-defined Python terms need autograd through box_vecs)')
             sig = sig + _density_opt.stress_terms(self.__box_vecs, self.__den, T)
         if 'IonElectron' in names:
-            sig = sig + ion_electron_stress(self.__box_vecs, self.__den, self.__species())
+            sig = sig + ion_electron_stress(self.__box_vecs, self.__den, self.__species(), self.__native_pme_order())
         if 'IonIon' in names:
             box = self.__box_vecs.detach().clone().requires_grad_(True)
             saved, self.__box_vecs = self.__box_vecs, box

@@ -78,3 +78,35 @@ def test_pme_ionic_potential_and_system(potentials_dir):
     assert np.allclose(res[0][1], res[1][1])
     assert np.allclose(res[0][2], res[1][2], atol=1e-8)
     assert np.allclose(res[0][3], res[1][3])
+
+
+@pytest.mark.parametrize('case', ['li2_odd', 'li2_even', 'alli_mixed'])
+@pytest.mark.parametrize('order', [4, 8])
+def test_pme_forces_and_stress_match_reference_autograd(case, order, golden_dir, potentials_dir):
+    """IonElectron with the particle-mesh structure factor: v_ext, forces (one c2r + gather of B-spline derivative weights,
+    pad_ion_forces_pme) and stress (pad_ion_stress_pme) against the UNMODIFIED reference's values / autograd through
+    structure_factor_spline (System(pme_order=n), tests/golden/ions_pme.npz from make_golden_pme_forces.py) -- and through
+    System.forces() / System.stress()."""
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import ion_utils as IU
+    from profess_ad_b200.system import System
+    from test_oracle_ions import load_case
+    g, box, den, species = load_case(case, golden_dir, potentials_dir)
+    ref = np.load(os.path.join(golden_dir, 'ions_pme.npz'))
+    key = f'{case}_o{order}_'
+    b, d = box.to(DEV), den.to(DEV)
+    sp = [(p, f.to(DEV)) for p, f in species]
+    v = IU.ionic_potential(b, tuple(den.shape), sp, pme_order=order).cpu().numpy()
+    assert np.abs(v - ref[key + 'vext']).max() <= 1e-10 * np.abs(ref[key + 'vext']).max()
+    Fp = IU.ion_electron_forces(b, d, sp, pme_order=order).cpu().numpy()
+    assert np.abs(Fp - ref[key + 'forces']).max() <= 1e-9 * np.abs(ref[key + 'forces']).max(), (Fp, ref[key + 'forces'])
+    # (and they are NOT the forces of the exact structure factor: the mesh error is differentiated, as in the reference)
+    assert np.abs(Fp - g['forces_IonElectron']).max() > 1e-6 * np.abs(g['forces_IonElectron']).max()
+    st = IU.ion_electron_stress(b, d, sp, pme_order=order).cpu().numpy()
+    assert np.abs(st - ref[key + 'stress']).max() <= 1e-9 * np.abs(ref[key + 'stress']).max(), (st, ref[key + 'stress'])
+    ions = [[os.path.basename(p)[:2].capitalize(), p, f] for p, f in species]
+    s = System(box, tuple(den.shape), ions, [F.IonElectron], units='b', coord_type='fractional', pme_order=order)
+    s.set_density(den)
+    assert abs(s.energy('Ha') - float(ref[key + 'energy'])) <= 1e-10 * abs(float(ref[key + 'energy']))
+    assert np.abs(s.forces('Ha/b').cpu().numpy() - ref[key + 'forces']).max() <= 1e-9 * np.abs(ref[key + 'forces']).max()
+    assert np.abs(s.stress('Ha/b3').cpu().numpy() - ref[key + 'stress']).max() <= 1e-9 * np.abs(ref[key + 'stress']).max()
