@@ -209,7 +209,8 @@ typedef struct pad_species {
 int pad_ionic_potential(pad_plan* plan, const pad_species* species, int n_species, double* v_ext_out, void* stream);
 /* Particle-mesh Ewald variants (System(pme_order=n), system.py:183-205 -> structure_factor_spline, ion_utils.py:218-286):
  * B-spline spreading + one r2c + exponential-spline factors instead of the O(N_k N_ion) exact structure factor.  order: even,
- * 2..32.  Not on slab plans.  pad_pme_structure_factor returns S(k) itself (n0 x n1 x (n2/2+1) complex), the quantity the
+ * 2..32.  On slab plans every rank sweeps all ions and keeps the stencil points on its own planes (frac_dev holds ALL ions on
+ * every rank; forces come out as per-rank partial sums).  pad_pme_structure_factor returns S(k) itself (n0 x n1 x (n2/2+1) complex), the quantity the
  * reference's tests/test_particle_mesh_ewald.py:46-63 compares with the exact structure factor. */
 int pad_ionic_potential_pme(pad_plan* plan, const pad_species* species, int n_species, int order, double* v_ext_out, void* stream);
 int pad_pme_structure_factor(pad_plan* plan, const double* frac_dev, int n_ions, int order, double* S_out_cplx, void* stream);

@@ -441,8 +441,9 @@ __host__ __device__ inline void bspline_weights(double x, int order, double* M /
     }
 }
 
+// (slab plans: every rank sweeps ALL ions and keeps the stencil points that fall on its own x-planes [x_lo, x_lo + n0_loc))
 __global__ void __launch_bounds__(128) k_pme_spread(const double* __restrict__ frac, int n_ions, int order, int N0, int N1, int N2,
-                                                   double* __restrict__ Q) {
+                                                   int x_lo, int n0_loc, double* __restrict__ Q) {
     __shared__ double w[3][PME_MAX_ORDER];
     __shared__ int fl[3];
     for (int ion = blockIdx.x; ion < n_ions; ion += gridDim.x) {
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__(128) k_pme_spread(const double* __restrict__ f
             if (a0 < 0) a0 += N0;
             if (a1 < 0) a1 += N1;
             if (a2 < 0) a2 += N2;
+            a0 -= x_lo;
+            if (a0 < 0 || a0 >= n0_loc) continue;
             atomicAdd(Q + ((size_t)a0 * N1 + a1) * N2 + a2, w[0][i] * w[1][j] * w[2][k]);
         }
     }
@@ -498,13 +501,16 @@ __global__ void __launch_bounds__(PAD_THREADS) k_pme_spectrum(KGeom g, uint32_t 
     const uint32_t stride = gridDim.x * PAD_THREADS;
     for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
         const KPoint p = make_kpoint(g, idx);
-        auto S_at = [&](int j0, int j1, int j2) {
-            const double2 q = Qh[((size_t)j0 * g.n1 + j1) * g.nzh + j2];
+        // Qhat is the transform of a REAL field: on the self-conjugate planes Qhat(pbar) = conj Qhat(p), so the partner value
+        // of a special point never has to be fetched (on slab plans it may live on another rank)
+        const double2 qh = Qh[idx];
+        auto S_at = [&](int j0, int j1, int j2, bool partner) {
+            const double2 q = partner ? make_double2(qh.x, -qh.y) : qh;
             const double2 b = cmul(cmul(b0[j0], b1[j1]), b2[j2]);
             const double2 t = cmul(b, q);
             return make_double2(t.x, -t.y);
         };
-        const double2 S = S_at(p.j0, p.j1, p.j2);
+        const double2 S = S_at(p.j0, p.j1, p.j2, false);
         double2 G;
         if (raw) {
             G = S;
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(PAD_THREADS) k_pme_spectrum(KGeom g, uint32_t 
             const double f = recpot_value(T, z, p.kx, p.ky, p.kz);
             G = make_double2(f * S.x, f * S.y);
             if (p.special) {
-                const double2 Sb = S_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2);
+                const double2 Sb = S_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2, true);
                 const double fb = recpot_value(T, z, p.px, p.py, p.pz);
                 G.x = 0.5 * (G.x + fb * Sb.x);
                 G.y = 0.5 * (G.y - fb * Sb.y);
@@ -529,14 +535,14 @@ int pme_b_tables(pad_plan* p, int order, cudaStream_t s, double2** btab);
 
 // spread + r2c + b tables of one species; Qhat in cbuf 1, b tables in *btab (device, caller frees)
 int pme_prepare(pad_plan* p, const double* frac_dev, int n_ions, int order, cudaStream_t s, cufftDoubleComplex** Qh, double2** btab) {
-    if (p->dist) { pad_set_error("particle-mesh Ewald structure factor: not available on slab plans (use the exact one)"); return PAD_ERR_ARG; }
     if (order < 2 || order > PME_MAX_ORDER || (order & 1)) { pad_set_error("Requires even order 2 <= n <= %d", PME_MAX_ORDER); return PAD_ERR_ARG; }
     double* Q;
     PAD_TRY(pad_get_rbuf(p, 0, &Q));
     PAD_TRY(pad_get_cbuf(p, 1, Qh));
     PAD_CUDA(cudaMemsetAsync(Q, 0, sizeof(double) * p->N, s));
     if (n_ions > 0) {
-        k_pme_spread<<<n_ions < 148 * 8 ? n_ions : 148 * 8, 128, 0, s>>>(frac_dev, n_ions, order, p->n0, p->n1, p->n2, Q);
+        k_pme_spread<<<n_ions < 148 * 8 ? n_ions : 148 * 8, 128, 0, s>>>(frac_dev, n_ions, order, p->n0, p->n1, p->n2,
+                                                                       p->dist ? p->rank * p->n0_loc : 0, p->dist ? p->n0_loc : p->n0, Q);
         ++g_pad_launches;
     }
     PAD_TRY(pad_fft_forward(p, Q, *Qh, s));
@@ -571,15 +577,16 @@ __global__ void __launch_bounds__(PAD_THREADS) k_pme_force_spectrum(KGeom g, uin
     const uint32_t stride = gridDim.x * PAD_THREADS;
     for (uint32_t idx = blockIdx.x * PAD_THREADS + threadIdx.x; idx < nk; idx += stride) {
         const KPoint p = make_kpoint(g, idx);
-        auto A_at = [&](int j0, int j1, int j2, double kx, double ky, double kz) {
-            const double2 r = R[((size_t)j0 * g.n1 + j1) * g.nzh + j2];
+        const double2 rh = R[idx];
+        auto A_at = [&](int j0, int j1, int j2, double kx, double ky, double kz, bool partner) {
+            const double2 r = partner ? make_double2(rh.x, -rh.y) : rh;      // rho_hat(pbar) = conj rho_hat(p) on these planes
             const double2 t = cmul(cmul(cmul(b0[j0], b1[j1]), b2[j2]), r);
             const double f = recpot_value(T, z, kx, ky, kz);
             return make_double2(f * t.x, -f * t.y);
         };
-        double2 A = A_at(p.j0, p.j1, p.j2, p.kx, p.ky, p.kz);
+        double2 A = A_at(p.j0, p.j1, p.j2, p.kx, p.ky, p.kz, false);
         if (p.special) {
-            const double2 Ab = A_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2, p.px, p.py, p.pz);
+            const double2 Ab = A_at((g.n0 - p.j0) % g.n0, (g.n1 - p.j1) % g.n1, p.j2, p.px, p.py, p.pz, true);
             A.x = 0.5 * (A.x + Ab.x);
             A.y = 0.5 * (A.y - Ab.y);
         }
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(PAD_THREADS) k_pme_force_spectrum(KGeom g, uin
 
 // one CTA per ion: F_c = -(dV / vol) sum_a N_a (B^-1)_{ca} sum_stencil dW_a/du_a prod_{b != a} W_b Phi(grid point)
 __global__ void __launch_bounds__(128) k_pme_force_gather(const double* __restrict__ frac, int n_ions, int order, int N0, int N1, int N2,
-                                                         const double* __restrict__ Phi, double scale, double bi00, double bi01, double bi02,
+                                                         int x_lo, int n0_loc, const double* __restrict__ Phi, double scale, double bi00, double bi01, double bi02,
                                                          double bi10, double bi11, double bi12, double bi20, double bi21, double bi22,
                                                          double* __restrict__ forces /* n_ions x 3 */) {
     __shared__ double w[3][PME_MAX_ORDER], dw[3][PME_MAX_ORDER];
@@ -617,6 +624,8 @@ __global__ void __launch_bounds__(128) k_pme_force_gather(const double* __restri
             if (a0 < 0) a0 += N0;
             if (a1 < 0) a1 += N1;
             if (a2 < 0) a2 += N2;
+            a0 -= x_lo;
+            if (a0 < 0 || a0 >= n0_loc) continue;          // slab plans: this rank's planes; the caller adds the ranks' partial forces
             const double ph = Phi[((size_t)a0 * N1 + a1) * N2 + a2];
             g0 += dw[0][i] * w[1][j] * w[2][k] * ph;
             g1 += w[0][i] * dw[1][j] * w[2][k] * ph;
@@ -712,7 +721,6 @@ extern "C" int pad_ion_forces_pme(pad_plan* p, const pad_species* species, int n
                                   double* forces_out, void* stream) {
     PAD_TRY(check_species(p, species, n_species, "pad_ion_forces_pme"));
     if (!den || !forces_out) { pad_set_error("pad_ion_forces_pme: null argument"); return PAD_ERR_ARG; }
-    if (p->dist) { pad_set_error("particle-mesh Ewald forces: not available on slab plans (use the exact structure factor)"); return PAD_ERR_ARG; }
     if (order < 2 || order > PME_MAX_ORDER || (order & 1)) { pad_set_error("Requires even order 2 <= n <= %d", PME_MAX_ORDER); return PAD_ERR_ARG; }
     PAD_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -748,7 +756,8 @@ extern "C" int pad_ion_forces_pme(pad_plan* p, const pad_species* species, int n
                                                                       bt + p->n0, bt + p->n0 + p->n1, reinterpret_cast<double2*>(A));
         PAD_CUDA(cudaGetLastError());
         PAD_TRY(pad_fft_inverse(p, A, Phi, s));
-        k_pme_force_gather<<<sp.n_ions < 148 * 8 ? sp.n_ions : 148 * 8, 128, 0, s>>>(sp.frac_dev, sp.n_ions, order, p->n0, p->n1, p->n2, Phi,
+        k_pme_force_gather<<<sp.n_ions < 148 * 8 ? sp.n_ions : 148 * 8, 128, 0, s>>>(sp.frac_dev, sp.n_ions, order, p->n0, p->n1, p->n2,
+                                                                                 p->dist ? p->rank * p->n0_loc : 0, p->dist ? p->n0_loc : p->n0, Phi,
                                                                                  p->dV / p->vol, inv[0], inv[1], inv[2], inv[3], inv[4],
                                                                                  inv[5], inv[6], inv[7], inv[8], forces_out + 3 * (size_t)ion_off);
         g_pad_launches += 2;

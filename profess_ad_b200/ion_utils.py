@@ -122,7 +122,7 @@ def ionic_potential(box_vecs, shape, species, pme_order=None):
 
 def ion_electron_forces(box_vecs, den, species, pme_order=None):
     """-d IonElectron / d R_I at fixed density, (N_ion, 3) Cartesian in Ha/bohr (pad_ion_forces); the IonElectron
-    part of System.__compute_forces (system.py:913-925).  ``pme_order`` (even, <= 32; single-GPU plans): the forces of the
+    part of System.__compute_forces (system.py:913-925).  ``pme_order`` (even, <= 32): the forces of the
     particle-mesh structure factor -- what the reference's autograd gives when the System was built with pme_order
     (pad_ion_forces_pme).  Inside ``parallel.slab(...)`` the partial sums of the ranks are added here."""
     from . import _native, parallel
@@ -133,13 +133,12 @@ def ion_electron_forces(box_vecs, den, species, pme_order=None):
     n_ions = sum(int(f.shape[0]) for _, f in species)
     forces = torch.zeros((n_ions, 3), dtype=torch.double, device=den.device)
     ctx = parallel.current()
-    if pme_order is not None and ctx is None:
+    if pme_order is not None:
         _native.check(plan.lib.pad_ion_forces_pme(plan.handle, arr, len(species), int(pme_order), _native.ptr(den), _native.ptr(forces),
                                                   _native.stream_ptr(den.device)))
-        del keep
-        return forces
-    _native.check(plan.lib.pad_ion_forces(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(forces),
-                                          _native.stream_ptr(den.device)))
+    else:
+        _native.check(plan.lib.pad_ion_forces(plan.handle, arr, len(species), _native.ptr(den), _native.ptr(forces),
+                                              _native.stream_ptr(den.device)))
     del keep
     if ctx is not None:
         ctx.comm.all_reduce(forces.view(-1))
@@ -149,14 +148,14 @@ def ion_electron_forces(box_vecs, den, species, pme_order=None):
 def ion_electron_stress(box_vecs, den, species, pme_order=None):
     """IonElectron part of the stress, (3, 3) in Ha/bohr^3 (pad_ion_stress; system.py:927-935): ions at fixed
     fractional coordinates, electron number conserved.  ``pme_order``: with the particle-mesh structure factor
-    (pad_ion_stress_pme; single-GPU plans)."""
+    (pad_ion_stress_pme)."""
     from . import _native, parallel
     _native.require_cuda(den)
     den = den.detach().contiguous()
     plan = _native.get_plan(box_vecs, den)
     arr, keep = _pad_species_array(species, den.device)
     out = torch.empty(9, dtype=torch.double, device=den.device)
-    if pme_order is not None and parallel.current() is None:
+    if pme_order is not None:
         _native.check(plan.lib.pad_ion_stress_pme(plan.handle, arr, len(species), int(pme_order), _native.ptr(den), _native.ptr(out), 0,
                                                   _native.stream_ptr(den.device)))
     else:
