@@ -12,7 +12,7 @@ try:
     d = json.load(open(f'gpurun_out/bench_n{n}.json'))
     print('N', n, 'value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'])
     for s in d.get('slab', []):
-        print('  slab', {k: s.get(k) for k in ('workload', 'ms_per_eval', 'hbm_frac_per_gpu', 'nvlink_GBps_each_way', 'exchange', 'error', 'ms')})
+        print('  slab', {k: s.get(k) for k in ('workload', 'ms_per_eval', 'hbm_frac_per_gpu', 'nvlink_GBps_each_way', 'exchange', 'error', 'ms', 'ms_pme_order_8')})
 except Exception as e:
     print('FAILED', e)
 PY
