@@ -325,6 +325,7 @@ extern int g_pad_own_xy;
 extern int g_pad_pipe;             // 1: software-pipelined (z, y) kernels where the shape allows (default)
 extern int g_pad_zinv_stream;      // 1: streamed inverse z kernel (results folded as they arrive, 3 CTAs/SM), 0: batch form
 extern int g_pad_local_tail;       // 1: fused term list with the local terms in the one-field Hartree inverse pass (0: inside the mid pass)
+extern int g_pad_pbe_fast;         // 1: PerdewBurkeErnzerhof on the fused passes where they cover the grid
 extern int g_pad_xone;             // 1: one-field x passes (-k^2, 4 pi / k^2) as the two-transform plain pass
 extern int g_pad_ywide;            // 1: y pass at L = 256 with 32 threads per line (8 points each)
 extern int g_pad_graphs;           // 1: repeated evaluations with the same arguments replay a CUDA graph
@@ -339,6 +340,8 @@ void pad_stage_begin(cudaStream_t s);
 void pad_stage_mark(const char* name, cudaStream_t s);
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
+int pad_pbe_fast_supported(const pad_plan* p);
+int pad_pbe_fast(pad_plan* p, const double* den, int which, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_hartree_fast_supported(const pad_plan* p);
 int pad_hartree_fast(pad_plan* p, const double* den, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_wt_fast_supported(const pad_plan* p);

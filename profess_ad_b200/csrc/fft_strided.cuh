@@ -322,7 +322,9 @@ struct XmixPush {
     int y0;                    // first global row of this rank: rank * n1_loc
 };
 
-template <int L, int NF, class Mix, bool PUSH = false>
+// NIN / NOUT (gradient: one spectrum in, three out; divergence: three in, one out): fields f >= NIN are neither loaded nor
+// transformed forward, fields f >= NOUT are neither transformed back nor stored; all NF take part in the multiply.
+template <int L, int NF, class Mix, bool PUSH = false, int NIN = NF, int NOUT = NF>
 __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_per_sm<L, NF>()))
     xmix_kernel(SPassFields fields, SPassGeom geo, KGeom kg, Mix mix, const __grid_constant__ XmixPush push) {
     constexpr bool W = kXmixWide<L>;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
     const uint32_t xs = (uint32_t)geo.axis_stride;                      // < 2^32 elements for every supported shape
     auto locate = [&](long long w0) { return spass_locate(geo, w0 + tile_in_cta, total, c); };
     auto issue = [&](int f, const TileAt& a) {
-        if (a.live) {
+        if (a.live && f < NIN) {
             const cd* base = fields.f[f] + a.off + (size_t)t * xs;
 #pragma unroll
             for (int j = 0; j < P::EPT; ++j) cp_async16(own + f * P::TILE_CD + j * ROWSTEP, base + (size_t)(P::TPL * j) * xs);
@@ -358,9 +360,13 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
         const size_t prow = ((size_t)cur.o) * kg.nzp_pad + cur.z;         // + kx n1_loc nzp  (tables cover the plan's own rows)
         const size_t kxs = (size_t)kg.n1_loc * kg.nzp_pad;
         cd v[P::EPT];
+        if constexpr (NIN < NF) {
+#pragma unroll
+            for (int j = 0; j < P::EPT; ++j) v[j] = cd{0.0, 0.0};
+        }
         // forward transforms; every spectrum but the last is parked in its thread-owned rows
 #pragma unroll
-        for (int f = 0; f < NF; ++f) {
+        for (int f = 0; f < NIN; ++f) {
             if (f == 0) cp_async_wait<NF - 1>();
             else if (f == 1) cp_async_wait<(NF > 2 ? NF - 2 : 0)>();
             else if (f == 2) cp_async_wait<(NF > 3 ? NF - 3 : 0)>();
@@ -394,16 +400,20 @@ __global__ void __launch_bounds__((SPass<L, kXmixWide<L>>::THREADS), (xmix_ctas_
                 }
                 cd q[NF];
 #pragma unroll
-                for (int f = 0; f < NF - 1; ++f) q[f] = own[f * P::TILE_CD + s * ROWSTEP];
+                for (int f = 0; f < NF - 1; ++f) q[f] = f < NIN ? own[f * P::TILE_CD + s * ROWSTEP] : cd{0.0, 0.0};
                 q[NF - 1] = v[s];
                 if (cur.live) mix.apply(coef, q);
 #pragma unroll
-                for (int f = 0; f < NF; ++f) own[f * P::TILE_CD + s * ROWSTEP] = q[f];
+                for (int f = 0; f < NOUT; ++f) own[f * P::TILE_CD + s * ROWSTEP] = q[f];
             }
         }
         // inverse transforms; the buffer of field f is refilled with the next tile as soon as it is free
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
+            if (f >= NOUT) {          // not an output: its buffer only has to take the next tile
+                issue(f, nxt);
+                continue;
+            }
             cd* Bf = own + f * P::TILE_CD;
             cd u[P::EPT];
 #pragma unroll

@@ -139,7 +139,7 @@ __device__ __forceinline__ void zfwd_field(const Gen& gen, const double (&sa)[Ge
 //   gen.stage(in[NIN] (double2 each: the points g, g + 1), a[NST], b[NST])
 //   gen.field<F>(st[NST])           value of field F at a point
 struct ZIn {
-    const double* f[2];
+    const double* f[3];
 };
 
 template <int M, int TPL, int NF, class Gen>
@@ -556,7 +556,8 @@ inline int zgrid(int nlines, int lines_per_block, int blocks_per_sm) {
 inline int z_lines(const pad_plan* p) { return (p->dist ? p->n0_loc : p->n0) * p->n1; }
 
 template <int M, int TPL, int NF, class Gen>
-int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3) {
+int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const double* in1, cd* o0, cd* o1, cd* o2, cd* o3,
+                const double* in2 = nullptr) {
     constexpr int warps = 4;
     using L = ZLayout<M, TPL>;
     constexpr int smem = L::kTwBytes + warps * L::kLinesPerWarp * L::fwd_line_bytes(Gen::NIN);
@@ -567,7 +568,7 @@ int launch_zfwd(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, const d
         attr_done[p->device & 63] = true;
     }
     const int nlines = z_lines(p);
-    ZIn in{{in0, in1}};
+    ZIn in{{in0, in1, in2}};
     kern<<<zgrid(nlines, warps * (32 / TPL), 4), warps * 32, smem, s>>>(gen, in, o0, o1, o2, o3, nlines, p->nzp);
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
@@ -778,7 +779,7 @@ int launch_zy_fwd_L(pad_plan* p, cudaStream_t s, Gen gen, const double* in0, con
     sh.items[2] = 0;
     constexpr int by_smem = (227 * 1024) / (smem + 1024);
     const int grid = 148 * (by_smem < 4 ? by_smem : 4);
-    ZIn in{{in0, in1}};
+    ZIn in{{in0, in1, nullptr}};
     SPassFields o;
     for (int i = 0; i < 4; ++i) o.f[i] = i < NF ? out[i] : nullptr;
     kern<<<grid, warps * 32, smem, s>>>(gen, in, o, reinterpret_cast<PipeCtl*>(p->pipe_ctl), sh, g);
@@ -1093,9 +1094,9 @@ int launch_spass_local(pad_plan* p, cudaStream_t s, int axis, int dir, cd* const
     return PAD_ERR_ARG;
 }
 
-template <int L, int NF, class Mix, bool PUSH = false>
+template <int L, int NF, class Mix, bool PUSH = false, int NIN = NF, int NOUT = NF>
 int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPassGeom& g, Mix mix, const XmixPush& push = XmixPush{}) {
-    auto kern = xmix_kernel<L, NF, Mix, PUSH>;
+    auto kern = xmix_kernel<L, NF, Mix, PUSH, NIN, NOUT>;
     using P = SPass<L, kXmixWide<L>>;
     constexpr int smem = spass_smem_bytes<L, kXmixWide<L>>(NF);
     static bool attr_done[64] = {false};
@@ -1115,6 +1116,23 @@ int launch_xmix_L(pad_plan* p, cudaStream_t s, const SPassFields& f, const SPass
     ++g_pad_launches;
     PAD_CUDA(cudaGetLastError());
     return PAD_OK;
+}
+
+// gradient (NIN = 1: one spectrum in, three out) and divergence (NOUT = 1: three in, one out) forms of the fused x pass
+template <int NIN, int NOUT, class Mix>
+int launch_xmix3_io(pad_plan* p, cudaStream_t s, cd* const* fields, Mix mix) {
+    if (p->dist) { pad_set_error("fused x pass (gradient / divergence form): single-GPU plans only"); return PAD_ERR_ARG; }
+    SPassFields f;
+    for (int i = 0; i < 4; ++i) f.f[i] = i < 3 ? fields[i] : nullptr;
+    const SPassGeom g = spass_geom(p, 0);
+    switch (p->n0) {
+        case 64: return launch_xmix_L<64, 3, Mix, false, NIN, NOUT>(p, s, f, g, mix);
+        case 128: return launch_xmix_L<128, 3, Mix, false, NIN, NOUT>(p, s, f, g, mix);
+        case 256: return launch_xmix_L<256, 3, Mix, false, NIN, NOUT>(p, s, f, g, mix);
+        case 512: return launch_xmix_L<512, 3, Mix, false, NIN, NOUT>(p, s, f, g, mix);
+    }
+    pad_set_error("fused x pass: length %d not supported", p->n0);
+    return PAD_ERR_ARG;
 }
 
 template <int L, class Mix>
@@ -2492,6 +2510,308 @@ static int wt_fast_impl(pad_plan* p, const double* den, double alpha, double bet
         a.E_out = E_out;
         pad_launch_finalize(p, a, s);
     }
+    return PAD_OK;
+}
+
+// =================================================================================================
+//  PerdewBurkeErnzerhof (functionals.py:1597-1635) on the fused passes: 8 transforms in 9 launches
+//     [z r2c of n] -> y -> [x . (i k_c / N, c = x, y, z) . x^-1: one spectrum in, three out] -> y^-1 (3)
+//       -> [z c2r (3) + PBE energy density, f_n -> v, w_c = 2 f_sigma d_c n + z r2c (3)] -> y (3)
+//       -> [x . (i k . w / N) . x^-1: three in, one out] -> y^-1 -> [z c2r: v -= div w]
+//  The multipliers i k_c use the effective wave vector of the special points (sym_kvec), as the cuFFT route does.
+// =================================================================================================
+struct MixGradCoef {
+    double kx, ky, kz;
+};
+struct MixGrad {                       // q[0] = F  ->  q[c] = i k_c F / N
+    static constexpr int kRing = 1;
+    double inv_n;
+    typedef MixGradCoef Coef;
+    struct Line { const KGeom* g; int ky, z; };
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return Line{&g, ky, z}; }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t, bool live) const {
+        Coef c{0.0, 0.0, 0.0};
+        if (live) {
+            const KPoint p = make_kpoint_at(*l.g, kx, l.ky, l.z);
+            sym_kvec(p, c.kx, c.ky, c.kz);
+            c.kx *= inv_n; c.ky *= inv_n; c.kz *= inv_n;
+        }
+        return c;
+    }
+    __device__ __forceinline__ void apply(const Coef& k, cd* q) const {
+        const cd a = q[0];
+        q[0] = cd{-a.y * k.kx, a.x * k.kx};
+        q[1] = cd{-a.y * k.ky, a.x * k.ky};
+        q[2] = cd{-a.y * k.kz, a.x * k.kz};
+    }
+};
+struct MixDiv {                        // q[0] = i (k . (q0, q1, q2)) / N
+    static constexpr int kRing = 1;
+    double inv_n;
+    typedef MixGradCoef Coef;
+    typedef MixGrad::Line Line;
+    __device__ __forceinline__ Line line(const KGeom& g, int ky, int z) const { return Line{&g, ky, z}; }
+    __device__ __forceinline__ Coef fetch(const Line& l, int kx, size_t pidx, bool live) const { return MixGrad{inv_n}.fetch(l, kx, pidx, live); }
+    __device__ __forceinline__ void apply(const Coef& k, cd* q) const {
+        const double re = k.kx * q[0].x + k.ky * q[1].x + k.kz * q[2].x, im = k.kx * q[0].y + k.ky * q[1].y + k.kz * q[2].y;
+        q[0] = cd{-im, re};
+    }
+};
+
+struct PbeOut {
+    double f, f_rho, wx, wy, wz;
+};
+__device__ __noinline__ PbeOut pbe_point_w(double n, double gx, double gy, double gz, int which) {
+    PbeOut o;
+    double f_sig;
+    pbe_point(n, gx * gx + gy * gy + gz * gz, cbrt(n), (which & 1) != 0, (which & 2) != 0, o.f, o.f_rho, f_sig);
+    const double w = 2.0 * f_sig;
+    o.wx = w * gx; o.wy = w * gy; o.wz = w * gz;
+    return o;
+}
+// The PBE point math does NOT ride on the inverse z pass: with it inside (and the forward z transform of w behind it, one
+// kernel, 255 registers, 8 warps per SM) that kernel took 1140 us at 256^3 -- the transcendental chains have nothing to hide
+// behind at that occupancy (the same finding as for the local terms of the WGC99 list).  So: a plain three-field inverse z pass
+// stores the gradient, a full-occupancy elementwise kernel does the point math in place (grad n -> w), a three-input forward z
+// pass transforms w.
+struct PostStore3 {                    // plain c2r of three real fields
+    static constexpr bool kDen = false, kVin = false;
+    static constexpr int NST = 0;
+    double *o0, *o1, *o2;
+    __device__ void apply(size_t g, double2, double2, const double* u0, const double* u1, double*, double*, double*) const {
+        *reinterpret_cast<double2*>(o0 + g) = make_double2(u0[0], u1[0]);
+        *reinterpret_cast<double2*>(o1 + g) = make_double2(u0[1], u1[1]);
+        *reinterpret_cast<double2*>(o2 + g) = make_double2(u0[2], u1[2]);
+    }
+    static constexpr int NACC = 0;
+    typedef int Ctx;
+    __device__ Ctx begin() const { return 0; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double, double*) const {}
+    __device__ void finish(const Ctx&, size_t, double2, const double*, const double*, double, double, double*, double*, double*) const {}
+};
+struct GenCopy3 {                      // plain r2c of three real fields
+    static constexpr int NST = 3, NIN = 3;
+    __device__ void stage(const double2* in, double* a, double* b) const {
+        a[0] = in[0].x; a[1] = in[1].x; a[2] = in[2].x;
+        b[0] = in[0].y; b[1] = in[1].y; b[2] = in[2].y;
+    }
+    template <int F>
+    __device__ double field(const double* s) const { return s[F]; }
+};
+// pbe_point (xc.cuh) with the table log / exp and rsqrt-based reciprocals of fastmath.cuh: one log of n gives n^(1/3), r_s and
+// sqrt(r_s); the library version (cbrt, sqrt, two logs, an exp and a dozen divisions) was 621 us of the 1.81 ms of a 256^3
+// evaluation at full occupancy.  Same formulas, same +1e-30 guards; arguments outside the fast range take pbe_point.
+__device__ __forceinline__ double fm_recip(double x) {
+    const double y = fm_rsqrt(x);
+    return y * y;
+}
+__device__ __forceinline__ void pbe_point_fast(double n, double sig, bool do_x, bool do_c, double& f, double& f_rho, double& f_sig) {
+    if (!(n > 1e-20 && n < 1e20 && sig < 1e40)) {          // (keeps every intermediate of the fast path far from the exponent limits)
+        pbe_point(n, sig, cbrt(n), do_x, do_c, f, f_rho, f_sig);
+        return;
+    }
+    f = 0.0; f_rho = 0.0; f_sig = 0.0;
+    const double l = fm_log(n);
+    const double c13 = fm_exp((1.0 / 3.0) * l);
+    const double inv_n = fm_recip(n);
+    if (do_x) {
+        const double cs = 0.026121172985233605;       // (1/4)(3 pi^2)^(-2/3)
+        const double kap = 0.804, mu = 0.2195164512208958;
+        const double ex = kCX * n * c13;
+        const double r83 = n * n * c13 * c13;
+        const double ir83 = fm_recip(r83);
+        const double s2 = cs * sig * ir83;
+        const double q = 1.0 + mu / kap * s2;
+        const double iq = fm_recip(q);
+        const double Fx = 1.0 + kap - kap * iq, dF = mu * (iq * iq);
+        f += Fx * ex;
+        f_rho += Fx * (4.0 / 3.0) * kCX * c13 + ex * dF * (-8.0 / 3.0) * s2 * inv_n;
+        f_sig += ex * dF * cs * ir83;
+    }
+    if (do_c) {
+        const double A1 = 0.0310907, a1 = 0.2137, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+        const double be = 0.066725, ga = 0.0310906908696549;   // (1 - ln 2) / pi^2
+        const double ct = 0.0634682060977037;                  // (1/16)(pi/3)^(1/3)
+        const double s6 = fm_exp((-1.0 / 6.0) * l);            // n^(-1/6)
+        const double sr = 0.78762331789974325 * s6;           // sqrt(r_s) = sqrt(kRS13) n^(-1/6)
+        const double rs = sr * sr;
+        const double isr = fm_recip(sr);
+        const double Q = 2.0 * A1 * (b1 * sr + b2 * rs + b3 * rs * sr + b4 * rs * rs);
+        const double iQ = fm_recip(Q);
+        const double lg = fm_log(1.0 + iQ);
+        const double eps = -2.0 * A1 * (1.0 + a1 * rs) * lg;
+        const double dQ = A1 * (b1 * isr + 2.0 * b2 + 3.0 * b3 * sr + 4.0 * b4 * rs);
+        const double deps = (-2.0 * A1 * a1 * lg + 2.0 * A1 * (1.0 + a1 * rs) * dQ * fm_recip(Q * (Q + 1.0))) * (-rs * inv_n * (1.0 / 3.0));
+        const double ee = fm_exp(-eps * (1.0 / ga));
+        const double em1 = ee - 1.0 + 1e-30;
+        if (!(em1 > 1e-20)) {           // r_s -> infinity: leave the cancellation to the library path
+            double f2, r2, s2_;
+            pbe_point(n, sig, c13, false, true, f2, r2, s2_);
+            f += f2; f_rho += r2; f_sig += s2_;
+            return;
+        }
+        const double Aa = be / ga * fm_recip(em1);
+        const double dAa = Aa * Aa / be * ee * deps;
+        const double r73 = n * n * c13 + 1e-30;
+        const double ir73 = fm_recip(r73);
+        const double t2 = ct * sig * ir73;
+        const double dt2_rho = -ct * sig * (7.0 / 3.0) * n * c13 * (ir73 * ir73);
+        const double dt2_sig = ct * ir73;
+        const double X = Aa * t2;
+        const double num = 1.0 + X, dnm = 1.0 + X + X * X;
+        const double idnm = fm_recip(dnm);
+        const double Rr = num * idnm;
+        const double dR = -X * (2.0 + X) * (idnm * idnm);
+        const double inner = 1.0 + be / ga * t2 * Rr;
+        const double H = ga * fm_log(inner);
+        const double iinner = fm_recip(inner);
+        const double dH_rho = be * iinner * (Rr * dt2_rho + t2 * dR * (Aa * dt2_rho + t2 * dAa));
+        const double dH_sig = be * iinner * (Rr + t2 * dR * Aa) * dt2_sig;
+        f += n * (eps + H);
+        f_rho += eps + H + n * (deps + dH_rho);
+        f_sig += n * dH_sig;
+    }
+}
+
+// n, grad n -> energy density (one block-reduced sum), v (+)= f_n, grad n <- w = 2 f_sigma grad n; two points per thread
+__global__ void __launch_bounds__(PAD_THREADS) pbe_point_kernel(const double* __restrict__ den, double* __restrict__ gx, double* __restrict__ gy,
+                                                               double* __restrict__ gz, double* __restrict__ v, size_t n, int which,
+                                                               int accumulate, double* __restrict__ partials) {
+    fm_load_tables();
+    double acc[1] = {0.0};
+    const size_t n2 = n / 2, stride = (size_t)gridDim.x * PAD_THREADS;
+    for (size_t i = (size_t)blockIdx.x * PAD_THREADS + threadIdx.x; i < n2; i += stride) {
+        const double2 d = reinterpret_cast<const double2*>(den)[i];
+        double2 x = reinterpret_cast<double2*>(gx)[i], y = reinterpret_cast<double2*>(gy)[i], z = reinterpret_cast<double2*>(gz)[i];
+        double fa, ra, sa, fb, rb, sb;
+        pbe_point_fast(d.x, x.x * x.x + y.x * y.x + z.x * z.x, (which & 1) != 0, (which & 2) != 0, fa, ra, sa);
+        pbe_point_fast(d.y, x.y * x.y + y.y * y.y + z.y * z.y, (which & 1) != 0, (which & 2) != 0, fb, rb, sb);
+        acc[0] += fa + fb;
+        if (v) {
+            double2 vv = accumulate ? reinterpret_cast<double2*>(v)[i] : make_double2(0.0, 0.0);
+            vv.x += ra; vv.y += rb;
+            reinterpret_cast<double2*>(v)[i] = vv;
+            sa *= 2.0; sb *= 2.0;
+            reinterpret_cast<double2*>(gx)[i] = make_double2(sa * x.x, sb * x.y);
+            reinterpret_cast<double2*>(gy)[i] = make_double2(sa * y.x, sb * y.y);
+            reinterpret_cast<double2*>(gz)[i] = make_double2(sa * z.x, sb * z.y);
+        }
+    }
+    block_reduce_store<1>(acc, partials);
+}
+
+template <bool ACC>
+struct PostPbeA {                      // (kept for comparison, option pbe_fast = 2) gradient -> energy density, f_n -> v, staged w for the forward part
+    static constexpr bool kDen = true, kVin = ACC;
+    static constexpr int NST = 3;
+    double* v_out;                     // null: energy only
+    int which;
+    __device__ void apply(size_t g, double2 n, double2 v, const double* u0, const double* u1, double* acc, double* sta, double* stb) const {
+        const PbeOut a = pbe_point_w(n.x, u0[0], u0[1], u0[2], which), b = pbe_point_w(n.y, u1[0], u1[1], u1[2], which);
+        acc[0] += a.f + b.f;
+        sta[0] = a.wx; sta[1] = a.wy; sta[2] = a.wz;
+        stb[0] = b.wx; stb[1] = b.wy; stb[2] = b.wz;
+        if (v_out) *reinterpret_cast<double2*>(v_out + g) = make_double2((ACC ? v.x : 0.0) + a.f_rho, (ACC ? v.y : 0.0) + b.f_rho);
+    }
+    static constexpr int NACC = 0;
+    typedef int Ctx;
+    __device__ Ctx begin() const { return 0; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double, double*) const {}
+    __device__ void finish(const Ctx&, size_t, double2, const double*, const double*, double, double, double*, double*, double*) const {}
+};
+struct GenPbeW {                       // forward part: the staged w_x, w_y, w_z
+    static constexpr int NST = 3, NIN = 0;
+    __device__ void stage(const double2*, double*, double*) const {}
+    template <int F>
+    __device__ double field(const double* s) const { return s[F]; }
+};
+struct PostPbeDiv {                    // v -= div w
+    static constexpr bool kDen = false, kVin = true;
+    static constexpr int NST = 0;
+    double* v_out;
+    __device__ void apply(size_t g, double2, double2 v, const double* u0, const double* u1, double*, double*, double*) const {
+        *reinterpret_cast<double2*>(v_out + g) = make_double2(v.x - u0[0], v.y - u1[0]);
+    }
+    static constexpr int NACC = 0;
+    typedef int Ctx;
+    __device__ Ctx begin() const { return 0; }
+    template <int F>
+    __device__ void fold(const Ctx&, double, double, double*) const {}
+    __device__ void finish(const Ctx&, size_t, double2, const double*, const double*, double, double, double*, double*, double*) const {}
+};
+
+int pad_pbe_fast_supported(const pad_plan* p) { return !p->dist && fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
+
+int pad_pbe_fast(pad_plan* p, const double* den, int which, double* E_out, double* v_out, int accumulate, cudaStream_t s) {
+    PAD_TRY(ensure_twiddles(p->device));
+    cd* B[3];
+    for (int i = 0; i < 3; ++i) PAD_TRY(get_zbuf(p, i, &B[i]));
+    const double inv_n = p->geom.inv_n;
+    pad_stage_begin(s);
+    ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 1>(p, s, GenCopy{}, den, nullptr, B[0], nullptr, nullptr, nullptr))));
+    pad_stage_mark("PBE: z-r2c", s);
+    PAD_TRY(launch_spass(p, s, 1, -1, B, 1));
+    pad_stage_mark("PBE: y-fwd", s);
+    PAD_TRY((launch_xmix3_io<1, 3>(p, s, B, MixGrad{inv_n})));
+    pad_stage_mark("PBE: x-fwd * (i k) * x-inv (1 -> 3)", s);
+    PAD_TRY(launch_spass(p, s, 1, +1, B, 3));
+    pad_stage_mark("PBE: y-inv (3)", s);
+    int grid = 1;
+    if (g_pad_pbe_fast != 2) {
+        double* G[3];
+        for (int i = 0; i < 3; ++i) PAD_TRY(pad_get_rbuf(p, i, &G[i]));
+        ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 0>(p, s, PostStore3{G[0], G[1], G[2]}, B[0], B[1], B[2], nullptr, nullptr, nullptr, nullptr))));
+        pad_stage_mark("PBE: z-c2r (3)", s);
+        grid = pad_grid_for(p->N / 2);
+        pbe_point_kernel<<<grid, PAD_THREADS, 0, s>>>(den, G[0], G[1], G[2], v_out, p->N, which, accumulate, p->partials);
+        ++g_pad_launches;
+        PAD_CUDA(cudaGetLastError());
+        pad_stage_mark("PBE: energy density, f_n, w (pointwise)", s);
+        if (E_out) {
+            FinalizeArgs a = wgc_energy_args(p, grid, 1, accumulate, E_out);
+            a.coef[0] = p->dV;
+            pad_launch_finalize(p, a, s);
+        }
+        if (!v_out) return PAD_OK;
+        ZDISPATCH(p, PAD_TRY((launch_zfwd<M, TPL, 3>(p, s, GenCopy3{}, G[0], G[1], B[0], B[1], B[2], nullptr, G[2]))));
+        pad_stage_mark("PBE: z-r2c (3)", s);
+        PAD_TRY(launch_spass(p, s, 1, -1, B, 3));
+        pad_stage_mark("PBE: y-fwd (3)", s);
+        PAD_TRY((launch_xmix3_io<3, 1>(p, s, B, MixDiv{inv_n})));
+        pad_stage_mark("PBE: x-fwd * (i k .) * x-inv (3 -> 1)", s);
+        PAD_TRY(launch_spass(p, s, 1, +1, B, 1));
+        pad_stage_mark("PBE: y-inv", s);
+        ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, PostPbeDiv{v_out}, B[0], nullptr, nullptr, nullptr, nullptr, v_out, nullptr))));
+        pad_stage_mark("PBE: z-c2r + v -= div w", s);
+        return PAD_OK;
+    }
+    if (!v_out) {
+        PostPbeA<false> post{nullptr, which};
+        ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 1>(p, s, post, B[0], B[1], B[2], nullptr, den, nullptr, &grid))));
+    } else if (accumulate) {
+        PostPbeA<true> post{v_out, which};
+        ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 1, PostPbeA<true>, 3, GenPbeW>(p, s, post, B[0], B[1], B[2], nullptr, den, v_out, &grid, GenPbeW{}))));
+    } else {
+        PostPbeA<false> post{v_out, which};
+        ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 3, 1, PostPbeA<false>, 3, GenPbeW>(p, s, post, B[0], B[1], B[2], nullptr, den, nullptr, &grid, GenPbeW{}))));
+    }
+    pad_stage_mark("PBE: z-c2r (3) + energy density, f_n, w + z-r2c (3)", s);
+    if (E_out) {
+        FinalizeArgs a = wgc_energy_args(p, grid, 1, accumulate, E_out);
+        a.coef[0] = p->dV;
+        pad_launch_finalize(p, a, s);
+    }
+    if (!v_out) return PAD_OK;
+    PAD_TRY(launch_spass(p, s, 1, -1, B, 3));
+    pad_stage_mark("PBE: y-fwd (3)", s);
+    PAD_TRY((launch_xmix3_io<3, 1>(p, s, B, MixDiv{inv_n})));
+    pad_stage_mark("PBE: x-fwd * (i k .) * x-inv (3 -> 1)", s);
+    PAD_TRY(launch_spass(p, s, 1, +1, B, 1));
+    pad_stage_mark("PBE: y-inv", s);
+    ZDISPATCH(p, PAD_TRY((launch_zinv<M, TPL, 1, 0>(p, s, PostPbeDiv{v_out}, B[0], nullptr, nullptr, nullptr, nullptr, v_out, nullptr))));
+    pad_stage_mark("PBE: z-c2r + v -= div w", s);
     return PAD_OK;
 }
 

@@ -902,6 +902,9 @@ extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E
     PAD_TRY(check_common(p, den, "pad_eval_pbe"));
     if (!(which & 3)) { pad_set_error("pad_eval_pbe: which must be 1, 2 or 3"); return PAD_ERR_ARG; }
     cudaStream_t s = as_stream(stream);
+    if (g_pad_fast_fft && g_pad_pbe_fast && pad_pbe_fast_supported(p) &&
+        ((reinterpret_cast<uintptr_t>(den) | reinterpret_cast<uintptr_t>(v_out)) & 15) == 0)
+        return pad_pbe_fast(p, den, which, E_out, v_out, accumulate, s);
     double* R[4];
     cufftDoubleComplex* C[4];
     for (int i = 0; i < 4; ++i) { PAD_TRY(pad_get_rbuf(p, i, &R[i])); PAD_TRY(pad_get_cbuf(p, i, &C[i])); }

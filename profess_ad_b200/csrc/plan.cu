@@ -21,6 +21,7 @@ int g_pad_fold_table = 1;
 int g_pad_zinv_stream = 0;     // measured at 256^3: the streamed form (12 warps/SM, 168 registers) is 7-13 % slower than the batch form
 int g_pad_local_tail = 1;      // measured at 256^3: locals in the mid pass 534 us + 4-field final pass 437 us; plain mid 264 + final 199 + tail
 int g_pad_ywide = 0;
+int g_pad_pbe_fast = 1;
 int g_pad_xone = 0;       // measured at 256^3: 107 us against 77 us for the persistent prefetching kernel
 int g_pad_graphs = 1;          // whole evaluations with unchanged arguments are captured once and replayed as ONE graph launch
 unsigned long long g_pad_option_epoch = 0;
@@ -40,6 +41,7 @@ extern "C" int pad_set_option(const char* name, int value) {
     else if (!strcmp(name, "graphs")) slot = &g_pad_graphs;
     else if (!strcmp(name, "ywide")) slot = &g_pad_ywide;
     else if (!strcmp(name, "xone")) slot = &g_pad_xone;
+    else if (!strcmp(name, "pbe_fast")) slot = &g_pad_pbe_fast;
     else if (!strcmp(name, "local_tail")) slot = &g_pad_local_tail;
     if (!slot) { pad_set_error("pad_set_option: unknown option %s", name); return -1; }
     const int old = *slot;

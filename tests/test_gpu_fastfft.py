@@ -108,6 +108,46 @@ def test_wgc99_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
 
 
+@pytest.mark.parametrize('shape,seed', [((64, 64, 128), 61), ((64, 128, 256), 62), ((128, 64, 128), 63)])
+def test_pbe_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
+    """PerdewBurkeErnzerhof, pbe_exchange, pbe_correlation on the fused passes (gradient and divergence as one-in / three-out
+    and three-in / one-out forms of the fused x pass, PBE point math + forward z transform of w inside the inverse z pass)
+    against the cuFFT route and the oracle; energy-only and accumulating calls."""
+    from oracle import ofdft_oracle as orc
+    import profess_ad_b200.functionals as F
+    from profess_ad_b200 import _native as nat
+    lib = nat.load_library()
+    dev = torch.device('cuda:0')
+    box, den = orc.synth_rough(shape, seed=seed, L=9.0)
+    b, d = box.to(dev), den.to(dev)
+    plan = nat.get_plan(b, d)
+    for which, f, fo in ((3, F.PerdewBurkeErnzerhof, orc.PerdewBurkeErnzerhof), (1, F.pbe_exchange, orc.pbe_exchange),
+                         (2, F.pbe_correlation, orc.pbe_correlation)):
+        E_ref, V_ref = orc.energy_and_potential(box, den, fo)
+        res = {}
+        for fast in (1, 0):
+            old = lib.pad_set_option(b'pbe_fast', fast)
+            try:
+                f0 = lib.pad_fft_exec_count()
+                E, V = F.energy_and_potential(b, d, f)
+                used_cufft = lib.pad_fft_exec_count() - f0
+                e_only = f(b, d).item()
+                Eacc = torch.full((), -0.5, dtype=torch.double, device=dev)
+                vacc = torch.full_like(d, 0.125)
+                nat.check(lib.pad_eval_pbe(plan.handle, nat.ptr(d), which, nat.ptr(Eacc), nat.ptr(vacc), 1, nat.stream_ptr(dev)))
+            finally:
+                lib.pad_set_option(b'pbe_fast', old)
+            assert (used_cufft == 0) == bool(fast), (which, fast, used_cufft)
+            assert abs(E.item() - E_ref.item()) <= 1e-10 * abs(E_ref.item()), (which, fast)
+            assert ((V.cpu() - V_ref).abs().max() / V_ref.abs().max()).item() < 1e-9, (which, fast)
+            assert abs(e_only - E.item()) <= 1e-13 * abs(E.item())
+            assert abs(Eacc.item() + 0.5 - E.item()) <= 1e-12 * abs(E.item()) + 1e-15
+            assert ((vacc - 0.125 - V).abs().max() / V.abs().max()).item() < 1e-12
+            res[fast] = (E.item(), V)
+        assert abs(res[1][0] - res[0][0]) <= 1e-12 * abs(res[0][0])
+        assert ((res[1][1] - res[0][1]).abs().max() / res[0][1].abs().max()).item() < 1e-11
+
+
 @pytest.mark.parametrize('shape,seed', [((64, 64, 128), 51), ((128, 64, 256), 52), ((64, 64, 512), 53)])
 def test_hartree_fused_pipeline_matches_oracle_and_plain_path(shape, seed):
     """Hartree alone on the fused passes (z r2c -> y -> x . 4 pi / k^2 . x^-1 -> y^-1 -> z c2r + energy + potential), also
