@@ -132,6 +132,9 @@ int pad_plan_set_slab_peer_buffers(pad_plan* plan, void* const* base_ptrs, int w
 int pad_plan_set_slab_peer_recv(pad_plan* plan, void* const* recv_ptrs, void* const* recv2_ptrs, int world);
 int pad_plan_set_slab_fast_buffers(pad_plan* plan, void* const* six_buffers);
 int pad_plan_set_box(pad_plan* plan, const double* box_host);      /* same grid, new lattice (strain scans) */
+/* Repeated pad_eval_wgc99 / pad_eval_total calls with unchanged arguments are captured once and replayed as one CUDA graph (option
+ * "graphs"); counters of captures and replays since the library was loaded. */
+int pad_graph_stats(unsigned long long* captures, unsigned long long* replays);
 size_t pad_plan_workspace_bytes(const pad_plan* plan);
 
 /* ---- single functionals: E (+)= F[n],  v (+)= dF/dn --------------------------------------- */

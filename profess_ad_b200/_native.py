@@ -35,6 +35,7 @@ SIGNATURES = {
     'pad_plan_set_slab_peer_recv': (_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int]),
     'pad_plan_destroy': (_int, [_vp]),
     'pad_plan_set_box': (_int, [_vp, _c_double_p]),
+    'pad_graph_stats': (_int, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     'pad_plan_workspace_bytes': (ctypes.c_size_t, [_vp]),
     'pad_eval_local': (_int, [_vp, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     'pad_eval_hartree': (_int, [_vp, _vp, _vp, _vp, _int, _vp]),

@@ -671,6 +671,14 @@ extern "C" int pad_eval_wgc99(pad_plan* p, const double* den, double alpha, doub
 static int wgc99_ex_direct(pad_plan* p, const double* den, double alpha, double beta, double gamma, double kappa, double* E_out,
                            double* v_out, int accumulate, void* stream, const pad_wgc_extras* ex);
 
+static unsigned long long g_graph_captures = 0, g_graph_replays = 0;
+// how many evaluation graphs have been captured / replayed so far (a benchmark warms up until its loop only replays)
+extern "C" int pad_graph_stats(unsigned long long* captures, unsigned long long* replays) {
+    if (captures) *captures = g_graph_captures;
+    if (replays) *replays = g_graph_replays;
+    return PAD_OK;
+}
+
 // An evaluation is 14-16 dependent launches with no host decision that depends on device data, so a repeated call with the
 // same arguments (the optimiser's closure, a benchmark loop, a scan at fixed buffers) is replayed as ONE cudaGraphLaunch: the
 // host cost per evaluation drops from ~0.3 ms of launch calls to ~10 us and launch jitter of a busy host (8 ranks per node)
@@ -705,6 +713,7 @@ int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta,
         PAD_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(slot->exec), s));
         if (E_in_graph != E_out) PAD_CUDA(cudaMemcpyAsync(E_out, E_in_graph, sizeof(double), cudaMemcpyDeviceToDevice, s));
         g_pad_launches += slot->launches;
+        ++g_graph_replays;
         return PAD_OK;
     }
     if (!slot) {                      // new argument set: remember it, run directly
@@ -739,6 +748,7 @@ int pad_eval_wgc99_ex(pad_plan* p, const double* den, double alpha, double beta,
     slot->exec = exec;
     slot->launches = g_pad_launches - l0;
     slot->state = 2;
+    ++g_graph_captures;
     PAD_CUDA(cudaGraphLaunch(exec, s));
     if (E_in_graph != E_out) PAD_CUDA(cudaMemcpyAsync(E_out, E_in_graph, sizeof(double), cudaMemcpyDeviceToDevice, s));
     return PAD_OK;
