@@ -340,6 +340,7 @@ void pad_stage_begin(cudaStream_t s);
 void pad_stage_mark(const char* name, cudaStream_t s);
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
+int pad_local_fast(pad_plan* p, const double* den, const double* v_ext, int mask, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_pbe_fast_supported(const pad_plan* p);
 int pad_pbe_fast(pad_plan* p, const double* den, int which, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_hartree_fast_supported(const pad_plan* p);

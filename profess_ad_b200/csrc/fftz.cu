@@ -1748,8 +1748,9 @@ struct LocalOut {
 };
 __device__ __noinline__ LocalOut local_terms_point(double n, int mask, double vext) {
     LocalOut o{0.0, 0.0};
-    if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
+    if (mask & (PAD_LOCAL_TF | PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
         const double c = cbrt(n);
+        if (mask & PAD_LOCAL_TF) { o.e += kCTF * n * c * c; o.v += (5.0 / 3.0) * kCTF * c * c; }
         if (mask & PAD_LOCAL_LDAX) { o.e += kCX * n * c; o.v += (4.0 / 3.0) * kCX * c; }
         if (mask & PAD_LOCAL_PZC) { const PZ r = pz_correlation(n, c); o.e += r.e; o.v += r.v; }
     }
@@ -1760,9 +1761,10 @@ __device__ __noinline__ LocalOut local_terms_point(double n, int mask, double ve
 __device__ __forceinline__ LocalOut local_terms_fast(double n, int mask, double vext) {
     if (!fm_ok(n)) return local_terms_point(n, mask, vext);
     LocalOut o{0.0, 0.0};
-    if (mask & (PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
+    if (mask & (PAD_LOCAL_TF | PAD_LOCAL_LDAX | PAD_LOCAL_PZC)) {
         const double l = fm_log(n);
         const double c13 = fm_exp((1.0 / 3.0) * l);                    // n^(1/3)
+        if (mask & PAD_LOCAL_TF) { o.e += kCTF * n * c13 * c13; o.v += (5.0 / 3.0) * kCTF * c13 * c13; }
         if (mask & PAD_LOCAL_LDAX) { o.e += kCX * n * c13; o.v += (4.0 / 3.0) * kCX * c13; }
         if (mask & PAD_LOCAL_PZC) {
             // pz_correlation (xc.cuh, functionals.py:1515-1521) with rs = kRS13 n^(-1/3)
@@ -1790,7 +1792,8 @@ __device__ __forceinline__ LocalOut local_terms_fast(double n, int mask, double 
 
 // v += local terms, one block-reduced energy sum; two points per thread and iteration (16-byte accesses)
 __global__ void __launch_bounds__(PAD_THREADS) local_fast_kernel(const double* __restrict__ den, const double* __restrict__ v_ext,
-                                                                double* __restrict__ v, size_t n, int mask, double* __restrict__ partials) {
+                                                                double* __restrict__ v /* may be null */, size_t n, int mask, int accumulate,
+                                                                double* __restrict__ partials) {
     fm_load_tables();
     double acc[1] = {0.0};
     const size_t n2 = n / 2, stride = (size_t)gridDim.x * PAD_THREADS;
@@ -1798,19 +1801,43 @@ __global__ void __launch_bounds__(PAD_THREADS) local_fast_kernel(const double* _
         const double2 d = reinterpret_cast<const double2*>(den)[i];
         double2 ve = make_double2(0.0, 0.0);
         if (mask & PAD_LOCAL_IONEL) ve = reinterpret_cast<const double2*>(v_ext)[i];
-        double2 vv = reinterpret_cast<double2*>(v)[i];
         const LocalOut a = local_terms_fast(d.x, mask, ve.x), b = local_terms_fast(d.y, mask, ve.y);
         acc[0] += a.e + b.e;
-        vv.x += a.v; vv.y += b.v;
-        reinterpret_cast<double2*>(v)[i] = vv;
+        if (v) {
+            double2 vv = accumulate ? reinterpret_cast<double2*>(v)[i] : make_double2(0.0, 0.0);
+            vv.x += a.v; vv.y += b.v;
+            reinterpret_cast<double2*>(v)[i] = vv;
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const LocalOut a = local_terms_fast(den[n - 1], mask, (mask & PAD_LOCAL_IONEL) ? v_ext[n - 1] : 0.0);
         acc[0] += a.e;
-        v[n - 1] += a.v;
+        if (v) v[n - 1] = (accumulate ? v[n - 1] : 0.0) + a.v;
     }
     block_reduce_store<1>(acc, partials);
 }
+
+}  // namespace
+// pad_eval_local (functionals.cu) for 16-byte aligned fields: the table-log kernel above (the log / exp tables live in this
+// translation unit)
+int pad_local_fast(pad_plan* p, const double* den, const double* v_ext, int mask, double* E_out, double* v_out, int accumulate, cudaStream_t s) {
+    PAD_TRY(ensure_twiddles(p->device));
+    const int grid = pad_grid_for(p->N / 2 > 0 ? p->N / 2 : 1);
+    local_fast_kernel<<<grid, PAD_THREADS, 0, s>>>(den, v_ext, v_out, p->N, mask, accumulate, p->partials);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    if (E_out) {
+        FinalizeArgs h;
+        h.nblocks = grid; h.nterms = 1; h.accumulate = accumulate;
+        for (int t = 0; t < PAD_MAX_RED; ++t) h.coef[t] = 0.0;
+        h.coef[0] = p->dV;
+        h.sums_out = nullptr;
+        h.E_out = E_out;
+        pad_launch_finalize(p, h, s);
+    }
+    return PAD_OK;
+}
+namespace {
 
 struct PostHartreeLocal {
     static constexpr bool kDen = true, kVin = true;
@@ -2123,7 +2150,7 @@ int pad_wgc99_fast(pad_plan* p, const double* den, double alpha, double beta, co
             if (ex->local_mask && !in_tail) {
                 if (aligned) {
                     const int grid = pad_grid_for(p->N / 2);
-                    local_fast_kernel<<<grid, PAD_THREADS, 0, s>>>(den, ex->v_ext, v_out, p->N, ex->local_mask, p->partials);
+                    local_fast_kernel<<<grid, PAD_THREADS, 0, s>>>(den, ex->v_ext, v_out, p->N, ex->local_mask, 1, p->partials);
                     ++g_pad_launches;
                     PAD_CUDA(cudaGetLastError());
                     if (E_out) {

@@ -74,6 +74,8 @@ extern "C" int pad_eval_local(pad_plan* p, const double* den, const double* v_ex
         return PAD_ERR_ARG;
     }
     cudaStream_t s = as_stream(stream);
+    if (g_pad_fast_fft && ((reinterpret_cast<uintptr_t>(den) | reinterpret_cast<uintptr_t>(v_out) | reinterpret_cast<uintptr_t>(v_ext)) & 15) == 0)
+        return pad_local_fast(p, den, v_ext, terms, E_out, v_out, accumulate, s);
     const bool tf = terms & PAD_LOCAL_TF, ldax = terms & PAD_LOCAL_LDAX, pzc = terms & PAD_LOCAL_PZC,
                ion = terms & PAD_LOCAL_IONEL;
     launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
