@@ -9,6 +9,7 @@ thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #include "fft_core.cuh"
 // the tile FFT part of fft_strided.cuh (SPass, spass_out_index, spass_slot_of_input, tile_fft), cut out of the real header by
 // tests/test_host_emulation.py
+#define PAD_Y256_CTAS 4      // (occupancy knob of the real header; irrelevant on host threads)
 #include "tile_part.h"
 #include <complex>
 #include <cstdio>
