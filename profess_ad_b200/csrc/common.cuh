@@ -341,6 +341,8 @@ void pad_stage_mark(const char* name, cudaStream_t s);
 extern int g_pad_fast_fft;    // 1: use the fused z-pass pipeline where the shape allows (default), 0: plain cuFFT 3-D
 int pad_wgc99_fast_supported(const pad_plan* p);
 int pad_local_fast(pad_plan* p, const double* den, const double* v_ext, int mask, double* E_out, double* v_out, int accumulate, cudaStream_t s);
+int pad_pbe_pointwise(pad_plan* p, cudaStream_t s, const double* den, double* gx, double* gy, double* gz, double* v, int which,
+                      int accumulate, int* grid_out);
 int pad_pbe_fast_supported(const pad_plan* p);
 int pad_pbe_fast(pad_plan* p, const double* den, int which, double* E_out, double* v_out, int accumulate, cudaStream_t s);
 int pad_hartree_fast_supported(const pad_plan* p);

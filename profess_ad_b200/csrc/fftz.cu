@@ -2725,6 +2725,17 @@ __global__ void __launch_bounds__(PAD_THREADS) pbe_point_kernel(const double* __
             reinterpret_cast<double2*>(gz)[i] = make_double2(sa * z.x, sb * z.y);
         }
     }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {          // odd grids (cuFFT route): the last point
+        const size_t i = n - 1;
+        double fa, ra, sa;
+        pbe_point_fast(den[i], gx[i] * gx[i] + gy[i] * gy[i] + gz[i] * gz[i], (which & 1) != 0, (which & 2) != 0, fa, ra, sa);
+        acc[0] += fa;
+        if (v) {
+            v[i] = (accumulate ? v[i] : 0.0) + ra;
+            sa *= 2.0;
+            gx[i] *= sa; gy[i] *= sa; gz[i] *= sa;
+        }
+    }
     block_reduce_store<1>(acc, partials);
 }
 
@@ -2768,6 +2779,19 @@ struct PostPbeDiv {                    // v -= div w
     __device__ void fold(const Ctx&, double, double, double*) const {}
     __device__ void finish(const Ctx&, size_t, double2, const double*, const double*, double, double, double*, double*, double*) const {}
 };
+
+// the point kernel on its own (the cuFFT route of pad_eval_pbe uses it too; the log / exp tables live in this translation unit):
+// energy density partial sums -> plan partials (returns the grid for the finalize), v (+)= f_n, (gx, gy, gz) <- w
+int pad_pbe_pointwise(pad_plan* p, cudaStream_t s, const double* den, double* gx, double* gy, double* gz, double* v, int which,
+                      int accumulate, int* grid_out) {
+    PAD_TRY(ensure_twiddles(p->device));
+    const int grid = pad_grid_for(p->N / 2 > 0 ? p->N / 2 : 1);
+    pbe_point_kernel<<<grid, PAD_THREADS, 0, s>>>(den, gx, gy, gz, v, p->N, which, accumulate, p->partials);
+    ++g_pad_launches;
+    PAD_CUDA(cudaGetLastError());
+    if (grid_out) *grid_out = grid;
+    return PAD_OK;
+}
 
 int pad_pbe_fast_supported(const pad_plan* p) { return !p->dist && fast_shape(p) && g_pad_own_xy && own_xy_shape(p) ? 1 : 0; }
 

@@ -933,6 +933,11 @@ extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E
     PAD_TRY(pad_fft_inverse_many(p, C + 1, R, 3, s));
     double *Gx = R[0], *Gy = R[1], *Gz = R[2], *Fr = R[3];
     const bool do_x = which & 1, do_c = which & 2, want_v = v_out != nullptr;
+    int pw_grid = 0;
+    if (g_pad_fast_fft && g_pad_pbe_fast && (reinterpret_cast<uintptr_t>(den) & 15) == 0) {
+        // point math with the table log / exp (fftz.cu:pbe_point_fast): 405 instead of 621 us per 256^3 points
+        PAD_TRY(pad_pbe_pointwise(p, s, den, Gx, Gy, Gz, want_v ? Fr : nullptr, which, 0, &pw_grid));
+    } else
     launch_ew<1>(p, s, [=] __device__(size_t i, double(&acc)[1]) {
         const double n = den[i];
         const double gx = Gx[i], gy = Gy[i], gz = Gz[i];
@@ -949,7 +954,19 @@ extern "C" int pad_eval_pbe(pad_plan* p, const double* den, int which, double* E
     });
     PAD_CHECK_LAUNCH();
     const double coef[1] = {p->dV};
-    if (E_out) finalize(p, s, 1, coef, E_out, accumulate);
+    if (E_out) {
+        if (pw_grid) {
+            FinalizeArgs a;
+            a.nblocks = pw_grid; a.nterms = 1; a.accumulate = accumulate;
+            for (int t = 0; t < PAD_MAX_RED; ++t) a.coef[t] = 0.0;
+            a.coef[0] = p->dV;
+            a.sums_out = nullptr;
+            a.E_out = E_out;
+            pad_launch_finalize(p, a, s);
+        } else {
+            finalize(p, s, 1, coef, E_out, accumulate);
+        }
+    }
     PAD_CHECK_LAUNCH();
     if (!want_v) return PAD_OK;
     PAD_TRY(pad_fft_forward_many(p, R, C, 3, s));
