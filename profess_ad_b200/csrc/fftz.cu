@@ -1,7 +1,11 @@
 // Hand-written z-axis (contiguous axis) real<->half-complex FFT passes with the real-space
-// elementwise work fused in, for power-of-two n2 in {128, 256, 512}.  The (x, y) axes are
-// transformed in place by one batched 2-D cuFFT Z2Z plan over the padded half-spectrum layout
+// elementwise work fused in, for power-of-two n2 in {128, 256, 512}.  The (x, y) axes are transformed by the
+// strided passes of fft_strided.cuh (n0, n1 in {64, 128, 256, 512}; the reciprocal-space multiply fused into the x
+// pass, the slab transposition carried by the y / x passes) -- or, for other (n0, n1) on single-GPU plans, by one
+// batched 2-D cuFFT Z2Z plan -- over the padded half-spectrum layout
 //      spec[x][y][nzp],  nzp = n2/2 + 8 (multiple of 8 complex = 128 B rows),  nzh = n2/2 + 1 used.
+// This translation unit also holds everything that needs the table log / exp of fastmath.cuh: the WGC99 / Wang-Teter /
+// Hartree / PBE pipelines, the fast local-term and PBE point kernels.
 //
 // Why: in the plain cuFFT pipeline every real-space pre/post kernel is a separate HBM round trip and
 // the r2c/c2r pass runs at ~3.7 TB/s.  Here a warp owns 32/TPL lines; TPL lanes share one line:
