@@ -104,7 +104,7 @@ def load_library():
         for env, opt in (('PAD_FAST_FFT', b'fast_fft'), ('PAD_OWN_XY', b'own_xy'), ('PAD_PIPE', b'pipe'),
                          ('PAD_PIPE_LPI', b'pipe_lpi'), ('PAD_PIPE_TPI', b'pipe_tpi'), ('PAD_FUSE_TERMS', b'fuse_terms'),
                          ('PAD_ZINV_STREAM', b'zinv_stream'), ('PAD_FUSE_MID', b'fuse_mid'), ('PAD_FOLD_TABLE', b'fold_table'),
-                         ('PAD_GRAPHS', b'graphs'), ('PAD_YWIDE', b'ywide'), ('PAD_XONE', b'xone'), ('PAD_LOCAL_TAIL', b'local_tail')):
+                         ('PAD_GRAPHS', b'graphs'), ('PAD_YWIDE', b'ywide'), ('PAD_XONE', b'xone'), ('PAD_PBE_FAST', b'pbe_fast'), ('PAD_LOCAL_TAIL', b'local_tail')):
             if os.environ.get(env, '').lstrip('-').isdigit():
                 lib.pad_set_option(opt, int(os.environ[env]))
         _lib = lib
